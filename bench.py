@@ -1,0 +1,245 @@
+#!/usr/bin/env python
+"""bench.py -- PLEN env-steps/sec on B200 (BASELINE.json metric) with roofline, end-to-end and CPU-baseline legs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs-per-gpu E] [--impl reference]
+
+A "step" is one vectorised env step (1 action -> 4 physics ticks -> obs/reward/done/auto-reset) of every env of the
+rank: ONE launch of k_step.  Workload = BASELINE config 5's shard: E = 131072 envs per GPU (1,048,576 envs at 8
+GPUs), actions U(-1,1)^18 drawn on the device with torch.Generator(seed 0 + rank), auto-reset on.  Envs are
+independent, so ranks share nothing on the data path ("scaling": "weak"); torch.distributed (NCCL) is used only for
+the barrier and the max-over-ranks of the device time.
+
+`--impl reference` times the CPU restatement of the reference path (oracle/, float64 C, one thread per host core):
+PyBullet itself is absent from the reference checkout and from this image, so the reference
+arm is the oracle PORT, labelled as such -- never presented as a PyBullet number.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "PLEN env-steps/sec"
+UNIT = "env-steps/s"
+# algorithmic HBM bytes per env-step (DESIGN.md "Data layout"): state record 96 words read + written, action 18 f32,
+# obs 26 f32, reward f32, done + timeout bytes
+BYTES_PER_ENV_STEP = 2 * 96 * 4 + 18 * 4 + 26 * 4 + 4 + 2
+FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for k, nme in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_throughput(n_threads, envs_per_thread, steps, seed=0):
+    """env-steps/s of the float64 oracle (kind "port") on n_threads host threads, random actions, auto-reset."""
+    from oracle.oracle import PlenOracle
+    n = n_threads * envs_per_thread
+    o = PlenOracle(n, n_threads=n_threads)
+    o.reset()
+    rng = np.random.default_rng(seed)
+    acts = rng.uniform(-1, 1, (steps + 1, n, 18))
+    o.step(acts[0], auto_reset=True)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        o.step(acts[s + 1], auto_reset=True)
+    dt = time.perf_counter() - t0
+    return n * steps / dt, dt, n
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    envs_per_thread = 16
+    # one "step" = one vector step of cores*16 envs on all host threads
+    val, dt, n = cpu_port_throughput(cores, envs_per_thread, args.steps + 0, seed=0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config5 shard workload (random actions U(-1,1)^18, auto-reset) on host cores; "
+                               "sample = %d envs x %d steps" % (n, args.steps)},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d envs x %d vector steps, oracle/plen_oracle.c float64, %d threads; PyBullet "
+                                   "itself is not installable here (SURVEY.md 8c)" % (n, args.steps, cores)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--envs-per-gpu", type=int, default=131072)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    from plen_ml_walk_b200 import _abi
+    from plen_ml_walk_b200.vec_env import PlenVecEnv
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=dev)
+        dist = dist_mod
+
+    E, K, W = args.envs_per_gpu, args.steps, max(3, args.warmup)
+    env = PlenVecEnv(E, device=dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(rank)
+    acts = [torch.empty((E, 18), device=dev).uniform_(-1, 1, generator=gen) for _ in range(8)]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MiB > 126 MB L2
+    env.reset()
+    for w in range(W):
+        env.step(acts[w % 8])
+    torch.cuda.synchronize(dev)
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident leg: K steps, each bracketed by CUDA events on the launching stream, L2 flushed in between
+    sampler = ClockSampler(local_rank)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    launches0 = env.launches
+    barrier()
+    sampler.start()
+    for k in range(K):
+        flush.zero_()
+        ev[k][0].record()
+        env.step(acts[k % 8])
+        ev[k][1].record()
+    barrier()
+    clocks = sampler.stop()
+    gpu_launches = env.launches - launches0
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * E * K / (total_ms * 1e-3)
+
+    # ---- end-to-end leg: HOST pinned buffers through plen_step_host (H2D actions, step, D2H obs/reward/done)
+    Ke = max(3, min(K, 10))
+    h_act = [torch.empty((E, 18), dtype=torch.float32).uniform_(-1, 1).pin_memory() for _ in range(2)]
+    h_obs = torch.empty((E, 26), dtype=torch.float32).pin_memory()
+    h_rew = torch.empty(E, dtype=torch.float32).pin_memory()
+    h_done = torch.empty(E, dtype=torch.uint8).pin_memory()
+    env.step_host(h_act[0], h_obs, h_rew, h_done)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(Ke):
+        env.step_host(h_act[k % 2], h_obs, h_rew, h_done)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * E * Ke / float(te.item())
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        step_ms = total_ms / K
+        achieved = E * BYTES_PER_ENV_STEP / (step_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config5 shard: %d envs/GPU (1,048,576 envs at 8 GPUs), random actions "
+                                   "U(-1,1)^18, auto-reset, 4 ticks/step" % E,
+                       "envs_per_gpu": E, "l2": "256 MiB flush between timed steps"},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": E * 18 * 4,
+                    "d2h_bytes_per_step": E * (26 * 4 + 4 + 1), "steps": Ke},
+            "gpu_launches": gpu_launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "bytes_per_env_step": BYTES_PER_ENV_STEP,
+                         "note": "k_step is FP32-issue bound, not HBM bound (DESIGN.md); see profiles/ for pipe utilisation"},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cores = len(os.sched_getaffinity(0))
+            v, dt, n = cpu_port_throughput(cores, 8, 12)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "%d envs x 12 vector steps (%.1f s), float64 oracle port" % (n, dt)}
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,157 @@
+/* plen_b200.h -- C ABI of the B200-native batched PLEN walking environment (libplen_b200.so).
+ *
+ * Drop-in boundary for the hot path of moribots/plen_ml_walk: the physics step behind
+ * plen_bullet/src/plen_bullet/plen_env.py and the observation / reward / termination / auto-reset logic around
+ * it.  In the reference that boundary is the in-process PyBullet C extension (module-global client 0); every entry
+ * point below names the reference call(s) it replaces.  Plain pointers and sizes only -- no torch, no C++ types.
+ *
+ * Conventions
+ *   - one ctx per GPU; calls on a ctx are stream-ordered, non-blocking (except *_host) and not re-entrant;
+ *   - all *_dev pointers are device memory owned by the caller; the ctx owns the per-env state and model tables;
+ *     no allocation happens inside plen_step;
+ *   - every function returns 0 on success, a negative PLEN_E_* code otherwise; text via plen_last_error();
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - there is NO CPU fallback: without a CUDA device plen_create fails with PLEN_E_CUDA.
+ *
+ * Layouts (row-major, float32 unless noted)
+ *   actions  [N,18]  agent space [-1,1] (or raw radians when config.joint_act), joint order plen_env.py:547-554
+ *   obs      [N,26]  [q1..q18, z, vx, roll, pitch, yaw, y, right_contact, left_contact]   (plen_env.py:816-822)
+ *   qpos     [N,25]  [pos xyz, quat xyzw, q1..q18]
+ *   qvel     [N,24]  [v_lin world xyz, omega world xyz, qd1..qd18]
+ *   aux      [N,PLEN_AUX_WORDS]  [lam_n[8], manifold bits, cnt, ds, hist_len, ep_t, last[6], sums[9], ep_ret]
+ */
+#ifndef PLEN_B200_H
+#define PLEN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLEN_LANES 24          /* 6 base velocity coordinates + 18 joints */
+#define PLEN_NJ 18
+#define PLEN_OBS 26
+#define PLEN_QPOS 25
+#define PLEN_QVEL 24
+#define PLEN_AUX_WORDS 29
+#define PLEN_STATE_WORDS 96    /* per-env state record in HBM: 3 x 128 B lines, one word per lane per line */
+
+#define PLEN_OK 0
+#define PLEN_E_ARG (-1)
+#define PLEN_E_CUDA (-2)
+#define PLEN_E_STATE (-3)
+
+/* Per-lane articulation tables produced by the URDF loader (plen_ml_walk_b200/urdf_loader.py).
+ * Replaces: p.loadURDF("plen.urdf", ...) (plen_env.py:312-315) + the dynamics overrides (plen_env.py:438-481). */
+typedef struct {
+    float R_pj[PLEN_LANES][9];     /* parent body frame -> joint frame at q = 0, row major (lanes 6..23) */
+    float p_pj[PLEN_LANES][3];     /* joint origin in the parent body frame */
+    float axis[PLEN_LANES][3];     /* joint axis in the body frame */
+    float mass[PLEN_LANES];        /* lane 0 = torso composite; 1..5 unused */
+    float com[PLEN_LANES][3];      /* centre of mass in the body frame */
+    float inertia[PLEN_LANES][6];  /* xx yy zz xy xz yz about the com, body axes */
+    float lower[PLEN_LANES], upper[PLEN_LANES];   /* joint limits (plen.urdf:1310 ...) */
+    int32_t chain_start[PLEN_LANES];              /* first lane of the limb this lane belongs to */
+    int32_t foot_lane[2];          /* [0] right foot (Bullet link 11), [1] left foot (link 19) */
+    float foot_pts[2][4][3];       /* sole contact vertices in the foot body frame */
+    float foot_break[2];           /* contact breaking threshold per foot */
+} plen_model;
+
+/* Every constant of the path; defaults = the reference literals (cited) or the PyBullet defaults they rely on. */
+typedef struct {
+    float dt;                  /* 1/240 s            plen_env.py:41 */
+    int32_t substeps;          /* 4                  plen_env.py:40-42 */
+    int32_t reset_ticks;       /* 8                  plen_env.py:569-570 */
+    float gravity_z;           /* -9.81              plen_env.py:296 */
+    float start_pos[3];        /* 0 0 0.158          plen_env.py:312 */
+    float motor_max_force;     /* 0.15 N m           plen_env.py:753 */
+    int32_t joint_act;         /* raw-radian actions plen_env.py:34, :652-654 */
+    float linear_damping;      /* 0 | 0.1            plen_env.py:472-481 */
+    float mu_lateral;          /* 0.8*0.8            plen_env.py:309, :444 */
+    float mu_spinning;         /* 0.1*0.8            plen_env.py:445 */
+    float mu_rolling;          /* (0.1|0.01)*0.8     plen_env.py:439-442 */
+    float restitution;         /* 0.5*0.5            plen_env.py:309, :481 */
+    double env_lo[PLEN_NJ], env_hi[PLEN_NJ];  /* env_ranges, plen_env.py:148-167 (double: the a=+-1 inset branch
+                                                 must fall on the same side as the reference's float64) */
+    int32_t max_episode_steps; /* 500                plen_env.py:15-19 */
+    float motor_kp, motor_kd;  /* 0.1, 1.0  PyBullet POSITION_CONTROL defaults */
+    int32_t solver_iterations; /* 50 */
+    float residual_threshold;  /* 1e-7 */
+    float erp_contact;         /* 0.08 */
+    float erp_joint;           /* 0.2 */
+    float linear_slop;         /* 1e-5 */
+    float warmstart_factor;    /* 0.1 */
+    float restitution_vel_threshold; /* 0.2 */
+    float hull_margin;         /* 0.001 */
+    float max_coord_velocity;  /* 100 */
+    int32_t auto_reset;        /* 1: plen_step resets finished envs in the same launch (the reference leaves it to
+                                  the caller, plen_td3.py:122-129) */
+} plen_config;
+
+typedef struct plen_ctx plen_ctx;
+
+const char *plen_version(void);
+
+/* Fill `cfg` with the reference defaults (joint_act selects the trajectory_eval.py variant, plen_env.py:439-475). */
+int plen_default_config(plen_config *cfg, int joint_act);
+
+/* Replaces PlenWalkEnv.__init__ (plen_env.py:34-556): p.connect / loadURDF / changeDynamics.  Allocates the per-env
+ * state for n_envs robots on CUDA device `device`, uploads the tables, and precomputes the post-reset snapshot
+ * (the reference reset is deterministic: fixed pose + 8 ticks, plen_env.py:561-570).  NULL on failure
+ * (plen_last_error(NULL) has the reason). */
+plen_ctx *plen_create(const plen_config *cfg, const plen_model *model, int n_envs, int device);
+void plen_destroy(plen_ctx *ctx);
+const char *plen_last_error(const plen_ctx *ctx);
+int plen_num_envs(const plen_ctx *ctx);
+
+/* Replaces PlenWalkEnv.reset (plen_env.py:558-614) for the envs whose mask byte is non-zero (NULL = all).
+ * obs_dev may be NULL. */
+int plen_reset(plen_ctx *ctx, const uint8_t *mask_dev, float *obs_dev, void *stream);
+
+/* Replaces PlenWalkEnv.step (plen_env.py:638-692) + the TimeLimit wrapper (plen_env.py:15-19) for all N envs in ONE
+ * kernel launch: agent_to_env -> motor targets -> 4 ticks (contact, dynamics, PGS, integrate) -> observation ->
+ * done -> reward -> counters -> optional auto-reset.
+ *   obs_dev          [N,26] observation the agent acts on next (the reset observation where done && auto_reset)
+ *   reward_dev       [N]
+ *   done_dev         [N] uint8, dead || ep_t >= max_episode_steps
+ *   timeout_dev      [N] uint8 (nullable), !dead && ep_t >= max_episode_steps (plen_td3.py:109-110 done_bool)
+ *   terminal_obs_dev [N,26] (nullable) observation of the finished episode's last step, written where done */
+int plen_step(plen_ctx *ctx, const float *actions_dev, float *obs_dev, float *reward_dev, uint8_t *done_dev,
+              uint8_t *timeout_dev, float *terminal_obs_dev, void *stream);
+
+/* Same call with HOST buffers (pinned memory recommended): H2D of the actions, the step, D2H of obs / reward / done,
+ * and a stream synchronise.  This is the end-to-end path a PyBullet user would see. */
+int plen_step_host(plen_ctx *ctx, const float *actions_host, float *obs_host, float *reward_host,
+                   uint8_t *done_host, uint8_t *timeout_host);
+
+/* Replaces getBasePositionAndOrientation / getJointStates / getBaseVelocity (plen_env.py:771-773) and
+ * resetBasePositionAndOrientation / resetJointState (plen_env.py:561-565) for all envs; any pointer may be NULL. */
+int plen_get_state(plen_ctx *ctx, float *qpos_dev, float *qvel_dev, float *aux_dev, void *stream);
+int plen_set_state(plen_ctx *ctx, const float *qpos_dev, const float *qvel_dev, const float *aux_dev, void *stream);
+
+/* Advance every env by n_ticks physics ticks with raw joint targets [N,18] (radians) and no env logic.
+ * Replaces move_joints + p.stepSimulation (plen_env.py:746-753, :665-667); used by the parity tests. */
+int plen_tick(plen_ctx *ctx, const float *targets_dev, int n_ticks, void *stream);
+
+/* Diagnostics: per-env generalized inverse mass matrix M^-1 [N,24,24] in coordinates [omega_w, v_w, qd]
+ * and world pose of the 19 body frames pos [N,24,3] / rot [N,24,9] (lanes 1..5 unused). */
+int plen_debug_dynamics(plen_ctx *ctx, float *minv_dev, float *pos_dev, float *rot_dev, void *stream);
+
+/* Sinewave gait + closed-form leg IK for n_gaits parameter sets in one launch.
+ * Replaces TrajectoryGenerator.main (plen_bullet/src/plen_bullet/trajectory_generator.py:54-277) and the trajectory
+ * assembly of trajectory_eval.py:180-261.
+ * All arithmetic and buffers are float64 (the reference is numpy float64; tolerance 1e-6 rad).
+ *   params_dev [n_gaits,5]  = height, stride, bend_distance, body_sway, fwd_bias (mm; defaults 30 30 10 5 10)
+ *   traj_dev   [n_gaits,40,18] one gait cycle (20 right-forward + 20 left-forward rows) in action order, sign map applied
+ *   bend_dev   [n_gaits,18]   the "bend_legs" pose
+ *   status_dev [n_gaits] uint8 (nullable): 1 where the IK target was unreachable (reference raises ValueError,
+ *              trajectory_generator.py:187-189); the row is then filled with NaN. */
+int plen_gait_ik(int device, const double *params_dev, int n_gaits, double *traj_dev, double *bend_dev,
+                 uint8_t *status_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

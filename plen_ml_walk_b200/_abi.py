@@ -1,0 +1,110 @@
+"""ctypes mirror of include/plen_b200.h (plen_model, plen_config) and the loader of libplen_b200.so.
+
+The CUDA library is the only implementation: if it is missing or no CUDA device is present the import of the library
+(or plen_create) raises -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .urdf_loader import N_LANES, PlenModel
+
+NJ = 18
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libplen_b200.so")
+
+STATE_WORDS = 96
+AUX_WORDS = 29
+OBS_DIM = 26
+ACT_DIM = 18
+
+
+class PlenModelC(C.Structure):
+    _fields_ = [
+        ("R_pj", (C.c_float * 9) * N_LANES), ("p_pj", (C.c_float * 3) * N_LANES), ("axis", (C.c_float * 3) * N_LANES),
+        ("mass", C.c_float * N_LANES), ("com", (C.c_float * 3) * N_LANES), ("inertia", (C.c_float * 6) * N_LANES),
+        ("lower", C.c_float * N_LANES), ("upper", C.c_float * N_LANES), ("chain_start", C.c_int32 * N_LANES),
+        ("foot_lane", C.c_int32 * 2), ("foot_pts", ((C.c_float * 3) * 4) * 2), ("foot_break", C.c_float * 2),
+    ]
+
+
+class PlenConfigC(C.Structure):
+    _fields_ = [
+        ("dt", C.c_float), ("substeps", C.c_int32), ("reset_ticks", C.c_int32), ("gravity_z", C.c_float),
+        ("start_pos", C.c_float * 3), ("motor_max_force", C.c_float), ("joint_act", C.c_int32),
+        ("linear_damping", C.c_float), ("mu_lateral", C.c_float), ("mu_spinning", C.c_float),
+        ("mu_rolling", C.c_float), ("restitution", C.c_float),
+        ("env_lo", C.c_double * NJ), ("env_hi", C.c_double * NJ), ("max_episode_steps", C.c_int32),
+        ("motor_kp", C.c_float), ("motor_kd", C.c_float), ("solver_iterations", C.c_int32),
+        ("residual_threshold", C.c_float), ("erp_contact", C.c_float), ("erp_joint", C.c_float),
+        ("linear_slop", C.c_float), ("warmstart_factor", C.c_float), ("restitution_vel_threshold", C.c_float),
+        ("hull_margin", C.c_float), ("max_coord_velocity", C.c_float), ("auto_reset", C.c_int32),
+    ]
+
+
+def model_to_c(model: PlenModel) -> PlenModelC:
+    m = PlenModelC()
+    for l in range(N_LANES):
+        for k in range(9):
+            m.R_pj[l][k] = float(model.R_pj[l].reshape(9)[k])
+        for k in range(3):
+            m.p_pj[l][k] = float(model.p_pj[l][k])
+            m.axis[l][k] = float(model.axis[l][k])
+            m.com[l][k] = float(model.com[l][k])
+        for k in range(6):
+            m.inertia[l][k] = float(model.inertia[l][k])
+        m.mass[l] = float(model.mass[l])
+        m.lower[l] = float(model.lower[l])
+        m.upper[l] = float(model.upper[l])
+        m.chain_start[l] = int(model.chain_start[l])
+    for f in range(2):
+        m.foot_lane[f] = int(model.foot_lane[f])
+        m.foot_break[f] = float(model.foot_break[f])
+        for p in range(4):
+            for k in range(3):
+                m.foot_pts[f][p][k] = float(model.foot_pts[f][p][k])
+    return m
+
+
+EXPORTS = (
+    "plen_version", "plen_default_config", "plen_create", "plen_destroy", "plen_last_error", "plen_num_envs",
+    "plen_reset", "plen_step", "plen_step_host", "plen_get_state", "plen_set_state", "plen_tick",
+    "plen_debug_dynamics", "plen_gait_ik",
+)
+
+_lib = None
+
+
+def load_library(path: str = LIB_PATH):
+    """dlopen libplen_b200.so and declare the prototypes of every symbol include/plen_b200.h exports."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise RuntimeError(
+            "libplen_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` or "
+            "`python -m plen_ml_walk_b200.build`. There is no CPU fallback." % path)
+    L = C.CDLL(path)
+    vp, ip = C.c_void_p, C.c_int
+    L.plen_version.restype = C.c_char_p
+    L.plen_default_config.argtypes = [C.POINTER(PlenConfigC), ip]
+    L.plen_create.argtypes = [C.POINTER(PlenConfigC), C.POINTER(PlenModelC), ip, ip]
+    L.plen_create.restype = vp
+    L.plen_destroy.argtypes = [vp]
+    L.plen_destroy.restype = None
+    L.plen_last_error.argtypes = [vp]
+    L.plen_last_error.restype = C.c_char_p
+    L.plen_num_envs.argtypes = [vp]
+    L.plen_reset.argtypes = [vp, vp, vp, vp]
+    L.plen_step.argtypes = [vp] * 8
+    L.plen_step_host.argtypes = [vp] * 6
+    L.plen_get_state.argtypes = [vp] * 5
+    L.plen_set_state.argtypes = [vp] * 5
+    L.plen_tick.argtypes = [vp, vp, ip, vp]
+    L.plen_debug_dynamics.argtypes = [vp] * 5
+    L.plen_gait_ik.argtypes = [ip, vp, ip, vp, vp, vp, vp]
+    _lib = L
+    return L

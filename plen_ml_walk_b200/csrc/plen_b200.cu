@@ -1,0 +1,439 @@
+// plen_b200.cu -- kernels + C ABI of libplen_b200.so (see include/plen_b200.h).  sm_100a only, no CPU path.
+//
+// Launch shape: one warp per robot, 4 warps per CTA; the lane-major model table (4 KB) is staged once per CTA in
+// shared memory, each warp owns a 10 KB scratch (state record, twists, M^-1, contact rows).  The per-env state
+// record is 96 words = 3 x 128 B lines, word w = 32 k + lane, so every global access of the step is one fully
+// coalesced line per warp.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "plen_host_tables.h"
+
+using namespace plen;
+
+#define WARPS_PER_CTA 4
+
+struct plen_ctx {
+    int n, device;
+    plen_config cfg;
+    plen_model model;
+    DevConfig dc;
+    EnvRanges er;
+    float *d_tab, *d_state, *d_snapshot;
+    float *d_act, *d_obs, *d_rew;
+    uint8_t *d_done, *d_tmo;
+    cudaStream_t stream;
+    char err[512];
+};
+
+static char g_err[512] = "";
+
+static int fail(plen_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    snprintf(ctx ? ctx->err : g_err, 512, "%s", buf);
+    return code;
+}
+#define CK(ctx, call)                                                                                       \
+    do {                                                                                                    \
+        cudaError_t e_ = (call);                                                                            \
+        if (e_ != cudaSuccess) return fail(ctx, PLEN_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_));      \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ kernels
+struct SmemLayout {
+    float tab[T_ROWS * 32];
+    WarpScratch ws[WARPS_PER_CTA];
+};
+
+__device__ __forceinline__ SmemLayout &stage_table(const float *tab_g) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemLayout &sm = *reinterpret_cast<SmemLayout *>(smem_raw);
+    for (int i = threadIdx.x; i < T_ROWS * 32; i += blockDim.x) sm.tab[i] = tab_g[i];
+    __syncthreads();
+    return sm;
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_step(const __grid_constant__ DevConfig dc, const __grid_constant__ EnvRanges er, const float *__restrict__ tab_g,
+       float *__restrict__ state, int n, const float *__restrict__ actions, float *__restrict__ obs,
+       float *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ timeout,
+       float *__restrict__ terminal_obs, const float *__restrict__ snapshot) {
+    SmemLayout &sm = stage_table(tab_g);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int env = blockIdx.x * WARPS_PER_CTA + warp;
+    if (env >= n) return;
+    WarpScratch &ws = sm.ws[warp];
+    LaneState L;
+    load_record(state + (size_t)env * PLEN_STATE_WORDS, ws, L, lane);
+    StepIO io{actions + (size_t)env * PLEN_NJ, obs + (size_t)env * PLEN_OBS, reward + env, done + env,
+              timeout ? timeout + env : nullptr, terminal_obs ? terminal_obs + (size_t)env * PLEN_OBS : nullptr,
+              snapshot};
+    env_step(dc, er, sm.tab, ws, L, lane, io);
+    store_record(state + (size_t)env * PLEN_STATE_WORDS, ws, L, lane);
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_tick(const __grid_constant__ DevConfig dc, const float *__restrict__ tab_g, float *__restrict__ state, int n,
+       const float *__restrict__ targets, int n_ticks, float *dbg_minv, float *dbg_pos, float *dbg_rot, int dbg_only) {
+    SmemLayout &sm = stage_table(tab_g);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int env = blockIdx.x * WARPS_PER_CTA + warp;
+    if (env >= n) return;
+    WarpScratch &ws = sm.ws[warp];
+    LaneState L;
+    load_record(state + (size_t)env * PLEN_STATE_WORDS, ws, L, lane);
+    if (lane >= 6 && lane < 24) L.tgt = targets ? targets[(size_t)env * PLEN_NJ + lane - 6] : 0.0f;
+    DebugOut dbg{dbg_minv ? dbg_minv + (size_t)env * 576 : nullptr, dbg_pos ? dbg_pos + (size_t)env * 72 : nullptr,
+                 dbg_rot ? dbg_rot + (size_t)env * 216 : nullptr};
+    const bool want_dbg = dbg_minv || dbg_pos || dbg_rot;
+    for (int t = 0; t < n_ticks; t++) physics_tick(dc, sm.tab, ws, L, lane, (want_dbg && t == n_ticks - 1) ? &dbg : nullptr);
+    if (!dbg_only) store_record(state + (size_t)env * PLEN_STATE_WORDS, ws, L, lane);
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_observe(const float *__restrict__ state, int n, float *__restrict__ obs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemLayout &sm = *reinterpret_cast<SmemLayout *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int env = blockIdx.x * WARPS_PER_CTA + warp;
+    if (env >= n) return;
+    WarpScratch &ws = sm.ws[warp];
+    LaneState L;
+    load_record(state + (size_t)env * PLEN_STATE_WORDS, ws, L, lane);
+    observe(ws, L, lane);
+    if (lane < PLEN_OBS) obs[(size_t)env * PLEN_OBS + lane] = ws.obs[lane];
+}
+
+// PlenWalkEnv.reset (plen_env.py:558-614): copy the post-reset snapshot into the selected envs
+__global__ void k_reset(float *__restrict__ state, int n, const uint8_t *__restrict__ mask,
+                        const float *__restrict__ snapshot, float *__restrict__ obs) {
+    const int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (env >= n) return;
+    if (mask && !mask[env]) return;
+    float *rec = state + (size_t)env * PLEN_STATE_WORDS;
+    rec[lane] = snapshot[lane];
+    rec[32 + lane] = snapshot[32 + lane];
+    rec[64 + lane] = snapshot[64 + lane];
+    if (obs && lane < PLEN_OBS) obs[(size_t)env * PLEN_OBS + lane] = snapshot[PLEN_STATE_WORDS + lane];
+}
+
+__global__ void k_fill(float *__restrict__ state, int n, const float *__restrict__ rec96) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (size_t)n * PLEN_STATE_WORDS) state[i] = rec96[i % PLEN_STATE_WORDS];
+}
+
+// aux = [lam_n[8], manifold bits, cnt, ds, hist_len, ep_t, last[6], sums[9], ep_ret]
+__global__ void k_get_state(const float *__restrict__ state, int n, float *qpos, float *qvel, float *aux) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const float *r = state + (size_t)e * PLEN_STATE_WORDS;
+    if (qpos) {
+        float *o = qpos + (size_t)e * PLEN_QPOS;
+        for (int k = 0; k < 3; k++) o[k] = r[W_POS + k];
+        for (int k = 0; k < 4; k++) o[3 + k] = r[W_QUAT + k];
+        for (int k = 0; k < 18; k++) o[7 + k] = r[W_Q + 6 + k];
+    }
+    if (qvel) {
+        float *o = qvel + (size_t)e * PLEN_QVEL;
+        for (int k = 0; k < 3; k++) { o[k] = r[W_U + 3 + k]; o[3 + k] = r[W_U + k]; }
+        for (int k = 0; k < 18; k++) o[6 + k] = r[W_U + 6 + k];
+    }
+    if (aux) {
+        float *o = aux + (size_t)e * PLEN_AUX_WORDS;
+        for (int k = 0; k < 8; k++) o[k] = r[W_U + 24 + k];
+        o[8] = r[W_MAN]; o[9] = r[W_CNT]; o[10] = r[W_DS]; o[11] = r[W_HIST]; o[12] = r[W_EPT];
+        for (int k = 0; k < 6; k++) o[13 + k] = r[W_LAST + k];
+        for (int k = 0; k < 9; k++) o[19 + k] = r[W_SUMS + k];
+        o[28] = r[W_EPRET];
+    }
+}
+
+__global__ void k_set_state(float *__restrict__ state, int n, const float *qpos, const float *qvel, const float *aux) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    float *r = state + (size_t)e * PLEN_STATE_WORDS;
+    if (qpos) {
+        const float *o = qpos + (size_t)e * PLEN_QPOS;
+        for (int k = 0; k < 3; k++) r[W_POS + k] = o[k];
+        for (int k = 0; k < 4; k++) r[W_QUAT + k] = o[3 + k];
+        for (int k = 0; k < 18; k++) r[W_Q + 6 + k] = o[7 + k];
+    }
+    if (qvel) {
+        const float *o = qvel + (size_t)e * PLEN_QVEL;
+        for (int k = 0; k < 3; k++) { r[W_U + 3 + k] = o[k]; r[W_U + k] = o[3 + k]; }
+        for (int k = 0; k < 18; k++) r[W_U + 6 + k] = o[6 + k];
+    }
+    if (aux) {
+        const float *o = aux + (size_t)e * PLEN_AUX_WORDS;
+        for (int k = 0; k < 8; k++) r[W_U + 24 + k] = o[k];
+        r[W_MAN] = o[8]; r[W_CNT] = o[9]; r[W_DS] = o[10]; r[W_HIST] = o[11]; r[W_EPT] = o[12];
+        for (int k = 0; k < 6; k++) r[W_LAST + k] = o[13 + k];
+        for (int k = 0; k < 9; k++) r[W_SUMS + k] = o[19 + k];
+        r[W_EPRET] = o[28];
+    }
+}
+
+// ---- sinewave gait + closed-form leg IK, float64, one thread per parameter set
+// (trajectory_generator.py:54-152 foot_path, :154-167 assemble, :169-233 IK, :235-270; trajectory_eval.py:180-261)
+namespace gait {
+constexpr int NDS = 5, NSS = 10, NROW = 20;   // trajectory_generator.py:10-11
+__device__ bool leg_ik(double x, double y, double z, bool right, double *out6) {
+    const double l1 = 25.0, l2 = 40.0;                                 // :35-37
+    const double Zx = x, Zy = y, Zz = l1 + l2 - z;                     // :181-183
+    const double th1 = right ? atan2(-Zy, Zz) : atan2(Zy, Zz);         // :185-188
+    const double arg = (Zx * Zx + Zy * Zy + Zz * Zz - l1 * l1 - l2 * l2) / (2.0 * l1 * l2);   // :190-192
+    if (!(arg >= -1.0 && arg <= 1.0)) return false;                    // math.acos raises ValueError
+    double th3 = acos(arg);
+    const double sqrtyz = sqrt(Zy * Zy + Zz * Zz), hok = l1 / l2;      // :194-195
+    double th2 = -atan2(sqrtyz * sin(th3) + Zx * cos(th3) + Zx * hok,
+                        sqrtyz * cos(th3) + sqrtyz * hok - Zx * sin(th3));   // :197-199
+    // real_ranges (plen_env.py:170-189): R knee [3] / L knee [9] = [-1.0, 1.57]; R thigh [2] = [-0.95, 1.2]; L [8] = [-1.2, 0.95]
+    th3 = fmin(fmax(th3, -1.0), 1.57);                                 // :203-207 / :215-218
+    if (right) th2 = fmin(fmax(th2, -0.95), 1.2); else th2 = fmin(fmax(th2, -1.2), 0.95);   // :209-212 / :220-223
+    const double th4 = -(th2 + th3), th5 = right ? -th1 : th1;         // :225-230
+    out6[0] = 0.0; out6[1] = th1; out6[2] = th2; out6[3] = th3; out6[4] = th4; out6[5] = th5;
+    return true;
+}
+__device__ void foot_point(int seg, int i, double height, double stride, double bend, double sway, double bias, double *p) {
+    // seg: 0 SS dominant, 1 DS dominant, 2 SS support, 3 DS support (trajectory_generator.py:66-125)
+    const double PI = 3.141592653589793;
+    double t;
+    switch (seg) {
+        case 0: t = i / (NSS - 1.0);
+            p[0] = t * stride; p[1] = sin(-PI * ((1 / 3.0) * (1 + t))) * sway; p[2] = sin(t * PI) * height + bend; break;
+        case 1: t = i / (2 * NDS - 1.0);
+            p[0] = -stride * (t / 2.0); p[1] = sin(-PI * ((-1.0 / 3.0) + (2 / 3.0) * t)) * sway; p[2] = bend; break;
+        case 2: t = i / (NSS - 1.0);
+            p[0] = stride * ((1.0 / 2.0) - t) / 2.0; p[1] = sin(PI * ((1 / 3.0) * (1 + t))) * sway; p[2] = bend; break;
+        default: t = i / (2.0 * NDS - 1.0);
+            p[0] = stride * (1.0 - t) / 2.0; p[1] = sin(-PI * ((2.0 / 3.0) + (2 / 3.0) * t)) * sway; p[2] = bend; break;
+    }
+    if (bias != 0) p[0] = p[0] - bias;                                  // :128-132
+}
+// column c (0..19) of foot_walk_rfwd_r (dominant: DS 2nd half, SS, support-DS 1st half) or foot_walk_lfwd_r (:135-145)
+__device__ void walk_point(bool dominant, int c, double h, double s, double b, double sw, double bias, double *p) {
+    if (dominant) {
+        if (c < NDS) foot_point(1, NDS + c, h, s, b, sw, bias, p);
+        else if (c < NDS + NSS) foot_point(0, c - NDS, h, s, b, sw, bias, p);
+        else foot_point(3, c - NDS - NSS, h, s, b, sw, bias, p);
+    } else {
+        if (c < NDS) foot_point(3, NDS + c, h, s, b, sw, bias, p);
+        else if (c < NDS + NSS) foot_point(2, c - NDS, h, s, b, sw, bias, p);
+        else foot_point(1, c - NDS - NSS, h, s, b, sw, bias, p);
+    }
+}
+__device__ void assemble_row(const double *row12, double *out18) {     // trajectory_eval.py:180-205
+    const double PI = 3.141592653589793;
+    out18[0] = -row12[0]; out18[1] = -row12[1]; out18[2] = -row12[2]; out18[3] = -row12[3];
+    out18[4] = row12[4]; out18[5] = row12[5];
+    out18[6] = row12[6]; out18[7] = row12[7]; out18[8] = row12[8]; out18[9] = row12[9];
+    out18[10] = -row12[10]; out18[11] = row12[11];
+    out18[12] = PI / 5; out18[13] = PI / 8; out18[14] = 0; out18[15] = -PI / 5; out18[16] = PI / 8; out18[17] = 0;
+}
+}  // namespace gait
+
+__global__ void k_gait_ik(const double *__restrict__ params, int n, double *__restrict__ traj, double *__restrict__ bend,
+                          uint8_t *__restrict__ status) {
+    using namespace gait;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const double h = params[5 * g], s = params[5 * g + 1], b = params[5 * g + 2], sw = params[5 * g + 3],
+                 bias = params[5 * g + 4];
+    bool ok = true;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int half = 0; half < 2; half++) {          // 0: foot_walk_rfwd, 1: foot_walk_lfwd
+        for (int c = 0; c < NROW; c++) {
+            double pr[3], pl[3], row[12], out[18];
+            // right leg follows *_r; left leg follows the complementary path with y negated (:154-167)
+            walk_point(half == 0, c, h, s, b, sw, bias, pr);
+            walk_point(half != 0, c, h, s, b, sw, bias, pl);
+            pl[1] = -pl[1];
+            bool good = leg_ik(pr[0], pr[1], pr[2], true, row) & leg_ik(pl[0], pl[1], pl[2], false, row + 6);
+            if (good) assemble_row(row, out);
+            else { ok = false; for (int k = 0; k < 18; k++) out[k] = nan; }
+            for (int k = 0; k < 18; k++) traj[((size_t)g * 40 + half * NROW + c) * 18 + k] = out[k];
+        }
+    }
+    {   // bend_legs (trajectory_generator.py:240-252, trajectory_eval.py:251-261)
+        double row[12], out[18];
+        bool good = leg_ik(0.0, 0.0, b, true, row) & leg_ik(0.0, 0.0, b, false, row + 6);
+        if (good) {
+            for (int k = 0; k < 12; k++) out[k] = row[k];
+            for (int k = 12; k < 18; k++) out[k] = 0.0;
+            out[13] = 0.5; out[16] = 0.5;
+            for (int k = 0; k < 4; k++) out[k] = -out[k];
+            out[10] = -out[10];
+        } else { ok = false; for (int k = 0; k < 18; k++) out[k] = nan; }
+        if (bend) for (int k = 0; k < 18; k++) bend[(size_t)g * 18 + k] = out[k];
+    }
+    if (status) status[g] = ok ? 0 : 1;
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI
+static const size_t kSmemBytes = sizeof(SmemLayout);
+
+static int grid_for(int n) { return (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA; }
+
+extern "C" {
+
+const char *plen_version(void) { return "plen_b200 0.1 (sm_100a)"; }
+
+int plen_default_config(plen_config *cfg, int joint_act) {
+    if (!cfg) return fail(nullptr, PLEN_E_ARG, "cfg is NULL");
+    return default_config(cfg, joint_act);
+}
+
+const char *plen_last_error(const plen_ctx *ctx) { return ctx ? ctx->err : g_err; }
+int plen_num_envs(const plen_ctx *ctx) { return ctx ? ctx->n : 0; }
+
+void plen_destroy(plen_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->d_tab); cudaFree(ctx->d_state); cudaFree(ctx->d_snapshot);
+    cudaFree(ctx->d_act); cudaFree(ctx->d_obs); cudaFree(ctx->d_rew); cudaFree(ctx->d_done); cudaFree(ctx->d_tmo);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+static int create_impl(plen_ctx *ctx) {
+    const int n = ctx->n;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    CK(ctx, cudaFuncSetAttribute(k_tick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    CK(ctx, cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    float tab[T_ROWS * 32], rec[PLEN_STATE_WORDS];
+    build_table(&ctx->model, &ctx->cfg, tab);
+    build_devconfig(&ctx->model, &ctx->cfg, &ctx->dc, &ctx->er);
+    CK(ctx, cudaMalloc(&ctx->d_tab, sizeof tab));
+    CK(ctx, cudaMalloc(&ctx->d_state, sizeof(float) * PLEN_STATE_WORDS * (size_t)n));
+    CK(ctx, cudaMalloc(&ctx->d_snapshot, sizeof(float) * (PLEN_STATE_WORDS + 32)));
+    CK(ctx, cudaMalloc(&ctx->d_act, sizeof(float) * PLEN_NJ * (size_t)n));
+    CK(ctx, cudaMalloc(&ctx->d_obs, sizeof(float) * PLEN_OBS * (size_t)n));
+    CK(ctx, cudaMalloc(&ctx->d_rew, sizeof(float) * (size_t)n));
+    CK(ctx, cudaMalloc(&ctx->d_done, (size_t)n));
+    CK(ctx, cudaMalloc(&ctx->d_tmo, (size_t)n));
+    CK(ctx, cudaMemcpy(ctx->d_tab, tab, sizeof tab, cudaMemcpyHostToDevice));
+    // post-reset snapshot: teleport to the start pose, zero joints and targets, settle for reset_ticks (plen_env.py:561-574)
+    init_record(&ctx->cfg, rec);
+    CK(ctx, cudaMemcpy(ctx->d_snapshot, rec, sizeof rec, cudaMemcpyHostToDevice));
+    k_tick<<<1, WARPS_PER_CTA * 32, kSmemBytes, ctx->stream>>>(ctx->dc, ctx->d_tab, ctx->d_snapshot, 1, nullptr,
+                                                               ctx->cfg.reset_ticks, nullptr, nullptr, nullptr, 0);
+    k_observe<<<1, WARPS_PER_CTA * 32, kSmemBytes, ctx->stream>>>(ctx->d_snapshot, 1, ctx->d_snapshot + PLEN_STATE_WORDS);
+    k_reset<<<(n * 32 + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_state, n, nullptr, ctx->d_snapshot, nullptr);
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return PLEN_OK;
+}
+
+plen_ctx *plen_create(const plen_config *cfg, const plen_model *model, int n_envs, int device) {
+    if (!cfg || !model || n_envs <= 0) { fail(nullptr, PLEN_E_ARG, "plen_create: bad arguments"); return nullptr; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        fail(nullptr, PLEN_E_CUDA, "plen_create: no usable CUDA device %d (%s); this library has no CPU fallback", device,
+             e == cudaSuccess ? "device count 0 or index out of range" : cudaGetErrorString(e));
+        return nullptr;
+    }
+    plen_ctx *ctx = new (std::nothrow) plen_ctx();
+    if (!ctx) { fail(nullptr, PLEN_E_ARG, "out of host memory"); return nullptr; }
+    memset(ctx, 0, sizeof *ctx);
+    ctx->n = n_envs; ctx->device = device; ctx->cfg = *cfg; ctx->model = *model;
+    if (create_impl(ctx) != PLEN_OK) {
+        snprintf(g_err, sizeof g_err, "%s", ctx->err);
+        plen_destroy(ctx);
+        return nullptr;
+    }
+    return ctx;
+}
+
+int plen_reset(plen_ctx *ctx, const uint8_t *mask_dev, float *obs_dev, void *stream) {
+    if (!ctx) return fail(nullptr, PLEN_E_ARG, "ctx is NULL");
+    CK(ctx, cudaSetDevice(ctx->device));
+    k_reset<<<(ctx->n * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->d_state, ctx->n, mask_dev, ctx->d_snapshot, obs_dev);
+    CK(ctx, cudaGetLastError());
+    return PLEN_OK;
+}
+
+int plen_step(plen_ctx *ctx, const float *actions_dev, float *obs_dev, float *reward_dev, uint8_t *done_dev,
+              uint8_t *timeout_dev, float *terminal_obs_dev, void *stream) {
+    if (!ctx) return fail(nullptr, PLEN_E_ARG, "ctx is NULL");
+    if (!actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(ctx, PLEN_E_ARG, "plen_step: NULL buffer");
+    CK(ctx, cudaSetDevice(ctx->device));
+    k_step<<<grid_for(ctx->n), WARPS_PER_CTA * 32, kSmemBytes, (cudaStream_t)stream>>>(
+        ctx->dc, ctx->er, ctx->d_tab, ctx->d_state, ctx->n, actions_dev, obs_dev, reward_dev, done_dev, timeout_dev,
+        terminal_obs_dev, ctx->d_snapshot);
+    CK(ctx, cudaGetLastError());
+    return PLEN_OK;
+}
+
+int plen_step_host(plen_ctx *ctx, const float *actions_host, float *obs_host, float *reward_host, uint8_t *done_host,
+                   uint8_t *timeout_host) {
+    if (!ctx) return fail(nullptr, PLEN_E_ARG, "ctx is NULL");
+    if (!actions_host || !obs_host || !reward_host || !done_host) return fail(ctx, PLEN_E_ARG, "plen_step_host: NULL buffer");
+    const size_t n = ctx->n;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemcpyAsync(ctx->d_act, actions_host, sizeof(float) * PLEN_NJ * n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = plen_step(ctx, ctx->d_act, ctx->d_obs, ctx->d_rew, ctx->d_done, ctx->d_tmo, nullptr, ctx->stream);
+    if (rc != PLEN_OK) return rc;
+    CK(ctx, cudaMemcpyAsync(obs_host, ctx->d_obs, sizeof(float) * PLEN_OBS * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(reward_host, ctx->d_rew, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(done_host, ctx->d_done, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (timeout_host) CK(ctx, cudaMemcpyAsync(timeout_host, ctx->d_tmo, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return PLEN_OK;
+}
+
+int plen_get_state(plen_ctx *ctx, float *qpos_dev, float *qvel_dev, float *aux_dev, void *stream) {
+    if (!ctx) return fail(nullptr, PLEN_E_ARG, "ctx is NULL");
+    CK(ctx, cudaSetDevice(ctx->device));
+    k_get_state<<<(ctx->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->d_state, ctx->n, qpos_dev, qvel_dev, aux_dev);
+    CK(ctx, cudaGetLastError());
+    return PLEN_OK;
+}
+
+int plen_set_state(plen_ctx *ctx, const float *qpos_dev, const float *qvel_dev, const float *aux_dev, void *stream) {
+    if (!ctx) return fail(nullptr, PLEN_E_ARG, "ctx is NULL");
+    CK(ctx, cudaSetDevice(ctx->device));
+    k_set_state<<<(ctx->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->d_state, ctx->n, qpos_dev, qvel_dev, aux_dev);
+    CK(ctx, cudaGetLastError());
+    return PLEN_OK;
+}
+
+int plen_tick(plen_ctx *ctx, const float *targets_dev, int n_ticks, void *stream) {
+    if (!ctx) return fail(nullptr, PLEN_E_ARG, "ctx is NULL");
+    if (n_ticks < 0) return fail(ctx, PLEN_E_ARG, "plen_tick: n_ticks < 0");
+    CK(ctx, cudaSetDevice(ctx->device));
+    k_tick<<<grid_for(ctx->n), WARPS_PER_CTA * 32, kSmemBytes, (cudaStream_t)stream>>>(
+        ctx->dc, ctx->d_tab, ctx->d_state, ctx->n, targets_dev, n_ticks, nullptr, nullptr, nullptr, 0);
+    CK(ctx, cudaGetLastError());
+    return PLEN_OK;
+}
+
+int plen_debug_dynamics(plen_ctx *ctx, float *minv_dev, float *pos_dev, float *rot_dev, void *stream) {
+    if (!ctx) return fail(nullptr, PLEN_E_ARG, "ctx is NULL");
+    CK(ctx, cudaSetDevice(ctx->device));
+    k_tick<<<grid_for(ctx->n), WARPS_PER_CTA * 32, kSmemBytes, (cudaStream_t)stream>>>(
+        ctx->dc, ctx->d_tab, ctx->d_state, ctx->n, nullptr, 1, minv_dev, pos_dev, rot_dev, 1);
+    CK(ctx, cudaGetLastError());
+    return PLEN_OK;
+}
+
+int plen_gait_ik(int device, const double *params_dev, int n_gaits, double *traj_dev, double *bend_dev,
+                 uint8_t *status_dev, void *stream) {
+    if (!params_dev || !traj_dev || n_gaits <= 0) return fail(nullptr, PLEN_E_ARG, "plen_gait_ik: bad arguments");
+    CK(nullptr, cudaSetDevice(device));
+    k_gait_ik<<<(n_gaits + 127) / 128, 128, 0, (cudaStream_t)stream>>>(params_dev, n_gaits, traj_dev, bend_dev, status_dev);
+    CK(nullptr, cudaGetLastError());
+    return PLEN_OK;
+}
+
+}  // extern "C"

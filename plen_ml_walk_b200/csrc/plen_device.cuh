@@ -1,0 +1,781 @@
+// plen_device.cuh -- warp-per-robot PLEN physics tick + env epilogue (sm_100a device code).
+//
+// One warp owns one robot.  Lane l < 24 owns generalized velocity l (0..2 omega_world, 3..5 v_world, 6..23 joints);
+// lane l >= 6 also owns body l-5 / joint l-6 (limb chains at lanes 6..11, 12..17, 18..20, 21..23); lanes 24..31
+// own the 8 cached contact impulses.  Tree traversals become segmented warp scans over the limb chains.
+//
+// Per tick (replaces p.stepSimulation, plen_env.py:665-667; algorithm is ours, not Bullet's):
+//   1. FK: local joint transforms -> prefix product along each chain -> world frames (origin = base position)
+//   2. world-frame composite-rigid-body mass matrix M (suffix sums of 10-parameter inertias) and bias forces C
+//      (prefix sums of twists / accelerations, suffix sums of body forces)
+//   3. M^-1 by block elimination: 4 limb blocks inverted in parallel (Gauss-Jordan across lanes), 6x6 base Schur
+//      complement inverted redundantly, M^-1 assembled column-major in shared memory
+//   4. v* = v - dt M^-1 C;  sole-vertex contacts vs z = 0;  constraint rows (limits, 18 servo rows, per contact
+//      normal + spin + 2 roll + 2 lateral) rebuilt ON THE FLY from per-lane twists (flat ground => every
+//      Jacobian/response entry is <= 2 FMAs), so no per-row Jacobian storage exists at all
+//   5. projected Gauss-Seidel in Bullet's row order with early exit on the max squared row residual
+//   6. semi-implicit integration (exponential-map quaternion update)
+//
+// The same source is compiled for the host by tests/emu (32 threads + barriers emulate the warp shuffles) so the
+// CPU test suite can check this code against the float64 oracle without a GPU.  That emulation is test-only; the
+// product library has no CPU path.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/plen_b200.h"
+
+#ifndef PLEN_HOST_EMU
+#define PLEN_DEV __device__ __forceinline__
+#define PLEN_DEV_NOINLINE __device__ __noinline__
+namespace plen {
+PLEN_DEV int lane_id() { return threadIdx.x & 31; }
+PLEN_DEV float shfl(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+PLEN_DEV float shfl_up(float v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+PLEN_DEV float shfl_down(float v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+PLEN_DEV float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+PLEN_DEV unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+PLEN_DEV unsigned redux_max(unsigned v) { return __reduce_max_sync(0xffffffffu, v); }
+PLEN_DEV void warp_sync() { __syncwarp(); }
+PLEN_DEV float f_as_u_max(float v) { return __uint_as_float(redux_max(__float_as_uint(v))); }
+PLEN_DEV void sincos_(float x, float *s, float *c) { sincosf(x, s, c); }
+PLEN_DEV float rcp_(float x) { return 1.0f / x; }
+PLEN_DEV int lowest_bit(unsigned m) { return __ffs((int)m) - 1; }
+PLEN_DEV int highest_bit(unsigned m) { return 31 - __clz((int)m); }
+}  // namespace plen
+#endif
+
+namespace plen {
+
+// ---- model table rows (each row is 32 floats, one per lane), staged in shared memory per CTA
+enum {
+    T_RPJ = 0, T_PPJ = 9, T_AXIS = 12, T_COM = 15, T_MASS = 18, T_INERTIA = 19, T_LOWER = 25, T_UPPER = 26,
+    T_CS = 27, T_CE = 28, T_ENVLO = 29, T_ENVHI = 30, T_ROWS = 31
+};
+
+// ---- per-env state record in HBM / smem: 96 words, word w = 32*k + lane
+enum {
+    W_U = 0,        // words 0..23: generalized velocity; 24..31: cached normal impulses lam_n[8]
+    W_Q = 32,       // words 38..55: joint angles (lane 6..23)
+    W_POS = 32,     // words 32..34: base position
+    W_MAN = 35,     // manifold bits (int)
+    W_EPRET = 36,   // episode return
+    W_QUAT = 56,    // words 56..59: base quaternion xyzw
+    W_CNT = 60, W_DS = 61, W_HIST = 62, W_EPT = 63,   // ints
+    W_LAST = 64,    // 6
+    W_SUMS = 70,    // 9
+    W_SPARE = 79
+};
+
+struct DevConfig {
+    float dt, inv_dt, gravity_z, motor_imp, kp_over_dt, one_minus_kd, linear_damping;
+    float mu_lateral, mu_spinning, mu_rolling, restitution, rest_thresh, erp_contact_over_dt, erp_joint_over_dt;
+    float linear_slop, warm, hull_margin, vmax, residual_threshold;
+    float foot_break[2];
+    float foot_pts[2][4][3];
+    float start_pos[3];
+    int foot_lane[2];
+    int substeps, reset_ticks, iterations, joint_act, max_episode_steps, auto_reset;
+};
+
+// per-warp shared scratch (floats)
+struct WarpScratch {
+    float st[96];
+    float tw[24][8];      // joint twists s_j = [a(3), m(3)] about the base origin, world axes
+    float kk[24][8];      // K rows = A_c M_c0
+    float gg[24][8];      // G rows = K S^-1
+    float cb[32];         // bias forces C, later S entries
+    float red[32 * 21];   // Schur complement partial products
+    float minv[24][32];   // M^-1, [column j][lane l]
+    float cp[8][4];       // contact point x,y,z (rel. base origin, on the inflated hull) and distance
+    float row[6][8][4];   // per contact row: rhs, dinv, lam, d    [type: 0 n, 1 spin, 2 roll1, 3 roll2, 4 f1, 5 f2]
+    float obs[32];
+};
+
+struct LaneState {
+    float u;          // generalized velocity of this lane (0 for lanes >= 24)
+    float q;          // joint angle (lanes 6..23)
+    float tgt;        // servo target (lanes 6..23)
+    float lam;        // cached normal impulse (lanes 24..31)
+    float pos[3];     // base position (uniform)
+    float quat[4];    // base orientation xyzw (uniform)
+    unsigned man;     // manifold bits (uniform)
+    int iters;        // PGS iterations of the last tick (diagnostic, uniform)
+};
+
+PLEN_DEV void mat3_mul(const float *A, const float *B, float *C) {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+PLEN_DEV void mat3_vec(const float *A, const float *v, float *o) {
+    o[0] = A[0] * v[0] + A[1] * v[1] + A[2] * v[2];
+    o[1] = A[3] * v[0] + A[4] * v[1] + A[5] * v[2];
+    o[2] = A[6] * v[0] + A[7] * v[1] + A[8] * v[2];
+}
+PLEN_DEV void cross(const float *a, const float *b, float *o) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+PLEN_DEV void quat_to_mat(const float *q, float *R) {
+    const float x = q[0], y = q[1], z = q[2], w = q[3];
+    R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - w * z); R[2] = 2 * (x * z + w * y);
+    R[3] = 2 * (x * y + w * z); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - w * x);
+    R[6] = 2 * (x * z - w * y); R[7] = 2 * (y * z + w * x); R[8] = 1 - 2 * (x * x + y * y);
+}
+PLEN_DEV float warp_sum(float v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += shfl_xor(v, m);
+    return v;
+}
+PLEN_DEV void warp_sum2(float &a, float &b) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) { a += shfl_xor(a, m); b += shfl_xor(b, m); }
+}
+
+// Forward kinematics of the 19 body frames.  Outputs for this lane: Rw (world rotation), pw (frame origin relative
+// to the base origin, world axes).  Lanes without a body (1..5, 24..31) get the base frame.
+PLEN_DEV void forward_kinematics(const float *tab, int lane, float q, const float *quat, float *Rw, float *pw) {
+    float R[9], p[3];
+    {
+        float s, c;
+        sincos_(q, &s, &c);
+        const float ax = tab[(T_AXIS + 0) * 32 + lane], ay = tab[(T_AXIS + 1) * 32 + lane], az = tab[(T_AXIS + 2) * 32 + lane];
+        const float t = 1.0f - c;
+        float Rq[9] = {t * ax * ax + c, t * ax * ay - s * az, t * ax * az + s * ay,
+                       t * ax * ay + s * az, t * ay * ay + c, t * ay * az - s * ax,
+                       t * ax * az - s * ay, t * ay * az + s * ax, t * az * az + c};
+        float Rpj[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) Rpj[k] = tab[(T_RPJ + k) * 32 + lane];
+        mat3_mul(Rpj, Rq, R);
+#pragma unroll
+        for (int k = 0; k < 3; k++) p[k] = tab[(T_PPJ + k) * 32 + lane];
+    }
+    const int cs = (int)tab[T_CS * 32 + lane];
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+        float Rp[9], pp[3];
+#pragma unroll
+        for (int k = 0; k < 9; k++) Rp[k] = shfl_up(R[k], d);
+#pragma unroll
+        for (int k = 0; k < 3; k++) pp[k] = shfl_up(p[k], d);
+        if (lane - d >= cs) {
+            float t[3], Rn[9];
+            mat3_vec(Rp, p, t);
+            p[0] = pp[0] + t[0]; p[1] = pp[1] + t[1]; p[2] = pp[2] + t[2];
+            mat3_mul(Rp, R, Rn);
+#pragma unroll
+            for (int k = 0; k < 9; k++) R[k] = Rn[k];
+        }
+    }
+    float R0[9];
+    quat_to_mat(quat, R0);
+    mat3_mul(R0, R, Rw);
+    mat3_vec(R0, p, pw);
+}
+
+// In-place Gauss-Jordan inverse (no pivoting, SPD) of a full 6x6 held redundantly by every lane.
+PLEN_DEV void inv6_inplace(float (*A)[6]) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const float inv = rcp_(A[k][k]);
+        A[k][k] = 1.0f;
+#pragma unroll
+        for (int j = 0; j < 6; j++) A[k][j] *= inv;
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            if (i == k) continue;
+            const float f = A[i][k];
+            A[i][k] = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 6; j++) A[i][j] -= f * A[k][j];
+        }
+    }
+}
+
+PLEN_DEV float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+// Contact-row Jacobian entry J and response entry B of this lane for row `type` of a contact at p (rel. base origin).
+// a/m: this lane's twist masked to {base, the foot's leg}; Y: this lane's row of M^-1 Jfoot^T.
+// Normal n = +z, tangents t1 = (0,-1,0), t2 = (1,0,0) (btPlaneSpace1 of +z).
+PLEN_DEV void row_entries(int type, const float *a, const float *m, const float *Y, float px, float py, float pz,
+                          float &J, float &B) {
+    switch (type) {
+        case 0: J = a[0] * py - a[1] * px + m[2]; B = Y[0] * py - Y[1] * px + Y[5]; break;          // normal
+        case 1: J = a[2]; B = Y[2]; break;                                                           // spin about n
+        case 2: J = -a[1]; B = -Y[1]; break;                                                         // roll about t1
+        case 3: J = a[0]; B = Y[0]; break;                                                           // roll about t2
+        case 4: J = a[0] * pz - a[2] * px - m[1]; B = Y[0] * pz - Y[2] * px - Y[4]; break;           // lateral t1
+        default: J = a[1] * pz - a[2] * py + m[0]; B = Y[1] * pz - Y[2] * py + Y[3]; break;          // lateral t2
+    }
+}
+
+// One physics tick for the robot owned by this warp.
+struct DebugOut { float *minv, *pos, *rot; };   // [24*24], [24*3], [24*9] of one env; all nullable
+
+PLEN_DEV void physics_tick(const DevConfig &cfg, const float *tab, WarpScratch &ws, LaneState &L, int lane,
+                           const DebugOut *dbg = nullptr) {
+    const bool is_joint = lane >= 6 && lane < 24;
+    const int cs = (int)tab[T_CS * 32 + lane], ce = (int)tab[T_CE * 32 + lane];
+    float Rw[9], pw[3];
+    forward_kinematics(tab, lane, L.q, L.quat, Rw, pw);
+
+    // ---- joint twist s = [a; m] about the base origin (world axes); base lanes carry the identity columns
+    float a[3] = {0, 0, 0}, m[3] = {0, 0, 0};
+    if (is_joint) {
+        float ax[3] = {tab[(T_AXIS + 0) * 32 + lane], tab[(T_AXIS + 1) * 32 + lane], tab[(T_AXIS + 2) * 32 + lane]};
+        mat3_vec(Rw, ax, a);
+        cross(pw, a, m);
+    } else if (lane < 3) {
+        a[lane] = 1.0f;
+    } else if (lane < 6) {
+        m[lane - 3] = 1.0f;
+    }
+    if (lane < 24) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { ws.tw[lane][k] = a[k]; ws.tw[lane][3 + k] = m[k]; }
+    }
+
+    // ---- body inertia about the base origin, world axes: mass, h = m c, Ibar (xx yy zz xy xz yz)
+    const float mass = tab[T_MASS * 32 + lane];
+    float h[3], Ib[6];
+    {
+        float com[3] = {tab[(T_COM + 0) * 32 + lane], tab[(T_COM + 1) * 32 + lane], tab[(T_COM + 2) * 32 + lane]};
+        float c[3];
+        mat3_vec(Rw, com, c);
+        c[0] += pw[0]; c[1] += pw[1]; c[2] += pw[2];
+        const float ixx = tab[(T_INERTIA + 0) * 32 + lane], iyy = tab[(T_INERTIA + 1) * 32 + lane],
+                    izz = tab[(T_INERTIA + 2) * 32 + lane], ixy = tab[(T_INERTIA + 3) * 32 + lane],
+                    ixz = tab[(T_INERTIA + 4) * 32 + lane], iyz = tab[(T_INERTIA + 5) * 32 + lane];
+        // Iw = Rw I Rw^T
+        float T[9] = {Rw[0] * ixx + Rw[1] * ixy + Rw[2] * ixz, Rw[0] * ixy + Rw[1] * iyy + Rw[2] * iyz, Rw[0] * ixz + Rw[1] * iyz + Rw[2] * izz,
+                      Rw[3] * ixx + Rw[4] * ixy + Rw[5] * ixz, Rw[3] * ixy + Rw[4] * iyy + Rw[5] * iyz, Rw[3] * ixz + Rw[4] * iyz + Rw[5] * izz,
+                      Rw[6] * ixx + Rw[7] * ixy + Rw[8] * ixz, Rw[6] * ixy + Rw[7] * iyy + Rw[8] * iyz, Rw[6] * ixz + Rw[7] * iyz + Rw[8] * izz};
+        const float cc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+        Ib[0] = T[0] * Rw[0] + T[1] * Rw[1] + T[2] * Rw[2] + mass * (cc - c[0] * c[0]);
+        Ib[1] = T[3] * Rw[3] + T[4] * Rw[4] + T[5] * Rw[5] + mass * (cc - c[1] * c[1]);
+        Ib[2] = T[6] * Rw[6] + T[7] * Rw[7] + T[8] * Rw[8] + mass * (cc - c[2] * c[2]);
+        Ib[3] = T[0] * Rw[3] + T[1] * Rw[4] + T[2] * Rw[5] - mass * c[0] * c[1];
+        Ib[4] = T[0] * Rw[6] + T[1] * Rw[7] + T[2] * Rw[8] - mass * c[0] * c[2];
+        Ib[5] = T[3] * Rw[6] + T[4] * Rw[7] + T[5] * Rw[8] - mass * c[1] * c[2];
+        h[0] = mass * c[0]; h[1] = mass * c[1]; h[2] = mass * c[2];
+    }
+
+    // ---- spatial velocity of this lane's body: V = V0 + sum_{ancestors} s_j qd_j
+    float V0[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) V0[k] = shfl(L.u, k);
+    float tv[6];   // own term s * u (joint lanes only)
+#pragma unroll
+    for (int k = 0; k < 3; k++) { tv[k] = is_joint ? a[k] * L.u : 0.0f; tv[3 + k] = is_joint ? m[k] * L.u : 0.0f; }
+    float V[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) V[k] = tv[k];
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const float t = shfl_up(V[k], d);
+            if (lane - d >= cs) V[k] += t;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) V[k] += V0[k];
+
+    // ---- velocity-product accelerations: ab = a0 + sum_{ancestors} V_j x s_j qd_j, a0 = [0; -w0 x v0 - g]
+    float ab[6];
+    {
+        float t1[3], t2[3], t3[3];
+        cross(V, tv, t1);          // w x t_ang
+        cross(V, tv + 3, t2);      // w x t_lin
+        cross(V + 3, tv, t3);      // v x t_ang
+#pragma unroll
+        for (int k = 0; k < 3; k++) { ab[k] = t1[k]; ab[3 + k] = t2[k] + t3[k]; }
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                const float t = shfl_up(ab[k], d);
+                if (lane - d >= cs) ab[k] += t;
+            }
+        }
+        float wv[3];
+        cross(V0, V0 + 3, wv);
+        ab[3] -= wv[0]; ab[4] -= wv[1]; ab[5] -= wv[2] + cfg.gravity_z;
+    }
+
+    // ---- body net force F = I ab + V x* (I V)  (about the base origin)
+    float F[6];
+    {
+        float IV[6], Ia[6], t[3], t2[3];
+        // I x = [Ibar xa + h x xl ; m xl - h x xa]
+        cross(h, V + 3, t);
+        IV[0] = Ib[0] * V[0] + Ib[3] * V[1] + Ib[4] * V[2] + t[0];
+        IV[1] = Ib[3] * V[0] + Ib[1] * V[1] + Ib[5] * V[2] + t[1];
+        IV[2] = Ib[4] * V[0] + Ib[5] * V[1] + Ib[2] * V[2] + t[2];
+        cross(h, V, t);
+        IV[3] = mass * V[3] - t[0]; IV[4] = mass * V[4] - t[1]; IV[5] = mass * V[5] - t[2];
+        cross(h, ab + 3, t);
+        Ia[0] = Ib[0] * ab[0] + Ib[3] * ab[1] + Ib[4] * ab[2] + t[0];
+        Ia[1] = Ib[3] * ab[0] + Ib[1] * ab[1] + Ib[5] * ab[2] + t[1];
+        Ia[2] = Ib[4] * ab[0] + Ib[5] * ab[1] + Ib[2] * ab[2] + t[2];
+        cross(h, ab, t);
+        Ia[3] = mass * ab[3] - t[0]; Ia[4] = mass * ab[4] - t[1]; Ia[5] = mass * ab[5] - t[2];
+        cross(V, IV, t);           // w x n
+        cross(V + 3, IV + 3, t2);  // v x f
+        F[0] = Ia[0] + t[0] + t2[0]; F[1] = Ia[1] + t[1] + t2[1]; F[2] = Ia[2] + t[2] + t2[2];
+        cross(V, IV + 3, t);       // w x f
+        F[3] = Ia[3] + t[0]; F[4] = Ia[4] + t[1]; F[5] = Ia[5] + t[2];
+        if (cfg.linear_damping != 0.0f && mass > 0.0f) {
+            // Bullet's multibody drag: f = -k m v_com (1 + |v_com|) at the com  (joint_act only, plen_env.py:472-481)
+            float c[3] = {h[0] / mass, h[1] / mass, h[2] / mass}, vc[3], fd[3], nd[3];
+            cross(V, c, t);
+            vc[0] = V[3] + t[0]; vc[1] = V[4] + t[1]; vc[2] = V[5] + t[2];
+            const float nv = sqrtf(vc[0] * vc[0] + vc[1] * vc[1] + vc[2] * vc[2]);
+            const float k = cfg.linear_damping * mass * (1.0f + nv);
+            fd[0] = -k * vc[0]; fd[1] = -k * vc[1]; fd[2] = -k * vc[2];
+            cross(c, fd, nd);
+            F[0] -= nd[0]; F[1] -= nd[1]; F[2] -= nd[2];
+            F[3] -= fd[0]; F[4] -= fd[1]; F[5] -= fd[2];
+        }
+    }
+
+    // ---- suffix sums along the chains: composite inertia (10 values) and subtree force (6 values)
+    float mc = mass, hc[3] = {h[0], h[1], h[2]}, Ic[6] = {Ib[0], Ib[1], Ib[2], Ib[3], Ib[4], Ib[5]};
+    float Fc[6] = {F[0], F[1], F[2], F[3], F[4], F[5]};
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+        const bool take = is_joint && (lane + d <= ce);
+        float t;
+        t = shfl_down(mc, d); if (take) mc += t;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { t = shfl_down(hc[k], d); if (take) hc[k] += t; }
+#pragma unroll
+        for (int k = 0; k < 6; k++) { t = shfl_down(Ic[k], d); if (take) Ic[k] += t; }
+#pragma unroll
+        for (int k = 0; k < 6; k++) { t = shfl_down(Fc[k], d); if (take) Fc[k] += t; }
+    }
+    // whole robot: torso (lane 0) + the four chain roots
+    float mt, ht[3], It[6], Ft[6];
+    {
+        const bool root = (lane == 0) || (is_joint && lane == cs);
+        mt = warp_sum(root ? mc : 0.0f);
+#pragma unroll
+        for (int k = 0; k < 3; k++) ht[k] = warp_sum(root ? hc[k] : 0.0f);
+#pragma unroll
+        for (int k = 0; k < 6; k++) It[k] = warp_sum(root ? Ic[k] : 0.0f);
+#pragma unroll
+        for (int k = 0; k < 6; k++) Ft[k] = warp_sum(root ? Fc[k] : 0.0f);
+    }
+
+    // ---- bias force of this lane's coordinate and f = Ic s (column of M restricted to ancestors)
+    float Cl = 0.0f, fM[6] = {0, 0, 0, 0, 0, 0};
+    if (is_joint) {
+        Cl = a[0] * Fc[0] + a[1] * Fc[1] + a[2] * Fc[2] + m[0] * Fc[3] + m[1] * Fc[4] + m[2] * Fc[5];
+        float t[3];
+        cross(hc, m, t);
+        fM[0] = Ic[0] * a[0] + Ic[3] * a[1] + Ic[4] * a[2] + t[0];
+        fM[1] = Ic[3] * a[0] + Ic[1] * a[1] + Ic[5] * a[2] + t[1];
+        fM[2] = Ic[4] * a[0] + Ic[5] * a[1] + Ic[2] * a[2] + t[2];
+        cross(hc, a, t);
+        fM[3] = mc * m[0] - t[0]; fM[4] = mc * m[1] - t[1]; fM[5] = mc * m[2] - t[2];
+    } else if (lane < 6) {
+        Cl = Ft[lane];
+    }
+    ws.cb[lane] = Cl;
+
+    // ---- limb block rows: Mrow[d] = M[lane][cs+d], Krow = M[lane][0..5] = fM
+    float Mrow[6], Krow[6];
+    const int off = lane - cs;
+    {
+        // exchange f through shared memory (kk is free at this point)
+        if (lane < 24) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) ws.kk[lane][k] = fM[k];
+        }
+        warp_sync();
+#pragma unroll
+        for (int d = 0; d < 6; d++) {
+            const int j = cs + d;
+            float v = (d == off) ? 1.0f : 0.0f;   // identity padding for short chains / non-joint lanes
+            if (is_joint && j <= ce) {
+                if (d <= off) {  // ancestor-or-self j: M = s_j . f_lane
+                    v = ws.tw[j][0] * fM[0] + ws.tw[j][1] * fM[1] + ws.tw[j][2] * fM[2] + ws.tw[j][3] * fM[3] +
+                        ws.tw[j][4] * fM[4] + ws.tw[j][5] * fM[5];
+                } else {         // descendant j: M = s_lane . f_j
+                    v = a[0] * ws.kk[j][0] + a[1] * ws.kk[j][1] + a[2] * ws.kk[j][2] + m[0] * ws.kk[j][3] +
+                        m[1] * ws.kk[j][4] + m[2] * ws.kk[j][5];
+                }
+            }
+            Mrow[d] = v;
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) Krow[k] = fM[k];
+        warp_sync();
+    }
+    // Gauss-Jordan across the lanes of each chain: Mrow -> row of A_c = M_cc^-1, Krow -> row of K_c = A_c M_c0
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const bool act = is_joint && (cs + k <= ce);
+        const int src = act ? cs + k : lane;
+        float pr[6], pk[6];
+#pragma unroll
+        for (int d = 0; d < 6; d++) pr[d] = shfl(Mrow[d], src);
+#pragma unroll
+        for (int d = 0; d < 6; d++) pk[d] = shfl(Krow[d], src);
+        if (act) {
+            const float inv = rcp_(pr[k]);
+            if (off == k) {
+#pragma unroll
+                for (int d = 0; d < 6; d++) Mrow[d] = (d == k) ? inv : pr[d] * inv;
+#pragma unroll
+                for (int d = 0; d < 6; d++) Krow[d] = pk[d] * inv;
+            } else {
+                const float f = Mrow[k] * inv;
+#pragma unroll
+                for (int d = 0; d < 6; d++) Mrow[d] = (d == k) ? -f : Mrow[d] - f * pr[d];
+#pragma unroll
+                for (int d = 0; d < 6; d++) Krow[d] -= f * pk[d];
+            }
+        }
+    }
+
+    // ---- base Schur complement S = M00 - sum_l fM_l (x) K_l, via a conflict-free smem transpose-reduce
+    {
+        int idx = 0;
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+            for (int c = r; c < 6; c++) { ws.red[lane * 21 + idx] = is_joint ? fM[r] * Krow[c] : 0.0f; idx++; }
+        warp_sync();
+        if (lane < 21) {
+            float s = 0.0f;
+            for (int j = 6; j < 24; j++) s += ws.red[j * 21 + lane];
+            ws.red[lane] = s;   // row 0 of red belongs to lane 0, which contributed zeros: safe to overwrite after sync
+        }
+    }
+    // note: red[0..20] is written by lanes < 21 while other lanes may still read red[j*21 + lane] for j >= 6 only
+    warp_sync();
+    float Si[6][6];
+    {
+        // M00 = [[Ibar, hx],[hx^T, m 1]] of the whole robot
+        float M00[6][6] = {{It[0], It[3], It[4], 0.0f, -ht[2], ht[1]},
+                           {It[3], It[1], It[5], ht[2], 0.0f, -ht[0]},
+                           {It[4], It[5], It[2], -ht[1], ht[0], 0.0f},
+                           {0.0f, ht[2], -ht[1], mt, 0.0f, 0.0f},
+                           {-ht[2], 0.0f, ht[0], 0.0f, mt, 0.0f},
+                           {ht[1], -ht[0], 0.0f, 0.0f, 0.0f, mt}};
+        int idx = 0;
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+            for (int c = r; c < 6; c++) {
+                const float v = M00[r][c] - ws.red[idx];
+                Si[r][c] = v; Si[c][r] = v; idx++;
+            }
+        inv6_inplace(Si);
+    }
+    // G = K S^-1
+    float G[6];
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        float s = 0.0f;
+#pragma unroll
+        for (int b = 0; b < 6; b++) s += Krow[b] * Si[b][c];
+        G[c] = is_joint ? s : 0.0f;
+    }
+    if (lane < 24) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) { ws.kk[lane][k] = is_joint ? Krow[k] : 0.0f; ws.gg[lane][k] = G[k]; }
+    }
+    warp_sync();
+    // ---- assemble M^-1 (this lane's row), stored column-major so later reads are conflict free
+    if (lane < 24) {
+        if (is_joint) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) ws.minv[k][lane] = -G[k];
+            for (int j = 6; j < 24; j++) {
+                float s = G[0] * ws.kk[j][0] + G[1] * ws.kk[j][1] + G[2] * ws.kk[j][2] + G[3] * ws.kk[j][3] +
+                          G[4] * ws.kk[j][4] + G[5] * ws.kk[j][5];
+                ws.minv[j][lane] = s;
+            }
+#pragma unroll
+            for (int d = 0; d < 6; d++)
+                if (cs + d <= ce) ws.minv[cs + d][lane] += Mrow[d];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                float v = Si[0][k];
+#pragma unroll
+                for (int r = 1; r < 6; r++) v = (lane == r) ? Si[r][k] : v;
+                ws.minv[k][lane] = v;
+            }
+            for (int j = 6; j < 24; j++) {
+                float v = ws.gg[j][0];
+#pragma unroll
+                for (int r = 1; r < 6; r++) v = (lane == r) ? ws.gg[j][r] : v;
+                ws.minv[j][lane] = -v;
+            }
+        }
+    }
+    warp_sync();
+
+    if (dbg != nullptr && lane < 24) {
+        if (dbg->minv) for (int j = 0; j < 24; j++) dbg->minv[lane * 24 + j] = ws.minv[j][lane];
+        if (dbg->pos) for (int k = 0; k < 3; k++) dbg->pos[lane * 3 + k] = pw[k] + L.pos[k];
+        if (dbg->rot) for (int k = 0; k < 9; k++) dbg->rot[lane * 9 + k] = Rw[k];
+    }
+
+    // ---- unconstrained velocity v* = clamp(v - dt M^-1 C)
+    float vstar = 0.0f;
+    if (lane < 24) {
+        float acc = 0.0f;
+        for (int j = 0; j < 24; j++) acc += ws.minv[j][lane] * ws.cb[j];
+        vstar = clampf(L.u - cfg.dt * acc, -cfg.vmax, cfg.vmax);
+    }
+
+    // ---- contacts: sole vertices vs z = 0 at the start-of-tick pose; lanes 24..31 own one candidate point each
+    unsigned man_new;
+    {
+        const int i = lane - 24, f = (lane >= 28) ? 1 : 0;
+        const int src = cfg.foot_lane[f];
+        float Rf[9], pf[3];
+#pragma unroll
+        for (int k = 0; k < 9; k++) Rf[k] = shfl(Rw[k], src);
+#pragma unroll
+        for (int k = 0; k < 3; k++) pf[k] = shfl(pw[k], src);
+        bool in = false;
+        if (lane >= 24) {
+            const float *pt = cfg.foot_pts[f][i & 3];
+            float w[3];
+            mat3_vec(Rf, pt, w);
+            w[0] += pf[0]; w[1] += pf[1]; w[2] += pf[2];
+            const float dist = (L.pos[2] + w[2]) - cfg.hull_margin;
+            in = dist <= cfg.foot_break[f];
+            ws.cp[i][0] = w[0]; ws.cp[i][1] = w[1]; ws.cp[i][2] = w[2] - cfg.hull_margin; ws.cp[i][3] = dist;
+            const bool was = (L.man >> i) & 1u;
+            if (!in || !was) L.lam = 0.0f;
+        }
+        man_new = ballot(in) >> 24;
+        L.man = man_new;
+    }
+    warp_sync();
+
+    // ---- masked twists and operational columns Y_f = M^-1 Jfoot_f^T per foot with active contacts
+    float aF[2][3], mF[2][3], Y[2][6];
+#pragma unroll
+    for (int f = 0; f < 2; f++) {
+        const int fl = cfg.foot_lane[f], fcs = fl - 5;
+        const bool mine = (lane < 6) || (lane >= fcs && lane <= fl);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { aF[f][k] = mine ? a[k] : 0.0f; mF[f][k] = mine ? m[k] : 0.0f; }
+#pragma unroll
+        for (int k = 0; k < 6; k++) Y[f][k] = 0.0f;
+        if (((man_new >> (4 * f)) & 0xFu) && lane < 24) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) Y[f][k] = ws.minv[k][lane];
+            for (int j = fcs; j <= fl; j++) {
+                const float w = ws.minv[j][lane];
+#pragma unroll
+                for (int k = 0; k < 6; k++) Y[f][k] += w * ws.tw[j][k];
+            }
+        }
+    }
+
+    // ---- servo rows (btMultiBodyJointMotor semantics): target velocity kp (q* - q)/dt + (1 - kd) v*, |impulse| <= f dt
+    float dv = 0.0f;                 // this lane's accumulated delta-v
+    float m_dinv = 0.0f, m_d = 0.0f, m_rhs = 0.0f, m_lam = 0.0f;
+    float l_rhs = 0.0f, l_lam = 0.0f, l_dir = 0.0f;   // joint-limit row (only when violated)
+    if (is_joint) {
+        m_d = ws.minv[lane][lane];
+        m_dinv = (m_d > 1.1920929e-7f) ? rcp_(m_d) : 0.0f;
+        const float desired = cfg.kp_over_dt * (L.tgt - L.q) + cfg.one_minus_kd * vstar;
+        m_rhs = (desired - vstar) * m_dinv;
+        const float lo = tab[T_LOWER * 32 + lane], hi = tab[T_UPPER * 32 + lane];
+        const float pen_lo = L.q - lo, pen_hi = hi - L.q;
+        if (pen_lo <= 0.0f) { l_dir = 1.0f; l_rhs = (-pen_lo * cfg.erp_joint_over_dt - vstar) * m_dinv; }
+        else if (pen_hi <= 0.0f) { l_dir = -1.0f; l_rhs = (-pen_hi * cfg.erp_joint_over_dt + vstar) * m_dinv; }
+    }
+    const unsigned lim_mask = ballot(l_dir != 0.0f);
+
+    // ---- contact rows: effective mass, rhs, warm start
+    for (int i = 0; i < 8; i++) {
+        if (!((man_new >> i) & 1u)) continue;
+        const int f = i >> 2;
+        const float px = ws.cp[i][0], py = ws.cp[i][1], pz = ws.cp[i][2], dist = ws.cp[i][3] + cfg.linear_slop;
+        const float lam_cached = shfl(L.lam, 24 + i);
+#pragma unroll
+        for (int type = 0; type < 6; type++) {
+            if (type == 1 && !(cfg.mu_spinning > 0.0f)) continue;
+            if ((type == 2 || type == 3) && !(cfg.mu_rolling > 0.0f)) continue;
+            float J, B;
+            row_entries(type, aF[f], mF[f], Y[f], px, py, pz, J, B);
+            float d = J * B, rel = J * vstar;
+            warp_sum2(d, rel);
+            const float dinv = (d > 1.1920929e-7f) ? rcp_(d) : 0.0f;
+            float rhs, lam0 = 0.0f;
+            if (type == 0) {
+                float rest = (fabsf(rel) < cfg.rest_thresh) ? 0.0f : cfg.restitution * -rel;
+                rest = fmaxf(rest, 0.0f);
+                float velerr = rest - rel, poserr = 0.0f;
+                if (dist > 0.0f) velerr -= dist * cfg.inv_dt; else poserr = -dist * cfg.erp_contact_over_dt;
+                rhs = (poserr + velerr) * dinv;
+                lam0 = lam_cached * cfg.warm;
+                dv += B * lam0;
+            } else {
+                rhs = -rel * dinv;
+            }
+            if (lane == 0) { ws.row[type][i][0] = rhs; ws.row[type][i][1] = dinv; ws.row[type][i][2] = lam0; ws.row[type][i][3] = d; }
+        }
+    }
+    warp_sync();
+
+    // ---- projected Gauss-Seidel (row order of btMultiBodyConstraintSolver::solveSingleIteration)
+    int it = 0;
+    for (; it < cfg.iterations; it++) {
+        float res_lane = 0.0f;   // per-lane residual of the lane-owned rows (servo / limit)
+        float res = 0.0f;        // uniform residual of the contact rows
+        // non-contact rows: list = [limits in joint order, servos in joint order]; odd iterations forward, even reversed
+        for (int half = 0; half < 2; half++) {
+            const bool do_limits = ((it & 1) != 0) == (half == 0);
+            if (do_limits) {
+                unsigned msk = lim_mask;
+                while (msk) {
+                    const int j = (it & 1) ? lowest_bit(msk) : highest_bit(msk);
+                    msk &= ~(1u << j);
+                    float delta = l_rhs - (l_dir * dv) * m_dinv;
+                    const float sum = l_lam + delta;
+                    const float nl = clampf(sum, 0.0f, 100.0f);
+                    delta = nl - l_lam;
+                    const float dj = shfl(delta * l_dir, j);
+                    if (lane == j) { l_lam = nl; res_lane = fmaxf(res_lane, (delta * m_d) * (delta * m_d)); }
+                    if (lane < 24) dv += ws.minv[j][lane] * dj;
+                }
+            } else {
+                for (int s = 0; s < 18; s++) {
+                    const int j = (it & 1) ? 6 + s : 23 - s;
+                    float delta = m_rhs - dv * m_dinv;
+                    const float sum = m_lam + delta;
+                    const float nl = clampf(sum, -cfg.motor_imp, cfg.motor_imp);
+                    delta = nl - m_lam;
+                    const float dj = shfl(delta, j);
+                    if (lane == j) { m_lam = nl; res_lane = fmaxf(res_lane, (delta * m_d) * (delta * m_d)); }
+                    if (lane < 24) dv += ws.minv[j][lane] * dj;
+                }
+            }
+        }
+        // contact rows: normals, spinning, rolling, then lateral pairs with the implicit friction cone
+        if (man_new) {
+            for (int type = 0; type < 4; type++) {
+                if (type == 1 && !(cfg.mu_spinning > 0.0f)) continue;
+                if ((type == 2 || type == 3) && !(cfg.mu_rolling > 0.0f)) continue;
+                // Bullet solves all spinning rows, then the rolling rows point by point (t1 then t2)
+                for (int i = 0; i < 8; i++) {
+                    if (!((man_new >> i) & 1u)) continue;
+                    const int f = i >> 2;
+                    const float px = ws.cp[i][0], py = ws.cp[i][1], pz = ws.cp[i][2];
+                    const int ntypes = (type == 2) ? 2 : 1;
+                    if (type == 3) continue;   // handled together with type 2 to keep the per-point t1,t2 order
+                    for (int tt = 0; tt < ntypes; tt++) {
+                        const int ty = type + tt;
+                        float lo = 0.0f, hi = 1e10f;
+                        if (ty != 0) {
+                            const float tot = ws.row[0][i][2];
+                            if (!(tot > 0.0f)) continue;
+                            const float mu = (ty == 1) ? cfg.mu_spinning : cfg.mu_rolling;
+                            lo = -mu * tot; hi = mu * tot;
+                        }
+                        float J, B;
+                        row_entries(ty, aF[f], mF[f], Y[f], px, py, pz, J, B);
+                        const float dot = warp_sum(J * dv);
+                        const float rhs = ws.row[ty][i][0], dinv = ws.row[ty][i][1], lam = ws.row[ty][i][2], d = ws.row[ty][i][3];
+                        float delta = rhs - dot * dinv;
+                        const float nl = clampf(lam + delta, lo, hi);
+                        delta = nl - lam;
+                        warp_sync();
+                        if (lane == 0) ws.row[ty][i][2] = nl;
+                        dv += B * delta;
+                        const float r = (dinv != 0.0f) ? delta * d : 0.0f;
+                        res = fmaxf(res, r * r);
+                        warp_sync();
+                    }
+                }
+            }
+            for (int i = 0; i < 8; i++) {
+                if (!((man_new >> i) & 1u)) continue;
+                const int f = i >> 2;
+                const float px = ws.cp[i][0], py = ws.cp[i][1], pz = ws.cp[i][2];
+                const float tot = ws.row[0][i][2];
+                const float lim = cfg.mu_lateral * tot;
+                float JA, BA, JB, BB;
+                row_entries(4, aF[f], mF[f], Y[f], px, py, pz, JA, BA);
+                row_entries(5, aF[f], mF[f], Y[f], px, py, pz, JB, BB);
+                float dotA = JA * dv, dotB = JB * dv;
+                warp_sum2(dotA, dotB);
+                const float rhsA = ws.row[4][i][0], dinvA = ws.row[4][i][1], lamA = ws.row[4][i][2], dA = ws.row[4][i][3];
+                const float rhsB = ws.row[5][i][0], dinvB = ws.row[5][i][1], lamB = ws.row[5][i][2], dB = ws.row[5][i][3];
+                float deltaA = rhsA - dotA * dinvA, deltaB = rhsB - dotB * dinvB;
+                const float sumA = lamA + deltaA, sumB = lamB + deltaB;
+                float nA = sumA, nB = sumB;
+                if (sumA < -lim || sumA > lim || sumB < -lim || sumB > lim) {
+                    // resolveConeFrictionConstraintRows: clip onto the circle of radius mu*lam_n along atan2(sumA,sumB)
+                    const float inv = rsqrtf(sumA * sumA + sumB * sumB);
+                    const float cA = fabsf(lim * sumA * inv), cB = fabsf(lim * sumB * inv);
+                    nA = clampf(sumA, -cA, cA);
+                    nB = clampf(sumB, -cB, cB);
+                }
+                deltaA = nA - lamA; deltaB = nB - lamB;
+                warp_sync();
+                if (lane == 0) { ws.row[4][i][2] = nA; ws.row[5][i][2] = nB; }
+                dv += BA * deltaA + BB * deltaB;
+                const float r = ((dinvA != 0.0f) ? deltaA * dA : 0.0f) + ((dinvB != 0.0f) ? deltaB * dB : 0.0f);
+                res = fmaxf(res, r * r);
+                warp_sync();
+            }
+        }
+        res = fmaxf(res, f_as_u_max(res_lane));
+        if (res <= cfg.residual_threshold) { it++; break; }
+    }
+    L.iters = it;
+
+    // ---- write back cached normal impulses, apply delta-v, integrate
+    if (lane >= 24) {
+        const int i = lane - 24;
+        L.lam = ((man_new >> i) & 1u) ? ws.row[0][i][2] : 0.0f;
+    }
+    L.u = (lane < 24) ? clampf(vstar + dv, -cfg.vmax, cfg.vmax) : 0.0f;
+    if (is_joint) L.q += L.u * cfg.dt;
+    {
+        float w[3], v[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { w[k] = shfl(L.u, k); v[k] = shfl(L.u, 3 + k); }
+#pragma unroll
+        for (int k = 0; k < 3; k++) L.pos[k] += v[k] * cfg.dt;
+        float fa = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+        if (fa * cfg.dt > 0.78539816339f) fa = 0.78539816339f * cfg.inv_dt;
+        float sc, cw;
+        if (fa < 0.001f) {
+            sc = 0.5f * cfg.dt - cfg.dt * cfg.dt * cfg.dt * 0.020833333333f * fa * fa;
+            cw = cosf(0.5f * fa * cfg.dt);
+        } else {
+            float sn;
+            sincos_(0.5f * fa * cfg.dt, &sn, &cw);
+            sc = sn / fa;
+        }
+        const float dx = w[0] * sc, dy = w[1] * sc, dz = w[2] * sc;
+        const float qx = L.quat[0], qy = L.quat[1], qz = L.quat[2], qw = L.quat[3];
+        float rx = cw * qx + dx * qw + dy * qz - dz * qy;
+        float ry = cw * qy - dx * qz + dy * qw + dz * qx;
+        float rz = cw * qz + dx * qy - dy * qx + dz * qw;
+        float rw = cw * qw - dx * qx - dy * qy - dz * qz;
+        const float nn = rsqrtf(rx * rx + ry * ry + rz * rz + rw * rw);
+        L.quat[0] = rx * nn; L.quat[1] = ry * nn; L.quat[2] = rz * nn; L.quat[3] = rw * nn;
+    }
+    warp_sync();
+}
+
+}  // namespace plen
