@@ -1,12 +1,13 @@
 // plen_b200.cu -- kernels + C ABI of libplen_b200.so (see include/plen_b200.h).  sm_100a only, no CPU path.
 //
-// Launch shape: one warp per robot, 4 warps per CTA; the lane-major model table (4 KB) is staged once per CTA in
-// shared memory, each warp owns a 10 KB scratch (state record, twists, M^-1, contact rows).  The per-env state
+// Launch shape: one warp per robot, 2-5 warps per CTA; the lane-major model table (4 KB) is staged once per CTA in
+// shared memory, each warp owns a ~19 KB scratch (state record, twists, M^-1, constraint-space A rows).  The per-env state
 // record is 96 words = 3 x 128 B lines, word w = 32 k + lane, so every global access of the step is one fully
 // coalesced line per warp.
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -15,7 +16,8 @@
 
 using namespace plen;
 
-#define WARPS_PER_CTA 4
+// warps (robots) per CTA: chosen at plen_create (env PLEN_WARPS_PER_CTA, default 2); kernels are instantiated for 2, 4, 5
+#define MAX_WARPS_PER_CTA 5
 
 struct plen_ctx {
     int n, device;
@@ -23,6 +25,7 @@ struct plen_ctx {
     plen_model model;
     DevConfig dc;
     EnvRanges er;
+    int wpc;   // warps per CTA
     float *d_tab, *d_state, *d_snapshot;
     float *d_act, *d_obs, *d_rew;
     uint8_t *d_done, *d_tmo;
@@ -50,8 +53,9 @@ static int fail(plen_ctx *ctx, int code, const char *fmt, ...) {
 // ------------------------------------------------------------------------------------------------ kernels
 struct SmemLayout {
     float tab[T_ROWS * 32];
-    WarpScratch ws[WARPS_PER_CTA];
+    WarpScratch ws[MAX_WARPS_PER_CTA];   // only blockDim.x / 32 entries are allocated
 };
+static size_t smem_bytes(int wpc) { return sizeof(float) * T_ROWS * 32 + sizeof(WarpScratch) * (size_t)wpc; }
 
 __device__ __forceinline__ SmemLayout &stage_table(const float *tab_g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -61,14 +65,15 @@ __device__ __forceinline__ SmemLayout &stage_table(const float *tab_g) {
     return sm;
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+template <int WPC>
+__global__ void __launch_bounds__(WPC * 32)
 k_step(const __grid_constant__ DevConfig dc, const __grid_constant__ EnvRanges er, const float *__restrict__ tab_g,
        float *__restrict__ state, int n, const float *__restrict__ actions, float *__restrict__ obs,
        float *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ timeout,
        float *__restrict__ terminal_obs, const float *__restrict__ snapshot) {
     SmemLayout &sm = stage_table(tab_g);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * WARPS_PER_CTA + warp;
+    const int env = blockIdx.x * (blockDim.x >> 5) + warp;
     if (env >= n) return;
     WarpScratch &ws = sm.ws[warp];
     LaneState L;
@@ -80,12 +85,13 @@ k_step(const __grid_constant__ DevConfig dc, const __grid_constant__ EnvRanges e
     store_record(state + (size_t)env * PLEN_STATE_WORDS, ws, L, lane);
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+template <int WPC>
+__global__ void __launch_bounds__(WPC * 32)
 k_tick(const __grid_constant__ DevConfig dc, const float *__restrict__ tab_g, float *__restrict__ state, int n,
        const float *__restrict__ targets, int n_ticks, float *dbg_minv, float *dbg_pos, float *dbg_rot, int dbg_only) {
     SmemLayout &sm = stage_table(tab_g);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * WARPS_PER_CTA + warp;
+    const int env = blockIdx.x * (blockDim.x >> 5) + warp;
     if (env >= n) return;
     WarpScratch &ws = sm.ws[warp];
     LaneState L;
@@ -98,12 +104,12 @@ k_tick(const __grid_constant__ DevConfig dc, const float *__restrict__ tab_g, fl
     if (!dbg_only) store_record(state + (size_t)env * PLEN_STATE_WORDS, ws, L, lane);
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(MAX_WARPS_PER_CTA * 32)
 k_observe(const float *__restrict__ state, int n, float *__restrict__ obs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemLayout &sm = *reinterpret_cast<SmemLayout *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * WARPS_PER_CTA + warp;
+    const int env = blockIdx.x * (blockDim.x >> 5) + warp;
     if (env >= n) return;
     WarpScratch &ws = sm.ws[warp];
     LaneState L;
@@ -278,9 +284,24 @@ __global__ void k_gait_ik(const double *__restrict__ params, int n, double *__re
 }
 
 // ------------------------------------------------------------------------------------------------ C ABI
-static const size_t kSmemBytes = sizeof(SmemLayout);
+static int grid_for(const plen_ctx *ctx, int n) { return (n + ctx->wpc - 1) / ctx->wpc; }
 
-static int grid_for(int n) { return (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA; }
+// dispatch over the instantiated CTA widths
+#define PLEN_DISPATCH_WPC(ctx, CALL)                     \
+    do {                                                 \
+        switch ((ctx)->wpc) {                            \
+            case 2: { constexpr int WPC = 2; CALL; } break; \
+            case 5: { constexpr int WPC = 5; CALL; } break; \
+            default: { constexpr int WPC = 4; CALL; } break; \
+        }                                                \
+    } while (0)
+
+static int launch_tick(plen_ctx *ctx, float *state, int n, const float *targets, int n_ticks, float *minv, float *pos,
+                       float *rot, int dbg_only, cudaStream_t st) {
+    PLEN_DISPATCH_WPC(ctx, (k_tick<WPC><<<grid_for(ctx, n), WPC * 32, smem_bytes(WPC), st>>>(
+                               ctx->dc, ctx->d_tab, state, n, targets, n_ticks, minv, pos, rot, dbg_only)));
+    return 0;
+}
 
 extern "C" {
 
@@ -306,9 +327,16 @@ void plen_destroy(plen_ctx *ctx) {
 static int create_impl(plen_ctx *ctx) {
     const int n = ctx->n;
     CK(ctx, cudaSetDevice(ctx->device));
-    CK(ctx, cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    CK(ctx, cudaFuncSetAttribute(k_tick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    CK(ctx, cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    {
+        const char *e = getenv("PLEN_WARPS_PER_CTA");
+        ctx->wpc = e ? atoi(e) : 2;
+        if (ctx->wpc != 2 && ctx->wpc != 4 && ctx->wpc != 5) ctx->wpc = 2;
+    }
+    PLEN_DISPATCH_WPC(ctx, {
+        CK(ctx, cudaFuncSetAttribute(k_step<WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(WPC)));
+        CK(ctx, cudaFuncSetAttribute(k_tick<WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(WPC)));
+    });
+    CK(ctx, cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(1)));
     CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     float tab[T_ROWS * 32], rec[PLEN_STATE_WORDS];
     build_table(&ctx->model, &ctx->cfg, tab);
@@ -325,9 +353,8 @@ static int create_impl(plen_ctx *ctx) {
     // post-reset snapshot: teleport to the start pose, zero joints and targets, settle for reset_ticks (plen_env.py:561-574)
     init_record(&ctx->cfg, rec);
     CK(ctx, cudaMemcpy(ctx->d_snapshot, rec, sizeof rec, cudaMemcpyHostToDevice));
-    k_tick<<<1, WARPS_PER_CTA * 32, kSmemBytes, ctx->stream>>>(ctx->dc, ctx->d_tab, ctx->d_snapshot, 1, nullptr,
-                                                               ctx->cfg.reset_ticks, nullptr, nullptr, nullptr, 0);
-    k_observe<<<1, WARPS_PER_CTA * 32, kSmemBytes, ctx->stream>>>(ctx->d_snapshot, 1, ctx->d_snapshot + PLEN_STATE_WORDS);
+    launch_tick(ctx, ctx->d_snapshot, 1, nullptr, ctx->cfg.reset_ticks, nullptr, nullptr, nullptr, 0, ctx->stream);
+    k_observe<<<1, 32, smem_bytes(1), ctx->stream>>>(ctx->d_snapshot, 1, ctx->d_snapshot + PLEN_STATE_WORDS);
     k_reset<<<(n * 32 + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_state, n, nullptr, ctx->d_snapshot, nullptr);
     CK(ctx, cudaGetLastError());
     CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -368,9 +395,9 @@ int plen_step(plen_ctx *ctx, const float *actions_dev, float *obs_dev, float *re
     if (!ctx) return fail(nullptr, PLEN_E_ARG, "ctx is NULL");
     if (!actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(ctx, PLEN_E_ARG, "plen_step: NULL buffer");
     CK(ctx, cudaSetDevice(ctx->device));
-    k_step<<<grid_for(ctx->n), WARPS_PER_CTA * 32, kSmemBytes, (cudaStream_t)stream>>>(
-        ctx->dc, ctx->er, ctx->d_tab, ctx->d_state, ctx->n, actions_dev, obs_dev, reward_dev, done_dev, timeout_dev,
-        terminal_obs_dev, ctx->d_snapshot);
+    PLEN_DISPATCH_WPC(ctx, (k_step<WPC><<<grid_for(ctx, ctx->n), WPC * 32, smem_bytes(WPC), (cudaStream_t)stream>>>(
+                               ctx->dc, ctx->er, ctx->d_tab, ctx->d_state, ctx->n, actions_dev, obs_dev, reward_dev,
+                               done_dev, timeout_dev, terminal_obs_dev, ctx->d_snapshot)));
     CK(ctx, cudaGetLastError());
     return PLEN_OK;
 }
@@ -412,8 +439,7 @@ int plen_tick(plen_ctx *ctx, const float *targets_dev, int n_ticks, void *stream
     if (!ctx) return fail(nullptr, PLEN_E_ARG, "ctx is NULL");
     if (n_ticks < 0) return fail(ctx, PLEN_E_ARG, "plen_tick: n_ticks < 0");
     CK(ctx, cudaSetDevice(ctx->device));
-    k_tick<<<grid_for(ctx->n), WARPS_PER_CTA * 32, kSmemBytes, (cudaStream_t)stream>>>(
-        ctx->dc, ctx->d_tab, ctx->d_state, ctx->n, targets_dev, n_ticks, nullptr, nullptr, nullptr, 0);
+    launch_tick(ctx, ctx->d_state, ctx->n, targets_dev, n_ticks, nullptr, nullptr, nullptr, 0, (cudaStream_t)stream);
     CK(ctx, cudaGetLastError());
     return PLEN_OK;
 }
@@ -421,8 +447,7 @@ int plen_tick(plen_ctx *ctx, const float *targets_dev, int n_ticks, void *stream
 int plen_debug_dynamics(plen_ctx *ctx, float *minv_dev, float *pos_dev, float *rot_dev, void *stream) {
     if (!ctx) return fail(nullptr, PLEN_E_ARG, "ctx is NULL");
     CK(ctx, cudaSetDevice(ctx->device));
-    k_tick<<<grid_for(ctx->n), WARPS_PER_CTA * 32, kSmemBytes, (cudaStream_t)stream>>>(
-        ctx->dc, ctx->d_tab, ctx->d_state, ctx->n, nullptr, 1, minv_dev, pos_dev, rot_dev, 1);
+    launch_tick(ctx, ctx->d_state, ctx->n, nullptr, 1, minv_dev, pos_dev, rot_dev, 1, (cudaStream_t)stream);
     CK(ctx, cudaGetLastError());
     return PLEN_OK;
 }

@@ -86,10 +86,13 @@ struct WarpScratch {
     float kk[24][8];      // K rows = A_c M_c0
     float gg[24][8];      // G rows = K S^-1
     float cb[32];         // bias forces C, later S entries
-    float red[32 * 21];   // Schur complement partial products
     float minv[24][32];   // M^-1, [column j][lane l]
     float cp[8][4];       // contact point x,y,z (rel. base origin, on the inflated hull) and distance
-    float row[6][8][4];   // per contact row: rhs, dinv, lam, d    [type: 0 n, 1 spin, 2 roll1, 3 roll2, 4 f1, 5 f2]
+    float lin[12][12];    // operational inverse inertia of the two feet, Lambda^-1 = Jfoot M^-1 Jfoot^T
+    union {
+        float ac[48][67]; // A rows of the contact constraints x 66 columns (18 servo, 32 C1, 16 C2), odd stride
+        float red[32 * 21];   // Schur complement partial products (dead before ac is built)
+    };
     float obs[32];
 };
 
@@ -586,8 +589,37 @@ PLEN_DEV void physics_tick(const DevConfig &cfg, const float *tab, WarpScratch &
         }
     }
 
+    // =====================================================================================================
+    // Constraint rows and projected Gauss-Seidel in CONSTRAINT SPACE.
+    //
+    // Every row keeps r = J.dv (its relative velocity change so far) in a register of its owner lane; a row update is
+    //   owner: delta = clamp(lam + rhs - r*dinv) - lam      broadcast delta (1 SHFL)      all lanes: r += A[.][row]*delta
+    // so the serial chain per row is one shuffle + ~6 dependent ALU ops and needs no warp reduction.  Row slots:
+    //   slot M : lane 6+j            servo row of joint j   (joint-limit row, when violated, shares the lane: J differs by sign)
+    //   slot C1: lane p / 8+p / 16+p / 24+p    normal / spin / roll-t1 / roll-t2 of contact point p (0..7)
+    //   slot C2: lane p / 8+p                   lateral t1 / t2 of contact point p
+    // A = J M^-1 J^T:  servo-servo block = M^-1 itself (ws.minv), contact rows x all 66 columns in ws.ac
+    // (contact-contact entries via the 12x12 operational inverse inertia Lambda^-1 = Jfoot M^-1 Jfoot^T).
+    // =====================================================================================================
+    const int myp = lane & 7, myf = myp >> 2;
+    const bool pt_on = (man_new >> myp) & 1u;
+    const int t1 = lane >> 3;                          // C1 row type of this lane
+    const bool has2 = lane < 16;                       // C2 rows live in lanes 0..15
+    float w1[6] = {0, 0, 0, 0, 0, 0}, w2[6] = {0, 0, 0, 0, 0, 0};
+    float pdist = 0.0f;
+    {
+        const float px = ws.cp[myp][0], py = ws.cp[myp][1], pz = ws.cp[myp][2];
+        pdist = ws.cp[myp][3] + cfg.linear_slop;
+        if (t1 == 0) { w1[0] = py; w1[1] = -px; w1[5] = 1.0f; }
+        else if (t1 == 1) { w1[2] = 1.0f; }
+        else if (t1 == 2) { w1[1] = -1.0f; }
+        else { w1[0] = 1.0f; }
+        if (lane < 8) { w2[0] = pz; w2[2] = -px; w2[4] = -1.0f; }
+        else { w2[1] = pz; w2[2] = -py; w2[3] = 1.0f; }
+    }
+
     // ---- servo rows (btMultiBodyJointMotor semantics): target velocity kp (q* - q)/dt + (1 - kd) v*, |impulse| <= f dt
-    float dv = 0.0f;                 // this lane's accumulated delta-v
+    float rM = 0.0f, r1 = 0.0f, r2 = 0.0f;            // J.dv of this lane's rows
     float m_dinv = 0.0f, m_d = 0.0f, m_rhs = 0.0f, m_lam = 0.0f;
     float l_rhs = 0.0f, l_lam = 0.0f, l_dir = 0.0f;   // joint-limit row (only when violated)
     if (is_joint) {
@@ -602,43 +634,132 @@ PLEN_DEV void physics_tick(const DevConfig &cfg, const float *tab, WarpScratch &
     }
     const unsigned lim_mask = ballot(l_dir != 0.0f);
 
-    // ---- contact rows: effective mass, rhs, warm start
-    for (int i = 0; i < 8; i++) {
-        if (!((man_new >> i) & 1u)) continue;
-        const int f = i >> 2;
-        const float px = ws.cp[i][0], py = ws.cp[i][1], pz = ws.cp[i][2], dist = ws.cp[i][3] + cfg.linear_slop;
-        const float lam_cached = shfl(L.lam, 24 + i);
+    // ---- contact rows
+    float dinv1 = 0.0f, d1 = 0.0f, rhs1 = 0.0f, lam1 = 0.0f, mu1 = 0.0f;
+    float dinv2 = 0.0f, d2 = 0.0f, rhs2 = 0.0f, lam2 = 0.0f;
+    float lamN = 0.0f;                                 // normal impulse of this lane's contact point
+    if (man_new) {
+        // foot twists at v*:  Vs_f = Jfoot_f v*
+        float Vs[2][6];
 #pragma unroll
-        for (int type = 0; type < 6; type++) {
-            if (type == 1 && !(cfg.mu_spinning > 0.0f)) continue;
-            if ((type == 2 || type == 3) && !(cfg.mu_rolling > 0.0f)) continue;
-            float J, B;
-            row_entries(type, aF[f], mF[f], Y[f], px, py, pz, J, B);
-            float d = J * B, rel = J * vstar;
-            warp_sum2(d, rel);
-            const float dinv = (d > 1.1920929e-7f) ? rcp_(d) : 0.0f;
-            float rhs, lam0 = 0.0f;
-            if (type == 0) {
+        for (int f = 0; f < 2; f++) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) { Vs[f][k] = aF[f][k] * vstar; Vs[f][3 + k] = mF[f][k] * vstar; }
+#pragma unroll
+            for (int mm = 16; mm > 0; mm >>= 1)
+#pragma unroll
+                for (int k = 0; k < 6; k++) Vs[f][k] += shfl_xor(Vs[f][k], mm);
+        }
+        // operational inverse inertia Lambda^-1[fa*6+a][fb*6+b] = Y_fb[a][b] + sum_{j in leg fa} s_j[a] Y_fb[j][b]
+        if (lane < 24) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) { ws.kk[lane][k] = Y[0][k]; ws.gg[lane][k] = Y[1][k]; }
+        }
+        warp_sync();
+        for (int e = lane; e < 144; e += 32) {
+            const int row = e / 12, col = e - 12 * row;
+            const int fa = row / 6, a6 = row - 6 * fa, fb = col / 6, b6 = col - 6 * fb;
+            const float(*Yb)[8] = fb ? ws.gg : ws.kk;
+            float acc = Yb[a6][b6];
+            const int fl = cfg.foot_lane[fa];
+            for (int j = fl - 5; j <= fl; j++) acc += ws.tw[j][a6] * Yb[j][b6];
+            ws.lin[row][col] = acc;
+        }
+        warp_sync();
+        // A rows of the contact constraints
+        unsigned msk = man_new;
+        while (msk) {
+            const int p = lowest_bit(msk);
+            msk &= msk - 1;
+            const int f = p >> 2;
+            const float px = ws.cp[p][0], py = ws.cp[p][1], pz = ws.cp[p][2];
+#pragma unroll
+            for (int type = 0; type < 6; type++) {
+                const int k = (type < 4) ? type * 8 + p : 32 + (type - 4) * 8 + p;
+                float J, B;
+                row_entries(type, aF[f], mF[f], Y[f], px, py, pz, J, B);
+                (void)J;
+                if (is_joint) ws.ac[k][lane - 6] = B;              // servo columns: (M^-1 J_k^T)[6+j]
+                // c = Lambda^-1[myf block rows][f block cols] . w_k   (w_k has <= 3 non-zeros, known at compile time)
+                float c[6];
+#pragma unroll
+                for (int a6 = 0; a6 < 6; a6++) {
+                    const float *lr = &ws.lin[myf * 6 + a6][f * 6];
+                    float v;
+                    switch (type) {
+                        case 0: v = lr[0] * py - lr[1] * px + lr[5]; break;
+                        case 1: v = lr[2]; break;
+                        case 2: v = -lr[1]; break;
+                        case 3: v = lr[0]; break;
+                        case 4: v = lr[0] * pz - lr[2] * px - lr[4]; break;
+                        default: v = lr[1] * pz - lr[2] * py + lr[3]; break;
+                    }
+                    c[a6] = v;
+                }
+                ws.ac[k][18 + lane] = w1[0] * c[0] + w1[1] * c[1] + w1[2] * c[2] + w1[3] * c[3] + w1[4] * c[4] + w1[5] * c[5];
+                if (has2)
+                    ws.ac[k][50 + lane] = w2[0] * c[0] + w2[1] * c[1] + w2[2] * c[2] + w2[3] * c[3] + w2[4] * c[4] + w2[5] * c[5];
+            }
+        }
+        warp_sync();
+        // per-lane row scalars
+        if (pt_on) {
+            d1 = ws.ac[lane][18 + lane];
+            dinv1 = (d1 > 1.1920929e-7f) ? rcp_(d1) : 0.0f;
+            const float rel = w1[0] * Vs[myf][0] + w1[1] * Vs[myf][1] + w1[2] * Vs[myf][2] + w1[3] * Vs[myf][3] +
+                              w1[4] * Vs[myf][4] + w1[5] * Vs[myf][5];
+            if (t1 == 0) {
                 float rest = (fabsf(rel) < cfg.rest_thresh) ? 0.0f : cfg.restitution * -rel;
                 rest = fmaxf(rest, 0.0f);
                 float velerr = rest - rel, poserr = 0.0f;
-                if (dist > 0.0f) velerr -= dist * cfg.inv_dt; else poserr = -dist * cfg.erp_contact_over_dt;
-                rhs = (poserr + velerr) * dinv;
-                lam0 = lam_cached * cfg.warm;
-                dv += B * lam0;
+                if (pdist > 0.0f) velerr -= pdist * cfg.inv_dt; else poserr = -pdist * cfg.erp_contact_over_dt;
+                rhs1 = (poserr + velerr) * dinv1;
             } else {
-                rhs = -rel * dinv;
+                rhs1 = -rel * dinv1;
+                mu1 = (t1 == 1) ? cfg.mu_spinning : cfg.mu_rolling;
+                if (!(mu1 > 0.0f)) { dinv1 = 0.0f; rhs1 = 0.0f; }   // row not created when its coefficient is 0
             }
-            if (lane == 0) { ws.row[type][i][0] = rhs; ws.row[type][i][1] = dinv; ws.row[type][i][2] = lam0; ws.row[type][i][3] = d; }
+            if (has2) {
+                d2 = ws.ac[32 + lane][50 + lane];
+                dinv2 = (d2 > 1.1920929e-7f) ? rcp_(d2) : 0.0f;
+                const float rel2 = w2[0] * Vs[myf][0] + w2[1] * Vs[myf][1] + w2[2] * Vs[myf][2] + w2[3] * Vs[myf][3] +
+                                   w2[4] * Vs[myf][4] + w2[5] * Vs[myf][5];
+                rhs2 = -rel2 * dinv2;
+            }
+        }
+        // warm start of the normal rows from the cached impulses (lanes 24..31 hold them)
+        {
+            const float cached = shfl(L.lam, 24 + myp);
+            if (pt_on && t1 == 0) lam1 = cached * cfg.warm;
+            unsigned wm = man_new;
+            while (wm) {
+                const int p = lowest_bit(wm);
+                wm &= wm - 1;
+                const float db = shfl(lam1, p);
+                if (db != 0.0f) {
+                    if (is_joint) rM += ws.ac[p][lane - 6] * db;
+                    r1 += ws.ac[p][18 + lane] * db;
+                    if (has2) r2 += ws.ac[p][50 + lane] * db;
+                }
+            }
+            lamN = shfl(lam1, myp);
         }
     }
-    warp_sync();
 
     // ---- projected Gauss-Seidel (row order of btMultiBodyConstraintSolver::solveSingleIteration)
+    // Branch-free row updates: every lane always executes the candidate computation and the three r-updates (its smem
+    // addresses are clamped to valid, possibly meaningless, entries for rows it does not own); ownership is a select.
+    // Each row is visited exactly once per iteration, so the iteration residual max_j (dlam_j / dinv_j)^2 is formed
+    // from lam_after - lam_before at the end of the iteration instead of inside every row update.
+    const int mcol = is_joint ? lane - 6 : 0;                    // servo column of this lane inside an A row
+    const int c2col = has2 ? 50 + lane : 50;
+    const float *acol1 = &ws.ac[lane][0];                        // A rows of this lane's C1 / C2 constraints (column reads)
+    const float *acol2 = &ws.ac[has2 ? 32 + lane : lane][0];
+    const float *mcolp = &ws.minv[0][lane];
+    const float sqrt_thr = sqrtf(cfg.residual_threshold);
     int it = 0;
     for (; it < cfg.iterations; it++) {
-        float res_lane = 0.0f;   // per-lane residual of the lane-owned rows (servo / limit)
-        float res = 0.0f;        // uniform residual of the contact rows
+        const float m_old = m_lam, l_old = l_lam, lam1_old = lam1, lam2_old = lam2;
         // non-contact rows: list = [limits in joint order, servos in joint order]; odd iterations forward, even reversed
         for (int half = 0; half < 2; half++) {
             const bool do_limits = ((it & 1) != 0) == (half == 0);
@@ -647,106 +768,137 @@ PLEN_DEV void physics_tick(const DevConfig &cfg, const float *tab, WarpScratch &
                 while (msk) {
                     const int j = (it & 1) ? lowest_bit(msk) : highest_bit(msk);
                     msk &= ~(1u << j);
-                    float delta = l_rhs - (l_dir * dv) * m_dinv;
-                    const float sum = l_lam + delta;
-                    const float nl = clampf(sum, 0.0f, 100.0f);
-                    delta = nl - l_lam;
-                    const float dj = shfl(delta * l_dir, j);
-                    if (lane == j) { l_lam = nl; res_lane = fmaxf(res_lane, (delta * m_d) * (delta * m_d)); }
-                    if (lane < 24) dv += ws.minv[j][lane] * dj;
+                    float delta = l_rhs - (l_dir * rM) * m_dinv;
+                    const float nl = clampf(l_lam + delta, 0.0f, 100.0f);
+                    delta = (nl - l_lam) * l_dir;
+                    const float db = shfl(delta, j);
+                    l_lam = (lane == j) ? nl : l_lam;
+                    rM += mcolp[j * 32] * db;
+                    r1 += acol1[j - 6] * db;
+                    r2 += acol2[j - 6] * db;
                 }
             } else {
-                for (int s = 0; s < 18; s++) {
-                    const int j = (it & 1) ? 6 + s : 23 - s;
-                    float delta = m_rhs - dv * m_dinv;
-                    const float sum = m_lam + delta;
-                    const float nl = clampf(sum, -cfg.motor_imp, cfg.motor_imp);
-                    delta = nl - m_lam;
-                    const float dj = shfl(delta, j);
-                    if (lane == j) { m_lam = nl; res_lane = fmaxf(res_lane, (delta * m_d) * (delta * m_d)); }
-                    if (lane < 24) dv += ws.minv[j][lane] * dj;
+                const int step = (it & 1) ? 1 : -1;
+                int j = (it & 1) ? 6 : 23;
+#pragma unroll 6
+                for (int s = 0; s < 18; s++, j += step) {
+                    const float nl = clampf(m_lam + (m_rhs - rM * m_dinv), -cfg.motor_imp, cfg.motor_imp);
+                    const float db = shfl(nl - m_lam, j);
+                    m_lam = (lane == j) ? nl : m_lam;
+                    rM += mcolp[j * 32] * db;
+                    r1 += acol1[j - 6] * db;
+                    r2 += acol2[j - 6] * db;
                 }
             }
         }
-        // contact rows: normals, spinning, rolling, then lateral pairs with the implicit friction cone
         if (man_new) {
-            for (int type = 0; type < 4; type++) {
-                if (type == 1 && !(cfg.mu_spinning > 0.0f)) continue;
-                if ((type == 2 || type == 3) && !(cfg.mu_rolling > 0.0f)) continue;
-                // Bullet solves all spinning rows, then the rolling rows point by point (t1 then t2)
-                for (int i = 0; i < 8; i++) {
-                    if (!((man_new >> i) & 1u)) continue;
-                    const int f = i >> 2;
-                    const float px = ws.cp[i][0], py = ws.cp[i][1], pz = ws.cp[i][2];
-                    const int ntypes = (type == 2) ? 2 : 1;
-                    if (type == 3) continue;   // handled together with type 2 to keep the per-point t1,t2 order
-                    for (int tt = 0; tt < ntypes; tt++) {
-                        const int ty = type + tt;
-                        float lo = 0.0f, hi = 1e10f;
-                        if (ty != 0) {
-                            const float tot = ws.row[0][i][2];
-                            if (!(tot > 0.0f)) continue;
-                            const float mu = (ty == 1) ? cfg.mu_spinning : cfg.mu_rolling;
-                            lo = -mu * tot; hi = mu * tot;
+            // normals, then all spinning rows, then the rolling rows point by point (t1, t2)
+            for (int phase = 0; phase < 3; phase++) {
+                unsigned msk = man_new;
+                while (msk) {
+                    const int p = lowest_bit(msk);
+                    msk &= msk - 1;
+                    const int nsub = (phase == 2) ? 2 : 1;
+                    for (int sub = 0; sub < nsub; sub++) {
+                        const int owner = (phase + sub) * 8 + p;   // C1 lane = A row index
+                        const float sum = lam1 + (rhs1 - r1 * dinv1);
+                        float nl;
+                        if (phase == 0) {
+                            nl = fminf(fmaxf(sum, 0.0f), 1e10f);     // lower 0, upper 1e10
+                        } else {
+                            const float lim = mu1 * lamN;
+                            nl = clampf(sum, -lim, lim);
+                            nl = (lamN > 0.0f) ? nl : lam1;          // row skipped while the normal impulse is not positive
                         }
-                        float J, B;
-                        row_entries(ty, aF[f], mF[f], Y[f], px, py, pz, J, B);
-                        const float dot = warp_sum(J * dv);
-                        const float rhs = ws.row[ty][i][0], dinv = ws.row[ty][i][1], lam = ws.row[ty][i][2], d = ws.row[ty][i][3];
-                        float delta = rhs - dot * dinv;
-                        const float nl = clampf(lam + delta, lo, hi);
-                        delta = nl - lam;
-                        warp_sync();
-                        if (lane == 0) ws.row[ty][i][2] = nl;
-                        dv += B * delta;
-                        const float r = (dinv != 0.0f) ? delta * d : 0.0f;
-                        res = fmaxf(res, r * r);
-                        warp_sync();
+                        const float db = shfl(nl - lam1, owner);
+                        lam1 = (lane == owner) ? nl : lam1;
+                        if (phase == 0) lamN += (myp == p) ? db : 0.0f;
+                        const float *arow = &ws.ac[owner][0];
+                        rM += arow[mcol] * db;
+                        r1 += arow[18 + lane] * db;
+                        r2 += arow[c2col] * db;
                     }
                 }
             }
-            for (int i = 0; i < 8; i++) {
-                if (!((man_new >> i) & 1u)) continue;
-                const int f = i >> 2;
-                const float px = ws.cp[i][0], py = ws.cp[i][1], pz = ws.cp[i][2];
-                const float tot = ws.row[0][i][2];
-                const float lim = cfg.mu_lateral * tot;
-                float JA, BA, JB, BB;
-                row_entries(4, aF[f], mF[f], Y[f], px, py, pz, JA, BA);
-                row_entries(5, aF[f], mF[f], Y[f], px, py, pz, JB, BB);
-                float dotA = JA * dv, dotB = JB * dv;
-                warp_sum2(dotA, dotB);
-                const float rhsA = ws.row[4][i][0], dinvA = ws.row[4][i][1], lamA = ws.row[4][i][2], dA = ws.row[4][i][3];
-                const float rhsB = ws.row[5][i][0], dinvB = ws.row[5][i][1], lamB = ws.row[5][i][2], dB = ws.row[5][i][3];
-                float deltaA = rhsA - dotA * dinvA, deltaB = rhsB - dotB * dinvB;
-                const float sumA = lamA + deltaA, sumB = lamB + deltaB;
+            // lateral pairs with the implicit friction cone (resolveConeFrictionConstraintRows)
+            unsigned msk = man_new;
+            while (msk) {
+                const int p = lowest_bit(msk);
+                msk &= msk - 1;
+                const float cand = lam2 + (rhs2 - r2 * dinv2);
+                const float sumA = shfl(cand, p), sumB = shfl(cand, 8 + p);
+                const float lim = cfg.mu_lateral * shfl(lamN, p);
                 float nA = sumA, nB = sumB;
                 if (sumA < -lim || sumA > lim || sumB < -lim || sumB > lim) {
-                    // resolveConeFrictionConstraintRows: clip onto the circle of radius mu*lam_n along atan2(sumA,sumB)
                     const float inv = rsqrtf(sumA * sumA + sumB * sumB);
                     const float cA = fabsf(lim * sumA * inv), cB = fabsf(lim * sumB * inv);
                     nA = clampf(sumA, -cA, cA);
                     nB = clampf(sumB, -cB, cB);
                 }
-                deltaA = nA - lamA; deltaB = nB - lamB;
-                warp_sync();
-                if (lane == 0) { ws.row[4][i][2] = nA; ws.row[5][i][2] = nB; }
-                dv += BA * deltaA + BB * deltaB;
-                const float r = ((dinvA != 0.0f) ? deltaA * dA : 0.0f) + ((dinvB != 0.0f) ? deltaB * dB : 0.0f);
-                res = fmaxf(res, r * r);
-                warp_sync();
+                const float nmine = (lane == p) ? nA : ((lane == 8 + p) ? nB : lam2);
+                const float dmine = nmine - lam2;
+                lam2 = nmine;
+                const float dA = shfl(dmine, p), dB = shfl(dmine, 8 + p);
+                const float *arowA = &ws.ac[32 + p][0], *arowB = &ws.ac[40 + p][0];
+                rM += arowA[mcol] * dA + arowB[mcol] * dB;
+                r1 += arowA[18 + lane] * dA + arowB[18 + lane] * dB;
+                r2 += arowA[c2col] * dA + arowB[c2col] * dB;
             }
         }
-        res = fmaxf(res, f_as_u_max(res_lane));
-        if (res <= cfg.residual_threshold) { it++; break; }
+        // residual of this iteration
+        float res_lane = fabsf((m_lam - m_old) * m_d);
+        res_lane = fmaxf(res_lane, fabsf((l_lam - l_old) * m_d));
+        if (man_new) {
+            const float v1 = pt_on ? fabsf((lam1 - lam1_old) * d1) : 0.0f;
+            float v2 = (pt_on && has2) ? (lam2 - lam2_old) * d2 : 0.0f;   // pair residual = dA/dinvA + dB/dinvB
+            v2 = (dinv2 != 0.0f) ? v2 : 0.0f;
+            v2 += shfl_xor(v2, 8);
+            res_lane = fmaxf(res_lane, fmaxf((dinv1 != 0.0f) ? v1 : 0.0f, fabsf(v2)));
+        }
+        const float res = f_as_u_max(res_lane);
+        if (res * res <= cfg.residual_threshold) { it++; break; }
     }
+    (void)sqrt_thr;
     L.iters = it;
 
-    // ---- write back cached normal impulses, apply delta-v, integrate
-    if (lane >= 24) {
-        const int i = lane - 24;
-        L.lam = ((man_new >> i) & 1u) ? ws.row[0][i][2] : 0.0f;
+    // ---- delta-v = M^-1 J^T lambda: generalized impulse tau, then one product with M^-1
+    float dv = 0.0f;
+    {
+        float tau = is_joint ? (m_lam + l_dir * l_lam) : 0.0f;
+        if (man_new) {
+            float W[2][6];
+#pragma unroll
+            for (int f = 0; f < 2; f++)
+#pragma unroll
+                for (int k = 0; k < 6; k++) {
+                    float v = 0.0f;
+                    if (pt_on && myf == f) v = w1[k] * lam1 + (has2 ? w2[k] * lam2 : 0.0f);
+                    W[f][k] = v;
+                }
+#pragma unroll
+            for (int mm = 16; mm > 0; mm >>= 1)
+#pragma unroll
+                for (int f = 0; f < 2; f++)
+#pragma unroll
+                    for (int k = 0; k < 6; k++) W[f][k] += shfl_xor(W[f][k], mm);
+#pragma unroll
+            for (int f = 0; f < 2; f++)
+                tau += aF[f][0] * W[f][0] + aF[f][1] * W[f][1] + aF[f][2] * W[f][2] + mF[f][0] * W[f][3] +
+                       mF[f][1] * W[f][4] + mF[f][2] * W[f][5];
+        }
+        warp_sync();
+        ws.cb[lane] = (lane < 24) ? tau : 0.0f;
+        warp_sync();
+        if (lane < 24)
+            for (int j = 0; j < 24; j++) dv += ws.minv[j][lane] * ws.cb[j];
     }
+    // cached normal impulses back to lanes 24..31
+    {
+        const float ln = shfl(lam1, lane & 7);
+        if (lane >= 24) L.lam = ((man_new >> (lane - 24)) & 1u) ? ln : 0.0f;
+    }
+
+    // ---- apply delta-v, integrate
     L.u = (lane < 24) ? clampf(vstar + dv, -cfg.vmax, cfg.vmax) : 0.0f;
     if (is_joint) L.q += L.u * cfg.dt;
     {
