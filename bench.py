@@ -109,8 +109,11 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
-    envs_per_thread = 16
-    # one "step" = one vector step of cores*16 envs on all host threads
+    # one "step" = one vector step of cores*E envs on all host threads; E sized from a probe so a step is ~0.3 s and
+    # the whole --steps K run stays within a few minutes
+    probe, _, _ = cpu_port_throughput(cores, 8, 4, seed=1)
+    per_step = min(0.3, 150.0 / max(1, args.steps))
+    envs_per_thread = int(max(8, min(4096, probe * per_step / cores)))
     val, dt, n = cpu_port_throughput(cores, envs_per_thread, args.steps + 0, seed=0)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -233,9 +236,13 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             cores = len(os.sched_getaffinity(0))
-            v, dt, n = cpu_port_throughput(cores, 8, 12)
+            probe, _, _ = cpu_port_throughput(cores, 8, 4, seed=1)
+            ept = int(max(8, min(2048, probe * 0.25 / cores)))          # ~0.25 s per vector step, ~12 s in total
+            v, dt, n = cpu_port_throughput(cores, ept, 48)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "%d envs x 12 vector steps (%.1f s), float64 oracle port" % (n, dt)}
+                                    "sample": "%d envs x 48 vector steps (%.1f s of wall time on %d threads), "
+                                              "float64 oracle port (oracle/plen_oracle.c); PyBullet itself is not "
+                                              "installable here (SURVEY.md 8c)" % (n, dt, cores)}
         print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()
