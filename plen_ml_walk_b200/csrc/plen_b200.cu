@@ -13,11 +13,13 @@
 #include <new>
 
 #include "plen_host_tables.h"
+#include "plen_solve.cuh"
 
 using namespace plen;
 
-// warps (robots) per CTA: chosen at plen_create (env PLEN_WARPS_PER_CTA, default 2); kernels are instantiated for 2, 4, 5
-#define MAX_WARPS_PER_CTA 5
+// warps per CTA of the warp-per-robot kernels (k_dyn, k_post) and of k_solve (4 robots per warp)
+#define DYN_WPC 4
+#define SOLVE_WPC 2
 
 struct plen_ctx {
     int n, device;
@@ -25,8 +27,9 @@ struct plen_ctx {
     plen_model model;
     DevConfig dc;
     EnvRanges er;
-    int wpc;   // warps per CTA
     float *d_tab, *d_state, *d_snapshot;
+    float *d_srec;   // [n][SR_WORDS] solve records (k_dyn -> k_solve)
+    float *d_tgt;    // [n][18] servo targets of the current env step
     float *d_act, *d_obs, *d_rew;
     uint8_t *d_done, *d_tmo;
     cudaStream_t stream;
@@ -51,63 +54,77 @@ static int fail(plen_ctx *ctx, int code, const char *fmt, ...) {
     } while (0)
 
 // ------------------------------------------------------------------------------------------------ kernels
-struct SmemLayout {
+struct DynSmem {
     float tab[T_ROWS * 32];
-    WarpScratch ws[MAX_WARPS_PER_CTA];   // only blockDim.x / 32 entries are allocated
+    WarpScratch ws[DYN_WPC];
 };
-static size_t smem_bytes(int wpc) { return sizeof(float) * T_ROWS * 32 + sizeof(WarpScratch) * (size_t)wpc; }
 
-__device__ __forceinline__ SmemLayout &stage_table(const float *tab_g) {
+__device__ __forceinline__ DynSmem &stage_table(const float *tab_g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SmemLayout &sm = *reinterpret_cast<SmemLayout *>(smem_raw);
+    DynSmem &sm = *reinterpret_cast<DynSmem *>(smem_raw);
     for (int i = threadIdx.x; i < T_ROWS * 32; i += blockDim.x) sm.tab[i] = tab_g[i];
     __syncthreads();
     return sm;
 }
 
-template <int WPC>
-__global__ void __launch_bounds__(WPC * 32)
-k_step(const __grid_constant__ DevConfig dc, const __grid_constant__ EnvRanges er, const float *__restrict__ tab_g,
-       float *__restrict__ state, int n, const float *__restrict__ actions, float *__restrict__ obs,
-       float *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ timeout,
-       float *__restrict__ terminal_obs, const float *__restrict__ snapshot) {
-    SmemLayout &sm = stage_table(tab_g);
+// First half of a tick, one warp per robot: FK, CRBA, M^-1, v*, contacts, row set-up -> solve record.
+//   actions != NULL : agent-space actions of a new env step; the servo targets are derived (agent_to_env) and kept in tgt
+//   actions == NULL : tgt holds the targets already (NULL = zero targets, the reset pose)
+__global__ void __launch_bounds__(DYN_WPC * 32)
+k_dyn(const __grid_constant__ DevConfig dc, const __grid_constant__ EnvRanges er, const float *__restrict__ tab_g,
+      const float *__restrict__ state, int n, const float *__restrict__ actions, float *__restrict__ tgt,
+      float *__restrict__ srec, float *dbg_minv, float *dbg_pos, float *dbg_rot) {
+    DynSmem &sm = stage_table(tab_g);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int env = blockIdx.x * DYN_WPC + warp;
     if (env >= n) return;
     WarpScratch &ws = sm.ws[warp];
     LaneState L;
     load_record(state + (size_t)env * PLEN_STATE_WORDS, ws, L, lane);
-    StepIO io{actions + (size_t)env * PLEN_NJ, obs + (size_t)env * PLEN_OBS, reward + env, done + env,
-              timeout ? timeout + env : nullptr, terminal_obs ? terminal_obs + (size_t)env * PLEN_OBS : nullptr,
-              snapshot};
-    env_step(dc, er, sm.tab, ws, L, lane, io);
+    if (lane >= 6 && lane < 24) {
+        const size_t o = (size_t)env * PLEN_NJ + lane - 6;
+        if (actions) { L.tgt = agent_target(dc, er, lane - 6, actions[o]); tgt[o] = L.tgt; }
+        else L.tgt = tgt ? tgt[o] : 0.0f;
+    }
+    DebugOut dbg{dbg_minv ? dbg_minv + (size_t)env * 576 : nullptr, dbg_pos ? dbg_pos + (size_t)env * 72 : nullptr,
+                 dbg_rot ? dbg_rot + (size_t)env * 216 : nullptr};
+    tick_dynamics(dc, sm.tab, ws, L, lane, srec + (size_t)env * SR_WORDS, (dbg_minv || dbg_pos || dbg_rot) ? &dbg : nullptr);
+}
+
+// Second half of a tick, 8 lanes per robot: PGS + delta-v + integration, state record updated in place.
+__global__ void __launch_bounds__(SOLVE_WPC * 32)
+k_solve(const __grid_constant__ DevConfig dc, const float *__restrict__ srec, float *__restrict__ state, int n) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *Gs = reinterpret_cast<float *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int robot = (blockIdx.x * SOLVE_WPC + warp) * 4 + (lane >> 3);
+    const bool valid = robot < n;
+    const size_t r = valid ? (size_t)robot : 0;
+    solve_tick(dc, srec + r * SR_WORDS, Gs + (size_t)(warp * 4 + (lane >> 3)) * 960, state + r * PLEN_STATE_WORDS, lane, valid);
+}
+
+// After the last tick of an env step, one warp per robot: observation, done, reward, counters, auto-reset.
+__global__ void __launch_bounds__(DYN_WPC * 32)
+k_post(const __grid_constant__ DevConfig dc, const float *__restrict__ tab_g, float *__restrict__ state, int n,
+       float *__restrict__ obs, float *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ timeout,
+       float *__restrict__ terminal_obs, const float *__restrict__ snapshot) {
+    DynSmem &sm = stage_table(tab_g);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int env = blockIdx.x * DYN_WPC + warp;
+    if (env >= n) return;
+    WarpScratch &ws = sm.ws[warp];
+    LaneState L;
+    load_record(state + (size_t)env * PLEN_STATE_WORDS, ws, L, lane);
+    StepIO io{nullptr, obs + (size_t)env * PLEN_OBS, reward + env, done + env, timeout ? timeout + env : nullptr,
+              terminal_obs ? terminal_obs + (size_t)env * PLEN_OBS : nullptr, snapshot};
+    env_post(dc, sm.tab, ws, L, lane, io);
     store_record(state + (size_t)env * PLEN_STATE_WORDS, ws, L, lane);
 }
 
-template <int WPC>
-__global__ void __launch_bounds__(WPC * 32)
-k_tick(const __grid_constant__ DevConfig dc, const float *__restrict__ tab_g, float *__restrict__ state, int n,
-       const float *__restrict__ targets, int n_ticks, float *dbg_minv, float *dbg_pos, float *dbg_rot, int dbg_only) {
-    SmemLayout &sm = stage_table(tab_g);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (env >= n) return;
-    WarpScratch &ws = sm.ws[warp];
-    LaneState L;
-    load_record(state + (size_t)env * PLEN_STATE_WORDS, ws, L, lane);
-    if (lane >= 6 && lane < 24) L.tgt = targets ? targets[(size_t)env * PLEN_NJ + lane - 6] : 0.0f;
-    DebugOut dbg{dbg_minv ? dbg_minv + (size_t)env * 576 : nullptr, dbg_pos ? dbg_pos + (size_t)env * 72 : nullptr,
-                 dbg_rot ? dbg_rot + (size_t)env * 216 : nullptr};
-    const bool want_dbg = dbg_minv || dbg_pos || dbg_rot;
-    for (int t = 0; t < n_ticks; t++) physics_tick(dc, sm.tab, ws, L, lane, (want_dbg && t == n_ticks - 1) ? &dbg : nullptr);
-    if (!dbg_only) store_record(state + (size_t)env * PLEN_STATE_WORDS, ws, L, lane);
-}
-
-__global__ void __launch_bounds__(MAX_WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(DYN_WPC * 32)
 k_observe(const float *__restrict__ state, int n, float *__restrict__ obs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SmemLayout &sm = *reinterpret_cast<SmemLayout *>(smem_raw);
+    DynSmem &sm = *reinterpret_cast<DynSmem *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * (blockDim.x >> 5) + warp;
     if (env >= n) return;
@@ -284,28 +301,23 @@ __global__ void k_gait_ik(const double *__restrict__ params, int n, double *__re
 }
 
 // ------------------------------------------------------------------------------------------------ C ABI
-static int grid_for(const plen_ctx *ctx, int n) { return (n + ctx->wpc - 1) / ctx->wpc; }
+static const size_t DYN_SMEM = sizeof(DynSmem);
+static const size_t SOLVE_SMEM = sizeof(float) * 960 * 4 * SOLVE_WPC;
+static int dyn_grid(int n) { return (n + DYN_WPC - 1) / DYN_WPC; }
+static int solve_grid(int n) { return (n + 4 * SOLVE_WPC - 1) / (4 * SOLVE_WPC); }
 
-// dispatch over the instantiated CTA widths
-#define PLEN_DISPATCH_WPC(ctx, CALL)                     \
-    do {                                                 \
-        switch ((ctx)->wpc) {                            \
-            case 2: { constexpr int WPC = 2; CALL; } break; \
-            case 5: { constexpr int WPC = 5; CALL; } break; \
-            default: { constexpr int WPC = 4; CALL; } break; \
-        }                                                \
-    } while (0)
-
-static int launch_tick(plen_ctx *ctx, float *state, int n, const float *targets, int n_ticks, float *minv, float *pos,
-                       float *rot, int dbg_only, cudaStream_t st) {
-    PLEN_DISPATCH_WPC(ctx, (k_tick<WPC><<<grid_for(ctx, n), WPC * 32, smem_bytes(WPC), st>>>(
-                               ctx->dc, ctx->d_tab, state, n, targets, n_ticks, minv, pos, rot, dbg_only)));
-    return 0;
+// n_ticks physics ticks of 1/240 s: (k_dyn, k_solve) per tick.  `actions` (agent space) only on the first tick.
+static void launch_ticks(plen_ctx *ctx, float *state, int n, const float *actions, float *tgt, int n_ticks, cudaStream_t st) {
+    for (int t = 0; t < n_ticks; t++) {
+        k_dyn<<<dyn_grid(n), DYN_WPC * 32, DYN_SMEM, st>>>(ctx->dc, ctx->er, ctx->d_tab, state, n, t == 0 ? actions : nullptr,
+                                                          tgt, ctx->d_srec, nullptr, nullptr, nullptr);
+        k_solve<<<solve_grid(n), SOLVE_WPC * 32, SOLVE_SMEM, st>>>(ctx->dc, ctx->d_srec, state, n);
+    }
 }
 
 extern "C" {
 
-const char *plen_version(void) { return "plen_b200 0.1 (sm_100a)"; }
+const char *plen_version(void) { return "plen_b200 0.2 (sm_100a)"; }
 
 int plen_default_config(plen_config *cfg, int joint_act) {
     if (!cfg) return fail(nullptr, PLEN_E_ARG, "cfg is NULL");
@@ -318,7 +330,7 @@ int plen_num_envs(const plen_ctx *ctx) { return ctx ? ctx->n : 0; }
 void plen_destroy(plen_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->d_tab); cudaFree(ctx->d_state); cudaFree(ctx->d_snapshot);
+    cudaFree(ctx->d_tab); cudaFree(ctx->d_state); cudaFree(ctx->d_snapshot); cudaFree(ctx->d_srec); cudaFree(ctx->d_tgt);
     cudaFree(ctx->d_act); cudaFree(ctx->d_obs); cudaFree(ctx->d_rew); cudaFree(ctx->d_done); cudaFree(ctx->d_tmo);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -327,16 +339,10 @@ void plen_destroy(plen_ctx *ctx) {
 static int create_impl(plen_ctx *ctx) {
     const int n = ctx->n;
     CK(ctx, cudaSetDevice(ctx->device));
-    {
-        const char *e = getenv("PLEN_WARPS_PER_CTA");
-        ctx->wpc = e ? atoi(e) : 2;
-        if (ctx->wpc != 2 && ctx->wpc != 4 && ctx->wpc != 5) ctx->wpc = 2;
-    }
-    PLEN_DISPATCH_WPC(ctx, {
-        CK(ctx, cudaFuncSetAttribute(k_step<WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(WPC)));
-        CK(ctx, cudaFuncSetAttribute(k_tick<WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(WPC)));
-    });
-    CK(ctx, cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(1)));
+    CK(ctx, cudaFuncSetAttribute(k_dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DYN_SMEM));
+    CK(ctx, cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DYN_SMEM));
+    CK(ctx, cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DYN_SMEM));
+    CK(ctx, cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
     CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     float tab[T_ROWS * 32], rec[PLEN_STATE_WORDS];
     build_table(&ctx->model, &ctx->cfg, tab);
@@ -344,6 +350,8 @@ static int create_impl(plen_ctx *ctx) {
     CK(ctx, cudaMalloc(&ctx->d_tab, sizeof tab));
     CK(ctx, cudaMalloc(&ctx->d_state, sizeof(float) * PLEN_STATE_WORDS * (size_t)n));
     CK(ctx, cudaMalloc(&ctx->d_snapshot, sizeof(float) * (PLEN_STATE_WORDS + 32)));
+    CK(ctx, cudaMalloc(&ctx->d_srec, sizeof(float) * SR_WORDS * (size_t)n));
+    CK(ctx, cudaMalloc(&ctx->d_tgt, sizeof(float) * PLEN_NJ * (size_t)n));
     CK(ctx, cudaMalloc(&ctx->d_act, sizeof(float) * PLEN_NJ * (size_t)n));
     CK(ctx, cudaMalloc(&ctx->d_obs, sizeof(float) * PLEN_OBS * (size_t)n));
     CK(ctx, cudaMalloc(&ctx->d_rew, sizeof(float) * (size_t)n));
@@ -353,8 +361,8 @@ static int create_impl(plen_ctx *ctx) {
     // post-reset snapshot: teleport to the start pose, zero joints and targets, settle for reset_ticks (plen_env.py:561-574)
     init_record(&ctx->cfg, rec);
     CK(ctx, cudaMemcpy(ctx->d_snapshot, rec, sizeof rec, cudaMemcpyHostToDevice));
-    launch_tick(ctx, ctx->d_snapshot, 1, nullptr, ctx->cfg.reset_ticks, nullptr, nullptr, nullptr, 0, ctx->stream);
-    k_observe<<<1, 32, smem_bytes(1), ctx->stream>>>(ctx->d_snapshot, 1, ctx->d_snapshot + PLEN_STATE_WORDS);
+    launch_ticks(ctx, ctx->d_snapshot, 1, nullptr, nullptr, ctx->cfg.reset_ticks, ctx->stream);
+    k_observe<<<1, 32, DYN_SMEM, ctx->stream>>>(ctx->d_snapshot, 1, ctx->d_snapshot + PLEN_STATE_WORDS);
     k_reset<<<(n * 32 + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_state, n, nullptr, ctx->d_snapshot, nullptr);
     CK(ctx, cudaGetLastError());
     CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -395,9 +403,10 @@ int plen_step(plen_ctx *ctx, const float *actions_dev, float *obs_dev, float *re
     if (!ctx) return fail(nullptr, PLEN_E_ARG, "ctx is NULL");
     if (!actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(ctx, PLEN_E_ARG, "plen_step: NULL buffer");
     CK(ctx, cudaSetDevice(ctx->device));
-    PLEN_DISPATCH_WPC(ctx, (k_step<WPC><<<grid_for(ctx, ctx->n), WPC * 32, smem_bytes(WPC), (cudaStream_t)stream>>>(
-                               ctx->dc, ctx->er, ctx->d_tab, ctx->d_state, ctx->n, actions_dev, obs_dev, reward_dev,
-                               done_dev, timeout_dev, terminal_obs_dev, ctx->d_snapshot)));
+    cudaStream_t st = (cudaStream_t)stream;
+    launch_ticks(ctx, ctx->d_state, ctx->n, actions_dev, ctx->d_tgt, ctx->cfg.substeps, st);
+    k_post<<<dyn_grid(ctx->n), DYN_WPC * 32, DYN_SMEM, st>>>(ctx->dc, ctx->d_tab, ctx->d_state, ctx->n, obs_dev, reward_dev,
+                                                            done_dev, timeout_dev, terminal_obs_dev, ctx->d_snapshot);
     CK(ctx, cudaGetLastError());
     return PLEN_OK;
 }
@@ -439,7 +448,10 @@ int plen_tick(plen_ctx *ctx, const float *targets_dev, int n_ticks, void *stream
     if (!ctx) return fail(nullptr, PLEN_E_ARG, "ctx is NULL");
     if (n_ticks < 0) return fail(ctx, PLEN_E_ARG, "plen_tick: n_ticks < 0");
     CK(ctx, cudaSetDevice(ctx->device));
-    launch_tick(ctx, ctx->d_state, ctx->n, targets_dev, n_ticks, nullptr, nullptr, nullptr, 0, (cudaStream_t)stream);
+    if (targets_dev)
+        CK(ctx, cudaMemcpyAsync(ctx->d_tgt, targets_dev, sizeof(float) * PLEN_NJ * (size_t)ctx->n, cudaMemcpyDeviceToDevice,
+                                (cudaStream_t)stream));
+    launch_ticks(ctx, ctx->d_state, ctx->n, nullptr, targets_dev ? ctx->d_tgt : nullptr, n_ticks, (cudaStream_t)stream);
     CK(ctx, cudaGetLastError());
     return PLEN_OK;
 }
@@ -447,7 +459,8 @@ int plen_tick(plen_ctx *ctx, const float *targets_dev, int n_ticks, void *stream
 int plen_debug_dynamics(plen_ctx *ctx, float *minv_dev, float *pos_dev, float *rot_dev, void *stream) {
     if (!ctx) return fail(nullptr, PLEN_E_ARG, "ctx is NULL");
     CK(ctx, cudaSetDevice(ctx->device));
-    launch_tick(ctx, ctx->d_state, ctx->n, nullptr, 1, minv_dev, pos_dev, rot_dev, 1, (cudaStream_t)stream);
+    k_dyn<<<dyn_grid(ctx->n), DYN_WPC * 32, DYN_SMEM, (cudaStream_t)stream>>>(ctx->dc, ctx->er, ctx->d_tab, ctx->d_state, ctx->n,
+                                                                            nullptr, nullptr, ctx->d_srec, minv_dev, pos_dev, rot_dev);
     CK(ctx, cudaGetLastError());
     return PLEN_OK;
 }

@@ -37,6 +37,7 @@ PLEN_DEV float shfl_down(float v, int d) { return __shfl_down_sync(0xffffffffu, 
 PLEN_DEV float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 PLEN_DEV unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 PLEN_DEV unsigned redux_max(unsigned v) { return __reduce_max_sync(0xffffffffu, v); }
+PLEN_DEV unsigned redux_or(unsigned v) { return __reduce_or_sync(0xffffffffu, v); }
 PLEN_DEV void warp_sync() { __syncwarp(); }
 PLEN_DEV float f_as_u_max(float v) { return __uint_as_float(redux_max(__float_as_uint(v))); }
 PLEN_DEV void sincos_(float x, float *s, float *c) { sincosf(x, s, c); }
@@ -65,7 +66,8 @@ enum {
     W_CNT = 60, W_DS = 61, W_HIST = 62, W_EPT = 63,   // ints
     W_LAST = 64,    // 6
     W_SUMS = 70,    // 9
-    W_SPARE = 79
+    W_ITERS = 79,   // PGS iterations of the last tick (diagnostic)
+    W_SPARE = 80
 };
 
 struct DevConfig {
@@ -79,19 +81,30 @@ struct DevConfig {
     int substeps, reset_ticks, iterations, joint_act, max_episode_steps, auto_reset;
 };
 
-// per-warp shared scratch (floats)
+// ---- solve record: per robot, per tick, written by k_dyn and consumed by k_solve (global memory, words)
+enum {
+    SR_G = 0,          // 30 columns x 32 words of G (see tick_dynamics)
+    SR_B = 960,        // 6 rows x 32 words: base rows of M^-1 J^T in the same word order
+    SR_MRHS = 1152, SR_MDINV = 1184, SR_LDIR = 1216, SR_LRHS = 1248, SR_VSTAR = 1280, SR_Q = 1312,   // 32 words each
+    SR_CRHS = 1344, SR_CDINV = 1408, SR_CD = 1472,   // 64 words each: [contact point p][solver lane g]
+    SR_PT = 1536,      // 8 x (x, y, z, distance) of the candidate contact points, relative to the base origin
+    SR_LAMC = 1568,    // 8 cached normal impulses
+    SR_BASE = 1576,    // v* of the base (6), base position (3), quaternion (4), manifold bits (1)
+    SR_WORDS = 1600
+};
+
+// per-warp shared scratch of k_dyn (floats)
 struct WarpScratch {
     float st[96];
     float tw[24][8];      // joint twists s_j = [a(3), m(3)] about the base origin, world axes
-    float kk[24][8];      // K rows = A_c M_c0
-    float gg[24][8];      // G rows = K S^-1
-    float cb[32];         // bias forces C, later S entries
+    float kk[24][8];      // K rows = A_c M_c0, later Y_right = M^-1 Jfoot_right^T
+    float gg[24][8];      // G rows = K S^-1, later Y_left
+    float cb[32];         // bias forces C
     float minv[24][32];   // M^-1, [column j][lane l]
     float cp[8][4];       // contact point x,y,z (rel. base origin, on the inflated hull) and distance
-    float lin[12][12];    // operational inverse inertia of the two feet, Lambda^-1 = Jfoot M^-1 Jfoot^T
     union {
-        float ac[48][67]; // A rows of the contact constraints x 66 columns (18 servo, 32 C1, 16 C2), odd stride
-        float red[32 * 21];   // Schur complement partial products (dead before ac is built)
+        float lin[12][12];    // operational inverse inertia of the two feet, Lambda^-1 = Jfoot M^-1 Jfoot^T
+        float red[32 * 21];   // Schur complement partial products (dead before lin is built)
     };
     float obs[32];
 };
@@ -217,11 +230,11 @@ PLEN_DEV void row_entries(int type, const float *a, const float *m, const float 
     }
 }
 
-// One physics tick for the robot owned by this warp.
+// First half of a physics tick for the robot owned by this warp: dynamics + constraint set-up (k_dyn).
 struct DebugOut { float *minv, *pos, *rot; };   // [24*24], [24*3], [24*9] of one env; all nullable
 
-PLEN_DEV void physics_tick(const DevConfig &cfg, const float *tab, WarpScratch &ws, LaneState &L, int lane,
-                           const DebugOut *dbg = nullptr) {
+PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch &ws, LaneState &L, int lane,
+                            float *srec, const DebugOut *dbg = nullptr) {
     const bool is_joint = lane >= 6 && lane < 24;
     const int cs = (int)tab[T_CS * 32 + lane], ce = (int)tab[T_CE * 32 + lane];
     float Rw[9], pw[3];
@@ -590,40 +603,17 @@ PLEN_DEV void physics_tick(const DevConfig &cfg, const float *tab, WarpScratch &
     }
 
     // =====================================================================================================
-    // Constraint rows and projected Gauss-Seidel in CONSTRAINT SPACE.
-    //
-    // Every row keeps r = J.dv (its relative velocity change so far) in a register of its owner lane; a row update is
-    //   owner: delta = clamp(lam + rhs - r*dinv) - lam      broadcast delta (1 SHFL)      all lanes: r += A[.][row]*delta
-    // so the serial chain per row is one shuffle + ~6 dependent ALU ops and needs no warp reduction.  Row slots:
-    //   slot M : lane 6+j            servo row of joint j   (joint-limit row, when violated, shares the lane: J differs by sign)
-    //   slot C1: lane p / 8+p / 16+p / 24+p    normal / spin / roll-t1 / roll-t2 of contact point p (0..7)
-    //   slot C2: lane p / 8+p                   lateral t1 / t2 of contact point p
-    // A = J M^-1 J^T:  servo-servo block = M^-1 itself (ws.minv), contact rows x all 66 columns in ws.ac
-    // (contact-contact entries via the 12x12 operational inverse inertia Lambda^-1 = Jfoot M^-1 Jfoot^T).
+    // Emit the SOLVE RECORD of this robot (global memory) for k_solve: everything the projected Gauss-Seidel needs,
+    // in the 30-dimensional operational space  x = [18 joint velocities; right-foot twist (6); left-foot twist (6)].
+    // Every constraint row of the tick is a functional of x: servo / limit rows read one joint velocity, the rows of
+    // a contact point on foot f read the foot twist (flat ground => <= 3 non-zeros, known per row type).  With
+    //   G = [ M^-1_jj  Y ; Y^T  Lambda^-1 ]   (30 x 30, symmetric),   Y = (M^-1 Jfoot^T) joint rows,
+    // a row update with impulse delta adds (a combination of <= 3 columns of) G * delta to x.
     // =====================================================================================================
-    const int myp = lane & 7, myf = myp >> 2;
-    const bool pt_on = (man_new >> myp) & 1u;
-    const int t1 = lane >> 3;                          // C1 row type of this lane
-    const bool has2 = lane < 16;                       // C2 rows live in lanes 0..15
-    float w1[6] = {0, 0, 0, 0, 0, 0}, w2[6] = {0, 0, 0, 0, 0, 0};
-    float pdist = 0.0f;
-    {
-        const float px = ws.cp[myp][0], py = ws.cp[myp][1], pz = ws.cp[myp][2];
-        pdist = ws.cp[myp][3] + cfg.linear_slop;
-        if (t1 == 0) { w1[0] = py; w1[1] = -px; w1[5] = 1.0f; }
-        else if (t1 == 1) { w1[2] = 1.0f; }
-        else if (t1 == 2) { w1[1] = -1.0f; }
-        else { w1[0] = 1.0f; }
-        if (lane < 8) { w2[0] = pz; w2[2] = -px; w2[4] = -1.0f; }
-        else { w2[1] = pz; w2[2] = -py; w2[3] = 1.0f; }
-    }
-
     // ---- servo rows (btMultiBodyJointMotor semantics): target velocity kp (q* - q)/dt + (1 - kd) v*, |impulse| <= f dt
-    float rM = 0.0f, r1 = 0.0f, r2 = 0.0f;            // J.dv of this lane's rows
-    float m_dinv = 0.0f, m_d = 0.0f, m_rhs = 0.0f, m_lam = 0.0f;
-    float l_rhs = 0.0f, l_lam = 0.0f, l_dir = 0.0f;   // joint-limit row (only when violated)
+    float m_dinv = 0.0f, m_rhs = 0.0f, l_rhs = 0.0f, l_dir = 0.0f;   // joint-limit row only when violated
     if (is_joint) {
-        m_d = ws.minv[lane][lane];
+        const float m_d = ws.minv[lane][lane];
         m_dinv = (m_d > 1.1920929e-7f) ? rcp_(m_d) : 0.0f;
         const float desired = cfg.kp_over_dt * (L.tgt - L.q) + cfg.one_minus_kd * vstar;
         m_rhs = (desired - vstar) * m_dinv;
@@ -632,15 +622,18 @@ PLEN_DEV void physics_tick(const DevConfig &cfg, const float *tab, WarpScratch &
         if (pen_lo <= 0.0f) { l_dir = 1.0f; l_rhs = (-pen_lo * cfg.erp_joint_over_dt - vstar) * m_dinv; }
         else if (pen_hi <= 0.0f) { l_dir = -1.0f; l_rhs = (-pen_hi * cfg.erp_joint_over_dt + vstar) * m_dinv; }
     }
-    const unsigned lim_mask = ballot(l_dir != 0.0f);
-
-    // ---- contact rows
-    float dinv1 = 0.0f, d1 = 0.0f, rhs1 = 0.0f, lam1 = 0.0f, mu1 = 0.0f;
-    float dinv2 = 0.0f, d2 = 0.0f, rhs2 = 0.0f, lam2 = 0.0f;
-    float lamN = 0.0f;                                 // normal impulse of this lane's contact point
+    // ---- foot twists at v*: Vs_f = Jfoot_f v*;  Y stash;  Lambda^-1 = Jfoot M^-1 Jfoot^T (12 x 12)
+    float Vs[2][6];
+#pragma unroll
+    for (int f = 0; f < 2; f++)
+#pragma unroll
+        for (int k = 0; k < 6; k++) Vs[f][k] = 0.0f;
+    if (lane < 24) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) { ws.kk[lane][k] = Y[0][k]; ws.gg[lane][k] = Y[1][k]; }
+    }
+    warp_sync();
     if (man_new) {
-        // foot twists at v*:  Vs_f = Jfoot_f v*
-        float Vs[2][6];
 #pragma unroll
         for (int f = 0; f < 2; f++) {
 #pragma unroll
@@ -650,12 +643,7 @@ PLEN_DEV void physics_tick(const DevConfig &cfg, const float *tab, WarpScratch &
 #pragma unroll
                 for (int k = 0; k < 6; k++) Vs[f][k] += shfl_xor(Vs[f][k], mm);
         }
-        // operational inverse inertia Lambda^-1[fa*6+a][fb*6+b] = Y_fb[a][b] + sum_{j in leg fa} s_j[a] Y_fb[j][b]
-        if (lane < 24) {
-#pragma unroll
-            for (int k = 0; k < 6; k++) { ws.kk[lane][k] = Y[0][k]; ws.gg[lane][k] = Y[1][k]; }
-        }
-        warp_sync();
+        // Lambda^-1[fa*6+a][fb*6+b] = Y_fb[a][b] + sum_{j in leg fa} s_j[a] Y_fb[j][b]
         for (int e = lane; e < 144; e += 32) {
             const int row = e / 12, col = e - 12 * row;
             const int fa = row / 6, a6 = row - 6 * fa, fb = col / 6, b6 = col - 6 * fb;
@@ -666,267 +654,105 @@ PLEN_DEV void physics_tick(const DevConfig &cfg, const float *tab, WarpScratch &
             ws.lin[row][col] = acc;
         }
         warp_sync();
-        // A rows of the contact constraints
-        unsigned msk = man_new;
-        while (msk) {
-            const int p = lowest_bit(msk);
-            msk &= msk - 1;
-            const int f = p >> 2;
-            const float px = ws.cp[p][0], py = ws.cp[p][1], pz = ws.cp[p][2];
-#pragma unroll
-            for (int type = 0; type < 6; type++) {
-                const int k = (type < 4) ? type * 8 + p : 32 + (type - 4) * 8 + p;
-                float J, B;
-                row_entries(type, aF[f], mF[f], Y[f], px, py, pz, J, B);
-                (void)J;
-                if (is_joint) ws.ac[k][lane - 6] = B;              // servo columns: (M^-1 J_k^T)[6+j]
-                // c = Lambda^-1[myf block rows][f block cols] . w_k   (w_k has <= 3 non-zeros, known at compile time)
-                float c[6];
-#pragma unroll
-                for (int a6 = 0; a6 < 6; a6++) {
-                    const float *lr = &ws.lin[myf * 6 + a6][f * 6];
-                    float v;
-                    switch (type) {
-                        case 0: v = lr[0] * py - lr[1] * px + lr[5]; break;
-                        case 1: v = lr[2]; break;
-                        case 2: v = -lr[1]; break;
-                        case 3: v = lr[0]; break;
-                        case 4: v = lr[0] * pz - lr[2] * px - lr[4]; break;
-                        default: v = lr[1] * pz - lr[2] * py + lr[3]; break;
-                    }
-                    c[a6] = v;
-                }
-                ws.ac[k][18 + lane] = w1[0] * c[0] + w1[1] * c[1] + w1[2] * c[2] + w1[3] * c[3] + w1[4] * c[4] + w1[5] * c[5];
-                if (has2)
-                    ws.ac[k][50 + lane] = w2[0] * c[0] + w2[1] * c[1] + w2[2] * c[2] + w2[3] * c[3] + w2[4] * c[4] + w2[5] * c[5];
-            }
+    }
+
+    // ---- G (30 columns x 32 words) and B (6 rows x 32 words): word w of a column = entry i(w) = (w >> 2) + 8 (w & 3),
+    //      i.e. the float4 of solver lane g = w >> 2 holds entries g, 8+g, 16+g, 24+g
+    {
+        const int i = (lane >> 2) + 8 * (lane & 3);
+        const bool ij = i < 18, ic = i >= 18 && i < 30;
+        const int fa = (i >= 24) ? 1 : 0, a6 = i - 18 - 6 * fa;
+        const float(*Ya)[8] = fa ? ws.gg : ws.kk;
+        float *G = srec + SR_G;
+        for (int c = 0; c < 18; c++) {
+            float v = 0.0f;
+            if (ij) v = ws.minv[6 + c][6 + i];
+            else if (ic) v = Ya[6 + c][a6];
+            G[c * 32 + lane] = v;
         }
-        warp_sync();
-        // per-lane row scalars
-        if (pt_on) {
-            d1 = ws.ac[lane][18 + lane];
-            dinv1 = (d1 > 1.1920929e-7f) ? rcp_(d1) : 0.0f;
-            const float rel = w1[0] * Vs[myf][0] + w1[1] * Vs[myf][1] + w1[2] * Vs[myf][2] + w1[3] * Vs[myf][3] +
-                              w1[4] * Vs[myf][4] + w1[5] * Vs[myf][5];
-            if (t1 == 0) {
+        for (int c = 18; c < 30; c++) {
+            const int fb = (c >= 24) ? 1 : 0, b6 = c - 18 - 6 * fb;
+            const float(*Yb)[8] = fb ? ws.gg : ws.kk;
+            float v = 0.0f;
+            if (ij) v = Yb[6 + i][b6];
+            else if (ic && man_new) v = ws.lin[fa * 6 + a6][c - 18];
+            G[c * 32 + lane] = v;
+        }
+        float *Bm = srec + SR_B;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            float v = 0.0f;
+            if (ij) v = ws.minv[6 + i][k];
+            else if (ic) v = Ya[k][a6];
+            Bm[k * 32 + lane] = v;
+        }
+        // per-joint scalars in the same word order (entries >= 18 are zero)
+        const int src = ij ? 6 + i : 0;
+        const float s_rhs = shfl(m_rhs, src), s_dinv = shfl(m_dinv, src), s_ldir = shfl(l_dir, src),
+                    s_lrhs = shfl(l_rhs, src), s_vs = shfl(vstar, src), s_q = shfl(L.q, src);
+        srec[SR_MRHS + lane] = ij ? s_rhs : 0.0f;
+        srec[SR_MDINV + lane] = ij ? s_dinv : 0.0f;
+        srec[SR_LDIR + lane] = ij ? s_ldir : 0.0f;
+        srec[SR_LRHS + lane] = ij ? s_lrhs : 0.0f;
+        srec[SR_VSTAR + lane] = ij ? s_vs : 0.0f;
+        srec[SR_Q + lane] = ij ? s_q : 0.0f;
+    }
+
+    // ---- contact rows: word p*8+g of SR_CRHS / SR_CDINV / SR_CD belongs to contact point p and solver lane g, which
+    //      owns the row whose "own" twist component is comp = g - 2 (right foot) / g (left foot):
+    //      comp 0 wx: roll about t2   1 wy: roll about t1 (sign flipped)   2 wz: spin
+    //           3 vx: lateral t2      4 vy: lateral t1 (sign flipped)      5 vz: normal
+    //      (flipping the sign of a row with symmetric bounds leaves the Gauss-Seidel iterates unchanged)
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const int p = (lane >> 3) + 4 * half, g = lane & 7, f = half;
+        const int comp = f ? g : g - 2;
+        const bool valid = comp >= 0 && comp < 6 && ((man_new >> p) & 1u);
+        float rhs = 0.0f, dinv = 0.0f, d = 0.0f;
+        if (valid) {
+            const float px = ws.cp[p][0], py = ws.cp[p][1], pz = ws.cp[p][2];
+            int i0 = comp, i1 = comp, i2 = comp;
+            float c0 = 1.0f, c1 = 0.0f, c2 = 0.0f;
+            if (comp == 3) { i0 = 1; i1 = 2; i2 = 3; c0 = pz; c1 = -py; c2 = 1.0f; }
+            else if (comp == 4) { i0 = 0; i1 = 2; i2 = 4; c0 = -pz; c1 = px; c2 = 1.0f; }
+            else if (comp == 5) { i0 = 0; i1 = 1; i2 = 5; c0 = py; c1 = -px; c2 = 1.0f; }
+            const int o = 6 * f;
+            d = c0 * (c0 * ws.lin[o + i0][o + i0] + c1 * ws.lin[o + i0][o + i1] + c2 * ws.lin[o + i0][o + i2]) +
+                c1 * (c0 * ws.lin[o + i1][o + i0] + c1 * ws.lin[o + i1][o + i1] + c2 * ws.lin[o + i1][o + i2]) +
+                c2 * (c0 * ws.lin[o + i2][o + i0] + c1 * ws.lin[o + i2][o + i1] + c2 * ws.lin[o + i2][o + i2]);
+            dinv = (d > 1.1920929e-7f) ? rcp_(d) : 0.0f;
+            float vs[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) vs[k] = f ? Vs[1][k] : Vs[0][k];
+            float v0 = vs[0], v1 = vs[0], v2 = vs[0];
+#pragma unroll
+            for (int k = 1; k < 6; k++) { v0 = (i0 == k) ? vs[k] : v0; v1 = (i1 == k) ? vs[k] : v1; v2 = (i2 == k) ? vs[k] : v2; }
+            const float rel = c0 * v0 + c1 * v1 + c2 * v2;
+            if (comp == 5) {
+                const float pdist = ws.cp[p][3] + cfg.linear_slop;
                 float rest = (fabsf(rel) < cfg.rest_thresh) ? 0.0f : cfg.restitution * -rel;
                 rest = fmaxf(rest, 0.0f);
                 float velerr = rest - rel, poserr = 0.0f;
                 if (pdist > 0.0f) velerr -= pdist * cfg.inv_dt; else poserr = -pdist * cfg.erp_contact_over_dt;
-                rhs1 = (poserr + velerr) * dinv1;
+                rhs = (poserr + velerr) * dinv;
             } else {
-                rhs1 = -rel * dinv1;
-                mu1 = (t1 == 1) ? cfg.mu_spinning : cfg.mu_rolling;
-                if (!(mu1 > 0.0f)) { dinv1 = 0.0f; rhs1 = 0.0f; }   // row not created when its coefficient is 0
-            }
-            if (has2) {
-                d2 = ws.ac[32 + lane][50 + lane];
-                dinv2 = (d2 > 1.1920929e-7f) ? rcp_(d2) : 0.0f;
-                const float rel2 = w2[0] * Vs[myf][0] + w2[1] * Vs[myf][1] + w2[2] * Vs[myf][2] + w2[3] * Vs[myf][3] +
-                                   w2[4] * Vs[myf][4] + w2[5] * Vs[myf][5];
-                rhs2 = -rel2 * dinv2;
-            }
-        }
-        // warm start of the normal rows from the cached impulses (lanes 24..31 hold them)
-        {
-            const float cached = shfl(L.lam, 24 + myp);
-            if (pt_on && t1 == 0) lam1 = cached * cfg.warm;
-            unsigned wm = man_new;
-            while (wm) {
-                const int p = lowest_bit(wm);
-                wm &= wm - 1;
-                const float db = shfl(lam1, p);
-                if (db != 0.0f) {
-                    if (is_joint) rM += ws.ac[p][lane - 6] * db;
-                    r1 += ws.ac[p][18 + lane] * db;
-                    if (has2) r2 += ws.ac[p][50 + lane] * db;
+                rhs = -rel * dinv;
+                if (comp < 3) {
+                    const float mu = (comp == 2) ? cfg.mu_spinning : cfg.mu_rolling;
+                    if (!(mu > 0.0f)) { dinv = 0.0f; rhs = 0.0f; d = 0.0f; }   // row not created when its coefficient is 0
                 }
             }
-            lamN = shfl(lam1, myp);
         }
+        srec[SR_CRHS + 32 * half + lane] = rhs;
+        srec[SR_CDINV + 32 * half + lane] = dinv;
+        srec[SR_CD + 32 * half + lane] = d;
     }
-
-    // ---- projected Gauss-Seidel (row order of btMultiBodyConstraintSolver::solveSingleIteration)
-    // Branch-free row updates: every lane always executes the candidate computation and the three r-updates (its smem
-    // addresses are clamped to valid, possibly meaningless, entries for rows it does not own); ownership is a select.
-    // Each row is visited exactly once per iteration, so the iteration residual max_j (dlam_j / dinv_j)^2 is formed
-    // from lam_after - lam_before at the end of the iteration instead of inside every row update.
-    const int mcol = is_joint ? lane - 6 : 0;                    // servo column of this lane inside an A row
-    const int c2col = has2 ? 50 + lane : 50;
-    const float *acol1 = &ws.ac[lane][0];                        // A rows of this lane's C1 / C2 constraints (column reads)
-    const float *acol2 = &ws.ac[has2 ? 32 + lane : lane][0];
-    const float *mcolp = &ws.minv[0][lane];
-    const float sqrt_thr = sqrtf(cfg.residual_threshold);
-    int it = 0;
-    for (; it < cfg.iterations; it++) {
-        const float m_old = m_lam, l_old = l_lam, lam1_old = lam1, lam2_old = lam2;
-        // non-contact rows: list = [limits in joint order, servos in joint order]; odd iterations forward, even reversed
-        for (int half = 0; half < 2; half++) {
-            const bool do_limits = ((it & 1) != 0) == (half == 0);
-            if (do_limits) {
-                unsigned msk = lim_mask;
-                while (msk) {
-                    const int j = (it & 1) ? lowest_bit(msk) : highest_bit(msk);
-                    msk &= ~(1u << j);
-                    float delta = l_rhs - (l_dir * rM) * m_dinv;
-                    const float nl = clampf(l_lam + delta, 0.0f, 100.0f);
-                    delta = (nl - l_lam) * l_dir;
-                    const float db = shfl(delta, j);
-                    l_lam = (lane == j) ? nl : l_lam;
-                    rM += mcolp[j * 32] * db;
-                    r1 += acol1[j - 6] * db;
-                    r2 += acol2[j - 6] * db;
-                }
-            } else {
-                const int step = (it & 1) ? 1 : -1;
-                int j = (it & 1) ? 6 : 23;
-#pragma unroll 6
-                for (int s = 0; s < 18; s++, j += step) {
-                    const float nl = clampf(m_lam + (m_rhs - rM * m_dinv), -cfg.motor_imp, cfg.motor_imp);
-                    const float db = shfl(nl - m_lam, j);
-                    m_lam = (lane == j) ? nl : m_lam;
-                    rM += mcolp[j * 32] * db;
-                    r1 += acol1[j - 6] * db;
-                    r2 += acol2[j - 6] * db;
-                }
-            }
-        }
-        if (man_new) {
-            // normals, then all spinning rows, then the rolling rows point by point (t1, t2)
-            for (int phase = 0; phase < 3; phase++) {
-                unsigned msk = man_new;
-                while (msk) {
-                    const int p = lowest_bit(msk);
-                    msk &= msk - 1;
-                    const int nsub = (phase == 2) ? 2 : 1;
-                    for (int sub = 0; sub < nsub; sub++) {
-                        const int owner = (phase + sub) * 8 + p;   // C1 lane = A row index
-                        const float sum = lam1 + (rhs1 - r1 * dinv1);
-                        float nl;
-                        if (phase == 0) {
-                            nl = fminf(fmaxf(sum, 0.0f), 1e10f);     // lower 0, upper 1e10
-                        } else {
-                            const float lim = mu1 * lamN;
-                            nl = clampf(sum, -lim, lim);
-                            nl = (lamN > 0.0f) ? nl : lam1;          // row skipped while the normal impulse is not positive
-                        }
-                        const float db = shfl(nl - lam1, owner);
-                        lam1 = (lane == owner) ? nl : lam1;
-                        if (phase == 0) lamN += (myp == p) ? db : 0.0f;
-                        const float *arow = &ws.ac[owner][0];
-                        rM += arow[mcol] * db;
-                        r1 += arow[18 + lane] * db;
-                        r2 += arow[c2col] * db;
-                    }
-                }
-            }
-            // lateral pairs with the implicit friction cone (resolveConeFrictionConstraintRows)
-            unsigned msk = man_new;
-            while (msk) {
-                const int p = lowest_bit(msk);
-                msk &= msk - 1;
-                const float cand = lam2 + (rhs2 - r2 * dinv2);
-                const float sumA = shfl(cand, p), sumB = shfl(cand, 8 + p);
-                const float lim = cfg.mu_lateral * shfl(lamN, p);
-                float nA = sumA, nB = sumB;
-                if (sumA < -lim || sumA > lim || sumB < -lim || sumB > lim) {
-                    const float inv = rsqrtf(sumA * sumA + sumB * sumB);
-                    const float cA = fabsf(lim * sumA * inv), cB = fabsf(lim * sumB * inv);
-                    nA = clampf(sumA, -cA, cA);
-                    nB = clampf(sumB, -cB, cB);
-                }
-                const float nmine = (lane == p) ? nA : ((lane == 8 + p) ? nB : lam2);
-                const float dmine = nmine - lam2;
-                lam2 = nmine;
-                const float dA = shfl(dmine, p), dB = shfl(dmine, 8 + p);
-                const float *arowA = &ws.ac[32 + p][0], *arowB = &ws.ac[40 + p][0];
-                rM += arowA[mcol] * dA + arowB[mcol] * dB;
-                r1 += arowA[18 + lane] * dA + arowB[18 + lane] * dB;
-                r2 += arowA[c2col] * dA + arowB[c2col] * dB;
-            }
-        }
-        // residual of this iteration
-        float res_lane = fabsf((m_lam - m_old) * m_d);
-        res_lane = fmaxf(res_lane, fabsf((l_lam - l_old) * m_d));
-        if (man_new) {
-            const float v1 = pt_on ? fabsf((lam1 - lam1_old) * d1) : 0.0f;
-            float v2 = (pt_on && has2) ? (lam2 - lam2_old) * d2 : 0.0f;   // pair residual = dA/dinvA + dB/dinvB
-            v2 = (dinv2 != 0.0f) ? v2 : 0.0f;
-            v2 += shfl_xor(v2, 8);
-            res_lane = fmaxf(res_lane, fmaxf((dinv1 != 0.0f) ? v1 : 0.0f, fabsf(v2)));
-        }
-        const float res = f_as_u_max(res_lane);
-        if (res * res <= cfg.residual_threshold) { it++; break; }
-    }
-    (void)sqrt_thr;
-    L.iters = it;
-
-    // ---- delta-v = M^-1 J^T lambda: generalized impulse tau, then one product with M^-1
-    float dv = 0.0f;
-    {
-        float tau = is_joint ? (m_lam + l_dir * l_lam) : 0.0f;
-        if (man_new) {
-            float W[2][6];
-#pragma unroll
-            for (int f = 0; f < 2; f++)
-#pragma unroll
-                for (int k = 0; k < 6; k++) {
-                    float v = 0.0f;
-                    if (pt_on && myf == f) v = w1[k] * lam1 + (has2 ? w2[k] * lam2 : 0.0f);
-                    W[f][k] = v;
-                }
-#pragma unroll
-            for (int mm = 16; mm > 0; mm >>= 1)
-#pragma unroll
-                for (int f = 0; f < 2; f++)
-#pragma unroll
-                    for (int k = 0; k < 6; k++) W[f][k] += shfl_xor(W[f][k], mm);
-#pragma unroll
-            for (int f = 0; f < 2; f++)
-                tau += aF[f][0] * W[f][0] + aF[f][1] * W[f][1] + aF[f][2] * W[f][2] + mF[f][0] * W[f][3] +
-                       mF[f][1] * W[f][4] + mF[f][2] * W[f][5];
-        }
-        warp_sync();
-        ws.cb[lane] = (lane < 24) ? tau : 0.0f;
-        warp_sync();
-        if (lane < 24)
-            for (int j = 0; j < 24; j++) dv += ws.minv[j][lane] * ws.cb[j];
-    }
-    // cached normal impulses back to lanes 24..31
-    {
-        const float ln = shfl(lam1, lane & 7);
-        if (lane >= 24) L.lam = ((man_new >> (lane - 24)) & 1u) ? ln : 0.0f;
-    }
-
-    // ---- apply delta-v, integrate
-    L.u = (lane < 24) ? clampf(vstar + dv, -cfg.vmax, cfg.vmax) : 0.0f;
-    if (is_joint) L.q += L.u * cfg.dt;
-    {
-        float w[3], v[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) { w[k] = shfl(L.u, k); v[k] = shfl(L.u, 3 + k); }
-#pragma unroll
-        for (int k = 0; k < 3; k++) L.pos[k] += v[k] * cfg.dt;
-        float fa = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
-        if (fa * cfg.dt > 0.78539816339f) fa = 0.78539816339f * cfg.inv_dt;
-        float sc, cw;
-        if (fa < 0.001f) {
-            sc = 0.5f * cfg.dt - cfg.dt * cfg.dt * cfg.dt * 0.020833333333f * fa * fa;
-            cw = cosf(0.5f * fa * cfg.dt);
-        } else {
-            float sn;
-            sincos_(0.5f * fa * cfg.dt, &sn, &cw);
-            sc = sn / fa;
-        }
-        const float dx = w[0] * sc, dy = w[1] * sc, dz = w[2] * sc;
-        const float qx = L.quat[0], qy = L.quat[1], qz = L.quat[2], qw = L.quat[3];
-        float rx = cw * qx + dx * qw + dy * qz - dz * qy;
-        float ry = cw * qy - dx * qz + dy * qw + dz * qx;
-        float rz = cw * qz + dx * qy - dy * qx + dz * qw;
-        float rw = cw * qw - dx * qx - dy * qy - dz * qz;
-        const float nn = rsqrtf(rx * rx + ry * ry + rz * rz + rw * rw);
-        L.quat[0] = rx * nn; L.quat[1] = ry * nn; L.quat[2] = rz * nn; L.quat[3] = rw * nn;
-    }
+    srec[SR_PT + lane] = ws.cp[lane >> 2][lane & 3];
+    if (lane >= 24) srec[SR_LAMC + lane - 24] = L.lam;
+    if (lane < 6) srec[SR_BASE + lane] = vstar;
+    if (lane < 3) srec[SR_BASE + 6 + lane] = L.pos[lane];
+    if (lane < 4) srec[SR_BASE + 9 + lane] = L.quat[lane];
+    if (lane == 0) srec[SR_BASE + 13] = (float)man_new;
     warp_sync();
 }
 

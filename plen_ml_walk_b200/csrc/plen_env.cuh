@@ -1,5 +1,5 @@
-// plen_env.cuh -- fused env step around the physics tick: agent_to_env -> 4 ticks -> observation -> done -> reward
-// -> counters -> auto-reset, one warp per robot.  Restates PlenWalkEnv.step (plen_bullet/src/plen_bullet/plen_env.py
+// plen_env.cuh -- env logic around the physics ticks: agent_to_env (before), observation -> done -> reward ->
+// counters -> auto-reset (after), one warp per robot.  Restates PlenWalkEnv.step (plen_bullet/src/plen_bullet/plen_env.py
 // :638-692) with the running-sum form of the joint histories; citations inline.
 #pragma once
 
@@ -84,25 +84,20 @@ struct StepIO {
 // the same side as the reference's float64 arithmetic.
 struct EnvRanges { double lo[18], hi[18]; };
 
-PLEN_DEV void env_step(const DevConfig &cfg, const EnvRanges &rng, const float *tab, WarpScratch &ws, LaneState &L,
-                       int lane, const StepIO &io) {
-    const bool is_joint = lane >= 6 && lane < 24;
-    // ---- agent_to_env (plen_env.py:694-714), bypassed when joint_act (:652-654)
-    if (is_joint) {
-        const float act = io.action[lane - 6];
-        if (cfg.joint_act) {
-            L.tgt = act;
-        } else {
-            const double lo = rng.lo[lane - 6], hi = rng.hi[lane - 6];
-            const double mm = (hi - lo) / (1.0 - (-1.0));
-            const double b = hi - (mm * 1.0);
-            double y = mm * (double)act + b;
-            if (y >= hi) y = hi - 0.001; else if (y <= lo) y = lo + 0.001;
-            L.tgt = (float)y;
-        }
-    }
-    for (int s = 0; s < cfg.substeps; s++) physics_tick(cfg, tab, ws, L, lane);     // :663-667
+// agent_to_env (plen_env.py:694-714), bypassed when joint_act (:652-654): servo target of joint j for action `act`
+PLEN_DEV float agent_target(const DevConfig &cfg, const EnvRanges &rng, int j, float act) {
+    if (cfg.joint_act) return act;
+    const double lo = rng.lo[j], hi = rng.hi[j];
+    const double mm = (hi - lo) / (1.0 - (-1.0));
+    const double b = hi - (mm * 1.0);
+    double y = mm * (double)act + b;
+    if (y >= hi) y = hi - 0.001; else if (y <= lo) y = lo + 0.001;
+    return (float)y;
+}
 
+// Everything of PlenWalkEnv.step after the 4 physics ticks (:671-678) + TimeLimit + optional auto-reset (k_post).
+PLEN_DEV void env_post(const DevConfig &cfg, const float *tab, WarpScratch &ws, LaneState &L, int lane,
+                       const StepIO &io) {
     // ---- compute_observation (:768-871)
     observe(ws, L, lane);
     const float z = ws.obs[18], vx = ws.obs[19], roll = ws.obs[20], pitch = ws.obs[21], yaw = ws.obs[22], y = ws.obs[23];

@@ -26,6 +26,7 @@
 #define fabsf fabs
 #define fminf fmin
 #define fmaxf fmax
+#define fmaf fma
 #endif
 
 #define PLEN_DEV static inline
@@ -54,6 +55,11 @@ static inline unsigned redux_max(unsigned v) {
     unsigned r = 0; for (int i = 0; i < 32; i++) r = g_u[i] > r ? g_u[i] : r;
     bar(); return r;
 }
+static inline unsigned redux_or(unsigned v) {
+    g_u[t_lane] = v; bar();
+    unsigned r = 0; for (int i = 0; i < 32; i++) r |= g_u[i];
+    bar(); return r;
+}
 static inline void warp_sync() { bar(); }
 static inline float f_as_u_max(float v) {   // max over lanes of a non-negative value
     g_x[t_lane] = v; bar();
@@ -69,6 +75,7 @@ static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 using plen::rsqrtf;
 
 #include "../../plen_ml_walk_b200/csrc/plen_host_tables.h"
+#include "../../plen_ml_walk_b200/csrc/plen_solve.cuh"
 
 using namespace plen;
 
@@ -91,6 +98,32 @@ int emu_sizeof_config() { return (int)sizeof(plen_config); }
 int emu_sizeof_model() { return (int)sizeof(plen_model); }
 void emu_init_record(const plen_config *c, float *rec) { init_record(c, rec); }
 
+// (k_dyn, k_solve) x n_ticks over n robots, exactly as plen_b200.cu launches them: one emulated warp per robot for the
+// dynamics, then one emulated warp per 4 robots for the solver.  tgt [n][18] nullable (zero targets).
+static void run_ticks(const DevConfig &dc, const float *tab, float *records, const float *tgt, int n, int n_ticks,
+                      const DebugOut *dbg0, int lane) {
+    static WarpScratch ws;
+    static std::vector<float> srec, Gs(4 * 960);
+    if (lane == 0) srec.assign((size_t)n * SR_WORDS, 0.0f);
+    bar();
+    for (int t = 0; t < n_ticks; t++) {
+        for (int e = 0; e < n; e++) {
+            LaneState L;
+            load_record(records + 96 * e, ws, L, lane);
+            if (lane >= 6 && lane < 24) L.tgt = tgt ? tgt[18 * e + lane - 6] : 0.0f;
+            tick_dynamics(dc, tab, ws, L, lane, srec.data() + (size_t)e * SR_WORDS,
+                          (e == 0 && t == n_ticks - 1) ? dbg0 : nullptr);
+        }
+        for (int b = 0; b < n; b += 4) {
+            const int r = b + (lane >> 3);
+            const bool valid = r < n;
+            const int rr = valid ? r : 0;
+            solve_tick(dc, srec.data() + (size_t)rr * SR_WORDS, Gs.data() + (lane >> 3) * 960, records + 96 * rr, lane, valid);
+            bar();
+        }
+    }
+}
+
 // n_ticks physics ticks with raw targets; records [n][96], targets [n][18]; dbg_* nullable (first env, last tick)
 void emu_tick(const plen_model *m, const plen_config *c, float *records, const float *targets, int n, int n_ticks,
               float *dbg_minv, float *dbg_pos, float *dbg_rot, int *iters_out) {
@@ -98,35 +131,28 @@ void emu_tick(const plen_model *m, const plen_config *c, float *records, const f
     DevConfig dc; EnvRanges er;
     build_table(m, c, tab.data());
     build_devconfig(m, c, &dc, &er);
-    static WarpScratch ws;
-    run_warp([&](int lane) {
-        for (int e = 0; e < n; e++) {
-            LaneState L;
-            load_record(records + 96 * e, ws, L, lane);
-            if (lane >= 6 && lane < 24) L.tgt = targets[18 * e + lane - 6];
-            DebugOut dbg{dbg_minv, dbg_pos, dbg_rot};
-            for (int t = 0; t < n_ticks; t++)
-                physics_tick(dc, tab.data(), ws, L, lane, (e == 0 && t == n_ticks - 1 && dbg_minv) ? &dbg : nullptr);
-            if (iters_out && lane == 0) iters_out[e] = L.iters;
-            store_record(records + 96 * e, ws, L, lane);
-        }
-    });
+    DebugOut dbg{dbg_minv, dbg_pos, dbg_rot};
+    run_warp([&](int lane) { run_ticks(dc, tab.data(), records, targets, n, n_ticks, dbg_minv ? &dbg : nullptr, lane); });
+    if (iters_out) for (int e = 0; e < n; e++) iters_out[e] = (int)records[96 * e + W_ITERS];
 }
 
 void emu_step(const plen_model *m, const plen_config *c, float *records, const float *actions, int n, float *obs,
               float *reward, uint8_t *done, uint8_t *timeout, float *terminal_obs, const float *snapshot) {
-    std::vector<float> tab(T_ROWS * 32);
+    std::vector<float> tab(T_ROWS * 32), tgt((size_t)n * 18);
     DevConfig dc; EnvRanges er;
     build_table(m, c, tab.data());
     build_devconfig(m, c, &dc, &er);
+    for (int e = 0; e < n; e++)
+        for (int j = 0; j < 18; j++) tgt[18 * e + j] = agent_target(dc, er, j, actions[18 * e + j]);
     static WarpScratch ws;
     run_warp([&](int lane) {
+        run_ticks(dc, tab.data(), records, tgt.data(), n, dc.substeps, nullptr, lane);
         for (int e = 0; e < n; e++) {
             LaneState L;
             load_record(records + 96 * e, ws, L, lane);
-            StepIO io{actions + 18 * e, obs + 26 * e, reward + e, done + e, timeout ? timeout + e : nullptr,
+            StepIO io{nullptr, obs + 26 * e, reward + e, done + e, timeout ? timeout + e : nullptr,
                       terminal_obs ? terminal_obs + 26 * e : nullptr, snapshot};
-            env_step(dc, er, tab.data(), ws, L, lane, io);
+            env_post(dc, tab.data(), ws, L, lane, io);
             store_record(records + 96 * e, ws, L, lane);
         }
     });
