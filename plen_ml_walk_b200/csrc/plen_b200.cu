@@ -30,6 +30,7 @@ struct plen_ctx {
     float *d_tab, *d_state, *d_snapshot;
     float *d_srec;   // [n][SR_WORDS] solve records (k_dyn -> k_solve)
     float *d_tgt;    // [n][18] servo targets of the current env step
+    uint8_t *d_key;  // [n] contact-load sort key of the current tick (k_dyn -> k_solve)
     float *d_act, *d_obs, *d_rew;
     uint8_t *d_done, *d_tmo;
     cudaStream_t stream;
@@ -73,7 +74,7 @@ __device__ __forceinline__ DynSmem &stage_table(const float *tab_g) {
 __global__ void __launch_bounds__(DYN_WPC * 32)
 k_dyn(const __grid_constant__ DevConfig dc, const __grid_constant__ EnvRanges er, const float *__restrict__ tab_g,
       const float *__restrict__ state, int n, const float *__restrict__ actions, float *__restrict__ tgt,
-      float *__restrict__ srec, float *dbg_minv, float *dbg_pos, float *dbg_rot) {
+      float *__restrict__ srec, uint8_t *__restrict__ keys, float *dbg_minv, float *dbg_pos, float *dbg_rot) {
     DynSmem &sm = stage_table(tab_g);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * DYN_WPC + warp;
@@ -88,19 +89,41 @@ k_dyn(const __grid_constant__ DevConfig dc, const __grid_constant__ EnvRanges er
     }
     DebugOut dbg{dbg_minv ? dbg_minv + (size_t)env * 576 : nullptr, dbg_pos ? dbg_pos + (size_t)env * 72 : nullptr,
                  dbg_rot ? dbg_rot + (size_t)env * 216 : nullptr};
-    tick_dynamics(dc, sm.tab, ws, L, lane, srec + (size_t)env * SR_WORDS, (dbg_minv || dbg_pos || dbg_rot) ? &dbg : nullptr);
+    tick_dynamics(dc, sm.tab, ws, L, lane, srec + (size_t)env * SR_WORDS, keys + env, (dbg_minv || dbg_pos || dbg_rot) ? &dbg : nullptr);
 }
 
 // Second half of a tick, 8 lanes per robot: PGS + delta-v + integration, state record updated in place.
+// A CTA (2 warps) solves 8 robots.  Robots are grouped by contact load: the 8 CTAs of a 64-robot tile each rank the
+// tile's sort keys (written by k_dyn) and CTA r takes ranks 8r .. 8r+7, so the four robots of a warp have similar
+// active-point counts and the per-foot loops of solve_tick stay short.
+#define SOLVE_TILE 64
 __global__ void __launch_bounds__(SOLVE_WPC * 32)
-k_solve(const __grid_constant__ DevConfig dc, const float *__restrict__ srec, float *__restrict__ state, int n) {
+k_solve(const __grid_constant__ DevConfig dc, const float *__restrict__ srec, const uint8_t *__restrict__ keys,
+        float *__restrict__ state, int n) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *Gs = reinterpret_cast<float *>(smem_raw);
+    __shared__ int s_key[SOLVE_TILE];
+    __shared__ int s_inv[SOLVE_TILE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int robot = (blockIdx.x * SOLVE_WPC + warp) * 4 + (lane >> 3);
+    const int tile0 = (blockIdx.x >> 3) * SOLVE_TILE, round = blockIdx.x & 7;
+    {
+        const int t = threadIdx.x, r = tile0 + t;                     // SOLVE_WPC * 32 == SOLVE_TILE threads
+        const int key = (r < n) ? (int)keys[r] : 255;
+        s_key[t] = key;
+        __syncthreads();
+        int rank = 0;
+#pragma unroll 8
+        for (int j = 0; j < SOLVE_TILE; j++) {
+            const int kj = s_key[j];
+            rank += (kj < key || (kj == key && j < t)) ? 1 : 0;
+        }
+        s_inv[rank] = r;
+        __syncthreads();
+    }
+    const int robot = s_inv[round * 8 + warp * 4 + (lane >> 3)];
     const bool valid = robot < n;
     const size_t r = valid ? (size_t)robot : 0;
-    solve_tick(dc, srec + r * SR_WORDS, Gs + (size_t)(warp * 4 + (lane >> 3)) * 960, state + r * PLEN_STATE_WORDS, lane, valid);
+    solve_tick(dc, srec + r * SR_WORDS, Gs + (size_t)(warp * 4 + (lane >> 3)) * 1024, state + r * PLEN_STATE_WORDS, lane, valid);
 }
 
 // After the last tick of an env step, one warp per robot: observation, done, reward, counters, auto-reset.
@@ -302,16 +325,17 @@ __global__ void k_gait_ik(const double *__restrict__ params, int n, double *__re
 
 // ------------------------------------------------------------------------------------------------ C ABI
 static const size_t DYN_SMEM = sizeof(DynSmem);
-static const size_t SOLVE_SMEM = sizeof(float) * 960 * 4 * SOLVE_WPC;
+static const size_t SOLVE_SMEM = sizeof(float) * 1024 * 4 * SOLVE_WPC;
+static_assert(SOLVE_WPC * 32 == SOLVE_TILE, "k_solve ranks one tile robot per thread");
 static int dyn_grid(int n) { return (n + DYN_WPC - 1) / DYN_WPC; }
-static int solve_grid(int n) { return (n + 4 * SOLVE_WPC - 1) / (4 * SOLVE_WPC); }
+static int solve_grid(int n) { return 8 * ((n + SOLVE_TILE - 1) / SOLVE_TILE); }
 
 // n_ticks physics ticks of 1/240 s: (k_dyn, k_solve) per tick.  `actions` (agent space) only on the first tick.
 static void launch_ticks(plen_ctx *ctx, float *state, int n, const float *actions, float *tgt, int n_ticks, cudaStream_t st) {
     for (int t = 0; t < n_ticks; t++) {
         k_dyn<<<dyn_grid(n), DYN_WPC * 32, DYN_SMEM, st>>>(ctx->dc, ctx->er, ctx->d_tab, state, n, t == 0 ? actions : nullptr,
-                                                          tgt, ctx->d_srec, nullptr, nullptr, nullptr);
-        k_solve<<<solve_grid(n), SOLVE_WPC * 32, SOLVE_SMEM, st>>>(ctx->dc, ctx->d_srec, state, n);
+                                                          tgt, ctx->d_srec, ctx->d_key, nullptr, nullptr, nullptr);
+        k_solve<<<solve_grid(n), SOLVE_WPC * 32, SOLVE_SMEM, st>>>(ctx->dc, ctx->d_srec, ctx->d_key, state, n);
     }
 }
 
@@ -330,7 +354,7 @@ int plen_num_envs(const plen_ctx *ctx) { return ctx ? ctx->n : 0; }
 void plen_destroy(plen_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->d_tab); cudaFree(ctx->d_state); cudaFree(ctx->d_snapshot); cudaFree(ctx->d_srec); cudaFree(ctx->d_tgt);
+    cudaFree(ctx->d_tab); cudaFree(ctx->d_state); cudaFree(ctx->d_snapshot); cudaFree(ctx->d_srec); cudaFree(ctx->d_tgt); cudaFree(ctx->d_key);
     cudaFree(ctx->d_act); cudaFree(ctx->d_obs); cudaFree(ctx->d_rew); cudaFree(ctx->d_done); cudaFree(ctx->d_tmo);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -352,6 +376,7 @@ static int create_impl(plen_ctx *ctx) {
     CK(ctx, cudaMalloc(&ctx->d_snapshot, sizeof(float) * (PLEN_STATE_WORDS + 32)));
     CK(ctx, cudaMalloc(&ctx->d_srec, sizeof(float) * SR_WORDS * (size_t)n));
     CK(ctx, cudaMalloc(&ctx->d_tgt, sizeof(float) * PLEN_NJ * (size_t)n));
+    CK(ctx, cudaMalloc(&ctx->d_key, (size_t)n));
     CK(ctx, cudaMalloc(&ctx->d_act, sizeof(float) * PLEN_NJ * (size_t)n));
     CK(ctx, cudaMalloc(&ctx->d_obs, sizeof(float) * PLEN_OBS * (size_t)n));
     CK(ctx, cudaMalloc(&ctx->d_rew, sizeof(float) * (size_t)n));
@@ -460,7 +485,7 @@ int plen_debug_dynamics(plen_ctx *ctx, float *minv_dev, float *pos_dev, float *r
     if (!ctx) return fail(nullptr, PLEN_E_ARG, "ctx is NULL");
     CK(ctx, cudaSetDevice(ctx->device));
     k_dyn<<<dyn_grid(ctx->n), DYN_WPC * 32, DYN_SMEM, (cudaStream_t)stream>>>(ctx->dc, ctx->er, ctx->d_tab, ctx->d_state, ctx->n,
-                                                                            nullptr, nullptr, ctx->d_srec, minv_dev, pos_dev, rot_dev);
+                                                                            nullptr, nullptr, ctx->d_srec, ctx->d_key, minv_dev, pos_dev, rot_dev);
     CK(ctx, cudaGetLastError());
     return PLEN_OK;
 }

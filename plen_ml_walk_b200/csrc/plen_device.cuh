@@ -44,6 +44,7 @@ PLEN_DEV void sincos_(float x, float *s, float *c) { sincosf(x, s, c); }
 PLEN_DEV float rcp_(float x) { return 1.0f / x; }
 PLEN_DEV int lowest_bit(unsigned m) { return __ffs((int)m) - 1; }
 PLEN_DEV int highest_bit(unsigned m) { return 31 - __clz((int)m); }
+PLEN_DEV int popc_(unsigned m) { return __popc(m); }
 }  // namespace plen
 #endif
 
@@ -82,16 +83,29 @@ struct DevConfig {
 };
 
 // ---- solve record: per robot, per tick, written by k_dyn and consumed by k_solve (global memory, words)
+// operational-space index i of x (32 slots): 0..17 joints, 18..23 right-foot twist, 24..25 unused, 26..31 left-foot twist
 enum {
-    SR_G = 0,          // 30 columns x 32 words of G (see tick_dynamics)
-    SR_B = 960,        // 6 rows x 32 words: base rows of M^-1 J^T in the same word order
-    SR_MRHS = 1152, SR_MDINV = 1184, SR_LDIR = 1216, SR_LRHS = 1248, SR_VSTAR = 1280, SR_Q = 1312,   // 32 words each
-    SR_CRHS = 1344, SR_CDINV = 1408, SR_CD = 1472,   // 64 words each: [contact point p][solver lane g]
-    SR_PT = 1536,      // 8 x (x, y, z, distance) of the candidate contact points, relative to the base origin
-    SR_LAMC = 1568,    // 8 cached normal impulses
-    SR_BASE = 1576,    // v* of the base (6), base position (3), quaternion (4), manifold bits (1)
-    SR_WORDS = 1600
+    SR_G = 0,          // 32 columns x 32 words of G (see tick_dynamics)
+    SR_B = 1024,       // 6 rows x 32 words: base rows of M^-1 J^T in the same word order
+    SR_MRHS = 1216, SR_MDINV = 1248, SR_LDIR = 1280, SR_LRHS = 1312, SR_VSTAR = 1344, SR_Q = 1376,   // 32 words each
+    SR_CRHS = 1408, SR_CDINV = 1472, SR_CD = 1536,   // 64 words each: [contact slot q = 4 foot + k][solver lane g]
+    SR_PT = 1600,      // 8 x (x, y, z, distance): k-th ACTIVE contact point of each foot, relative to the base origin
+    SR_LAMC = 1632,    // 8 cached normal impulses, same slot order
+    SR_BASE = 1640,    // v* of the base (6), base position (3), quaternion (4), manifold bits (1)
+    SR_WORDS = 1664
 };
+
+// index (0..3) of the k-th set bit of a 4-bit mask, -1 if there are fewer
+PLEN_DEV int nth_bit4(unsigned m, int k) {
+    int r = -1, c = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        const bool on = (m >> b) & 1u;
+        r = (on && c == k) ? b : r;
+        c += on ? 1 : 0;
+    }
+    return r;
+}
 
 // per-warp shared scratch of k_dyn (floats)
 struct WarpScratch {
@@ -234,7 +248,7 @@ PLEN_DEV void row_entries(int type, const float *a, const float *m, const float 
 struct DebugOut { float *minv, *pos, *rot; };   // [24*24], [24*3], [24*9] of one env; all nullable
 
 PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch &ws, LaneState &L, int lane,
-                            float *srec, const DebugOut *dbg = nullptr) {
+                            float *srec, uint8_t *sort_key, const DebugOut *dbg = nullptr) {
     const bool is_joint = lane >= 6 && lane < 24;
     const int cs = (int)tab[T_CS * 32 + lane], ce = (int)tab[T_CE * 32 + lane];
     float Rw[9], pw[3];
@@ -656,12 +670,12 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
         warp_sync();
     }
 
-    // ---- G (30 columns x 32 words) and B (6 rows x 32 words): word w of a column = entry i(w) = (w >> 2) + 8 (w & 3),
+    // ---- G (32 columns x 32 words) and B (6 rows x 32 words): word w of a column = entry i(w) = (w >> 2) + 8 (w & 3),
     //      i.e. the float4 of solver lane g = w >> 2 holds entries g, 8+g, 16+g, 24+g
     {
         const int i = (lane >> 2) + 8 * (lane & 3);
-        const bool ij = i < 18, ic = i >= 18 && i < 30;
-        const int fa = (i >= 24) ? 1 : 0, a6 = i - 18 - 6 * fa;
+        const bool ij = i < 18, ic = (i >= 18 && i < 24) || i >= 26;
+        const int fa = (i >= 26) ? 1 : 0, a6 = fa ? i - 26 : i - 18;
         const float(*Ya)[8] = fa ? ws.gg : ws.kk;
         float *G = srec + SR_G;
         for (int c = 0; c < 18; c++) {
@@ -670,12 +684,13 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
             else if (ic) v = Ya[6 + c][a6];
             G[c * 32 + lane] = v;
         }
-        for (int c = 18; c < 30; c++) {
-            const int fb = (c >= 24) ? 1 : 0, b6 = c - 18 - 6 * fb;
+        for (int c = 18; c < 32; c++) {
+            const bool cc = c < 24 || c >= 26;
+            const int fb = (c >= 26) ? 1 : 0, b6 = fb ? c - 26 : c - 18;
             const float(*Yb)[8] = fb ? ws.gg : ws.kk;
             float v = 0.0f;
-            if (ij) v = Yb[6 + i][b6];
-            else if (ic && man_new) v = ws.lin[fa * 6 + a6][c - 18];
+            if (cc && ij) v = Yb[6 + i][b6];
+            else if (cc && ic && man_new) v = ws.lin[fa * 6 + a6][fb * 6 + b6];
             G[c * 32 + lane] = v;
         }
         float *Bm = srec + SR_B;
@@ -698,16 +713,17 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
         srec[SR_Q + lane] = ij ? s_q : 0.0f;
     }
 
-    // ---- contact rows: word p*8+g of SR_CRHS / SR_CDINV / SR_CD belongs to contact point p and solver lane g, which
-    //      owns the row whose "own" twist component is comp = g - 2 (right foot) / g (left foot):
+    // ---- contact rows, COMPACTED per foot: slot q = 4 f + k is the k-th active point of foot f.  Word q*8+g of
+    //      SR_CRHS / SR_CDINV / SR_CD belongs to solver lane g, which owns the row whose "own" twist component is g - 2:
     //      comp 0 wx: roll about t2   1 wy: roll about t1 (sign flipped)   2 wz: spin
     //           3 vx: lateral t2      4 vy: lateral t1 (sign flipped)      5 vz: normal
     //      (flipping the sign of a row with symmetric bounds leaves the Gauss-Seidel iterates unchanged)
 #pragma unroll
     for (int half = 0; half < 2; half++) {
-        const int p = (lane >> 3) + 4 * half, g = lane & 7, f = half;
-        const int comp = f ? g : g - 2;
-        const bool valid = comp >= 0 && comp < 6 && ((man_new >> p) & 1u);
+        const int f = half, g = lane & 7, comp = g - 2;
+        const int pb = nth_bit4((man_new >> (4 * f)) & 15u, lane >> 3);
+        const int p = 4 * f + (pb < 0 ? 0 : pb);
+        const bool valid = comp >= 0 && pb >= 0;
         float rhs = 0.0f, dinv = 0.0f, d = 0.0f;
         if (valid) {
             const float px = ws.cp[p][0], py = ws.cp[p][1], pz = ws.cp[p][2];
@@ -747,12 +763,22 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
         srec[SR_CDINV + 32 * half + lane] = dinv;
         srec[SR_CD + 32 * half + lane] = d;
     }
-    srec[SR_PT + lane] = ws.cp[lane >> 2][lane & 3];
-    if (lane >= 24) srec[SR_LAMC + lane - 24] = L.lam;
+    {
+        const int q = lane >> 2, pb = nth_bit4((man_new >> (4 * (q >> 2))) & 15u, q & 3);
+        srec[SR_PT + lane] = (pb >= 0) ? ws.cp[4 * (q >> 2) + pb][lane & 3] : 0.0f;
+        const int q2 = lane & 7, pb2 = nth_bit4((man_new >> (4 * (q2 >> 2))) & 15u, q2 & 3);
+        const float lc = shfl(L.lam, 24 + 4 * (q2 >> 2) + (pb2 < 0 ? 0 : pb2));
+        if (lane >= 24) srec[SR_LAMC + q2] = (pb2 >= 0) ? lc : 0.0f;
+    }
     if (lane < 6) srec[SR_BASE + lane] = vstar;
     if (lane < 3) srec[SR_BASE + 6 + lane] = L.pos[lane];
     if (lane < 4) srec[SR_BASE + 9 + lane] = L.quat[lane];
-    if (lane == 0) srec[SR_BASE + 13] = (float)man_new;
+    if (lane == 0) {
+        srec[SR_BASE + 13] = (float)man_new;
+        // k_solve groups robots of similar contact load into the same warp (tile-local sort by this key)
+        const int n0 = popc_(man_new & 15u), n1 = popc_((man_new >> 4) & 15u);
+        if (sort_key) *sort_key = (uint8_t)((n0 > n1 ? n0 : n1) * 25 + n0 * 5 + n1);
+    }
     warp_sync();
 }
 

@@ -5,7 +5,10 @@
 //   x = [18 joint velocity changes; right-foot twist change (6); left-foot twist change (6)]
 // spread over the 8 lanes g of its group as four registers s[slot] = x[g + 8 slot]:
 //   s[0] = joint g      s[1] = joint 8+g      s[2] = joint 16+g (g < 2) | right-foot component g-2 (g >= 2)
-//   s[3] = left-foot component g (g < 6)
+//   s[3] = left-foot component g-2 (g >= 2)
+// Contact points are COMPACTED per foot (slot q = 4 f + k = k-th active point of foot f), so a warp only loops to the
+// largest active-point count among its four robots; k_solve additionally sorts robots by contact load inside 64-robot
+// tiles so that the four robots of a warp have similar counts.
 // foot twist components: 0..2 angular (wx wy wz), 3..5 linear (vx vy vz) about the base origin, world axes.
 // A row update with impulse change delta is   s += (float4 of a column of G, one LDS.128) * delta   on every lane;
 // the owner lane of a row (the lane whose register holds the row's "own" velocity component) computes the candidate.
@@ -28,10 +31,21 @@ struct vec4 { float x, y, z, w; };
 
 PLEN_DEV float sel3(const float *a, int k) { return (k == 0) ? a[0] : ((k == 1) ? a[1] : a[2]); }
 
-// solver lane that holds twist component k of foot f
-#define PLEN_LN(f, k) ((f) ? (k) : 2 + (k))
+// solver lane that holds twist component k of either foot
+#define PLEN_LN(f, k) (2 + (k))
 // G column of twist component k of foot f
-#define PLEN_COL(f, k) (18 + 6 * (f) + (k))
+#define PLEN_COL(f, k) (18 + 8 * (f) + (k))
+
+// s01 += (x0, x1) * d  as one packed FFMA2 (sm_100a fma.rn.f32x2 with a broadcast scalar multiplier)
+PLEN_DEV void fma2(float &a0, float &a1, float x0, float x1, float d) {
+#ifndef PLEN_HOST_EMU
+    asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%0, %1}; mov.b64 rb, {%2, %3}; mov.b64 rc, {%4, %4};\n\t"
+        "fma.rn.f32x2 ra, rb, rc, ra; mov.b64 {%0, %1}, ra; }"
+        : "+f"(a0), "+f"(a1) : "f"(x0), "f"(x1), "f"(d));
+#else
+    a0 = fmaf(x0, d, a0); a1 = fmaf(x1, d, a1);
+#endif
+}
 
 struct SolveState {
     float s[4];
@@ -40,11 +54,11 @@ struct SolveState {
 
 PLEN_DEV void apply_col(SolveState &S, const vec4 *Gs4, int g, int c, float db) {
     const vec4 v = Gs4[c * 8 + g];
-    S.s[0] = fmaf(v.x, db, S.s[0]); S.s[1] = fmaf(v.y, db, S.s[1]);
-    S.s[2] = fmaf(v.z, db, S.s[2]); S.s[3] = fmaf(v.w, db, S.s[3]);
+    fma2(S.s[0], S.s[1], v.x, v.y, db);
+    fma2(S.s[2], S.s[3], v.z, v.w, db);
 }
 
-// One robot = lanes (lane & 24) .. +7 of the warp.  srec: this robot's solve record (global); Gs: this robot's 960-word
+// One robot = lanes (lane & 24) .. +7 of the warp.  srec: this robot's solve record (global); Gs: this robot's 1024-word
 // shared staging area; state: this robot's 96-word state record (global), updated in place.
 PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, float *Gs, float *__restrict__ state,
                          int lane, bool valid) {
@@ -54,8 +68,8 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
     {
         const vec4 *src4 = reinterpret_cast<const vec4 *>(srec + SR_G);
         const vec4 z4 = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll 6
-        for (int k = g; k < 240; k += 8) Gs4[k] = valid ? src4[k] : z4;
+#pragma unroll 8
+        for (int k = g; k < 256; k += 8) Gs4[k] = valid ? src4[k] : z4;
     }
     warp_sync();
 
@@ -74,7 +88,10 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
         m_d[2] = (g < 2) ? Gs[(16 + g) * 32 + 4 * g + 2] : 0.0f;
         man = (unsigned)srec[SR_BASE + 13];
     }
-    const unsigned man_any = redux_or(man);
+    // active-point counts per foot: this robot's and the largest among the four robots of the warp
+    const int n0 = popc_(man & 15u), n1 = popc_((man >> 4) & 15u);
+    const int nmax0 = (int)redux_max((unsigned)n0), nmax1 = (int)redux_max((unsigned)n1);
+    const bool man_any = (nmax0 | nmax1) != 0;
     const unsigned lim_any = redux_or(((l_dir[0] != 0.0f) ? (1u << g) : 0u) | ((l_dir[1] != 0.0f) ? (256u << g) : 0u) |
                                       ((l_dir[2] != 0.0f) ? (65536u << g) : 0u));
     float c_rhs[8], c_dinv[8], c_d[8], c_lam[8], lamN[8], px[8], py[8], pz[8];
@@ -88,7 +105,7 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
             c_d[p] = srec[SR_CD + 8 * p + g];
             const vec4 t = *reinterpret_cast<const vec4 *>(srec + SR_PT + 4 * p);
             px[p] = t.x; py[p] = t.y; pz[p] = t.z;
-            lamN[p] = ((man >> p) & 1u) ? srec[SR_LAMC + p] * cfg.warm : 0.0f;
+            lamN[p] = srec[SR_LAMC + p] * cfg.warm;      // zero for unused slots
         }
     }
 
@@ -107,7 +124,7 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
     if (man_any) {
 #pragma unroll
         for (int p = 0; p < 8; p++)
-            if ((man_any >> p) & 1u) NORMAL_COLUMN(p, (p >> 2), lamN[p]);
+            if ((p & 3) < ((p >> 2) ? nmax1 : nmax0)) NORMAL_COLUMN(p, (p >> 2), lamN[p]);
     }
 
 #define SERVO_ROW(slot, l)                                                                              \
@@ -178,7 +195,7 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
             // ---- contact normals (lower bound 0; the 1e10 upper bound of the reference never binds)
 #pragma unroll
             for (int p = 0; p < 8; p++) {
-                if (!((man_any >> p) & 1u)) continue;
+                if ((p & 3) >= ((p >> 2) ? nmax1 : nmax0)) continue;
                 const int f = p >> 2;
                 const float wx = GSH(S.s[2 + f], PLEN_LN(f, 0)), wy = GSH(S.s[2 + f], PLEN_LN(f, 1));
                 const float r_ = fmaf(wx, py[p], fmaf(-wy, px[p], S.s[2 + f]));
@@ -192,19 +209,19 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
             // ---- all spinning rows, then the rolling rows point by point (t1, t2)
 #pragma unroll
             for (int p = 0; p < 8; p++) {
-                if (!((man_any >> p) & 1u)) continue;
+                if ((p & 3) >= ((p >> 2) ? nmax1 : nmax0)) continue;
                 TORSION_ROW(p, (p >> 2), 2, cfg.mu_spinning);
             }
 #pragma unroll
             for (int p = 0; p < 8; p++) {
-                if (!((man_any >> p) & 1u)) continue;
+                if ((p & 3) >= ((p >> 2) ? nmax1 : nmax0)) continue;
                 TORSION_ROW(p, (p >> 2), 1, cfg.mu_rolling);
                 TORSION_ROW(p, (p >> 2), 0, cfg.mu_rolling);
             }
             // ---- lateral pairs with the implicit friction cone (resolveConeFrictionConstraintRows)
 #pragma unroll
             for (int p = 0; p < 8; p++) {
-                if (!((man_any >> p) & 1u)) continue;
+                if ((p & 3) >= ((p >> 2) ? nmax1 : nmax0)) continue;
                 const int f = p >> 2, LA = PLEN_LN(f, 4), LB = PLEN_LN(f, 3);
                 const float wx = GSH(S.s[2 + f], PLEN_LN(f, 0)), wy = GSH(S.s[2 + f], PLEN_LN(f, 1)),
                             wz = GSH(S.s[2 + f], PLEN_LN(f, 2));
@@ -262,7 +279,7 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
     if (man_any) {
 #pragma unroll
         for (int f = 0; f < 2; f++) {
-            const int comp = f ? g : g - 2;     // this lane's row type on foot f (out of range: no rows)
+            const int comp = g - 2;              // this lane's row type (negative: no contact rows)
             float w6[6] = {0, 0, 0, 0, 0, 0};
             float own = 0.0f;
 #pragma unroll
@@ -285,7 +302,7 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
             float mine = 0.0f;
 #pragma unroll
             for (int k = 0; k < 6; k++) mine = (comp == k) ? w6[k] : mine;
-            if (f == 0) z[2] = (g < 2) ? z[2] : mine; else z[3] = mine;
+            if (f == 0) z[2] = (g < 2) ? z[2] : mine; else z[3] = (g < 2) ? 0.0f : mine;
         }
     }
     float dvb[6];
@@ -312,12 +329,18 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
         state[W_U + 6 + g] = u0; state[W_Q + 6 + g] = q4.x + u0 * cfg.dt;
         state[W_U + 14 + g] = u1; state[W_Q + 14 + g] = q4.y + u1 * cfg.dt;
         if (g < 2) { state[W_U + 22 + g] = u2; state[W_Q + 22 + g] = q4.z + u2 * cfg.dt; }
+        {   // cached normal impulse of ORIGINAL contact point g: slot = 4 f + (number of active points of the foot below it)
+            const int f = g >> 2, q = 4 * f + popc_((man >> (4 * f)) & ((1u << (g & 3)) - 1u));
+            float v = lamN[0];
+#pragma unroll
+            for (int k = 1; k < 8; k++) v = (q == k) ? lamN[k] : v;
+            state[W_U + 24 + g] = ((man >> g) & 1u) ? v : 0.0f;
+        }
         if (g == 0) {
             float ub[6];
 #pragma unroll
             for (int k = 0; k < 6; k++) { ub[k] = clampf(srec[SR_BASE + k] + dvb[k], -cfg.vmax, cfg.vmax); state[W_U + k] = ub[k]; }
-#pragma unroll
-            for (int p = 0; p < 8; p++) state[W_U + 24 + p] = ((man >> p) & 1u) ? lamN[p] : 0.0f;
+
 #pragma unroll
             for (int k = 0; k < 3; k++) state[W_POS + k] = srec[SR_BASE + 6 + k] + ub[3 + k] * cfg.dt;
             float fa = sqrtf(ub[0] * ub[0] + ub[1] * ub[1] + ub[2] * ub[2]);

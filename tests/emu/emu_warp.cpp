@@ -70,6 +70,7 @@ static inline void sincos_(float x, float *s, float *c) { *s = sinf(x); *c = cos
 static inline float rcp_(float x) { return 1.0f / x; }
 static inline int lowest_bit(unsigned m) { return __builtin_ffs((int)m) - 1; }
 static inline int highest_bit(unsigned m) { return 31 - __builtin_clz(m); }
+static inline int popc_(unsigned m) { return __builtin_popcount(m); }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 }  // namespace plen
 using plen::rsqrtf;
@@ -103,7 +104,7 @@ void emu_init_record(const plen_config *c, float *rec) { init_record(c, rec); }
 static void run_ticks(const DevConfig &dc, const float *tab, float *records, const float *tgt, int n, int n_ticks,
                       const DebugOut *dbg0, int lane) {
     static WarpScratch ws;
-    static std::vector<float> srec, Gs(4 * 960);
+    static std::vector<float> srec, Gs(4 * 1024);
     if (lane == 0) srec.assign((size_t)n * SR_WORDS, 0.0f);
     bar();
     for (int t = 0; t < n_ticks; t++) {
@@ -111,14 +112,14 @@ static void run_ticks(const DevConfig &dc, const float *tab, float *records, con
             LaneState L;
             load_record(records + 96 * e, ws, L, lane);
             if (lane >= 6 && lane < 24) L.tgt = tgt ? tgt[18 * e + lane - 6] : 0.0f;
-            tick_dynamics(dc, tab, ws, L, lane, srec.data() + (size_t)e * SR_WORDS,
+            tick_dynamics(dc, tab, ws, L, lane, srec.data() + (size_t)e * SR_WORDS, nullptr,
                           (e == 0 && t == n_ticks - 1) ? dbg0 : nullptr);
         }
         for (int b = 0; b < n; b += 4) {
             const int r = b + (lane >> 3);
             const bool valid = r < n;
             const int rr = valid ? r : 0;
-            solve_tick(dc, srec.data() + (size_t)rr * SR_WORDS, Gs.data() + (lane >> 3) * 960, records + 96 * rr, lane, valid);
+            solve_tick(dc, srec.data() + (size_t)rr * SR_WORDS, Gs.data() + (lane >> 3) * 1024, records + 96 * rr, lane, valid);
             bar();
         }
     }
