@@ -33,6 +33,10 @@ UNIT = "env-steps/s"
 # algorithmic HBM bytes per env-step (DESIGN.md "Data layout"): state record 96 words read + written, action 18 f32,
 # obs 26 f32, reward f32, done + timeout bytes
 BYTES_PER_ENV_STEP = 2 * 96 * 4 + 18 * 4 + 26 * 4 + 4 + 2
+TICKS_PER_STEP = 4
+# measured DRAM traffic of one k_solve launch per robot (ncu --set full, profiles/r1_v3_summary.md): it reads the
+# 6.4 KB solve record k_dyn wrote for the tick -- a deliberate trade of HBM bytes for issue slots
+SOLVE_DRAM_BYTES_PER_ROBOT = (219.58e6 + 9.55e6) / 32768
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 
 
@@ -177,6 +181,7 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- device-resident leg: K steps, each bracketed by CUDA events on the launching stream, L2 flushed in between
+    env.profile_enable(K)
     sampler = ClockSampler(local_rank)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     launches0 = env.launches
@@ -190,6 +195,7 @@ def main():
     barrier()
     clocks = sampler.stop()
     gpu_launches = env.launches - launches0
+    prof = env.profile_read()
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if dist:
@@ -218,7 +224,10 @@ def main():
     if rank == 0:
         peak, peak_src = _peaks()
         step_ms = total_ms / K
-        achieved = E * BYTES_PER_ENV_STEP / (step_ms * 1e-3) / 1e9
+        # dominant kernel = k_solve (one launch per physics tick over all E robots): CUDA events recorded around every
+        # launch of the timed region by the library itself (plen_profile_enable), on the launching stream
+        solve_ms = prof["ms_solve"] / max(1, prof["steps"] * TICKS_PER_STEP)
+        achieved = E * (BYTES_PER_ENV_STEP / TICKS_PER_STEP) / (solve_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -231,8 +240,15 @@ def main():
             "gpu_launches": gpu_launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "bytes_per_env_step": BYTES_PER_ENV_STEP,
-                         "note": "k_step is FP32-issue bound, not HBM bound (DESIGN.md); see profiles/ for pipe utilisation"},
+                         "traffic": SOLVE_DRAM_BYTES_PER_ROBOT * E, "peak_source": peak_src, "kernel": "k_solve",
+                         "kernel_ms_per_launch": solve_ms, "launches_per_step": TICKS_PER_STEP,
+                         "algorithmic_bytes_per_launch": E * BYTES_PER_ENV_STEP / TICKS_PER_STEP,
+                         "bytes_per_env_step": BYTES_PER_ENV_STEP,
+                         "note": "the path is FP32 instruction-issue / dependency-latency bound inside the projected "
+                                 "Gauss-Seidel (DESIGN.md), neither HBM nor tensor bound; traffic = ncu DRAM bytes per "
+                                 "robot (32768-robot capture) x robots per launch"},
+            "kernel_ms_per_step": {"k_dyn": prof["ms_dyn"] / max(1, prof["steps"]), "k_solve": prof["ms_solve"] / max(1, prof["steps"]),
+                                   "k_post": prof["ms_post"] / max(1, prof["steps"])},
         }
         if not args.no_cpu_baseline and world == 1:
             cores = len(os.sched_getaffinity(0))

@@ -110,9 +110,10 @@ int plen_num_envs(const plen_ctx *ctx);
  * obs_dev may be NULL. */
 int plen_reset(plen_ctx *ctx, const uint8_t *mask_dev, float *obs_dev, void *stream);
 
-/* Replaces PlenWalkEnv.step (plen_env.py:638-692) + the TimeLimit wrapper (plen_env.py:15-19) for all N envs in ONE
- * kernel launch: agent_to_env -> motor targets -> 4 ticks (contact, dynamics, PGS, integrate) -> observation ->
- * done -> reward -> counters -> optional auto-reset.
+/* Replaces PlenWalkEnv.step (plen_env.py:638-692) + the TimeLimit wrapper (plen_env.py:15-19) for all N envs:
+ * agent_to_env -> motor targets -> 4 ticks (contact, dynamics, PGS, integrate) -> observation -> done -> reward ->
+ * counters -> optional auto-reset.  2*substeps+1 kernel launches on `stream` (k_dyn + k_solve per tick, then k_post),
+ * no host synchronisation.
  *   obs_dev          [N,26] observation the agent acts on next (the reset observation where done && auto_reset)
  *   reward_dev       [N]
  *   done_dev         [N] uint8, dead || ep_t >= max_episode_steps
@@ -138,6 +139,13 @@ int plen_tick(plen_ctx *ctx, const float *targets_dev, int n_ticks, void *stream
 /* Diagnostics: per-env generalized inverse mass matrix M^-1 [N,24,24] in coordinates [omega_w, v_w, qd]
  * and world pose of the 19 body frames pos [N,24,3] / rot [N,24,9] (lanes 1..5 unused). */
 int plen_debug_dynamics(plen_ctx *ctx, float *minv_dev, float *pos_dev, float *rot_dev, void *stream);
+
+/* Per-kernel device timing of plen_step (measurement aid for bench.py, no reference counterpart): after
+ * plen_profile_enable the next max_steps plen_step calls record CUDA events around their launches on the caller's
+ * stream; plen_profile_read synchronises on them, returns the summed milliseconds of the dynamics (k_dyn), solver
+ * (k_solve) and env-epilogue (k_post) kernels and the number of recorded steps, and re-arms the recorder. */
+int plen_profile_enable(plen_ctx *ctx, int max_steps);
+int plen_profile_read(plen_ctx *ctx, float *ms_dyn, float *ms_solve, float *ms_post, int *steps);
 
 /* Sinewave gait + closed-form leg IK for n_gaits parameter sets in one launch.
  * Replaces TrajectoryGenerator.main (plen_bullet/src/plen_bullet/trajectory_generator.py:54-277) and the trajectory

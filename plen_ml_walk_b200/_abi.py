@@ -72,7 +72,7 @@ def model_to_c(model: PlenModel) -> PlenModelC:
 EXPORTS = (
     "plen_version", "plen_default_config", "plen_create", "plen_destroy", "plen_last_error", "plen_num_envs",
     "plen_reset", "plen_step", "plen_step_host", "plen_get_state", "plen_set_state", "plen_tick",
-    "plen_debug_dynamics", "plen_gait_ik",
+    "plen_debug_dynamics", "plen_gait_ik", "plen_profile_enable", "plen_profile_read",
 )
 
 _lib = None
@@ -105,6 +105,8 @@ def load_library(path: str = LIB_PATH):
     L.plen_set_state.argtypes = [vp] * 5
     L.plen_tick.argtypes = [vp, vp, ip, vp]
     L.plen_debug_dynamics.argtypes = [vp] * 5
+    L.plen_profile_enable.argtypes = [vp, ip]
+    L.plen_profile_read.argtypes = [vp] * 5
     L.plen_gait_ik.argtypes = [ip, vp, ip, vp, vp, vp, vp]
     _lib = L
     return L

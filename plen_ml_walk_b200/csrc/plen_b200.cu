@@ -34,6 +34,9 @@ struct plen_ctx {
     float *d_act, *d_obs, *d_rew;
     uint8_t *d_done, *d_tmo;
     cudaStream_t stream;
+    // optional per-kernel timing of plen_step (plen_profile_enable): 2*substeps+2 events per recorded step
+    cudaEvent_t *prof_ev;
+    int prof_cap, prof_steps;
     char err[512];
 };
 
@@ -123,7 +126,7 @@ k_solve(const __grid_constant__ DevConfig dc, const float *__restrict__ srec, co
     const int robot = s_inv[round * 8 + warp * 4 + (lane >> 3)];
     const bool valid = robot < n;
     const size_t r = valid ? (size_t)robot : 0;
-    solve_tick(dc, srec + r * SR_WORDS, Gs + (size_t)(warp * 4 + (lane >> 3)) * 1024, state + r * PLEN_STATE_WORDS, lane, valid);
+    solve_tick(dc, srec + r * SR_WORDS, Gs + (size_t)(warp * 4 + (lane >> 3)) * 960, state + r * PLEN_STATE_WORDS, lane, valid);
 }
 
 // After the last tick of an env step, one warp per robot: observation, done, reward, counters, auto-reset.
@@ -325,16 +328,20 @@ __global__ void k_gait_ik(const double *__restrict__ params, int n, double *__re
 
 // ------------------------------------------------------------------------------------------------ C ABI
 static const size_t DYN_SMEM = sizeof(DynSmem);
-static const size_t SOLVE_SMEM = sizeof(float) * 1024 * 4 * SOLVE_WPC;
+static const size_t SOLVE_SMEM = sizeof(float) * 960 * 4 * SOLVE_WPC;
 static_assert(SOLVE_WPC * 32 == SOLVE_TILE, "k_solve ranks one tile robot per thread");
 static int dyn_grid(int n) { return (n + DYN_WPC - 1) / DYN_WPC; }
 static int solve_grid(int n) { return 8 * ((n + SOLVE_TILE - 1) / SOLVE_TILE); }
 
 // n_ticks physics ticks of 1/240 s: (k_dyn, k_solve) per tick.  `actions` (agent space) only on the first tick.
-static void launch_ticks(plen_ctx *ctx, float *state, int n, const float *actions, float *tgt, int n_ticks, cudaStream_t st) {
+// ev (nullable): 2*n_ticks events recorded before each kernel.
+static void launch_ticks(plen_ctx *ctx, float *state, int n, const float *actions, float *tgt, int n_ticks, cudaStream_t st,
+                         cudaEvent_t *ev = nullptr) {
     for (int t = 0; t < n_ticks; t++) {
+        if (ev) cudaEventRecord(ev[2 * t], st);
         k_dyn<<<dyn_grid(n), DYN_WPC * 32, DYN_SMEM, st>>>(ctx->dc, ctx->er, ctx->d_tab, state, n, t == 0 ? actions : nullptr,
                                                           tgt, ctx->d_srec, ctx->d_key, nullptr, nullptr, nullptr);
+        if (ev) cudaEventRecord(ev[2 * t + 1], st);
         k_solve<<<solve_grid(n), SOLVE_WPC * 32, SOLVE_SMEM, st>>>(ctx->dc, ctx->d_srec, ctx->d_key, state, n);
     }
 }
@@ -357,6 +364,10 @@ void plen_destroy(plen_ctx *ctx) {
     cudaFree(ctx->d_tab); cudaFree(ctx->d_state); cudaFree(ctx->d_snapshot); cudaFree(ctx->d_srec); cudaFree(ctx->d_tgt); cudaFree(ctx->d_key);
     cudaFree(ctx->d_act); cudaFree(ctx->d_obs); cudaFree(ctx->d_rew); cudaFree(ctx->d_done); cudaFree(ctx->d_tmo);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->prof_ev) {
+        for (int i = 0; i < ctx->prof_cap * (2 * ctx->cfg.substeps + 2); i++) cudaEventDestroy(ctx->prof_ev[i]);
+        free(ctx->prof_ev);
+    }
     delete ctx;
 }
 
@@ -367,6 +378,9 @@ static int create_impl(plen_ctx *ctx) {
     CK(ctx, cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DYN_SMEM));
     CK(ctx, cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DYN_SMEM));
     CK(ctx, cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
+    // both hot kernels are occupancy-limited by shared memory: ask for the largest carve-out (7 k_solve CTAs per SM)
+    CK(ctx, cudaFuncSetAttribute(k_solve, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(ctx, cudaFuncSetAttribute(k_dyn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     float tab[T_ROWS * 32], rec[PLEN_STATE_WORDS];
     build_table(&ctx->model, &ctx->cfg, tab);
@@ -429,9 +443,13 @@ int plen_step(plen_ctx *ctx, const float *actions_dev, float *obs_dev, float *re
     if (!actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(ctx, PLEN_E_ARG, "plen_step: NULL buffer");
     CK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    launch_ticks(ctx, ctx->d_state, ctx->n, actions_dev, ctx->d_tgt, ctx->cfg.substeps, st);
+    const int nev = 2 * ctx->cfg.substeps + 2;
+    cudaEvent_t *ev = (ctx->prof_ev && ctx->prof_steps < ctx->prof_cap) ? ctx->prof_ev + (size_t)nev * ctx->prof_steps : nullptr;
+    launch_ticks(ctx, ctx->d_state, ctx->n, actions_dev, ctx->d_tgt, ctx->cfg.substeps, st, ev);
+    if (ev) cudaEventRecord(ev[nev - 2], st);
     k_post<<<dyn_grid(ctx->n), DYN_WPC * 32, DYN_SMEM, st>>>(ctx->dc, ctx->d_tab, ctx->d_state, ctx->n, obs_dev, reward_dev,
                                                             done_dev, timeout_dev, terminal_obs_dev, ctx->d_snapshot);
+    if (ev) { cudaEventRecord(ev[nev - 1], st); ctx->prof_steps++; }
     CK(ctx, cudaGetLastError());
     return PLEN_OK;
 }
@@ -487,6 +505,42 @@ int plen_debug_dynamics(plen_ctx *ctx, float *minv_dev, float *pos_dev, float *r
     k_dyn<<<dyn_grid(ctx->n), DYN_WPC * 32, DYN_SMEM, (cudaStream_t)stream>>>(ctx->dc, ctx->er, ctx->d_tab, ctx->d_state, ctx->n,
                                                                             nullptr, nullptr, ctx->d_srec, ctx->d_key, minv_dev, pos_dev, rot_dev);
     CK(ctx, cudaGetLastError());
+    return PLEN_OK;
+}
+
+int plen_profile_enable(plen_ctx *ctx, int max_steps) {
+    if (!ctx || max_steps <= 0) return fail(ctx, PLEN_E_ARG, "plen_profile_enable: bad arguments");
+    if (ctx->prof_ev) return fail(ctx, PLEN_E_STATE, "plen_profile_enable: already enabled");
+    CK(ctx, cudaSetDevice(ctx->device));
+    const int nev = 2 * ctx->cfg.substeps + 2;
+    ctx->prof_ev = (cudaEvent_t *)calloc((size_t)max_steps * nev, sizeof(cudaEvent_t));
+    if (!ctx->prof_ev) return fail(ctx, PLEN_E_ARG, "out of host memory");
+    for (int i = 0; i < max_steps * nev; i++) CK(ctx, cudaEventCreate(&ctx->prof_ev[i]));
+    ctx->prof_cap = max_steps;
+    ctx->prof_steps = 0;
+    return PLEN_OK;
+}
+
+int plen_profile_read(plen_ctx *ctx, float *ms_dyn, float *ms_solve, float *ms_post, int *steps) {
+    if (!ctx || !ctx->prof_ev) return fail(ctx, PLEN_E_STATE, "plen_profile_read: profiling is not enabled");
+    CK(ctx, cudaSetDevice(ctx->device));
+    const int nev = 2 * ctx->cfg.substeps + 2;
+    double d = 0, s = 0, p = 0;
+    for (int k = 0; k < ctx->prof_steps; k++) {
+        cudaEvent_t *ev = ctx->prof_ev + (size_t)nev * k;
+        CK(ctx, cudaEventSynchronize(ev[nev - 1]));
+        float ms;
+        for (int t = 0; t < ctx->cfg.substeps; t++) {
+            CK(ctx, cudaEventElapsedTime(&ms, ev[2 * t], ev[2 * t + 1])); d += ms;
+            CK(ctx, cudaEventElapsedTime(&ms, ev[2 * t + 1], ev[2 * t + 2])); s += ms;
+        }
+        CK(ctx, cudaEventElapsedTime(&ms, ev[nev - 2], ev[nev - 1])); p += ms;
+    }
+    if (ms_dyn) *ms_dyn = (float)d;
+    if (ms_solve) *ms_solve = (float)s;
+    if (ms_post) *ms_post = (float)p;
+    if (steps) *steps = ctx->prof_steps;
+    ctx->prof_steps = 0;
     return PLEN_OK;
 }
 

@@ -85,14 +85,14 @@ struct DevConfig {
 // ---- solve record: per robot, per tick, written by k_dyn and consumed by k_solve (global memory, words)
 // operational-space index i of x (32 slots): 0..17 joints, 18..23 right-foot twist, 24..25 unused, 26..31 left-foot twist
 enum {
-    SR_G = 0,          // 32 columns x 32 words of G (see tick_dynamics)
-    SR_B = 1024,       // 6 rows x 32 words: base rows of M^-1 J^T in the same word order
-    SR_MRHS = 1216, SR_MDINV = 1248, SR_LDIR = 1280, SR_LRHS = 1312, SR_VSTAR = 1344, SR_Q = 1376,   // 32 words each
-    SR_CRHS = 1408, SR_CDINV = 1472, SR_CD = 1536,   // 64 words each: [contact slot q = 4 foot + k][solver lane g]
-    SR_PT = 1600,      // 8 x (x, y, z, distance): k-th ACTIVE contact point of each foot, relative to the base origin
-    SR_LAMC = 1632,    // 8 cached normal impulses, same slot order
-    SR_BASE = 1640,    // v* of the base (6), base position (3), quaternion (4), manifold bits (1)
-    SR_WORDS = 1664
+    SR_G = 0,          // 30 columns (18 joints, 6 right-foot, 6 left-foot components) x 32 words (rows i) of G
+    SR_B = 960,        // 6 rows x 32 words: base rows of M^-1 J^T in the same word order
+    SR_MRHS = 1152, SR_MDINV = 1184, SR_LDIR = 1216, SR_LRHS = 1248, SR_VSTAR = 1280, SR_Q = 1312,   // 32 words each
+    SR_CRHS = 1344, SR_CDINV = 1408, SR_CD = 1472,   // 64 words each: [contact slot q = 4 foot + k][solver lane g]
+    SR_PT = 1536,      // 8 x (x, y, z, distance): k-th ACTIVE contact point of each foot, relative to the base origin
+    SR_LAMC = 1568,    // 8 cached normal impulses, same slot order
+    SR_BASE = 1576,    // v* of the base (6), base position (3), quaternion (4), manifold bits (1)
+    SR_WORDS = 1600
 };
 
 // index (0..3) of the k-th set bit of a 4-bit mask, -1 if there are fewer
@@ -670,7 +670,7 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
         warp_sync();
     }
 
-    // ---- G (32 columns x 32 words) and B (6 rows x 32 words): word w of a column = entry i(w) = (w >> 2) + 8 (w & 3),
+    // ---- G (30 columns x 32 words) and B (6 rows x 32 words): word w of a column = entry i(w) = (w >> 2) + 8 (w & 3),
     //      i.e. the float4 of solver lane g = w >> 2 holds entries g, 8+g, 16+g, 24+g
     {
         const int i = (lane >> 2) + 8 * (lane & 3);
@@ -684,13 +684,12 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
             else if (ic) v = Ya[6 + c][a6];
             G[c * 32 + lane] = v;
         }
-        for (int c = 18; c < 32; c++) {
-            const bool cc = c < 24 || c >= 26;
-            const int fb = (c >= 26) ? 1 : 0, b6 = fb ? c - 26 : c - 18;
+        for (int c = 18; c < 30; c++) {
+            const int fb = (c >= 24) ? 1 : 0, b6 = c - 18 - 6 * fb;
             const float(*Yb)[8] = fb ? ws.gg : ws.kk;
             float v = 0.0f;
-            if (cc && ij) v = Yb[6 + i][b6];
-            else if (cc && ic && man_new) v = ws.lin[fa * 6 + a6][fb * 6 + b6];
+            if (ij) v = Yb[6 + i][b6];
+            else if (ic && man_new) v = ws.lin[fa * 6 + a6][c - 18];
             G[c * 32 + lane] = v;
         }
         float *Bm = srec + SR_B;

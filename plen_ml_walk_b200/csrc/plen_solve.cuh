@@ -34,7 +34,7 @@ PLEN_DEV float sel3(const float *a, int k) { return (k == 0) ? a[0] : ((k == 1) 
 // solver lane that holds twist component k of either foot
 #define PLEN_LN(f, k) (2 + (k))
 // G column of twist component k of foot f
-#define PLEN_COL(f, k) (18 + 8 * (f) + (k))
+#define PLEN_COL(f, k) (18 + 6 * (f) + (k))
 
 // s01 += (x0, x1) * d  as one packed FFMA2 (sm_100a fma.rn.f32x2 with a broadcast scalar multiplier)
 PLEN_DEV void fma2(float &a0, float &a1, float x0, float x1, float d) {
@@ -58,7 +58,7 @@ PLEN_DEV void apply_col(SolveState &S, const vec4 *Gs4, int g, int c, float db) 
     fma2(S.s[2], S.s[3], v.z, v.w, db);
 }
 
-// One robot = lanes (lane & 24) .. +7 of the warp.  srec: this robot's solve record (global); Gs: this robot's 1024-word
+// One robot = lanes (lane & 24) .. +7 of the warp.  srec: this robot's solve record (global); Gs: this robot's 960-word
 // shared staging area; state: this robot's 96-word state record (global), updated in place.
 PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, float *Gs, float *__restrict__ state,
                          int lane, bool valid) {
@@ -68,8 +68,8 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
     {
         const vec4 *src4 = reinterpret_cast<const vec4 *>(srec + SR_G);
         const vec4 z4 = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll 8
-        for (int k = g; k < 256; k += 8) Gs4[k] = valid ? src4[k] : z4;
+#pragma unroll 6
+        for (int k = g; k < 240; k += 8) Gs4[k] = valid ? src4[k] : z4;
     }
     warp_sync();
 

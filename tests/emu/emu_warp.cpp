@@ -104,7 +104,7 @@ void emu_init_record(const plen_config *c, float *rec) { init_record(c, rec); }
 static void run_ticks(const DevConfig &dc, const float *tab, float *records, const float *tgt, int n, int n_ticks,
                       const DebugOut *dbg0, int lane) {
     static WarpScratch ws;
-    static std::vector<float> srec, Gs(4 * 1024);
+    static std::vector<float> srec, Gs(4 * 960);
     if (lane == 0) srec.assign((size_t)n * SR_WORDS, 0.0f);
     bar();
     for (int t = 0; t < n_ticks; t++) {
@@ -119,7 +119,7 @@ static void run_ticks(const DevConfig &dc, const float *tab, float *records, con
             const int r = b + (lane >> 3);
             const bool valid = r < n;
             const int rr = valid ? r : 0;
-            solve_tick(dc, srec.data() + (size_t)rr * SR_WORDS, Gs.data() + (lane >> 3) * 1024, records + 96 * rr, lane, valid);
+            solve_tick(dc, srec.data() + (size_t)rr * SR_WORDS, Gs.data() + (lane >> 3) * 960, records + 96 * rr, lane, valid);
             bar();
         }
     }
