@@ -152,6 +152,7 @@ def main():
 
     import torch
     from plen_ml_walk_b200 import _abi
+    from plen_ml_walk_b200.sharding import env_seed, max_over_ranks
     from plen_ml_walk_b200.vec_env import PlenVecEnv
 
     if not torch.cuda.is_available():
@@ -167,7 +168,7 @@ def main():
     E, K, W = args.envs_per_gpu, args.steps, max(3, args.warmup)
     env = PlenVecEnv(E, device=dev)
     gen = torch.Generator(device=dev)
-    gen.manual_seed(rank)
+    gen.manual_seed(env_seed(0, rank))
     acts = [torch.empty((E, 18), device=dev).uniform_(-1, 1, generator=gen) for _ in range(8)]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MiB > 126 MB L2
     env.reset()
@@ -197,10 +198,7 @@ def main():
     gpu_launches = env.launches - launches0
     prof = env.profile_read()
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+    total_ms = max_over_ranks(total_ms, dist, dev)
     value = world * E * K / (total_ms * 1e-3)
 
     # ---- end-to-end leg: HOST pinned buffers through plen_step_host (H2D actions, step, D2H obs/reward/done)
@@ -216,10 +214,7 @@ def main():
         env.step_host(h_act[k % 2], h_obs, h_rew, h_done)
     barrier()
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if dist:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = world * E * Ke / float(te.item())
+    e2e_val = world * E * Ke / max_over_ranks(e2e_s, dist, dev)
 
     if rank == 0:
         peak, peak_src = _peaks()

@@ -1,0 +1,39 @@
+"""Multi-GPU plumbing of the PLEN path: envs are independent (no shared world state, static ground), so they shard by
+env index across ranks with NO collective on the physics path.  torch.distributed is used only
+for the barrier and for the max-over-ranks of the device time (bench.py) -- backend "nccl" on GPUs, "gloo" in the CPU
+tests.
+"""
+from __future__ import annotations
+
+
+def shard_range(n_total: int, rank: int, world: int):
+    """Contiguous block [lo, hi) of env indices owned by `rank`; blocks differ by at most one env."""
+    if not (0 <= rank < world):
+        raise ValueError("rank %d outside world of %d" % (rank, world))
+    base, rem = divmod(int(n_total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def env_seed(seed: int, rank: int) -> int:
+    """Action-stream seed of a rank: distinct per rank, reproducible for a fixed world size."""
+    return int(seed) * 1000003 + int(rank)
+
+
+def max_over_ranks(value: float, dist=None, device=None) -> float:
+    """MAX all-reduce of a host float (device time in ms); identity without a process group."""
+    if dist is None or not dist.is_initialized():
+        return float(value)
+    import torch
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, dist=None, device=None) -> float:
+    if dist is None or not dist.is_initialized():
+        return float(value)
+    import torch
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
