@@ -74,7 +74,8 @@ __device__ __forceinline__ DynSmem &stage_table(const float *tab_g) {
 // First half of a tick, one warp per robot: FK, CRBA, M^-1, v*, contacts, row set-up -> solve record.
 //   actions != NULL : agent-space actions of a new env step; the servo targets are derived (agent_to_env) and kept in tgt
 //   actions == NULL : tgt holds the targets already (NULL = zero targets, the reset pose)
-__global__ void __launch_bounds__(DYN_WPC * 32)
+// 5 CTAs (20 warps) per SM: the register cap (<= 102) costs 16 B of spills outside the hot loops and measured +2.4 %
+__global__ void __launch_bounds__(DYN_WPC * 32, 5)
 k_dyn(const __grid_constant__ DevConfig dc, const __grid_constant__ EnvRanges er, const float *__restrict__ tab_g,
       const float *__restrict__ state, int n, const float *__restrict__ actions, float *__restrict__ tgt,
       float *__restrict__ srec, uint8_t *__restrict__ keys, float *dbg_minv, float *dbg_pos, float *dbg_rot) {
@@ -322,6 +323,10 @@ __global__ void k_gait_ik(const double *__restrict__ params, int n, double *__re
             out[10] = -out[10];
         } else { ok = false; for (int k = 0; k < 18; k++) out[k] = nan; }
         if (bend) for (int k = 0; k < 18; k++) bend[(size_t)g * 18 + k] = out[k];
+    }
+    if (!ok) {   // the reference generator raises for the whole parameter set: no partial trajectory survives
+        for (int k = 0; k < 40 * 18; k++) traj[(size_t)g * 40 * 18 + k] = nan;
+        if (bend) for (int k = 0; k < 18; k++) bend[(size_t)g * 18 + k] = nan;
     }
     if (status) status[g] = ok ? 0 : 1;
 }

@@ -3,7 +3,7 @@
 
 Mirrors plen_bullet/src/trajectory_eval.py:154-300: TrajectoryGenerator().main(), sign map, 20 x step(bend_legs), then
 800 x step(row) with joint_act=True; `done` is ignored there and no metric is computed, so fall = any
-`done` within the 820 steps and distance = final torso_x.  Env 0 uses the default gait; the others a seeded +-10 %
+`dead` (done without timeout) within the 820 steps and distance = final torso_x.  Env 0 uses the default gait; the others a seeded +-10 %
 jitter of height / stride / body_sway / fwd_bias.
 
     python scripts/trajectory_eval_batched.py [--envs 65536] [--seed 0]
@@ -42,11 +42,11 @@ def run(n, seed, device="cuda:0"):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(20):                                   # trajectory_eval.py:276-279
-        _, _, done, _ = env.step(bend)
-        fell |= done
+        _, _, done, info = env.step(bend)
+        fell |= done & ~info["timeout"]          # dead, not the TimeLimit(500) truncation
     for t in range(800):                                  # :282-300
-        _, _, done, _ = env.step(cyc[:, t % 40].contiguous())
-        fell |= done
+        _, _, done, info = env.step(cyc[:, t % 40].contiguous())
+        fell |= done & ~info["timeout"]
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     qpos, _, _ = env.get_state()

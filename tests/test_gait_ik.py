@@ -70,3 +70,27 @@ def test_open_loop_gait_replay_vs_oracle(oracle_lib):
     print("gait replay: obs err median %.2e p90 %.2e max %.2e, contact-flag mismatches %d / %d" %
           (np.median(errs), np.quantile(errs, .9), errs.max(), flags, 2 * n * 140))
     assert np.median(errs) < 1e-4 and flags <= 0.03 * 2 * n * 140
+
+
+def test_config3_free_running_gait_statistics_vs_oracle(oracle_lib):
+    """BASELINE config 3 on a 256-env subset, FREE-RUNNING (no teacher forcing): 20 bend + 800 gait steps of the
+    jittered sinewave gaits; fall rate and final torso_x statistics of the CUDA path vs the float64 oracle."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("teb", os.path.join(os.path.dirname(__file__), "..", "scripts", "trajectory_eval_batched.py"))
+    teb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(teb)
+    n = 256
+    res, gen, env = teb.run(n, seed=0)
+    bend, cyc = gen.bend_legs.cpu().numpy(), gen.cycle.cpu().numpy()
+    o = oracle_lib.PlenOracle(n, joint_act=True, n_threads=16)
+    o.reset()
+    fell = np.zeros(n, dtype=bool)
+    for t in range(820):
+        act = bend if t < 20 else cyc[:, (t - 20) % 40]
+        _, _, d, tmo = o.step(act)
+        fell |= d & ~tmo
+    x = o.get_state()["qpos"][:, 0]
+    print("config 3 (256 envs): GPU fall %.3f x %.4f +- %.4f | oracle fall %.3f x %.4f +- %.4f" %
+          (res["fall_rate"], res["torso_x_mean"], res["torso_x_std"], fell.mean(), x.mean(), x.std()))
+    assert abs(res["fall_rate"] - fell.mean()) <= 0.02
+    assert abs(res["torso_x_mean"] - x.mean()) < 0.02 and abs(res["torso_x_std"] - x.std()) < 0.02
