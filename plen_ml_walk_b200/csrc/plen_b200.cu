@@ -1,9 +1,12 @@
 // plen_b200.cu -- kernels + C ABI of libplen_b200.so (see include/plen_b200.h).  sm_100a only, no CPU path.
 //
-// Launch shape: one warp per robot, 2-5 warps per CTA; the lane-major model table (4 KB) is staged once per CTA in
-// shared memory, each warp owns a ~19 KB scratch (state record, twists, M^-1, constraint-space A rows).  The per-env state
-// record is 96 words = 3 x 128 B lines, word w = 32 k + lane, so every global access of the step is one fully
-// coalesced line per warp.
+// One env step = (k_dyn, k_solve) x substeps + k_post on the caller's stream:
+//   k_dyn   one warp per robot: FK, CRBA, M^-1, v*, contacts, row set-up -> 6.4 KB solve record per robot (HBM)
+//   k_solve eight lanes per robot, four robots per warp: projected Gauss-Seidel in the 30-dim operational space,
+//           delta-v, integration; robots grouped by contact load inside 64-robot tiles
+//   k_post  one warp per robot: observation, done, reward, counters, auto-reset
+// The per-env state record is 96 words = 3 x 128 B lines, word w = 32 k + lane, so the warp-per-robot kernels touch it
+// with fully coalesced lines.
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>

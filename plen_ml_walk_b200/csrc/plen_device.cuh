@@ -1,4 +1,4 @@
-// plen_device.cuh -- warp-per-robot PLEN physics tick + env epilogue (sm_100a device code).
+// plen_device.cuh -- warp-per-robot PLEN dynamics: first half of a physics tick (k_dyn) (sm_100a device code).
 //
 // One warp owns one robot.  Lane l < 24 owns generalized velocity l (0..2 omega_world, 3..5 v_world, 6..23 joints);
 // lane l >= 6 also owns body l-5 / joint l-6 (limb chains at lanes 6..11, 12..17, 18..20, 21..23); lanes 24..31
@@ -10,11 +10,11 @@
 //      (prefix sums of twists / accelerations, suffix sums of body forces)
 //   3. M^-1 by block elimination: 4 limb blocks inverted in parallel (Gauss-Jordan across lanes), 6x6 base Schur
 //      complement inverted redundantly, M^-1 assembled column-major in shared memory
-//   4. v* = v - dt M^-1 C;  sole-vertex contacts vs z = 0;  constraint rows (limits, 18 servo rows, per contact
-//      normal + spin + 2 roll + 2 lateral) rebuilt ON THE FLY from per-lane twists (flat ground => every
-//      Jacobian/response entry is <= 2 FMAs), so no per-row Jacobian storage exists at all
-//   5. projected Gauss-Seidel in Bullet's row order with early exit on the max squared row residual
-//   6. semi-implicit integration (exponential-map quaternion update)
+//   4. v* = v - dt M^-1 C;  sole-vertex contacts vs z = 0;  Y = M^-1 Jfoot^T and Lambda^-1 = Jfoot M^-1 Jfoot^T
+//   5. the SOLVE RECORD: G = [M^-1_jj Y; Y^T Lambda^-1] and the scalars of every constraint row (limits, 18 servo rows,
+//      per contact normal + spin + 2 roll + 2 lateral); flat ground => every contact row is a functional of the foot
+//      twist with <= 3 non-zeros, so no per-row Jacobian storage exists at all
+// plen_solve.cuh (k_solve) then runs the projected Gauss-Seidel, applies delta-v and integrates.
 //
 // The same source is compiled for the host by tests/emu (32 threads + barriers emulate the warp shuffles) so the
 // CPU test suite can check this code against the float64 oracle without a GPU.  That emulation is test-only; the
