@@ -159,6 +159,33 @@ int plen_profile_read(plen_ctx *ctx, float *ms_dyn, float *ms_solve, float *ms_p
 int plen_gait_ik(int device, const double *params_dev, int n_gaits, double *traj_dev, double *bend_dev,
                  uint8_t *status_dev, void *stream);
 
+/* ---- device-resident TD3 pieces (reference: plen_ros/src/plen_ros_helpers/td3.py, driven by plen_bullet/src/plen_td3.py)
+ *
+ * Replay ring: replaces ReplayBuffer (td3.py:122-193).  One transition = 72 floats [s 26 | a 18 | s' 26 | r | done];
+ * `add` appends until `capacity` tuples are stored, then overwrites from index 0 upwards (td3.py:136-147), n tuples per
+ * call; `sample` draws `batch` rows uniformly WITH replacement (td3.py:175) from a counter-based generator keyed by
+ * `seed` (pass a fresh value per call) and returns not_done = 1 - done (td3.py:189-191).  index_dev (nullable) receives
+ * the sampled rows.  All *_dev pointers are caller-owned device memory; calls are stream-ordered. */
+typedef struct plen_replay plen_replay;
+plen_replay *plen_replay_create(long long capacity, int device);
+void plen_replay_destroy(plen_replay *rb);
+long long plen_replay_size(const plen_replay *rb);
+long long plen_replay_ptr(const plen_replay *rb);
+const float *plen_replay_storage(const plen_replay *rb);       /* device pointer to [capacity][72] */
+int plen_replay_add(plen_replay *rb, const float *state_dev, const float *action_dev, const float *next_state_dev,
+                    const float *reward_dev, const uint8_t *done_dev, int n, void *stream);
+int plen_replay_sample(plen_replay *rb, int batch, unsigned long long seed, float *state_dev, float *action_dev,
+                       float *next_state_dev, float *reward_dev, float *not_done_dev, int *index_dev, void *stream);
+
+/* Replaces Actor.forward / TD3Agent.select_action (td3.py:45-57, :243-257) for n observations in one launch:
+ * action = max_action * tanh(W3 relu(W2 relu(W1 s + b1) + b2) + b3), weights in nn.Linear layout (row-major [out][in]:
+ * w1 [256][26], w2 [256][256], w3 [18][256]), float32 throughout.  noise_std > 0 adds the exploration noise of
+ * plen_td3.py:101-104 (N(0, noise_std), then clip to +-max_action), drawn from a counter-based generator keyed by seed. */
+int plen_actor_forward(int device, const float *w1, const float *b1, const float *w2, const float *b2, const float *w3,
+                       const float *b3, const float *obs_dev, int n, float max_action, float noise_std,
+                       unsigned long long seed, float *action_dev, void *stream);
+const char *plen_td3_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

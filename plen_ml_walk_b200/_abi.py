@@ -73,6 +73,8 @@ EXPORTS = (
     "plen_version", "plen_default_config", "plen_create", "plen_destroy", "plen_last_error", "plen_num_envs",
     "plen_reset", "plen_step", "plen_step_host", "plen_get_state", "plen_set_state", "plen_tick",
     "plen_debug_dynamics", "plen_gait_ik", "plen_profile_enable", "plen_profile_read",
+    "plen_replay_create", "plen_replay_destroy", "plen_replay_size", "plen_replay_ptr", "plen_replay_storage",
+    "plen_replay_add", "plen_replay_sample", "plen_actor_forward", "plen_td3_last_error",
 )
 
 _lib = None
@@ -107,6 +109,21 @@ def load_library(path: str = LIB_PATH):
     L.plen_debug_dynamics.argtypes = [vp] * 5
     L.plen_profile_enable.argtypes = [vp, ip]
     L.plen_profile_read.argtypes = [vp] * 5
+    ll, ull = C.c_longlong, C.c_ulonglong
+    L.plen_replay_create.argtypes = [ll, ip]
+    L.plen_replay_create.restype = vp
+    L.plen_replay_destroy.argtypes = [vp]
+    L.plen_replay_destroy.restype = None
+    L.plen_replay_size.argtypes = [vp]
+    L.plen_replay_size.restype = ll
+    L.plen_replay_ptr.argtypes = [vp]
+    L.plen_replay_ptr.restype = ll
+    L.plen_replay_storage.argtypes = [vp]
+    L.plen_replay_storage.restype = vp
+    L.plen_replay_add.argtypes = [vp] * 6 + [ip, vp]
+    L.plen_replay_sample.argtypes = [vp, ip, ull] + [vp] * 7
+    L.plen_actor_forward.argtypes = [ip] + [vp] * 7 + [ip, C.c_float, C.c_float, ull, vp, vp]
+    L.plen_td3_last_error.restype = C.c_char_p
     L.plen_gait_ik.argtypes = [ip, vp, ip, vp, vp, vp, vp]
     _lib = L
     return L

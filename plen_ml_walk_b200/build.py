@@ -7,8 +7,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = os.path.join(HERE, "csrc", "plen_b200.cu")
-DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("plen_device.cuh", "plen_env.cuh", "plen_host_tables.h")] + \
+SRCS = [os.path.join(HERE, "csrc", "plen_b200.cu"), os.path.join(HERE, "csrc", "plen_td3.cu")]
+DEPS = SRCS + [os.path.join(HERE, "csrc", f) for f in ("plen_device.cuh", "plen_solve.cuh", "plen_env.cuh", "plen_host_tables.h")] + \
        [os.path.join(ROOT, "include", "plen_b200.h")]
 OUT = os.path.join(HERE, "libplen_b200.so")
 
@@ -22,7 +22,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if (not force) and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in DEPS):
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-ccbin", "/usr/bin/g++", "-I", ROOT, "-o", OUT, SRC]
+    cmd = [nvcc] + NVCC_FLAGS + ["-ccbin", "/usr/bin/g++", "-I", ROOT, "-o", OUT] + SRCS
     p = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or p.returncode != 0:
         sys.stderr.write(p.stdout + p.stderr)

@@ -1,0 +1,76 @@
+#!/usr/bin/env python
+"""Batched plen_td3 (BASELINE config 4): TD3 with N device-resident PLEN envs and an on-GPU replay ring.
+
+Mirrors plen_bullet/src/plen_td3.py:16-159 with the constants of :22-30 and td3.py:211-219 (start_timesteps 1e4,
+expl_noise 0.1, batch 100, discount 0.99, tau 0.005, policy noise 0.2 clip 0.5, delay 2, Adam 3e-4, replay 1e6):
+random actions until start_timesteps transitions are stored, then actor + N(0, 0.1) noise clipped to +-1;
+done_bool = done and not timeout (plen_td3.py:109-110); the env auto-resets, so next_state of a finished episode is
+info["terminal_obs"].  The reference does ONE gradient step per env step on ONE env; with N envs per vector step the
+update-to-data ratio is a parameter: --updates-per-step U gradient steps per vector step (U2D = U / N).
+
+    python scripts/plen_td3_batched.py [--envs 16384] [--env-steps 1048576] [--updates-per-step 8]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from plen_ml_walk_b200.td3 import ReplayBuffer, TD3Agent
+from plen_ml_walk_b200.vec_env import PlenVecEnv
+
+
+def run(n_envs, total_env_steps, updates_per_step, start_timesteps=10000, expl_noise=0.1, batch_size=100, seed=0,
+        device="cuda:0", replay_size=1000000, learner=True):
+    dev = torch.device(device)
+    torch.manual_seed(seed)
+    env = PlenVecEnv(n_envs, device=dev, seed=seed)
+    agent = TD3Agent(26, 18, 1.0, device=dev)
+    rb = ReplayBuffer(replay_size, device=dev, seed=seed)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    state = env.reset().clone()
+    ep_ret = torch.zeros(n_envs, device=dev)
+    done_count, ret_sum, updates, t = 0, 0.0, 0, 0
+    vec_steps = (total_env_steps + n_envs - 1) // n_envs
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(vec_steps):
+        if t < start_timesteps:
+            action = torch.empty((n_envs, 18), device=dev).uniform_(-1, 1, generator=gen)        # action_space.sample()
+        else:
+            action = agent.select_action(state, expl_noise=expl_noise)                           # plen_td3.py:101-104
+        obs, reward, done, info = env.step(action)
+        done_bool = done & ~info["timeout"]                                                      # plen_td3.py:109-110
+        next_state = torch.where(done[:, None], info["terminal_obs"], obs)
+        rb.add(state, action, next_state, reward, done_bool)
+        ep_ret += reward
+        if bool(done.any()):
+            done_count += int(done.sum())
+            ret_sum += float(ep_ret[done].sum())
+            ep_ret[done] = 0
+        state = obs.clone()
+        t += n_envs
+        if learner and t >= start_timesteps:
+            for _ in range(updates_per_step):
+                agent.train(rb, batch_size)
+                updates += 1
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    return {"envs": n_envs, "env_steps": vec_steps * n_envs, "vector_steps": vec_steps, "updates": updates,
+            "update_to_data": updates / max(1, vec_steps * n_envs), "seconds": dt, "env_steps_per_s": vec_steps * n_envs / dt,
+            "episodes": done_count, "mean_episode_return": ret_sum / max(1, done_count), "replay_len": len(rb),
+            "learner": learner}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs", type=int, default=16384)
+    ap.add_argument("--env-steps", type=int, default=1048576)
+    ap.add_argument("--updates-per-step", type=int, default=8)
+    ap.add_argument("--no-learner", action="store_true")
+    a = ap.parse_args()
+    print(json.dumps(run(a.envs, a.env_steps, a.updates_per_step, learner=not a.no_learner)))

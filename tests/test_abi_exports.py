@@ -21,7 +21,7 @@ def test_every_declared_symbol_is_exported(lib):
     from plen_ml_walk_b200 import _abi
     hdr = open(os.path.join(ROOT, "include", "plen_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    declared = set(re.findall(r"\b(plen_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(plen_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(_abi.EXPORTS), declared ^ set(_abi.EXPORTS)
     for sym in declared:
         assert getattr(lib, sym) is not None

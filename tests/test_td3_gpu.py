@@ -1,0 +1,114 @@
+"""GPU: device replay ring, fused actor-forward kernel and the TD3 update against the reference semantics."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "td3_golden.npz")
+
+
+def _tuples(lo, hi, dev):
+    k = torch.arange(lo, hi, device=dev, dtype=torch.float32)
+    return (k[:, None].expand(-1, 26).contiguous(), (k[:, None] + 0.25).expand(-1, 18).contiguous(),
+            (k[:, None] + 0.5).expand(-1, 26).contiguous(), k.clone(), (k.long() % 3 == 0))
+
+
+def test_replay_ring_matches_reference_order():
+    """Batched adds of ragged sizes reproduce the reference's one-by-one ring (append, then overwrite from index 0)."""
+    from oracle.replay_oracle import ReplayRing
+    from plen_ml_walk_b200.td3 import ReplayBuffer
+    g = np.load(GOLD)
+    dev = torch.device("cuda:0")
+    rb = ReplayBuffer(max_size=3, device=dev)
+    for k in range(5):
+        rb.add(*_tuples(k, k + 1, dev))
+    assert rb.storage()[:, 70].cpu().tolist() == list(g["ring_rewards"]) and rb.ptr == int(g["ring_ptr"])
+    cap = 1000
+    rb, ring = ReplayBuffer(max_size=cap, device=dev), ReplayRing(cap)
+    lo = 0
+    for n in (1, 7, 640, 352, 0, 999, 1000, 2500, 3):        # fills, wraps, and adds larger than the ring
+        rb.add(*_tuples(lo, lo + n, dev))
+        for k in range(lo, lo + n):
+            ring.add((k, k + 0.25, k + 0.5, float(k), float(k % 3 == 0)))
+        lo += n
+        st = rb.storage().cpu().numpy()
+        assert len(rb) == len(ring.storage) and rb.ptr == ring.ptr
+        assert (st[:, 70] == np.array([t[3] for t in ring.storage])).all()
+        assert (st[:, 0] == st[:, 70]).all() and (st[:, 26] == st[:, 70] + 0.25).all() and (st[:, 44] == st[:, 70] + 0.5).all()
+        assert (st[:, 71] == np.array([t[4] for t in ring.storage])).all()
+
+
+def test_replay_sample_is_uniform_with_replacement_and_consistent():
+    from plen_ml_walk_b200.td3 import ReplayBuffer
+    dev = torch.device("cuda:0")
+    rb = ReplayBuffer(max_size=4096, device=dev, seed=1)
+    rb.add(*_tuples(0, 3000, dev))                                  # partially filled: only rows < len may be drawn
+    s, a, s2, r, nd, idx = rb.sample(200000, return_index=True)
+    idx = idx.long()
+    assert int(idx.min()) >= 0 and int(idx.max()) < 3000
+    assert torch.equal(r[:, 0], idx.float()) and torch.equal(s[:, 5], idx.float()) and torch.equal(a[:, 17], idx.float() + 0.25)
+    assert torch.equal(s2[:, 25], idx.float() + 0.5) and torch.equal(nd[:, 0], 1.0 - (idx % 3 == 0).float())
+    counts = torch.bincount(idx, minlength=3000).float()
+    assert counts.min() > 20 and abs(float(counts.mean()) - 200000 / 3000) < 1e-3      # every row reachable
+    assert float(counts.std()) < 1.3 * (200000 / 3000) ** 0.5                           # Poisson-like spread
+    i1 = rb.sample(100, return_index=True)[5]
+    i2 = rb.sample(100, return_index=True)[5]
+    assert not torch.equal(i1, i2)                                                      # fresh draw per call
+    with pytest.raises(RuntimeError):
+        ReplayBuffer(max_size=8, device=dev).sample(4)                                  # empty buffer (np.random.randint(0, 0) raises)
+
+
+def test_actor_forward_kernel_vs_reference_checkpoint_and_torch():
+    from plen_ml_walk_b200.td3 import Actor, actor_forward
+    g = np.load(GOLD)
+    dev = torch.device("cuda:0")
+    a = Actor().to(dev)
+    a.load_state_dict({k: torch.from_numpy(g["actor_" + k.replace(".", "_")]) for k in a.state_dict().keys()})
+    out = actor_forward(a, torch.from_numpy(g["obs"]).to(dev)).cpu().numpy()
+    assert np.abs(out - g["actor_out"]).max() < 1e-5                 # vs the reference Actor on the shipped checkpoint
+    torch.manual_seed(0)
+    b = Actor(max_action=1.0).to(dev)
+    for n in (1, 31, 32, 33, 4096, 70001):                           # ragged tails of the 32-row CTA tile
+        obs = torch.randn(n, 26, device=dev)
+        with torch.no_grad():
+            ref = b(obs)
+        got = actor_forward(b, obs)
+        assert float((got - ref).abs().max()) < 1e-5, n
+    # exploration noise of plen_td3.py:101-104: N(0, 0.1) added, then clipped to +-max_action
+    obs = torch.zeros(200000, 26, device=dev)
+    clean = actor_forward(b, obs)
+    noisy = actor_forward(b, obs, noise_std=0.1, seed=7)
+    d = (noisy - clean)
+    inside = noisy.abs() < 0.999
+    assert float(noisy.abs().max()) <= 1.0
+    assert abs(float(d[inside].mean())) < 2e-3 and abs(float(d[inside].std()) - 0.1) < 5e-3
+    assert not torch.equal(noisy, actor_forward(b, obs, noise_std=0.1, seed=8))
+
+
+def test_td3_update_follows_reference_rule():
+    """TD3Agent.train (td3.py:259-356): critic step every call, actor + Polyak every policy_freq calls; the critic loss on
+    a fixed synthetic buffer goes down."""
+    from plen_ml_walk_b200.td3 import ReplayBuffer, TD3Agent
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    agent = TD3Agent(device=dev)
+    rb = ReplayBuffer(max_size=5000, device=dev)
+    s = torch.randn(5000, 26, device=dev)
+    a = torch.rand(5000, 18, device=dev) * 2 - 1
+    rb.add(s, a, s + 0.01, -(a ** 2).sum(1), torch.zeros(5000, dtype=torch.bool, device=dev))
+    actor0 = [p.clone() for p in agent.actor.parameters()]
+    tgt0 = [p.clone() for p in agent.critic_target.parameters()]
+    al, cl0 = agent.train(rb, 100)
+    assert al is None and all(torch.equal(p, q) for p, q in zip(agent.actor.parameters(), actor0))      # delayed policy update
+    assert all(torch.equal(p, q) for p, q in zip(agent.critic_target.parameters(), tgt0))
+    al, _ = agent.train(rb, 100)
+    assert al is not None and not all(torch.equal(p, q) for p, q in zip(agent.actor.parameters(), actor0))
+    d = [float((p - q).abs().max()) for p, q in zip(agent.critic_target.parameters(), tgt0)]
+    assert 0 < max(d) < 0.01                                                                              # tau = 0.005
+    losses = [float(agent.train(rb, 100)[1]) for _ in range(300)]
+    assert np.mean(losses[-50:]) < 0.5 * float(cl0)
+    act = agent.select_action(s[:1000])
+    with torch.no_grad():
+        assert float((act - agent.actor(s[:1000])).abs().max()) < 1e-5
