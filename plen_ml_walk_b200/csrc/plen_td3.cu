@@ -213,8 +213,10 @@ const float *plen_replay_storage(const plen_replay *rb) { return rb ? rb->d_stor
 
 int plen_replay_add(plen_replay *rb, const float *state_dev, const float *action_dev, const float *next_state_dev,
                     const float *reward_dev, const uint8_t *done_dev, int n, void *stream) {
-    if (!rb || !state_dev || !action_dev || !next_state_dev || !reward_dev || !done_dev || n < 0)
-        return td3_fail(PLEN_E_ARG, "plen_replay_add: bad arguments");
+    if (!rb || n < 0) return td3_fail(PLEN_E_ARG, "plen_replay_add: bad arguments");
+    if (n == 0) return PLEN_OK;        // an empty batch is a no-op (its buffers may be NULL)
+    if (!state_dev || !action_dev || !next_state_dev || !reward_dev || !done_dev)
+        return td3_fail(PLEN_E_ARG, "plen_replay_add: NULL buffer");
     TCK(cudaSetDevice(rb->device));
     cudaStream_t st = (cudaStream_t)stream;
     int off = 0;
