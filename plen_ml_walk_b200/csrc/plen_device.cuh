@@ -83,11 +83,15 @@ struct DevConfig {
 };
 
 // ---- solve record: per robot, per tick, written by k_dyn and consumed by k_solve (global memory, words)
-// operational-space index i of x (32 slots): 0..17 joints, 18..23 right-foot twist, 24..25 unused, 26..31 left-foot twist
+// operational-space index i of x (32 slots): 0..17 joints, 18..23 right-foot twist, 24..25 unused, 26..31 left-foot twist;
+// word i of a 32-word row holds entry i, so solver lane g = i >> 3 (four lanes per robot) owns entries 8 g .. 8 g + 7 and
+// each foot's twist lives in ONE lane (lane 2: right, lane 3: left; component c at slot 2 + c of either).
+// Servo / limit rows are kept in VELOCITY units (impulse times G_jj): joint columns of G and B are pre-divided by G_jj, so
+// the row update needs no per-row multiply and its velocity change (the residual term) is the broadcast value itself.
 enum {
     SR_G = 0,          // 30 columns (18 joints, 6 right-foot, 6 left-foot components) x 32 words (rows i) of G
     SR_B = 960,        // 6 rows x 32 words: base rows of M^-1 J^T in the same word order
-    SR_MRHS = 1152, SR_MDINV = 1184, SR_LDIR = 1216, SR_LRHS = 1248, SR_VSTAR = 1280, SR_Q = 1312,   // 32 words each
+    SR_MRHS = 1152, SR_MD = 1184, SR_LDIR = 1216, SR_LRHS = 1248, SR_VSTAR = 1280, SR_Q = 1312,   // 32 words each
     SR_CRHS = 1344, SR_CDINV = 1408, SR_CD = 1472,   // 64 words each: [contact slot q = 4 foot + k][solver lane g]
     SR_PT = 1536,      // 8 x (x, y, z, distance): k-th ACTIVE contact point of each foot, relative to the base origin
     SR_LAMC = 1568,    // 8 cached normal impulses, same slot order
@@ -630,11 +634,13 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
         const float m_d = ws.minv[lane][lane];
         m_dinv = (m_d > 1.1920929e-7f) ? rcp_(m_d) : 0.0f;
         const float desired = cfg.kp_over_dt * (L.tgt - L.q) + cfg.one_minus_kd * vstar;
-        m_rhs = (desired - vstar) * m_dinv;
+        m_rhs = (m_dinv > 0.0f) ? (desired - vstar) : 0.0f;          // velocity units
         const float lo = tab[T_LOWER * 32 + lane], hi = tab[T_UPPER * 32 + lane];
         const float pen_lo = L.q - lo, pen_hi = hi - L.q;
-        if (pen_lo <= 0.0f) { l_dir = 1.0f; l_rhs = (-pen_lo * cfg.erp_joint_over_dt - vstar) * m_dinv; }
-        else if (pen_hi <= 0.0f) { l_dir = -1.0f; l_rhs = (-pen_hi * cfg.erp_joint_over_dt + vstar) * m_dinv; }
+        if (m_dinv > 0.0f) {
+            if (pen_lo <= 0.0f) { l_dir = 1.0f; l_rhs = -pen_lo * cfg.erp_joint_over_dt - vstar; }
+            else if (pen_hi <= 0.0f) { l_dir = -1.0f; l_rhs = -pen_hi * cfg.erp_joint_over_dt + vstar; }
+        }
     }
     // ---- foot twists at v*: Vs_f = Jfoot_f v*;  Y stash;  Lambda^-1 = Jfoot M^-1 Jfoot^T (12 x 12)
     float Vs[2][6];
@@ -670,10 +676,10 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
         warp_sync();
     }
 
-    // ---- G (30 columns x 32 words) and B (6 rows x 32 words): word w of a column = entry i(w) = (w >> 2) + 8 (w & 3),
-    //      i.e. the float4 of solver lane g = w >> 2 holds entries g, 8+g, 16+g, 24+g
+    // ---- G (30 columns x 32 words) and B (6 rows x 32 words): word w of a column = entry i = w; joint columns are
+    //      divided by their diagonal entry (velocity-unit servo rows, see the SR_ enum)
     {
-        const int i = (lane >> 2) + 8 * (lane & 3);
+        const int i = lane;
         const bool ij = i < 18, ic = (i >= 18 && i < 24) || i >= 26;
         const int fa = (i >= 26) ? 1 : 0, a6 = fa ? i - 26 : i - 18;
         const float(*Ya)[8] = fa ? ws.gg : ws.kk;
@@ -682,7 +688,7 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
             float v = 0.0f;
             if (ij) v = ws.minv[6 + c][6 + i];
             else if (ic) v = Ya[6 + c][a6];
-            G[c * 32 + lane] = v;
+            G[c * 32 + lane] = v * shfl(m_dinv, 6 + c);
         }
         for (int c = 18; c < 30; c++) {
             const int fb = (c >= 24) ? 1 : 0, b6 = c - 18 - 6 * fb;
@@ -692,20 +698,21 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
             else if (ic && man_new) v = ws.lin[fa * 6 + a6][c - 18];
             G[c * 32 + lane] = v;
         }
+        // per-joint scalars in the same word order (entries >= 18 are zero)
+        const int src = ij ? 6 + i : 0;
+        const float s_rhs = shfl(m_rhs, src), s_dinv = shfl(m_dinv, src), s_ldir = shfl(l_dir, src),
+                    s_lrhs = shfl(l_rhs, src), s_vs = shfl(vstar, src), s_q = shfl(L.q, src),
+                    s_d = shfl(is_joint ? ws.minv[lane][lane] : 0.0f, src);
         float *Bm = srec + SR_B;
 #pragma unroll
         for (int k = 0; k < 6; k++) {
             float v = 0.0f;
-            if (ij) v = ws.minv[6 + i][k];
+            if (ij) v = ws.minv[6 + i][k] * s_dinv;
             else if (ic) v = Ya[k][a6];
             Bm[k * 32 + lane] = v;
         }
-        // per-joint scalars in the same word order (entries >= 18 are zero)
-        const int src = ij ? 6 + i : 0;
-        const float s_rhs = shfl(m_rhs, src), s_dinv = shfl(m_dinv, src), s_ldir = shfl(l_dir, src),
-                    s_lrhs = shfl(l_rhs, src), s_vs = shfl(vstar, src), s_q = shfl(L.q, src);
         srec[SR_MRHS + lane] = ij ? s_rhs : 0.0f;
-        srec[SR_MDINV + lane] = ij ? s_dinv : 0.0f;
+        srec[SR_MD + lane] = (ij && s_dinv > 0.0f) ? s_d : 0.0f;
         srec[SR_LDIR + lane] = ij ? s_ldir : 0.0f;
         srec[SR_LRHS + lane] = ij ? s_lrhs : 0.0f;
         srec[SR_VSTAR + lane] = ij ? s_vs : 0.0f;

@@ -1,22 +1,24 @@
 // plen_solve.cuh -- second half of a physics tick (k_solve): projected Gauss-Seidel over the rows set up by
 // tick_dynamics, then delta-v and semi-implicit integration.  sm_100a device code (also compiled by tests/emu).
 //
-// Mapping: EIGHT lanes per robot, four robots per warp.  The solver state of a robot is the 30-vector
-//   x = [18 joint velocity changes; right-foot twist change (6); left-foot twist change (6)]
-// spread over the 8 lanes g of its group as four registers s[slot] = x[g + 8 slot]:
-//   s[0] = joint g      s[1] = joint 8+g      s[2] = joint 16+g (g < 2) | right-foot component g-2 (g >= 2)
-//   s[3] = left-foot component g-2 (g >= 2)
-// Contact points are COMPACTED per foot (slot q = 4 f + k = k-th active point of foot f), so a warp only loops to the
-// largest active-point count among its four robots; k_solve additionally sorts robots by contact load inside 64-robot
-// tiles so that the four robots of a warp have similar counts.
-// foot twist components: 0..2 angular (wx wy wz), 3..5 linear (vx vy vz) about the base origin, world axes.
-// A row update with impulse change delta is   s += (float4 of a column of G, one LDS.128) * delta   on every lane;
-// the owner lane of a row (the lane whose register holds the row's "own" velocity component) computes the candidate.
+// Mapping: FOUR lanes per robot, eight robots per warp.  The solver state of a robot is the 32-slot vector
+//   x = [18 joint velocity changes; right-foot twist change (6); 2 unused; left-foot twist change (6)]
+// and lane g of the robot holds the eight consecutive entries s[k] = x[8 g + k]:
+//   lane 0: joints 0..7    lane 1: joints 8..15    lane 2: joints 16, 17 + right-foot twist    lane 3: -, - + left-foot twist
+// so either foot's twist (wx wy wz vx vy vz about the base origin, world axes) sits in slots 2..7 of ONE lane.  That lane
+// owns every contact row of its foot: the row velocity is a local combination of its own registers (no gather), it
+// computes the clamped candidate and broadcasts the impulse change with one SHFL.
+// A row update with impulse change delta is   s += (8 entries of a column of G, two LDS.128) * delta   = four packed
+// FFMA2 on every lane.  Servo rows are kept in velocity units (joint columns of G are pre-divided by G_jj in k_dyn):
+// candidate = rhs - s, bounds (lo, hi) = -+ max impulse * G_jj minus the accumulated row value, and the row's velocity
+// change -- the residual term -- is the broadcast value itself.
+// Contact points are COMPACTED per foot (slot k = k-th active point), so a warp only loops to the largest active-point
+// count among its eight robots; k_rank sorts robots by contact load so that the robots of a warp have similar counts.
 // Row order, clamps, friction cone, warm start and early exit follow Bullet's btMultiBodyConstraintSolver as restated
 // in oracle/plen_oracle.c (the parity checker): per iteration [limits, servos] (alternating direction), contact
 // normals, spinning rows, rolling rows, lateral pairs with the implicit cone; exit when the largest squared row
-// velocity change of the iteration is <= residual_threshold.  A robot that has converged is frozen (its row scalars are
-// zeroed, so every later update is exactly zero) while the other robots of the warp keep iterating.
+// velocity change of the iteration is <= residual_threshold.  A robot that has converged is frozen (its bounds / row
+// scalars are zeroed, so every later update is exactly zero) while the other robots of the warp keep iterating.
 #pragma once
 
 #include "plen_device.cuh"
@@ -29,14 +31,15 @@ struct __align__(16) vec4 { float x, y, z, w; };
 struct vec4 { float x, y, z, w; };
 #endif
 
-PLEN_DEV float sel3(const float *a, int k) { return (k == 0) ? a[0] : ((k == 1) ? a[1] : a[2]); }
+// words of shared memory per robot: 30 columns x 32 words, plus one float4 so that the two robots of a quarter-warp
+// hit disjoint banks with their LDS.128 (robot stride = 16 B mod 128 B)
+#define PLEN_GS_WORDS 964
+#define PLEN_SOLVE_ROBOTS 8      // robots per warp
 
-// solver lane that holds twist component k of either foot
-#define PLEN_LN(f, k) (2 + (k))
 // G column of twist component k of foot f
 #define PLEN_COL(f, k) (18 + 6 * (f) + (k))
 
-// s01 += (x0, x1) * d  as one packed FFMA2 (sm_100a fma.rn.f32x2 with a broadcast scalar multiplier)
+// (a0, a1) += (x0, x1) * d  as one packed FFMA2 (sm_100a fma.rn.f32x2 with a broadcast scalar multiplier)
 PLEN_DEV void fma2(float &a0, float &a1, float x0, float x1, float d) {
 #ifndef PLEN_HOST_EMU
     asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%0, %1}; mov.b64 rb, {%2, %3}; mov.b64 rc, {%4, %4};\n\t"
@@ -47,111 +50,156 @@ PLEN_DEV void fma2(float &a0, float &a1, float x0, float x1, float d) {
 #endif
 }
 
-struct SolveState {
-    float s[4];
-    float res;
-};
-
-PLEN_DEV void apply_col(SolveState &S, const vec4 *Gs4, int g, int c, float db) {
-    const vec4 v = Gs4[c * 8 + g];
-    fma2(S.s[0], S.s[1], v.x, v.y, db);
-    fma2(S.s[2], S.s[3], v.z, v.w, db);
+PLEN_DEV void apply_col(float (&s)[8], const vec4 *Gl, int c, float db) {
+    const vec4 a = Gl[c * 8], b = Gl[c * 8 + 1];
+    fma2(s[0], s[1], a.x, a.y, db);
+    fma2(s[2], s[3], a.z, a.w, db);
+    fma2(s[4], s[5], b.x, b.y, db);
+    fma2(s[6], s[7], b.z, b.w, db);
 }
 
-// One robot = lanes (lane & 24) .. +7 of the warp.  srec: this robot's solve record (global); Gs: this robot's 960-word
-// shared staging area; state: this robot's 96-word state record (global), updated in place.
+PLEN_DEV void load8(const float *p, float (&o)[8]) {
+    const vec4 a = *reinterpret_cast<const vec4 *>(p), b = *reinterpret_cast<const vec4 *>(p + 4);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+
+// One robot = lanes (lane & 28) .. +3 of the warp.  srec: this robot's solve record (global); Gs: this robot's
+// PLEN_GS_WORDS shared staging area; state: this robot's 96-word state record (global), updated in place.
 PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, float *Gs, float *__restrict__ state,
                          int lane, bool valid) {
-    const int g = lane & 7, gb = lane & 24;
+    const int g = lane & 3, gb = lane & 28;
 #define GSH(v, l) shfl((v), gb | (l))
-    vec4 *Gs4 = reinterpret_cast<vec4 *>(Gs);
     {
+        vec4 *dst4 = reinterpret_cast<vec4 *>(Gs);
         const vec4 *src4 = reinterpret_cast<const vec4 *>(srec + SR_G);
         const vec4 z4 = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll 6
-        for (int k = g; k < 240; k += 8) Gs4[k] = valid ? src4[k] : z4;
+#pragma unroll 10
+        for (int k = g; k < 240; k += 4) dst4[k] = valid ? src4[k] : z4;
     }
     warp_sync();
+    const vec4 *Gl = reinterpret_cast<const vec4 *>(Gs) + 2 * g;      // this lane's 8 rows of column c: Gl[8 c], Gl[8 c + 1]
 
-    // ---- per-lane row scalars
-    float m_rhs[3] = {0, 0, 0}, m_dinv[3] = {0, 0, 0}, m_d[3] = {0, 0, 0}, m_lam[3] = {0, 0, 0};
-    float l_dir[3] = {0, 0, 0}, l_rhs[3] = {0, 0, 0}, l_lam[3] = {0, 0, 0};
+    // ---- servo rows of this lane (entries >= 18 carry zeros): velocity-unit rhs and bounds
+    float m_rhs[8], m_lo[8], m_hi[8];
+    unsigned limbits = 0;          // bit k: joint 8 g + k is beyond a URDF limit (its limit row exists this tick)
     unsigned man = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) m_rhs[k] = m_lo[k] = m_hi[k] = 0.0f;
     if (valid) {
-        vec4 t;
-        t = *reinterpret_cast<const vec4 *>(srec + SR_MRHS + 4 * g); m_rhs[0] = t.x; m_rhs[1] = t.y; m_rhs[2] = t.z;
-        t = *reinterpret_cast<const vec4 *>(srec + SR_MDINV + 4 * g); m_dinv[0] = t.x; m_dinv[1] = t.y; m_dinv[2] = t.z;
-        t = *reinterpret_cast<const vec4 *>(srec + SR_LDIR + 4 * g); l_dir[0] = t.x; l_dir[1] = t.y; l_dir[2] = t.z;
-        t = *reinterpret_cast<const vec4 *>(srec + SR_LRHS + 4 * g); l_rhs[0] = t.x; l_rhs[1] = t.y; l_rhs[2] = t.z;
-        m_d[0] = Gs[g * 32 + 4 * g];                 // G[j][j], j = g
-        m_d[1] = Gs[(8 + g) * 32 + 4 * g + 1];       // j = 8 + g
-        m_d[2] = (g < 2) ? Gs[(16 + g) * 32 + 4 * g + 2] : 0.0f;
+        float d[8], ld[8];
+        load8(srec + SR_MRHS + 8 * g, m_rhs);
+        load8(srec + SR_MD + 8 * g, d);
+        load8(srec + SR_LDIR + 8 * g, ld);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            m_hi[k] = cfg.motor_imp * d[k];
+            m_lo[k] = -m_hi[k];
+            limbits |= (ld[k] != 0.0f) ? (1u << k) : 0u;
+        }
         man = (unsigned)srec[SR_BASE + 13];
     }
-    // active-point counts per foot: this robot's and the largest among the four robots of the warp
+    // active-point counts per foot: this robot's and the largest among the robots of the warp
     const int n0 = popc_(man & 15u), n1 = popc_((man >> 4) & 15u);
     const int nmax0 = (int)redux_max((unsigned)n0), nmax1 = (int)redux_max((unsigned)n1);
     const bool man_any = (nmax0 | nmax1) != 0;
-    const unsigned lim_any = redux_or(((l_dir[0] != 0.0f) ? (1u << g) : 0u) | ((l_dir[1] != 0.0f) ? (256u << g) : 0u) |
-                                      ((l_dir[2] != 0.0f) ? (65536u << g) : 0u));
-    float c_rhs[8], c_dinv[8], c_d[8], c_lam[8], lamN[8], px[8], py[8], pz[8];
+    const unsigned lim_any = redux_or(limbits << (8 * g));       // joint j <-> bit j (lanes 0..2 only carry joints)
+    float l_lam[8];                                              // limit-row impulses (velocity units); rare path only
 #pragma unroll
-    for (int p = 0; p < 8; p++) { c_rhs[p] = c_dinv[p] = c_d[p] = c_lam[p] = lamN[p] = px[p] = py[p] = pz[p] = 0.0f; }
+    for (int k = 0; k < 8; k++) l_lam[k] = 0.0f;
+
+    // ---- contact rows of this lane's foot (lane 2: right, lane 3: left; lanes 0, 1 hold zeros):
+    //      [point k][component c]: c = 0 roll(wx) 1 roll(wy) 2 spin(wz) 3 lateral B (vx) 4 lateral A (vy) 5 normal (vz)
+    float c_rhs[4][6], c_dinv[4][6], c_d[4][6], c_lam[4][6];
+    float px[8], py[8], pz[8];     // all eight compacted points (every lane scales the columns of either foot)
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int c = 0; c < 6; c++) c_rhs[k][c] = c_dinv[k][c] = c_d[k][c] = c_lam[k][c] = 0.0f;
+#pragma unroll
+    for (int p = 0; p < 8; p++) px[p] = py[p] = pz[p] = 0.0f;
     if (man_any && valid) {
 #pragma unroll
         for (int p = 0; p < 8; p++) {
-            c_rhs[p] = srec[SR_CRHS + 8 * p + g];
-            c_dinv[p] = srec[SR_CDINV + 8 * p + g];
-            c_d[p] = srec[SR_CD + 8 * p + g];
             const vec4 t = *reinterpret_cast<const vec4 *>(srec + SR_PT + 4 * p);
             px[p] = t.x; py[p] = t.y; pz[p] = t.z;
-            lamN[p] = srec[SR_LAMC + p] * cfg.warm;      // zero for unused slots
+        }
+        if (g >= 2) {
+            const int f = g - 2;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int o = 8 * (4 * f + k) + 2;
+#pragma unroll
+                for (int c = 0; c < 6; c++) {
+                    c_rhs[k][c] = srec[SR_CRHS + o + c];
+                    c_dinv[k][c] = srec[SR_CDINV + o + c];
+                    c_d[k][c] = srec[SR_CD + o + c];
+                }
+                c_lam[k][5] = srec[SR_LAMC + 4 * f + k] * cfg.warm;      // zero for unused slots
+            }
         }
     }
 
-    SolveState S;
-    S.s[0] = S.s[1] = S.s[2] = S.s[3] = 0.0f;
-    S.res = 0.0f;
+    float s[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) s[k] = 0.0f;
+    float res = 0.0f, resF = 0.0f;
 
-#define NORMAL_COLUMN(p, f, db)                                                   \
-    {                                                                             \
-        apply_col(S, Gs4, g, PLEN_COL(f, 0), py[p] * (db));                       \
-        apply_col(S, Gs4, g, PLEN_COL(f, 1), -px[p] * (db));                      \
-        apply_col(S, Gs4, g, PLEN_COL(f, 5), (db));                               \
+#define NORMAL_COLUMN(p, f, db)                              \
+    {                                                        \
+        apply_col(s, Gl, PLEN_COL(f, 0), py[p] * (db));      \
+        apply_col(s, Gl, PLEN_COL(f, 1), -px[p] * (db));     \
+        apply_col(s, Gl, PLEN_COL(f, 5), (db));              \
     }
 
     // ---- warm start of the normal rows from the cached impulses
     if (man_any) {
 #pragma unroll
         for (int p = 0; p < 8; p++)
-            if ((p & 3) < ((p >> 2) ? nmax1 : nmax0)) NORMAL_COLUMN(p, (p >> 2), lamN[p]);
+            if ((p & 3) < ((p >> 2) ? nmax1 : nmax0)) {
+                const float db_ = GSH(c_lam[p & 3][5], 2 + (p >> 2));
+                NORMAL_COLUMN(p, (p >> 2), db_);
+            }
     }
 
-#define SERVO_ROW(slot, l)                                                                              \
-    {                                                                                                   \
-        const float x_ = fmaf(-S.s[slot], m_dinv[slot], m_rhs[slot]);                                   \
-        const float dl_ = fminf(fmaxf(x_, -cfg.motor_imp - m_lam[slot]), cfg.motor_imp - m_lam[slot]); \
-        const float db_ = GSH(dl_, l);                                                                  \
-        if (g == (l)) { m_lam[slot] += dl_; S.res = fmaxf(S.res, fabsf(dl_ * m_d[slot])); }             \
-        apply_col(S, Gs4, g, 8 * (slot) + (l), db_);                                                    \
+    // servo row of joint 8 b + k (owner lane b)
+#define SERVO_ROW(b, k)                                                \
+    {                                                                  \
+        const float dl_ = fminf(fmaxf(m_rhs[k] - s[k], m_lo[k]), m_hi[k]); \
+        const float db_ = GSH(dl_, b);                                 \
+        if (g == (b)) { m_lo[k] -= dl_; m_hi[k] -= dl_; }              \
+        res = fmaxf(res, fabsf(db_));                                  \
+        apply_col(s, Gl, 8 * (b) + (k), db_);                          \
     }
 
-    // spinning / rolling row of point p: own component k of foot f, friction coefficient mu
-#define TORSION_ROW(p, f, k, mu)                                                                \
-    {                                                                                           \
-        const float x_ = fmaf(-S.s[2 + (f)], c_dinv[p], c_rhs[p]);                              \
-        const float lim_ = (mu) * lamN[p];                                                      \
-        float dl_ = fminf(fmaxf(x_, -lim_ - c_lam[p]), lim_ - c_lam[p]);                        \
-        dl_ = (lamN[p] > 0.0f) ? dl_ : 0.0f;   /* row skipped while the normal impulse is not positive */ \
-        const float db_ = GSH(dl_, PLEN_LN(f, k));                                              \
-        if (g == PLEN_LN(f, k)) { c_lam[p] += dl_; S.res = fmaxf(S.res, fabsf(dl_ * c_d[p])); } \
-        apply_col(S, Gs4, g, PLEN_COL(f, k), db_);                                              \
+    // joint-limit row of joint 8 b + k (rare: the joint is beyond +-1.7 rad); lower bound 0, upper bound 100 (impulse units)
+#define LIMIT_ROW(b, k)                                                                  \
+    {                                                                                    \
+        const float ldir_ = srec[SR_LDIR + 8 * g + (k)], up_ = 100.0f * srec[SR_MD + 8 * g + (k)]; \
+        const float x_ = srec[SR_LRHS + 8 * g + (k)] - ldir_ * s[k];                     \
+        const float nl_ = alive ? clampf(l_lam[k] + x_, 0.0f, up_) : l_lam[k];           \
+        const float dl_ = (nl_ - l_lam[k]) * ldir_;                                      \
+        const float db_ = GSH(dl_, b);                                                   \
+        if (g == (b)) l_lam[k] = nl_;                                                    \
+        res = fmaxf(res, fabsf(db_));                                                    \
+        apply_col(s, Gl, 8 * (b) + (k), db_);                                            \
+    }
+
+    // spinning / rolling row of point k of foot f: own twist component c, friction coefficient mu
+#define TORSION_ROW(k, f, c, mu)                                                                          \
+    {                                                                                                     \
+        const float x_ = fmaf(-s[2 + (c)], c_dinv[k][c], c_rhs[k][c]);                                    \
+        const float lim_ = (mu) * c_lam[k][5];                                                            \
+        float dl_ = fminf(fmaxf(x_, -lim_ - c_lam[k][c]), lim_ - c_lam[k][c]);                            \
+        dl_ = (c_lam[k][5] > 0.0f) ? dl_ : 0.0f;   /* row skipped while the normal impulse is not positive */ \
+        const float db_ = GSH(dl_, 2 + (f));                                                              \
+        if (g == 2 + (f)) { c_lam[k][c] += dl_; resF = fmaxf(resF, fabsf(dl_ * c_d[k][c])); }             \
+        apply_col(s, Gl, PLEN_COL(f, c), db_);                                                            \
     }
 
     bool alive = valid;
     int my_iters = 0;
     for (int it = 0; it < cfg.iterations; it++) {
-        S.res = 0.0f;
+        res = 0.0f; resF = 0.0f;
         const bool fwd = (it & 1) != 0;
         // ---- non-contact rows: list = [limits in joint order, servos in joint order]; odd iterations forward, even reversed
         for (int half = 0; half < 2; half++) {
@@ -161,34 +209,32 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
                 while (msk) {
                     const int j = fwd ? lowest_bit(msk) : highest_bit(msk);
                     msk &= ~(1u << j);
-                    const int slot = j >> 3, l = j & 7;
-                    const float ldir = sel3(l_dir, slot), llam = sel3(l_lam, slot);
-                    const float x_ = sel3(l_rhs, slot) - (ldir * sel3(S.s, slot)) * sel3(m_dinv, slot);
-                    const float nl = clampf(llam + x_, 0.0f, 100.0f);
-                    const float dl_ = nl - llam;
-                    const float db_ = GSH(dl_ * ldir, l);
-                    if (g == l) {
-                        l_lam[0] = (slot == 0) ? nl : l_lam[0];
-                        l_lam[1] = (slot == 1) ? nl : l_lam[1];
-                        l_lam[2] = (slot == 2) ? nl : l_lam[2];
-                        S.res = fmaxf(S.res, fabsf(dl_ * sel3(m_d, slot)));
+                    const int b = j >> 3;
+                    switch (j & 7) {
+                        case 0: LIMIT_ROW(b, 0); break;
+                        case 1: LIMIT_ROW(b, 1); break;
+                        case 2: LIMIT_ROW(b, 2); break;
+                        case 3: LIMIT_ROW(b, 3); break;
+                        case 4: LIMIT_ROW(b, 4); break;
+                        case 5: LIMIT_ROW(b, 5); break;
+                        case 6: LIMIT_ROW(b, 6); break;
+                        default: LIMIT_ROW(b, 7); break;
                     }
-                    apply_col(S, Gs4, g, j, db_);
                 }
             } else if (fwd) {
 #pragma unroll
-                for (int l = 0; l < 8; l++) SERVO_ROW(0, l);
+                for (int k = 0; k < 8; k++) SERVO_ROW(0, k);
 #pragma unroll
-                for (int l = 0; l < 8; l++) SERVO_ROW(1, l);
+                for (int k = 0; k < 8; k++) SERVO_ROW(1, k);
 #pragma unroll
-                for (int l = 0; l < 2; l++) SERVO_ROW(2, l);
+                for (int k = 0; k < 2; k++) SERVO_ROW(2, k);
             } else {
 #pragma unroll
-                for (int l = 1; l >= 0; l--) SERVO_ROW(2, l);
+                for (int k = 1; k >= 0; k--) SERVO_ROW(2, k);
 #pragma unroll
-                for (int l = 7; l >= 0; l--) SERVO_ROW(1, l);
+                for (int k = 7; k >= 0; k--) SERVO_ROW(1, k);
 #pragma unroll
-                for (int l = 7; l >= 0; l--) SERVO_ROW(0, l);
+                for (int k = 7; k >= 0; k--) SERVO_ROW(0, k);
             }
         }
         if (man_any) {
@@ -196,41 +242,36 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
 #pragma unroll
             for (int p = 0; p < 8; p++) {
                 if ((p & 3) >= ((p >> 2) ? nmax1 : nmax0)) continue;
-                const int f = p >> 2;
-                const float wx = GSH(S.s[2 + f], PLEN_LN(f, 0)), wy = GSH(S.s[2 + f], PLEN_LN(f, 1));
-                const float r_ = fmaf(wx, py[p], fmaf(-wy, px[p], S.s[2 + f]));
-                const float x_ = fmaf(-r_, c_dinv[p], c_rhs[p]);
-                const float dl_ = fmaxf(x_, -lamN[p]);
-                const float db_ = GSH(dl_, PLEN_LN(f, 5));
-                lamN[p] += db_;
-                if (g == PLEN_LN(f, 5)) S.res = fmaxf(S.res, fabsf(dl_ * c_d[p]));
+                const int f = p >> 2, k = p & 3;
+                const float r_ = fmaf(s[2], py[p], fmaf(-s[3], px[p], s[7]));
+                const float x_ = fmaf(-r_, c_dinv[k][5], c_rhs[k][5]);
+                const float dl_ = fmaxf(x_, -c_lam[k][5]);
+                const float db_ = GSH(dl_, 2 + f);
+                if (g == 2 + f) { c_lam[k][5] += dl_; resF = fmaxf(resF, fabsf(dl_ * c_d[k][5])); }
                 NORMAL_COLUMN(p, f, db_);
             }
             // ---- all spinning rows, then the rolling rows point by point (t1, t2)
 #pragma unroll
             for (int p = 0; p < 8; p++) {
                 if ((p & 3) >= ((p >> 2) ? nmax1 : nmax0)) continue;
-                TORSION_ROW(p, (p >> 2), 2, cfg.mu_spinning);
+                TORSION_ROW((p & 3), (p >> 2), 2, cfg.mu_spinning);
             }
 #pragma unroll
             for (int p = 0; p < 8; p++) {
                 if ((p & 3) >= ((p >> 2) ? nmax1 : nmax0)) continue;
-                TORSION_ROW(p, (p >> 2), 1, cfg.mu_rolling);
-                TORSION_ROW(p, (p >> 2), 0, cfg.mu_rolling);
+                TORSION_ROW((p & 3), (p >> 2), 1, cfg.mu_rolling);
+                TORSION_ROW((p & 3), (p >> 2), 0, cfg.mu_rolling);
             }
             // ---- lateral pairs with the implicit friction cone (resolveConeFrictionConstraintRows)
 #pragma unroll
             for (int p = 0; p < 8; p++) {
                 if ((p & 3) >= ((p >> 2) ? nmax1 : nmax0)) continue;
-                const int f = p >> 2, LA = PLEN_LN(f, 4), LB = PLEN_LN(f, 3);
-                const float wx = GSH(S.s[2 + f], PLEN_LN(f, 0)), wy = GSH(S.s[2 + f], PLEN_LN(f, 1)),
-                            wz = GSH(S.s[2 + f], PLEN_LN(f, 2));
-                const float rA = fmaf(wz, px[p], fmaf(-wx, pz[p], S.s[2 + f]));     // lane LA: own = vy
-                const float rB = fmaf(wy, pz[p], fmaf(-wz, py[p], S.s[2 + f]));     // lane LB: own = vx
-                const float r_ = (g == LA) ? rA : rB;
-                const float sum_ = c_lam[p] + fmaf(-r_, c_dinv[p], c_rhs[p]);
-                const float sumA = GSH(sum_, LA), sumB = GSH(sum_, LB);
-                const float lim = cfg.mu_lateral * lamN[p];
+                const int f = p >> 2, k = p & 3;
+                const float rA = fmaf(s[4], px[p], fmaf(-s[2], pz[p], s[6]));     // row A: own = vy
+                const float rB = fmaf(s[3], pz[p], fmaf(-s[4], py[p], s[5]));     // row B: own = vx
+                const float sumA = c_lam[k][4] + fmaf(-rA, c_dinv[k][4], c_rhs[k][4]);
+                const float sumB = c_lam[k][3] + fmaf(-rB, c_dinv[k][3], c_rhs[k][3]);
+                const float lim = cfg.mu_lateral * c_lam[k][5];
                 float nA = sumA, nB = sumB;
                 if (fabsf(sumA) > lim || fabsf(sumB) > lim) {
                     const float inv = rsqrtf(sumA * sumA + sumB * sumB);
@@ -238,71 +279,68 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
                     nA = clampf(sumA, -cA, cA);
                     nB = clampf(sumB, -cB, cB);
                 }
-                const float nmine = (g == LA) ? nA : nB;
-                const float dmine = nmine - c_lam[p];
-                const float dA = GSH(dmine, LA), dB = GSH(dmine, LB);
-                const float v_ = dmine * c_d[p];
-                const float vB = GSH(v_, LB);
-                if (g == LA || g == LB) c_lam[p] = nmine;
-                if (g == LA) S.res = fmaxf(S.res, fabsf(v_ + vB));     // pair residual = dA/dinvA + dB/dinvB
-                apply_col(S, Gs4, g, PLEN_COL(f, 0), -pz[p] * dA);
-                apply_col(S, Gs4, g, PLEN_COL(f, 1), pz[p] * dB);
-                apply_col(S, Gs4, g, PLEN_COL(f, 2), px[p] * dA - py[p] * dB);
-                apply_col(S, Gs4, g, PLEN_COL(f, 3), dB);
-                apply_col(S, Gs4, g, PLEN_COL(f, 4), dA);
+                const float dlA = nA - c_lam[k][4], dlB = nB - c_lam[k][3];
+                const float dA = GSH(dlA, 2 + f), dB = GSH(dlB, 2 + f);
+                if (g == 2 + f) {
+                    c_lam[k][4] = nA; c_lam[k][3] = nB;
+                    resF = fmaxf(resF, fabsf(dlA * c_d[k][4] + dlB * c_d[k][3]));     // pair residual = dA/dinvA + dB/dinvB
+                }
+                apply_col(s, Gl, PLEN_COL(f, 0), -pz[p] * dA);
+                apply_col(s, Gl, PLEN_COL(f, 1), pz[p] * dB);
+                apply_col(s, Gl, PLEN_COL(f, 2), px[p] * dA - py[p] * dB);
+                apply_col(s, Gl, PLEN_COL(f, 3), dB);
+                apply_col(s, Gl, PLEN_COL(f, 4), dA);
             }
         }
-        // ---- residual of this iteration, per robot
-        float res = S.res;
-        res = fmaxf(res, shfl_xor(res, 1));
-        res = fmaxf(res, shfl_xor(res, 2));
-        res = fmaxf(res, shfl_xor(res, 4));
+        // ---- residual of this iteration, per robot: servo / limit part is already robot-uniform, the contact part
+        //      lives in the two foot lanes
+        float rf = (g >= 2) ? resF : 0.0f;
+        rf = fmaxf(rf, shfl_xor(rf, 1));
+        rf = fmaxf(rf, shfl_xor(rf, 2));
+        const float rr = fmaxf(res, rf);
         if (alive) {
             my_iters = it + 1;
-            if (res * res <= cfg.residual_threshold) {
+            if (rr * rr <= cfg.residual_threshold) {
                 alive = false;      // freeze: every later row update of this robot is exactly zero
 #pragma unroll
-                for (int k = 0; k < 3; k++) { m_rhs[k] = 0.0f; m_dinv[k] = 0.0f; l_rhs[k] = 0.0f; }
+                for (int k = 0; k < 8; k++) {     // park the accumulated servo row value in m_rhs, close the bounds
+                    m_rhs[k] = -0.5f * (m_lo[k] + m_hi[k]);
+                    m_lo[k] = 0.0f; m_hi[k] = 0.0f;
+                }
 #pragma unroll
-                for (int p = 0; p < 8; p++) { c_rhs[p] = 0.0f; c_dinv[p] = 0.0f; }
+                for (int k = 0; k < 4; k++)
+#pragma unroll
+                    for (int c = 0; c < 6; c++) { c_rhs[k][c] = 0.0f; c_dinv[k][c] = 0.0f; }
             }
         }
         if (!ballot(alive)) break;
     }
 
-    // ---- delta-v: joints = s[0..2]; base = B z with z = [servo + limit impulses; foot wrenches]
-    float z[4];
-    z[0] = m_lam[0] + l_dir[0] * l_lam[0];
-    z[1] = m_lam[1] + l_dir[1] * l_lam[1];
-    z[2] = (g < 2) ? m_lam[2] + l_dir[2] * l_lam[2] : 0.0f;
-    z[3] = 0.0f;
+    // ---- delta-v: joints = s; base = B z with z = [servo + limit row values (velocity units; B is pre-divided);
+    //      foot wrenches about the base origin]
+    float z[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) z[k] = alive ? -0.5f * (m_lo[k] + m_hi[k]) : m_rhs[k];
+    if (lim_any && valid) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) z[k] += srec[SR_LDIR + 8 * g + k] * l_lam[k];
+    }
     if (man_any) {
+        // wrench of this lane's foot (lanes 0, 1 hold zero rows): normal (py,-px,0 | vz), lateral A (-pz,0,px | vy),
+        // lateral B (0,pz,-py | vx), roll / spin rows on their own component
+        float w[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
-        for (int f = 0; f < 2; f++) {
-            const int comp = g - 2;              // this lane's row type (negative: no contact rows)
-            float w6[6] = {0, 0, 0, 0, 0, 0};
-            float own = 0.0f;
+        for (int k = 0; k < 4; k++) {
+            const float qx = (g == 3) ? px[4 + k] : px[k], qy = (g == 3) ? py[4 + k] : py[k], qz = (g == 3) ? pz[4 + k] : pz[k];
+            const float lN = c_lam[k][5], lA = c_lam[k][4], lB = c_lam[k][3];
+            w[0] += c_lam[k][0] + qy * lN - qz * lA;
+            w[1] += c_lam[k][1] - qx * lN + qz * lB;
+            w[2] += c_lam[k][2] + qx * lA - qy * lB;
+            w[3] += lB; w[4] += lA; w[5] += lN;
+        }
+        if (g >= 2) {
 #pragma unroll
-            for (int pp = 0; pp < 4; pp++) {
-                const int p = 4 * f + pp;
-                const float lam = (comp == 5) ? lamN[p] : c_lam[p];
-                own += lam;
-                // angular parts of the 3-component rows: normal (py,-px,0), lateral t2 (0,pz,-py), flipped t1 (-pz,0,px)
-                const float a0 = (comp == 5) ? py[p] : ((comp == 4) ? -pz[p] : 0.0f);
-                const float a1 = (comp == 5) ? -px[p] : ((comp == 3) ? pz[p] : 0.0f);
-                const float a2 = (comp == 3) ? -py[p] : ((comp == 4) ? px[p] : 0.0f);
-                w6[0] = fmaf(a0, lam, w6[0]); w6[1] = fmaf(a1, lam, w6[1]); w6[2] = fmaf(a2, lam, w6[2]);
-            }
-#pragma unroll
-            for (int k = 0; k < 6; k++) w6[k] += (comp == k) ? own : 0.0f;
-#pragma unroll
-            for (int m = 1; m < 8; m <<= 1)
-#pragma unroll
-                for (int k = 0; k < 6; k++) w6[k] += shfl_xor(w6[k], m);
-            float mine = 0.0f;
-#pragma unroll
-            for (int k = 0; k < 6; k++) mine = (comp == k) ? w6[k] : mine;
-            if (f == 0) z[2] = (g < 2) ? z[2] : mine; else z[3] = (g < 2) ? 0.0f : mine;
+            for (int c = 0; c < 6; c++) z[2 + c] = w[c];
         }
     }
     float dvb[6];
@@ -310,31 +348,45 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
     for (int k = 0; k < 6; k++) {
         float acc = 0.0f;
         if (valid) {
-            const vec4 b = *reinterpret_cast<const vec4 *>(srec + SR_B + 32 * k + 4 * g);
-            acc = b.x * z[0] + b.y * z[1] + b.z * z[2] + b.w * z[3];
+            float b[8];
+            load8(srec + SR_B + 32 * k + 8 * g, b);
+#pragma unroll
+            for (int m = 0; m < 8; m++) acc = fmaf(b[m], z[m], acc);
         }
         dvb[k] = acc;
     }
 #pragma unroll
-    for (int m = 1; m < 8; m <<= 1)
+    for (int m = 1; m < 4; m <<= 1)
 #pragma unroll
         for (int k = 0; k < 6; k++) dvb[k] += shfl_xor(dvb[k], m);
 
     if (valid) {
         // ---- apply delta-v, integrate (semi-implicit; exponential-map quaternion update), write the state record back
-        const vec4 vs = *reinterpret_cast<const vec4 *>(srec + SR_VSTAR + 4 * g);
-        const vec4 q4 = *reinterpret_cast<const vec4 *>(srec + SR_Q + 4 * g);
-        const float u0 = clampf(vs.x + S.s[0], -cfg.vmax, cfg.vmax), u1 = clampf(vs.y + S.s[1], -cfg.vmax, cfg.vmax),
-                    u2 = clampf(vs.z + S.s[2], -cfg.vmax, cfg.vmax);
-        state[W_U + 6 + g] = u0; state[W_Q + 6 + g] = q4.x + u0 * cfg.dt;
-        state[W_U + 14 + g] = u1; state[W_Q + 14 + g] = q4.y + u1 * cfg.dt;
-        if (g < 2) { state[W_U + 22 + g] = u2; state[W_Q + 22 + g] = q4.z + u2 * cfg.dt; }
-        {   // cached normal impulse of ORIGINAL contact point g: slot = 4 f + (number of active points of the foot below it)
-            const int f = g >> 2, q = 4 * f + popc_((man >> (4 * f)) & ((1u << (g & 3)) - 1u));
-            float v = lamN[0];
+        if (g < 3) {
+            float vs[8], q8[8];
+            load8(srec + SR_VSTAR + 8 * g, vs);
+            load8(srec + SR_Q + 8 * g, q8);
 #pragma unroll
-            for (int k = 1; k < 8; k++) v = (q == k) ? lamN[k] : v;
-            state[W_U + 24 + g] = ((man >> g) & 1u) ? v : 0.0f;
+            for (int k = 0; k < 8; k++) {
+                if (g == 2 && k >= 2) continue;
+                const float u = clampf(vs[k] + s[k], -cfg.vmax, cfg.vmax);
+                state[W_U + 6 + 8 * g + k] = u;
+                state[W_Q + 6 + 8 * g + k] = q8[k] + u * cfg.dt;
+            }
+        } else {
+            state[W_MAN] = (float)man;
+            state[W_ITERS] = (float)my_iters;
+        }
+        if (g >= 2) {   // cached normal impulses of this foot's ORIGINAL contact points: slot = number of active points below
+            const int f = g - 2;
+            const unsigned mf = (man >> (4 * f)) & 15u;
+#pragma unroll
+            for (int o = 0; o < 4; o++) {
+                const int q = popc_(mf & ((1u << o) - 1u));
+                float v = c_lam[0][5];
+                v = (q == 1) ? c_lam[1][5] : v; v = (q == 2) ? c_lam[2][5] : v; v = (q == 3) ? c_lam[3][5] : v;
+                state[W_U + 24 + 4 * f + o] = ((mf >> o) & 1u) ? v : 0.0f;
+            }
         }
         if (g == 0) {
             float ub[6];
@@ -362,12 +414,11 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
             const float rw = cw * qw - dx * qx - dy * qy - dz * qz;
             const float nn = rsqrtf(rx * rx + ry * ry + rz * rz + rw * rw);
             state[W_QUAT + 0] = rx * nn; state[W_QUAT + 1] = ry * nn; state[W_QUAT + 2] = rz * nn; state[W_QUAT + 3] = rw * nn;
-            state[W_MAN] = (float)man;
-            state[W_ITERS] = (float)my_iters;
         }
     }
 #undef GSH
 #undef SERVO_ROW
+#undef LIMIT_ROW
 #undef TORSION_ROW
 #undef NORMAL_COLUMN
 }

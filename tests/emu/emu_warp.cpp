@@ -100,11 +100,11 @@ int emu_sizeof_model() { return (int)sizeof(plen_model); }
 void emu_init_record(const plen_config *c, float *rec) { init_record(c, rec); }
 
 // (k_dyn, k_solve) x n_ticks over n robots, exactly as plen_b200.cu launches them: one emulated warp per robot for the
-// dynamics, then one emulated warp per 4 robots for the solver.  tgt [n][18] nullable (zero targets).
+// dynamics, then one emulated warp per 8 robots for the solver (identity permutation: grouping never changes a result).  tgt [n][18] nullable (zero targets).
 static void run_ticks(const DevConfig &dc, const float *tab, float *records, const float *tgt, int n, int n_ticks,
                       const DebugOut *dbg0, int lane) {
     static WarpScratch ws;
-    static std::vector<float> srec, Gs(4 * 960);
+    static std::vector<float> srec, Gs(PLEN_SOLVE_ROBOTS * PLEN_GS_WORDS);
     if (lane == 0) srec.assign((size_t)n * SR_WORDS, 0.0f);
     bar();
     for (int t = 0; t < n_ticks; t++) {
@@ -115,11 +115,11 @@ static void run_ticks(const DevConfig &dc, const float *tab, float *records, con
             tick_dynamics(dc, tab, ws, L, lane, srec.data() + (size_t)e * SR_WORDS, nullptr,
                           (e == 0 && t == n_ticks - 1) ? dbg0 : nullptr);
         }
-        for (int b = 0; b < n; b += 4) {
-            const int r = b + (lane >> 3);
+        for (int b = 0; b < n; b += PLEN_SOLVE_ROBOTS) {
+            const int r = b + (lane >> 2);
             const bool valid = r < n;
             const int rr = valid ? r : 0;
-            solve_tick(dc, srec.data() + (size_t)rr * SR_WORDS, Gs.data() + (lane >> 3) * 960, records + 96 * rr, lane, valid);
+            solve_tick(dc, srec.data() + (size_t)rr * SR_WORDS, Gs.data() + (lane >> 2) * PLEN_GS_WORDS, records + 96 * rr, lane, valid);
             bar();
         }
     }

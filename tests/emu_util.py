@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU_SRC = os.path.join(ROOT, "tests", "emu", "emu_warp.cpp")
 EMU_LIB = os.path.join(ROOT, "tests", "emu", "libplen_emu.so")
 _DEPS = [EMU_SRC] + [os.path.join(ROOT, "plen_ml_walk_b200", "csrc", f)
-                     for f in ("plen_device.cuh", "plen_env.cuh", "plen_host_tables.h")] + \
+                     for f in ("plen_device.cuh", "plen_solve.cuh", "plen_env.cuh", "plen_host_tables.h")] + \
         [os.path.join(ROOT, "include", "plen_b200.h")]
 
 
