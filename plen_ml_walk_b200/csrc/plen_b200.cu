@@ -134,7 +134,7 @@ k_rank(const uint8_t *__restrict__ keys, int n, int *__restrict__ perm) {
 // Second half of a tick, 4 lanes per robot: PGS + delta-v + integration, state record updated in place.
 // A CTA is ONE warp = 8 robots (30.1 KB of G in shared memory, 7 CTAs per SM).  CTA b takes group b / n_tiles of tile
 // b % n_tiles, so the heavy groups of all tiles run first and the tail of the grid is made of light ones.
-__global__ void __launch_bounds__(32)
+__global__ void __maxnreg__(224)
 k_solve(const __grid_constant__ DevConfig dc, const float *__restrict__ srec, const int *__restrict__ perm,
         float *__restrict__ state, int n, int n_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -31,13 +31,20 @@ struct __align__(16) vec4 { float x, y, z, w; };
 struct vec4 { float x, y, z, w; };
 #endif
 
-// words of shared memory per robot: 30 columns x 32 words, plus one float4 so that the two robots of a quarter-warp
-// hit disjoint banks with their LDS.128 (robot stride = 16 B mod 128 B)
-#define PLEN_GS_WORDS 964
+// Shared memory holds 24 of the 30 columns of G per robot: the 18 joint columns and the linear (vx vy vz) columns of
+// either foot.  The six ANGULAR foot columns -- the ones the contact rows use most (normal 2 of 3, spinning, rolling,
+// lateral 3 of 5 column updates) -- live in registers, which (a) takes 8 of the 11 LDS pairs out of every contact point
+// and (b) shrinks the staging area to 24.1 KB per warp: 9 resident warps per SM instead of 7 (the kernel is bound by the
+// latency of the Gauss-Seidel dependency chain, so resident warps are throughput).
+// Words per robot: 24 columns x 32 words, plus one float4 so that the two robots of a quarter-warp hit disjoint banks
+// with their LDS.128 (robot stride = 16 B mod 128 B)
+#define PLEN_GS_COLS 24
+#define PLEN_GS_WORDS (PLEN_GS_COLS * 32 + 4)
 #define PLEN_SOLVE_ROBOTS 8      // robots per warp
 
-// G column of twist component k of foot f
+// column of twist component k of foot f in the solve record (30 columns) / in the shared staging area (k >= 3 only)
 #define PLEN_COL(f, k) (18 + 6 * (f) + (k))
+#define PLEN_SCOL(f, k) (18 + 3 * (f) + (k) - 3)
 
 // (a0, a1) += (x0, x1) * d  as one packed FFMA2 (sm_100a fma.rn.f32x2 with a broadcast scalar multiplier)
 PLEN_DEV void fma2(float &a0, float &a1, float x0, float x1, float d) {
@@ -50,12 +57,40 @@ PLEN_DEV void fma2(float &a0, float &a1, float x0, float x1, float d) {
 #endif
 }
 
-PLEN_DEV void apply_col(float (&s)[8], const vec4 *Gl, int c, float db) {
-    const vec4 a = Gl[c * 8], b = Gl[c * 8 + 1];
+// This lane's slice of G (8 rows of every column) is addressed through ONE 32-bit shared-window address plus immediate
+// offsets: a generic pointer costs a 64-bit register pair, and under the register pressure of this kernel ptxas used to
+// rematerialise it (S2R tid / S2R cta-window base / 10 integer instructions) in front of every contact row.
+#ifndef PLEN_HOST_EMU
+typedef unsigned GSlice;
+PLEN_DEV GSlice g_slice(const float *Gs, int g) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(Gs) + 32u * (unsigned)g;
+    asm volatile("" : "+r"(a) : : "memory");      // orders every later g_ld after the staging stores + warp_sync
+    return a;
+}
+PLEN_DEV vec4 g_ld(GSlice a, int v4) {             // vec4 number v4 of the slice (column c -> 8 c, 8 c + 1)
+    vec4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a + 16u * (unsigned)v4));
+    return v;
+}
+#else
+typedef const vec4 *GSlice;
+PLEN_DEV GSlice g_slice(const float *Gs, int g) { return reinterpret_cast<const vec4 *>(Gs) + 2 * g; }
+PLEN_DEV vec4 g_ld(GSlice a, int v4) { return a[v4]; }
+#endif
+
+PLEN_DEV void apply_col(float (&s)[8], GSlice Gl, int c, float db) {
+    const vec4 a = g_ld(Gl, c * 8), b = g_ld(Gl, c * 8 + 1);
     fma2(s[0], s[1], a.x, a.y, db);
     fma2(s[2], s[3], a.z, a.w, db);
     fma2(s[4], s[5], b.x, b.y, db);
     fma2(s[6], s[7], b.z, b.w, db);
+}
+
+PLEN_DEV void apply_reg(float (&s)[8], const float (&a)[8], float db) {
+    fma2(s[0], s[1], a[0], a[1], db);
+    fma2(s[2], s[3], a[2], a[3], db);
+    fma2(s[4], s[5], a[4], a[5], db);
+    fma2(s[6], s[7], a[6], a[7], db);
 }
 
 PLEN_DEV void load8(const float *p, float (&o)[8]) {
@@ -73,11 +108,23 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
         vec4 *dst4 = reinterpret_cast<vec4 *>(Gs);
         const vec4 *src4 = reinterpret_cast<const vec4 *>(srec + SR_G);
         const vec4 z4 = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll 10
-        for (int k = g; k < 240; k += 4) dst4[k] = valid ? src4[k] : z4;
+#pragma unroll 8
+        for (int k = g; k < 8 * PLEN_GS_COLS; k += 4) {
+            const int col = k >> 3, scol = (col < 18) ? col : ((col < 21) ? col + 3 : col + 6);      // skip the angular columns
+            dst4[k] = valid ? src4[8 * scol + (k & 7)] : z4;
+        }
     }
+    float A[2][3][8];      // this lane's 8 rows of the angular columns (wx wy wz) of either foot
+#pragma unroll
+    for (int f = 0; f < 2; f++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) A[f][c][k] = 0.0f;
+            if (valid) load8(srec + SR_G + 32 * PLEN_COL(f, c) + 8 * g, A[f][c]);
+        }
     warp_sync();
-    const vec4 *Gl = reinterpret_cast<const vec4 *>(Gs) + 2 * g;      // this lane's 8 rows of column c: Gl[8 c], Gl[8 c + 1]
+    const GSlice Gl = g_slice(Gs, g);      // this lane's 8 rows of column c: vec4 8 c and 8 c + 1 of the slice
 
     // ---- servo rows of this lane (entries >= 18 carry zeros): velocity-unit rhs and bounds
     float m_rhs[8], m_lo[8], m_hi[8];
@@ -103,18 +150,27 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
     const int nmax0 = (int)redux_max((unsigned)n0), nmax1 = (int)redux_max((unsigned)n1);
     const bool man_any = (nmax0 | nmax1) != 0;
     const unsigned lim_any = redux_or(limbits << (8 * g));       // joint j <-> bit j (lanes 0..2 only carry joints)
-    float l_lam[8];                                              // limit-row impulses (velocity units); rare path only
-#pragma unroll
-    for (int k = 0; k < 8; k++) l_lam[k] = 0.0f;
+    // limit-row impulses (velocity units; rare path only) are kept in shared memory, in the unused row 24 of column j
+    // of this robot's G (k_dyn writes zeros there; lane 3 reads it into its unused slot s[0])
+#define L_LAM(j) Gs[((j) < 18 ? (j) : 0) * 32 + 24]
 
-    // ---- contact rows of this lane's foot (lane 2: right, lane 3: left; lanes 0, 1 hold zeros):
-    //      [point k][component c]: c = 0 roll(wx) 1 roll(wy) 2 spin(wz) 3 lateral B (vx) 4 lateral A (vy) 5 normal (vz)
-    float c_rhs[4][6], c_dinv[4][6], c_d[4][6], c_lam[4][6];
+    // ---- contact rows of this lane's foot (lane 2: right, lane 3: left; lanes 0, 1 hold zeros).  Twist component c of a
+    //      row: 0 roll(wx) 1 roll(wy) 2 spin(wz) 3 lateral B (vx) 4 lateral A (vy) 5 normal (vz).  The spinning / rolling
+    //      rows are functionals of ONE angular twist component, so their rhs / dinv / d are the same for every point
+    //      of a foot (t_*[c], read from the foot's first slot); only their impulses are per point.
+    float c_rhs[4][3], c_dinv[4][3], c_d[4][3];      // [point k][c - 3]
+    float t_rhs[3], t_dinv[3], t_d[3];
+    float c_lam[4][6];
     float px[8], py[8], pz[8];     // all eight compacted points (every lane scales the columns of either foot)
 #pragma unroll
-    for (int k = 0; k < 4; k++)
+    for (int k = 0; k < 4; k++) {
 #pragma unroll
-        for (int c = 0; c < 6; c++) c_rhs[k][c] = c_dinv[k][c] = c_d[k][c] = c_lam[k][c] = 0.0f;
+        for (int c = 0; c < 3; c++) c_rhs[k][c] = c_dinv[k][c] = c_d[k][c] = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 6; c++) c_lam[k][c] = 0.0f;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) t_rhs[c] = t_dinv[c] = t_d[c] = 0.0f;
 #pragma unroll
     for (int p = 0; p < 8; p++) px[p] = py[p] = pz[p] = 0.0f;
     if (man_any && valid) {
@@ -126,10 +182,15 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
         if (g >= 2) {
             const int f = g - 2;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int o = 8 * (4 * f + k) + 2;
+            for (int c = 0; c < 3; c++) {
+                const int o = 8 * (4 * f) + 2 + c;       // an empty foot has zeros here
+                t_rhs[c] = srec[SR_CRHS + o]; t_dinv[c] = srec[SR_CDINV + o]; t_d[c] = srec[SR_CD + o];
+            }
 #pragma unroll
-                for (int c = 0; c < 6; c++) {
+            for (int k = 0; k < 4; k++) {
+                const int o = 8 * (4 * f + k) + 2 + 3;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
                     c_rhs[k][c] = srec[SR_CRHS + o + c];
                     c_dinv[k][c] = srec[SR_CDINV + o + c];
                     c_d[k][c] = srec[SR_CD + o + c];
@@ -146,9 +207,9 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
 
 #define NORMAL_COLUMN(p, f, db)                              \
     {                                                        \
-        apply_col(s, Gl, PLEN_COL(f, 0), py[p] * (db));      \
-        apply_col(s, Gl, PLEN_COL(f, 1), -px[p] * (db));     \
-        apply_col(s, Gl, PLEN_COL(f, 5), (db));              \
+        apply_reg(s, A[f][0], py[p] * (db));                 \
+        apply_reg(s, A[f][1], -px[p] * (db));                \
+        apply_col(s, Gl, PLEN_SCOL(f, 5), (db));             \
     }
 
     // ---- warm start of the normal rows from the cached impulses
@@ -176,10 +237,11 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
     {                                                                                    \
         const float ldir_ = srec[SR_LDIR + 8 * g + (k)], up_ = 100.0f * srec[SR_MD + 8 * g + (k)]; \
         const float x_ = srec[SR_LRHS + 8 * g + (k)] - ldir_ * s[k];                     \
-        const float nl_ = alive ? clampf(l_lam[k] + x_, 0.0f, up_) : l_lam[k];           \
-        const float dl_ = (nl_ - l_lam[k]) * ldir_;                                      \
+        const float ol_ = L_LAM(8 * g + (k));                                            \
+        const float nl_ = alive ? clampf(ol_ + x_, 0.0f, up_) : ol_;                     \
+        const float dl_ = (nl_ - ol_) * ldir_;                                           \
         const float db_ = GSH(dl_, b);                                                   \
-        if (g == (b)) l_lam[k] = nl_;                                                    \
+        if (g == (b)) L_LAM(8 * g + (k)) = nl_;                                          \
         res = fmaxf(res, fabsf(db_));                                                    \
         apply_col(s, Gl, 8 * (b) + (k), db_);                                            \
     }
@@ -187,13 +249,13 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
     // spinning / rolling row of point k of foot f: own twist component c, friction coefficient mu
 #define TORSION_ROW(k, f, c, mu)                                                                          \
     {                                                                                                     \
-        const float x_ = fmaf(-s[2 + (c)], c_dinv[k][c], c_rhs[k][c]);                                    \
+        const float x_ = fmaf(-s[2 + (c)], t_dinv[c], t_rhs[c]);                                          \
         const float lim_ = (mu) * c_lam[k][5];                                                            \
         float dl_ = fminf(fmaxf(x_, -lim_ - c_lam[k][c]), lim_ - c_lam[k][c]);                            \
         dl_ = (c_lam[k][5] > 0.0f) ? dl_ : 0.0f;   /* row skipped while the normal impulse is not positive */ \
         const float db_ = GSH(dl_, 2 + (f));                                                              \
-        if (g == 2 + (f)) { c_lam[k][c] += dl_; resF = fmaxf(resF, fabsf(dl_ * c_d[k][c])); }             \
-        apply_col(s, Gl, PLEN_COL(f, c), db_);                                                            \
+        if (g == 2 + (f)) { c_lam[k][c] += dl_; resF = fmaxf(resF, fabsf(dl_ * t_d[c])); }                \
+        apply_reg(s, A[f][c], db_);                                                                       \
     }
 
     bool alive = valid;
@@ -244,10 +306,10 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
                 if ((p & 3) >= ((p >> 2) ? nmax1 : nmax0)) continue;
                 const int f = p >> 2, k = p & 3;
                 const float r_ = fmaf(s[2], py[p], fmaf(-s[3], px[p], s[7]));
-                const float x_ = fmaf(-r_, c_dinv[k][5], c_rhs[k][5]);
+                const float x_ = fmaf(-r_, c_dinv[k][2], c_rhs[k][2]);
                 const float dl_ = fmaxf(x_, -c_lam[k][5]);
                 const float db_ = GSH(dl_, 2 + f);
-                if (g == 2 + f) { c_lam[k][5] += dl_; resF = fmaxf(resF, fabsf(dl_ * c_d[k][5])); }
+                if (g == 2 + f) { c_lam[k][5] += dl_; resF = fmaxf(resF, fabsf(dl_ * c_d[k][2])); }
                 NORMAL_COLUMN(p, f, db_);
             }
             // ---- all spinning rows, then the rolling rows point by point (t1, t2)
@@ -269,8 +331,8 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
                 const int f = p >> 2, k = p & 3;
                 const float rA = fmaf(s[4], px[p], fmaf(-s[2], pz[p], s[6]));     // row A: own = vy
                 const float rB = fmaf(s[3], pz[p], fmaf(-s[4], py[p], s[5]));     // row B: own = vx
-                const float sumA = c_lam[k][4] + fmaf(-rA, c_dinv[k][4], c_rhs[k][4]);
-                const float sumB = c_lam[k][3] + fmaf(-rB, c_dinv[k][3], c_rhs[k][3]);
+                const float sumA = c_lam[k][4] + fmaf(-rA, c_dinv[k][1], c_rhs[k][1]);
+                const float sumB = c_lam[k][3] + fmaf(-rB, c_dinv[k][0], c_rhs[k][0]);
                 const float lim = cfg.mu_lateral * c_lam[k][5];
                 float nA = sumA, nB = sumB;
                 if (fabsf(sumA) > lim || fabsf(sumB) > lim) {
@@ -283,13 +345,13 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
                 const float dA = GSH(dlA, 2 + f), dB = GSH(dlB, 2 + f);
                 if (g == 2 + f) {
                     c_lam[k][4] = nA; c_lam[k][3] = nB;
-                    resF = fmaxf(resF, fabsf(dlA * c_d[k][4] + dlB * c_d[k][3]));     // pair residual = dA/dinvA + dB/dinvB
+                    resF = fmaxf(resF, fabsf(dlA * c_d[k][1] + dlB * c_d[k][0]));     // pair residual = dA/dinvA + dB/dinvB
                 }
-                apply_col(s, Gl, PLEN_COL(f, 0), -pz[p] * dA);
-                apply_col(s, Gl, PLEN_COL(f, 1), pz[p] * dB);
-                apply_col(s, Gl, PLEN_COL(f, 2), px[p] * dA - py[p] * dB);
-                apply_col(s, Gl, PLEN_COL(f, 3), dB);
-                apply_col(s, Gl, PLEN_COL(f, 4), dA);
+                apply_reg(s, A[f][0], -pz[p] * dA);
+                apply_reg(s, A[f][1], pz[p] * dB);
+                apply_reg(s, A[f][2], px[p] * dA - py[p] * dB);
+                apply_col(s, Gl, PLEN_SCOL(f, 3), dB);
+                apply_col(s, Gl, PLEN_SCOL(f, 4), dA);
             }
         }
         // ---- residual of this iteration, per robot: servo / limit part is already robot-uniform, the contact part
@@ -310,7 +372,9 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
 #pragma unroll
                 for (int k = 0; k < 4; k++)
 #pragma unroll
-                    for (int c = 0; c < 6; c++) { c_rhs[k][c] = 0.0f; c_dinv[k][c] = 0.0f; }
+                    for (int c = 0; c < 3; c++) { c_rhs[k][c] = 0.0f; c_dinv[k][c] = 0.0f; }
+#pragma unroll
+                for (int c = 0; c < 3; c++) { t_rhs[c] = 0.0f; t_dinv[c] = 0.0f; }
             }
         }
         if (!ballot(alive)) break;
@@ -323,7 +387,7 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
     for (int k = 0; k < 8; k++) z[k] = alive ? -0.5f * (m_lo[k] + m_hi[k]) : m_rhs[k];
     if (lim_any && valid) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) z[k] += srec[SR_LDIR + 8 * g + k] * l_lam[k];
+        for (int k = 0; k < 8; k++) z[k] += (g < 3) ? srec[SR_LDIR + 8 * g + k] * L_LAM(8 * g + k) : 0.0f;
     }
     if (man_any) {
         // wrench of this lane's foot (lanes 0, 1 hold zero rows): normal (py,-px,0 | vz), lateral A (-pz,0,px | vy),
@@ -419,6 +483,7 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
 #undef GSH
 #undef SERVO_ROW
 #undef LIMIT_ROW
+#undef L_LAM
 #undef TORSION_ROW
 #undef NORMAL_COLUMN
 }
