@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--envs-per-gpu E] [--impl reference]
 
 A "step" is one vectorised env step (1 action -> 4 physics ticks -> obs/reward/done/auto-reset) of every env of the
-rank: ONE launch of k_step.  Workload = BASELINE config 5's shard: E = 131072 envs per GPU (1,048,576 envs at 8
+rank: 3 launches per tick (k_dyn, k_rank, k_solve) + k_post.  Workload = BASELINE config 5's shard: E = 131072 envs per GPU (1,048,576 envs at 8
 GPUs), actions U(-1,1)^18 drawn on the device with torch.Generator(seed 0 + rank), auto-reset on.  Envs are
 independent, so ranks share nothing on the data path ("scaling": "weak"); torch.distributed (NCCL) is used only for
 the barrier and the max-over-ranks of the device time.
@@ -34,9 +34,14 @@ UNIT = "env-steps/s"
 # obs 26 f32, reward f32, done + timeout bytes
 BYTES_PER_ENV_STEP = 2 * 96 * 4 + 18 * 4 + 26 * 4 + 4 + 2
 TICKS_PER_STEP = 4
-# measured DRAM traffic of one k_solve launch per robot (ncu --set full, profiles/r1_v3_summary.md): it reads the
+# measured DRAM traffic of one k_solve launch per robot (ncu --set full, profiles/r1_v5_summary.md): it reads the
 # 6.4 KB solve record k_dyn wrote for the tick -- a deliberate trade of HBM bytes for issue slots
-SOLVE_DRAM_BYTES_PER_ROBOT = (219.58e6 + 9.55e6) / 32768
+SOLVE_DRAM_BYTES_PER_ROBOT = (207.16e6 + 8.27e6) / 32768
+# executed FP32 work per robot-tick, counted by ncu (smsp__sass_thread_inst_executed_op_{fadd,fmul,ffma}_pred_on, FFMA = 2
+# flop; 32768-robot capture, profiles/r1_v5_summary.md): k_dyn 55.3 kflop + k_solve 50.6 kflop.  It replaces SURVEY 8d's
+# estimate (0.65-1.6 Mflop per env-step for Bullet's ABA + velocity-space PGS): this solver iterates in the 30-dim
+# operational space, so a row update is 30 FMAs instead of a Jacobian-wide one.
+FLOP_PER_ENV_STEP = 4 * (55.3e3 + 50.6e3)
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 
 
@@ -219,6 +224,12 @@ def main():
 
     if rank == 0:
         peak, peak_src = _peaks()
+        import ctypes as C
+        tf, mhz = C.c_float(), C.c_float()
+        if env.lib.plen_measure_fp32_peak(local_rank, 1, C.byref(tf), C.byref(mhz)) == 0 and tf.value > 0:
+            fp32_peak, fp32_src = float(tf.value), "measured live (plen_measure_fp32_peak, FFMA2 chains, best of 4)"
+        else:
+            fp32_peak, fp32_src = FP32_NOMINAL_TFLOPS, "nominal 148 SM x 128 lanes x 2 x 1.965 GHz"
         step_ms = total_ms / K
         # dominant kernel = k_solve (one launch per physics tick over all E robots): CUDA events recorded around every
         # launch of the timed region by the library itself (plen_profile_enable), on the launching stream
@@ -243,6 +254,12 @@ def main():
                          "note": "the path is FP32 instruction-issue / dependency-latency bound inside the projected "
                                  "Gauss-Seidel (DESIGN.md), neither HBM nor tensor bound; traffic = ncu DRAM bytes per "
                                  "robot (32768-robot capture) x robots per launch"},
+            "roofline_fp32": {"bound": "fp32 FMA pipe (CUDA cores)", "achieved": FLOP_PER_ENV_STEP * value / world / 1e12,
+                              "peak": fp32_peak, "unit": "TFLOP/s", "frac": FLOP_PER_ENV_STEP * value / world / 1e12 / fp32_peak,
+                              "peak_source": fp32_src, "flop_per_env_step": FLOP_PER_ENV_STEP,
+                              "note": "per GPU; executed FADD + FMUL + 2 FFMA thread operations per env-step counted by ncu "
+                                      "(profiles/r1_v5_summary.md) x measured env-steps/s; the limiter is the dependency "
+                                      "latency of the Gauss-Seidel row chain at 2 warps per scheduler, not the pipe"},
             "kernel_ms_per_step": {"k_dyn": prof["ms_dyn"] / max(1, prof["steps"]), "k_solve": prof["ms_solve"] / max(1, prof["steps"]),
                                    "k_post": prof["ms_post"] / max(1, prof["steps"])},
         }

@@ -140,12 +140,22 @@ int plen_tick(plen_ctx *ctx, const float *targets_dev, int n_ticks, void *stream
  * and world pose of the 19 body frames pos [N,24,3] / rot [N,24,9] (lanes 1..5 unused). */
 int plen_debug_dynamics(plen_ctx *ctx, float *minv_dev, float *pos_dev, float *rot_dev, void *stream);
 
+/* Diagnostics: raw copy of the per-env state records [N,PLEN_STATE_WORDS] (layout: csrc/plen_device.cuh, W_* words;
+ * word 79 = PGS iterations of the last tick, the figure DESIGN.md's work accounting uses). */
+int plen_debug_records(plen_ctx *ctx, float *records_dev, void *stream);
+
 /* Per-kernel device timing of plen_step (measurement aid for bench.py, no reference counterpart): after
  * plen_profile_enable the next max_steps plen_step calls record CUDA events around their launches on the caller's
  * stream; plen_profile_read synchronises on them, returns the summed milliseconds of the dynamics (k_dyn), solver
  * (k_solve) and env-epilogue (k_post) kernels and the number of recorded steps, and re-arms the recorder. */
 int plen_profile_enable(plen_ctx *ctx, int max_steps);
 int plen_profile_read(plen_ctx *ctx, float *ms_dyn, float *ms_solve, float *ms_post, int *steps);
+
+/* FP32 FMA-pipe peak of `device` measured with a register-resident FMA chain kernel (mode 0: scalar FFMA, mode 1:
+ * packed FFMA2 = fma.rn.f32x2), best of 4 timed launches after 2 warm-up launches, CUDA events.  Measurement aid for
+ * bench.py's FP32 roofline (MEASURED_PEAKS.json carries only HBM and bf16 figures); no reference counterpart.
+ * sm_mhz_hint (nullable): the SM clock that figure implies at 128 FP32 lanes per SM. */
+int plen_measure_fp32_peak(int device, int mode, float *tflops, float *sm_mhz_hint);
 
 /* Sinewave gait + closed-form leg IK for n_gaits parameter sets in one launch.
  * Replaces TrajectoryGenerator.main (plen_bullet/src/plen_bullet/trajectory_generator.py:54-277) and the trajectory

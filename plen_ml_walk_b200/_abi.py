@@ -72,7 +72,7 @@ def model_to_c(model: PlenModel) -> PlenModelC:
 EXPORTS = (
     "plen_version", "plen_default_config", "plen_create", "plen_destroy", "plen_last_error", "plen_num_envs",
     "plen_reset", "plen_step", "plen_step_host", "plen_get_state", "plen_set_state", "plen_tick",
-    "plen_debug_dynamics", "plen_gait_ik", "plen_profile_enable", "plen_profile_read",
+    "plen_debug_dynamics", "plen_debug_records", "plen_gait_ik", "plen_profile_enable", "plen_profile_read", "plen_measure_fp32_peak",
     "plen_replay_create", "plen_replay_destroy", "plen_replay_size", "plen_replay_ptr", "plen_replay_storage",
     "plen_replay_add", "plen_replay_sample", "plen_actor_forward", "plen_td3_last_error",
 )
@@ -107,6 +107,7 @@ def load_library(path: str = LIB_PATH):
     L.plen_set_state.argtypes = [vp] * 5
     L.plen_tick.argtypes = [vp, vp, ip, vp]
     L.plen_debug_dynamics.argtypes = [vp] * 5
+    L.plen_debug_records.argtypes = [vp] * 3
     L.plen_profile_enable.argtypes = [vp, ip]
     L.plen_profile_read.argtypes = [vp] * 5
     ll, ull = C.c_longlong, C.c_ulonglong
@@ -125,5 +126,6 @@ def load_library(path: str = LIB_PATH):
     L.plen_actor_forward.argtypes = [ip] + [vp] * 7 + [ip, C.c_float, C.c_float, ull, vp, vp]
     L.plen_td3_last_error.restype = C.c_char_p
     L.plen_gait_ik.argtypes = [ip, vp, ip, vp, vp, vp, vp]
+    L.plen_measure_fp32_peak.argtypes = [ip, ip, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     _lib = L
     return L

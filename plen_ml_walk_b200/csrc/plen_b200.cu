@@ -348,6 +348,39 @@ __global__ void k_gait_ik(const double *__restrict__ params, int n, double *__re
     if (status) status[g] = ok ? 0 : 1;
 }
 
+
+// ---- FP32 FMA-pipe peak (measurement aid; SURVEY.md 8d asks for it: MEASURED_PEAKS.json has no FP32 figure).
+// Every thread runs 8 independent FFMA (mode 0) or 4 packed FFMA2 (mode 1, fma.rn.f32x2) chains; 2 flop per lane-FMA.
+__global__ void __launch_bounds__(256)
+k_fp32_peak(float *out, int iters, int mode, float seed) {
+    float a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = seed + (float)(threadIdx.x + k);
+    const float x = 0.999f + seed, y = 1e-3f;
+    if (mode == 0) {
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int r = 0; r < 16; r++)
+#pragma unroll
+                for (int k = 0; k < 8; k++) a[k] = fmaf(a[k], x, y);
+        }
+    } else {
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int r = 0; r < 16; r++)
+#pragma unroll
+                for (int k = 0; k < 8; k += 2)
+                    asm volatile("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%0, %1}; mov.b64 rb, {%2, %2}; mov.b64 rc, {%3, %3};\n\t"
+                                 "fma.rn.f32x2 ra, ra, rb, rc; mov.b64 {%0, %1}, ra; }"
+                                 : "+f"(a[k]), "+f"(a[k + 1]) : "f"(x), "f"(y));
+        }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += a[k];
+    if (s == 12345.678f) out[0] = s;      // never true in practice: keeps the chains alive
+}
+
 // ------------------------------------------------------------------------------------------------ C ABI
 static const size_t DYN_SMEM = sizeof(DynSmem);
 static const size_t SOLVE_SMEM = sizeof(float) * PLEN_GS_WORDS * PLEN_SOLVE_ROBOTS;
@@ -532,6 +565,14 @@ int plen_debug_dynamics(plen_ctx *ctx, float *minv_dev, float *pos_dev, float *r
     return PLEN_OK;
 }
 
+int plen_debug_records(plen_ctx *ctx, float *records_dev, void *stream) {
+    if (!ctx || !records_dev) return fail(ctx, PLEN_E_ARG, "plen_debug_records: bad arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemcpyAsync(records_dev, ctx->d_state, sizeof(float) * PLEN_STATE_WORDS * (size_t)ctx->n, cudaMemcpyDeviceToDevice,
+                            (cudaStream_t)stream));
+    return PLEN_OK;
+}
+
 int plen_profile_enable(plen_ctx *ctx, int max_steps) {
     if (!ctx || max_steps <= 0) return fail(ctx, PLEN_E_ARG, "plen_profile_enable: bad arguments");
     if (ctx->prof_ev) return fail(ctx, PLEN_E_STATE, "plen_profile_enable: already enabled");
@@ -574,6 +615,35 @@ int plen_gait_ik(int device, const double *params_dev, int n_gaits, double *traj
     CK(nullptr, cudaSetDevice(device));
     k_gait_ik<<<(n_gaits + 127) / 128, 128, 0, (cudaStream_t)stream>>>(params_dev, n_gaits, traj_dev, bend_dev, status_dev);
     CK(nullptr, cudaGetLastError());
+    return PLEN_OK;
+}
+
+int plen_measure_fp32_peak(int device, int mode, float *tflops, float *sm_mhz_hint) {
+    if (!tflops || mode < 0 || mode > 1) return fail(nullptr, PLEN_E_ARG, "plen_measure_fp32_peak: bad arguments");
+    CK(nullptr, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(nullptr, cudaGetDeviceProperties(&prop, device));
+    float *d_out = nullptr;
+    CK(nullptr, cudaMalloc(&d_out, sizeof(float)));
+    cudaEvent_t e0, e1;
+    CK(nullptr, cudaEventCreate(&e0));
+    CK(nullptr, cudaEventCreate(&e1));
+    const int grid = prop.multiProcessorCount * 8, block = 256, iters = 4096;
+    float best = 0.0f;
+    for (int rep = 0; rep < 6; rep++) {        // first repetitions warm the clocks up; best of the rest
+        CK(nullptr, cudaEventRecord(e0, 0));
+        k_fp32_peak<<<grid, block>>>(d_out, iters, mode, 0.0f);
+        CK(nullptr, cudaEventRecord(e1, 0));
+        CK(nullptr, cudaEventSynchronize(e1));
+        float ms = 0.0f;
+        CK(nullptr, cudaEventElapsedTime(&ms, e0, e1));
+        const double flop = 2.0 * 8.0 * 16.0 * (double)iters * (double)grid * (double)block;
+        const float tf = (float)(flop / (ms * 1e-3) / 1e12);
+        if (rep >= 2 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    *tflops = best;
+    if (sm_mhz_hint) *sm_mhz_hint = best * 1e12f / (2.0f * 128.0f * (float)prop.multiProcessorCount) / 1e6f;   // clock implied by 128 lanes/SM
     return PLEN_OK;
 }
 

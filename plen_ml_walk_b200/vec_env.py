@@ -136,7 +136,7 @@ class PlenVecEnv:
             self._check(self.lib.plen_step(self._ctx, self._p(a), self._p(self._obs), self._p(self._reward),
                                            self._p(self._done), self._p(self._timeout), self._p(self._terminal_obs),
                                            self._stream()))
-        self.launches += 2 * int(self.cfg.substeps) + 1
+        self.launches += 3 * int(self.cfg.substeps) + 1
         info = {"terminal_obs": self._terminal_obs, "timeout": self._timeout.bool()}
         return self._obs, self._reward, self._done.bool(), info
 
@@ -148,7 +148,7 @@ class PlenVecEnv:
             return C.c_void_p(x.data_ptr() if isinstance(x, torch.Tensor) else x.ctypes.data)
         self._check(self.lib.plen_step_host(self._ctx, hp(actions_host), hp(obs_host), hp(reward_host), hp(done_host),
                                             hp(timeout_host)))
-        self.launches += 2 * int(self.cfg.substeps) + 1
+        self.launches += 3 * int(self.cfg.substeps) + 1
 
     def profile_enable(self, max_steps):
         """Record CUDA events around every kernel of the next max_steps step() calls (bench.py's roofline leg)."""
@@ -194,7 +194,14 @@ class PlenVecEnv:
         t = self._dev_f32(targets, (self.num_envs, ACT_DIM))
         with torch.cuda.device(self.device):
             self._check(self.lib.plen_tick(self._ctx, self._p(t), int(n_ticks), self._stream()))
-        self.launches += 2 * int(n_ticks)
+        self.launches += 3 * int(n_ticks)
+
+    def debug_records(self):
+        """Raw per-env state records [N,96] (word 79 = PGS iterations of the last tick)."""
+        rec = torch.empty((self.num_envs, _abi.STATE_WORDS), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.plen_debug_records(self._ctx, self._p(rec), self._stream()))
+        return rec
 
     def debug_dynamics(self):
         n, dev = self.num_envs, self.device
