@@ -1,0 +1,19 @@
+#!/bin/bash
+# One GPU-box pass: GPU tests, bench (both arms), ncu launch list, ncu --set full of the two hot kernels.
+# Usage (from the repo root, under gpurun): bash scripts/gpu_round.sh <tag>
+TAG=${1:-cur}
+O=gpurun_out/$TAG
+mkdir -p $O
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/smi.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1
+timeout 600 python bench.py > $O/bench.json 2> $O/bench.err
+timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > $O/bench_ref.json 2> $O/bench_ref.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 60 --csv --log-file $O/launches.csv \
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/launches.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_solve|k_dyn|k_rank|k_post" -s 40 -c 6 \
+    -o $O/full -f python scripts/profile_step.py 32768 5 > $O/full.log 2>&1
+ncu -i $O/full.ncu-rep --page raw --csv > $O/full_raw.csv 2>/dev/null
+ncu -i $O/full.ncu-rep --page source --csv -k regex:k_solve > $O/solve_sass.csv 2>/dev/null
+ncu -i $O/full.ncu-rep --page source --csv -k regex:k_dyn > $O/dyn_sass.csv 2>/dev/null
+tail -3 $O/pytest_gpu.log; cat $O/smoke.log | tail -2; cat $O/bench.json; cat $O/bench_ref.json
