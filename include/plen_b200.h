@@ -196,6 +196,54 @@ int plen_actor_forward(int device, const float *w1, const float *b1, const float
                        unsigned long long seed, float *action_dev, void *stream);
 const char *plen_td3_last_error(void);
 
+/* ---- TD3 learner: replaces TD3Agent.train (td3.py:259-356) -- target Q with clipped policy noise, twin-critic MSE step,
+ * delayed actor step through Q1, Polyak target updates -- with hand-written CUDA (strided fp32 GEMM with fused
+ * bias / ReLU / tanh / mask / bias-gradient epilogues, fused Adam, fused target update); no cuBLAS, no autograd.
+ *
+ * Every network is ONE flat float32 vector in state_dict order (weight, bias per layer; nn.Linear layout [out][in]):
+ *   actor  (PLEN_TD3_ACTOR_PARAMS):  fc1 [256][26] b[256] | fc2 [256][256] b[256] | fc3 [18][256] b[18]          td3.py:37-41
+ *   critic (PLEN_TD3_CRITIC_PARAMS): fc1 [256][44] b | fc2 [256][256] b | fc3 [1][256] b[1] | fc4 | fc5 | fc6     td3.py:72-81
+ * The gradient vectors have the same layouts; a data-parallel learner all-reduces critic_grad / actor_grad between
+ * plen_td3_*_grads and plen_td3_adam.  All pointers are caller-owned device memory. */
+#define PLEN_TD3_ACTOR_PARAMS 77330
+#define PLEN_TD3_CRITIC_PARAMS 155138
+typedef struct plen_td3 plen_td3;
+typedef struct plen_td3_hyper {
+    float discount, tau, policy_noise, noise_clip, max_action;   /* td3.py:211-219: 0.99 0.005 0.2 0.5 1.0 */
+    float lr, beta1, beta2, eps;                                 /* torch.optim.Adam(lr=3e-4), td3.py:226-233 */
+    int policy_freq;                                             /* 2 */
+} plen_td3_hyper;
+typedef struct plen_td3_params {
+    float *actor, *actor_target, *critic, *critic_target;        /* parameters */
+    float *actor_m, *actor_v, *critic_m, *critic_v;              /* Adam exp_avg / exp_avg_sq */
+    float *actor_grad, *critic_grad;                             /* gradients of the last *_grads call */
+} plen_td3_params;
+int plen_td3_default_hyper(plen_td3_hyper *h);
+plen_td3 *plen_td3_create(int max_batch, int device);            /* workspace for minibatches of <= max_batch rows */
+void plen_td3_destroy(plen_td3 *t);
+long long plen_td3_launches(const plen_td3 *t);                  /* kernels launched so far (bench accounting) */
+/* minibatch: drawn from the replay ring (uniform with replacement, td3.py:175) or given explicitly */
+int plen_td3_sample(plen_td3 *t, plen_replay *rb, int batch, unsigned long long seed, void *stream);
+int plen_td3_set_batch(plen_td3 *t, const float *state_dev, const float *action_dev, const float *next_state_dev,
+                       const float *reward_dev, const float *not_done_dev, int batch, void *stream);
+/* td3.py:303-333: critic_loss and d critic_loss / d critic parameters -> params->critic_grad.  noise_dev (nullable)
+ * [batch,18] standard-normal samples for the target policy smoothing; NULL draws them from a counter-based generator
+ * keyed by seed.  critic_loss_dev (nullable) receives the scalar loss. */
+int plen_td3_critic_grads(plen_td3 *t, const plen_td3_params *p, const plen_td3_hyper *h, const float *noise_dev,
+                          unsigned long long seed, float *critic_loss_dev, void *stream);
+/* td3.py:342-346: actor_loss = -Q1(s, actor(s)).mean() and its gradient -> params->actor_grad */
+int plen_td3_actor_grads(plen_td3 *t, const plen_td3_params *p, const plen_td3_hyper *h, float *actor_loss_dev, void *stream);
+/* one torch.optim.Adam step (step = 1, 2, ...) over a flat parameter vector; one Polyak update target = tau p + (1 - tau) target */
+int plen_td3_adam(float *param_dev, const float *grad_dev, float *m_dev, float *v_dev, int n, long long step,
+                  const plen_td3_hyper *h, int device, void *stream);
+int plen_td3_soft_update(float *target_dev, const float *source_dev, int n, float tau, int device, void *stream);
+/* The whole TD3Agent.train call: sample (rb nullable: reuse the minibatch already set), critic step (Adam step number
+ * critic_step), and when total_it % policy_freq == 0 the actor step (actor_step) and both target updates.
+ * losses_dev (nullable) = [actor_loss, critic_loss]. */
+int plen_td3_train(plen_td3 *t, const plen_td3_params *p, const plen_td3_hyper *h, plen_replay *rb, int batch,
+                   long long total_it, long long critic_step, long long actor_step, unsigned long long seed,
+                   float *losses_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,7 +75,23 @@ EXPORTS = (
     "plen_debug_dynamics", "plen_debug_records", "plen_gait_ik", "plen_profile_enable", "plen_profile_read", "plen_measure_fp32_peak",
     "plen_replay_create", "plen_replay_destroy", "plen_replay_size", "plen_replay_ptr", "plen_replay_storage",
     "plen_replay_add", "plen_replay_sample", "plen_actor_forward", "plen_td3_last_error",
+    "plen_td3_default_hyper", "plen_td3_create", "plen_td3_destroy", "plen_td3_launches", "plen_td3_sample",
+    "plen_td3_set_batch", "plen_td3_critic_grads", "plen_td3_actor_grads", "plen_td3_adam", "plen_td3_soft_update",
+    "plen_td3_train",
 )
+
+TD3_ACTOR_PARAMS, TD3_CRITIC_PARAMS = 77330, 155138
+
+
+class PlenTd3HyperC(C.Structure):
+    _fields_ = [("discount", C.c_float), ("tau", C.c_float), ("policy_noise", C.c_float), ("noise_clip", C.c_float),
+                ("max_action", C.c_float), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("policy_freq", C.c_int32)]
+
+
+class PlenTd3ParamsC(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("actor", "actor_target", "critic", "critic_target", "actor_m", "actor_v",
+                                          "critic_m", "critic_v", "actor_grad", "critic_grad")]
 
 _lib = None
 
@@ -125,6 +141,21 @@ def load_library(path: str = LIB_PATH):
     L.plen_replay_sample.argtypes = [vp, ip, ull] + [vp] * 7
     L.plen_actor_forward.argtypes = [ip] + [vp] * 7 + [ip, C.c_float, C.c_float, ull, vp, vp]
     L.plen_td3_last_error.restype = C.c_char_p
+    hp, pp = C.POINTER(PlenTd3HyperC), C.POINTER(PlenTd3ParamsC)
+    L.plen_td3_default_hyper.argtypes = [hp]
+    L.plen_td3_create.argtypes = [ip, ip]
+    L.plen_td3_create.restype = vp
+    L.plen_td3_destroy.argtypes = [vp]
+    L.plen_td3_destroy.restype = None
+    L.plen_td3_launches.argtypes = [vp]
+    L.plen_td3_launches.restype = ll
+    L.plen_td3_sample.argtypes = [vp, vp, ip, ull, vp]
+    L.plen_td3_set_batch.argtypes = [vp] * 6 + [ip, vp]
+    L.plen_td3_critic_grads.argtypes = [vp, pp, hp, vp, ull, vp, vp]
+    L.plen_td3_actor_grads.argtypes = [vp, pp, hp, vp, vp]
+    L.plen_td3_adam.argtypes = [vp, vp, vp, vp, ip, ll, hp, ip, vp]
+    L.plen_td3_soft_update.argtypes = [vp, vp, ip, C.c_float, ip, vp]
+    L.plen_td3_train.argtypes = [vp, pp, hp, vp, ip, ll, ll, ll, ull, vp, vp]
     L.plen_gait_ik.argtypes = [ip, vp, ip, vp, vp, vp, vp]
     L.plen_measure_fp32_peak.argtypes = [ip, ip, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     _lib = L

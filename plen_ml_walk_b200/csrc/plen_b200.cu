@@ -25,7 +25,7 @@ using namespace plen;
 #define DYN_WPC 4
 
 struct plen_ctx {
-    int n, device;
+    int n, device, sm_count;
     plen_config cfg;
     plen_model model;
     DevConfig dc;
@@ -85,19 +85,22 @@ k_dyn(const __grid_constant__ DevConfig dc, const __grid_constant__ EnvRanges er
       float *__restrict__ srec, uint8_t *__restrict__ keys, float *dbg_minv, float *dbg_pos, float *dbg_rot) {
     DynSmem &sm = stage_table(tab_g);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * DYN_WPC + warp;
-    if (env >= n) return;
     WarpScratch &ws = sm.ws[warp];
-    LaneState L;
-    load_record(state + (size_t)env * PLEN_STATE_WORDS, ws, L, lane);
-    if (lane >= 6 && lane < 24) {
-        const size_t o = (size_t)env * PLEN_NJ + lane - 6;
-        if (actions) { L.tgt = agent_target(dc, er, lane - 6, actions[o]); tgt[o] = L.tgt; }
-        else L.tgt = tgt ? tgt[o] : 0.0f;
+    // persistent CTAs (grid = resident CTAs of the device, dyn_grid): the 4 KB model table is staged once per CTA and
+    // every warp walks its robots with a grid stride; warps only synchronise with themselves from here on
+    for (int env = blockIdx.x * DYN_WPC + warp; env < n; env += gridDim.x * DYN_WPC) {
+        LaneState L;
+        load_record(state + (size_t)env * PLEN_STATE_WORDS, ws, L, lane);
+        if (lane >= 6 && lane < 24) {
+            const size_t o = (size_t)env * PLEN_NJ + lane - 6;
+            if (actions) { L.tgt = agent_target(dc, er, lane - 6, actions[o]); tgt[o] = L.tgt; }
+            else L.tgt = tgt ? tgt[o] : 0.0f;
+        }
+        DebugOut dbg{dbg_minv ? dbg_minv + (size_t)env * 576 : nullptr, dbg_pos ? dbg_pos + (size_t)env * 72 : nullptr,
+                     dbg_rot ? dbg_rot + (size_t)env * 216 : nullptr};
+        tick_dynamics(dc, sm.tab, ws, L, lane, srec + (size_t)env * SR_WORDS, keys + env, (dbg_minv || dbg_pos || dbg_rot) ? &dbg : nullptr);
+        warp_sync();
     }
-    DebugOut dbg{dbg_minv ? dbg_minv + (size_t)env * 576 : nullptr, dbg_pos ? dbg_pos + (size_t)env * 72 : nullptr,
-                 dbg_rot ? dbg_rot + (size_t)env * 216 : nullptr};
-    tick_dynamics(dc, sm.tab, ws, L, lane, srec + (size_t)env * SR_WORDS, keys + env, (dbg_minv || dbg_pos || dbg_rot) ? &dbg : nullptr);
 }
 
 // Robots are grouped by contact load before the solve: k_rank counting-sorts the keys k_dyn wrote inside tiles of
@@ -134,7 +137,10 @@ k_rank(const uint8_t *__restrict__ keys, int n, int *__restrict__ perm) {
 // Second half of a tick, 4 lanes per robot: PGS + delta-v + integration, state record updated in place.
 // A CTA is ONE warp = 8 robots (30.1 KB of G in shared memory, 7 CTAs per SM).  CTA b takes group b / n_tiles of tile
 // b % n_tiles, so the heavy groups of all tiles run first and the tail of the grid is made of light ones.
-__global__ void __maxnreg__(224)
+#ifndef PLEN_SOLVE_MAXREG
+#define PLEN_SOLVE_MAXREG 224
+#endif
+__global__ void __maxnreg__(PLEN_SOLVE_MAXREG)
 k_solve(const __grid_constant__ DevConfig dc, const float *__restrict__ srec, const int *__restrict__ perm,
         float *__restrict__ state, int n, int n_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -385,6 +391,11 @@ k_fp32_peak(float *out, int iters, int mode, float seed) {
 static const size_t DYN_SMEM = sizeof(DynSmem);
 static const size_t SOLVE_SMEM = sizeof(float) * PLEN_GS_WORDS * PLEN_SOLVE_ROBOTS;
 static int dyn_grid(int n) { return (n + DYN_WPC - 1) / DYN_WPC; }
+// k_dyn runs persistent CTAs: no more than the device holds at once (5 per SM, its launch bound)
+static int dyn_grid_persistent(const plen_ctx *ctx, int n) {
+    const int full = dyn_grid(n), resident = 5 * ctx->sm_count;
+    return full < resident ? full : resident;
+}
 static int rank_tiles(int n) { return (n + RANK_TILE - 1) / RANK_TILE; }
 
 // n_ticks physics ticks of 1/240 s: (k_dyn, k_solve) per tick.  `actions` (agent space) only on the first tick.
@@ -393,7 +404,7 @@ static void launch_ticks(plen_ctx *ctx, float *state, int n, const float *action
                          cudaEvent_t *ev = nullptr) {
     for (int t = 0; t < n_ticks; t++) {
         if (ev) cudaEventRecord(ev[2 * t], st);
-        k_dyn<<<dyn_grid(n), DYN_WPC * 32, DYN_SMEM, st>>>(ctx->dc, ctx->er, ctx->d_tab, state, n, t == 0 ? actions : nullptr,
+        k_dyn<<<dyn_grid_persistent(ctx, n), DYN_WPC * 32, DYN_SMEM, st>>>(ctx->dc, ctx->er, ctx->d_tab, state, n, t == 0 ? actions : nullptr,
                                                           tgt, ctx->d_srec, ctx->d_key, nullptr, nullptr, nullptr);
         if (ev) cudaEventRecord(ev[2 * t + 1], st);
         const int nt = rank_tiles(n);
@@ -478,6 +489,9 @@ plen_ctx *plen_create(const plen_config *cfg, const plen_model *model, int n_env
     if (!ctx) { fail(nullptr, PLEN_E_ARG, "out of host memory"); return nullptr; }
     memset(ctx, 0, sizeof *ctx);
     ctx->n = n_envs; ctx->device = device; ctx->cfg = *cfg; ctx->model = *model;
+    ctx->sm_count = 148;
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (ctx->sm_count <= 0) ctx->sm_count = 148;
     if (create_impl(ctx) != PLEN_OK) {
         snprintf(g_err, sizeof g_err, "%s", ctx->err);
         plen_destroy(ctx);
@@ -559,7 +573,7 @@ int plen_tick(plen_ctx *ctx, const float *targets_dev, int n_ticks, void *stream
 int plen_debug_dynamics(plen_ctx *ctx, float *minv_dev, float *pos_dev, float *rot_dev, void *stream) {
     if (!ctx) return fail(nullptr, PLEN_E_ARG, "ctx is NULL");
     CK(ctx, cudaSetDevice(ctx->device));
-    k_dyn<<<dyn_grid(ctx->n), DYN_WPC * 32, DYN_SMEM, (cudaStream_t)stream>>>(ctx->dc, ctx->er, ctx->d_tab, ctx->d_state, ctx->n,
+    k_dyn<<<dyn_grid_persistent(ctx, ctx->n), DYN_WPC * 32, DYN_SMEM, (cudaStream_t)stream>>>(ctx->dc, ctx->er, ctx->d_tab, ctx->d_state, ctx->n,
                                                                             nullptr, nullptr, ctx->d_srec, ctx->d_key, minv_dev, pos_dev, rot_dev);
     CK(ctx, cudaGetLastError());
     return PLEN_OK;

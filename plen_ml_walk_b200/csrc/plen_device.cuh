@@ -679,24 +679,38 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
     // ---- G (30 columns x 32 words) and B (6 rows x 32 words): word w of a column = entry i = w; joint columns are
     //      divided by their diagonal entry (velocity-unit servo rows, see the SR_ enum)
     {
+        // Branch free: every lane reads its entries through ONE base pointer + a stride fixed per lane class (joint rows
+        // from M^-1 / Y, foot-twist rows from Y^T / Lambda^-1, the two unused words zero), so the 30 column stores are
+        // straight-line LDS -> (FMUL) -> STG with the loops fully unrolled.
         const int i = lane;
         const bool ij = i < 18, ic = (i >= 18 && i < 24) || i >= 26;
         const int fa = (i >= 26) ? 1 : 0, a6 = fa ? i - 26 : i - 18;
         const float(*Ya)[8] = fa ? ws.gg : ws.kk;
         float *G = srec + SR_G;
-        for (int c = 0; c < 18; c++) {
-            float v = 0.0f;
-            if (ij) v = ws.minv[6 + c][6 + i];
-            else if (ic) v = Ya[6 + c][a6];
-            G[c * 32 + lane] = v * shfl(m_dinv, 6 + c);
+        ws.obs[lane] = m_dinv;                      // obs is free scratch in k_dyn; word 6 + c = 1 / G_cc of joint column c
+        warp_sync();
+        {
+            const float *b1 = ij ? &ws.minv[6][6 + i] : (ic ? &Ya[6][a6] : &ws.cb[0]);
+            const int st1 = ij ? 32 : (ic ? 8 : 0);
+            const bool on1 = ij || ic;
+#pragma unroll
+            for (int c = 0; c < 18; c++) {
+                const float v = b1[c * st1];
+                G[c * 32 + lane] = on1 ? v * ws.obs[6 + c] : 0.0f;
+            }
         }
-        for (int c = 18; c < 30; c++) {
-            const int fb = (c >= 24) ? 1 : 0, b6 = c - 18 - 6 * fb;
-            const float(*Yb)[8] = fb ? ws.gg : ws.kk;
-            float v = 0.0f;
-            if (ij) v = Yb[6 + i][b6];
-            else if (ic && man_new) v = ws.lin[fa * 6 + a6][c - 18];
-            G[c * 32 + lane] = v;
+        {
+            // column c = 18 + 6 fb + b6:  joint rows Y_fb[6 + i][b6] (kk / gg are adjacent [24][8] arrays), twist rows
+            // Lambda^-1[fa 6 + a6][c - 18] when any contact is active
+            const bool on2 = ij || (ic && man_new);
+            const float *b2 = ij ? &ws.kk[6 + i][0] : (on2 ? &ws.lin[fa * 6 + a6][0] : &ws.cb[0]);
+            const int jump = ij ? (int)(&ws.gg[0][0] - &ws.kk[0][0]) - 6 : 0, st2 = on2 ? 1 : 0;
+#pragma unroll
+            for (int c = 18; c < 30; c++) {
+                const int fb = (c >= 24) ? 1 : 0;
+                const float v = b2[(c - 18) * st2 + (fb ? jump : 0)];
+                G[c * 32 + lane] = on2 ? v : 0.0f;
+            }
         }
         // per-joint scalars in the same word order (entries >= 18 are zero)
         const int src = ij ? 6 + i : 0;
@@ -704,12 +718,12 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
                     s_lrhs = shfl(l_rhs, src), s_vs = shfl(vstar, src), s_q = shfl(L.q, src),
                     s_d = shfl(is_joint ? ws.minv[lane][lane] : 0.0f, src);
         float *Bm = srec + SR_B;
+        {
+            const float *b3 = ij ? &ws.minv[6 + i][0] : (ic ? &Ya[0][a6] : &ws.cb[0]);
+            const int st3 = ij ? 1 : (ic ? 8 : 0);
+            const float sc3 = ij ? s_dinv : (ic ? 1.0f : 0.0f);
 #pragma unroll
-        for (int k = 0; k < 6; k++) {
-            float v = 0.0f;
-            if (ij) v = ws.minv[6 + i][k] * s_dinv;
-            else if (ic) v = Ya[k][a6];
-            Bm[k * 32 + lane] = v;
+            for (int k = 0; k < 6; k++) Bm[k * 32 + lane] = (ij || ic) ? b3[k * st3] * sc3 : 0.0f;
         }
         srec[SR_MRHS + lane] = ij ? s_rhs : 0.0f;
         srec[SR_MD + lane] = (ij && s_dinv > 0.0f) ? s_d : 0.0f;

@@ -31,6 +31,21 @@ struct __align__(16) vec4 { float x, y, z, w; };
 struct vec4 { float x, y, z, w; };
 #endif
 
+// Owner look-ahead (see solve_tick) per row family; each costs extra FFMA2 issue slots and removes one SHFL round trip
+// from the dependency chain of the family.  Chosen by A/B timing on B200 (profiles/r1_v6_summary.md).
+#ifndef PLEN_LA_SERVO
+#define PLEN_LA_SERVO 1
+#endif
+#ifndef PLEN_LA_NORMAL
+#define PLEN_LA_NORMAL 0
+#endif
+#ifndef PLEN_LA_TORSION
+#define PLEN_LA_TORSION 0
+#endif
+#ifndef PLEN_LA_LATERAL
+#define PLEN_LA_LATERAL 0
+#endif
+
 // Shared memory holds 24 of the 30 columns of G per robot: the 18 joint columns and the linear (vx vy vz) columns of
 // either foot.  The six ANGULAR foot columns -- the ones the contact rows use most (normal 2 of 3, spinning, rolling,
 // lateral 3 of 5 column updates) -- live in registers, which (a) takes 8 of the 11 LDS pairs out of every contact point
@@ -54,6 +69,25 @@ PLEN_DEV void fma2(float &a0, float &a1, float x0, float x1, float d) {
         : "+f"(a0), "+f"(a1) : "f"(x0), "f"(x1), "f"(d));
 #else
     a0 = fmaf(x0, d, a0); a1 = fmaf(x1, d, a1);
+#endif
+}
+
+// keep a kernel-parameter constant in a register for the whole loop (ptxas otherwise re-reads it from the constant bank
+// with an LDCU in front of every use and waits for it)
+PLEN_DEV float pin_reg(float v) {
+#ifndef PLEN_HOST_EMU
+    asm volatile("" : "+f"(v));
+#endif
+    return v;
+}
+// 1/sqrt(x) as one MUFU.RSQ: rsqrtf() adds a subnormal-input rescue (FSETP + two predicated FMUL on the row chain)
+PLEN_DEV float rsqrt_fast(float x) {
+#ifndef PLEN_HOST_EMU
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / sqrtf(x);
 #endif
 }
 
@@ -91,6 +125,24 @@ PLEN_DEV void apply_reg(float (&s)[8], const float (&a)[8], float db) {
     fma2(s[2], s[3], a[2], a[3], db);
     fma2(s[4], s[5], a[4], a[5], db);
     fma2(s[6], s[7], a[6], a[7], db);
+}
+
+// Owner look-ahead copies: entries 2..7 (a foot twist) of a register column / a staged column
+PLEN_DEV void apply_reg6(float (&o)[8], const float (&a)[8], float d) {
+    fma2(o[2], o[3], a[2], a[3], d);
+    fma2(o[4], o[5], a[4], a[5], d);
+    fma2(o[6], o[7], a[6], a[7], d);
+}
+PLEN_DEV void apply_vec(float (&o)[8], const vec4 &a, const vec4 &b, float d) {
+    fma2(o[0], o[1], a.x, a.y, d);
+    fma2(o[2], o[3], a.z, a.w, d);
+    fma2(o[4], o[5], b.x, b.y, d);
+    fma2(o[6], o[7], b.z, b.w, d);
+}
+PLEN_DEV void apply_vec6(float (&o)[8], const vec4 &a, const vec4 &b, float d) {
+    fma2(o[2], o[3], a.z, a.w, d);
+    fma2(o[4], o[5], b.x, b.y, d);
+    fma2(o[6], o[7], b.z, b.w, d);
 }
 
 PLEN_DEV void load8(const float *p, float (&o)[8]) {
@@ -204,6 +256,15 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
 #pragma unroll
     for (int k = 0; k < 8; k++) s[k] = 0.0f;
     float res = 0.0f, resF = 0.0f;
+    // Owner look-ahead.  Consecutive rows of a block (8 joints of a lane / the points of one foot) are owned by the SAME
+    // lane, and the next candidate only needs the owner's own entries of x.  The owner therefore keeps a private copy o of
+    // its entries that it advances with its own impulse change dl_ BEFORE the broadcast, while s (every lane's slice of
+    // x) takes the same update after the SHFL.  In the owner lane o and s receive identical operations in identical
+    // order, so they agree bit for bit; in the other lanes o is scratch.  This takes the SHFL round trip (the longest
+    // link of the Gauss-Seidel dependency chain) off the critical path except once per block, where o is refreshed from s.
+    float o[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+#define OWN_SYNC()  { _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++) o[k_] = s[k_]; }
+#define OWN_SYNC6() { _Pragma("unroll") for (int k_ = 2; k_ < 8; k_++) o[k_] = s[k_]; }
 
 #define NORMAL_COLUMN(p, f, db)                              \
     {                                                        \
@@ -225,11 +286,13 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
     // servo row of joint 8 b + k (owner lane b)
 #define SERVO_ROW(b, k)                                                \
     {                                                                  \
-        const float dl_ = fminf(fmaxf(m_rhs[k] - s[k], m_lo[k]), m_hi[k]); \
+        const float dl_ = fminf(fmaxf(m_rhs[k] - (PLEN_LA_SERVO ? o[k] : s[k]), m_lo[k]), m_hi[k]); \
+        const vec4 ca_ = g_ld(Gl, (8 * (b) + (k)) * 8), cb_ = g_ld(Gl, (8 * (b) + (k)) * 8 + 1); \
+        if (PLEN_LA_SERVO) apply_vec(o, ca_, cb_, dl_);                \
         const float db_ = GSH(dl_, b);                                 \
         if (g == (b)) { m_lo[k] -= dl_; m_hi[k] -= dl_; }              \
         res = fmaxf(res, fabsf(db_));                                  \
-        apply_col(s, Gl, 8 * (b) + (k), db_);                          \
+        apply_vec(s, ca_, cb_, db_);                                   \
     }
 
     // joint-limit row of joint 8 b + k (rare: the joint is beyond +-1.7 rad); lower bound 0, upper bound 100 (impulse units)
@@ -249,19 +312,23 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
     // spinning / rolling row of point k of foot f: own twist component c, friction coefficient mu
 #define TORSION_ROW(k, f, c, mu)                                                                          \
     {                                                                                                     \
-        const float x_ = fmaf(-s[2 + (c)], t_dinv[c], t_rhs[c]);                                          \
+        const float x_ = fmaf(-(PLEN_LA_TORSION ? o[2 + (c)] : s[2 + (c)]), t_dinv[c], t_rhs[c]);                                        \
         const float lim_ = (mu) * c_lam[k][5];                                                            \
         float dl_ = fminf(fmaxf(x_, -lim_ - c_lam[k][c]), lim_ - c_lam[k][c]);                            \
         dl_ = (c_lam[k][5] > 0.0f) ? dl_ : 0.0f;   /* row skipped while the normal impulse is not positive */ \
+        if (PLEN_LA_TORSION) apply_reg6(o, A[f][c], dl_);                                                 \
         const float db_ = GSH(dl_, 2 + (f));                                                              \
-        if (g == 2 + (f)) { c_lam[k][c] += dl_; resF = fmaxf(resF, fabsf(dl_ * t_d[c])); }                \
+        if (g == 2 + (f)) { c_lam[k][c] += dl_; resT[c] = fmaxf(resT[c], fabsf(dl_)); }                   \
         apply_reg(s, A[f][c], db_);                                                                       \
     }
 
+    const float mu_spin = pin_reg(cfg.mu_spinning), mu_roll = pin_reg(cfg.mu_rolling), mu_lat = pin_reg(cfg.mu_lateral);
+    const float res_thr = pin_reg(cfg.residual_threshold);
     bool alive = valid;
     int my_iters = 0;
     for (int it = 0; it < cfg.iterations; it++) {
         res = 0.0f; resF = 0.0f;
+        float resT[3] = {0.0f, 0.0f, 0.0f};      // largest |impulse change| of the spinning / rolling rows per twist component
         const bool fwd = (it & 1) != 0;
         // ---- non-contact rows: list = [limits in joint order, servos in joint order]; odd iterations forward, even reversed
         for (int half = 0; half < 2; half++) {
@@ -284,17 +351,23 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
                     }
                 }
             } else if (fwd) {
+                if (PLEN_LA_SERVO) OWN_SYNC();
 #pragma unroll
                 for (int k = 0; k < 8; k++) SERVO_ROW(0, k);
+                if (PLEN_LA_SERVO) OWN_SYNC();
 #pragma unroll
                 for (int k = 0; k < 8; k++) SERVO_ROW(1, k);
+                if (PLEN_LA_SERVO) OWN_SYNC();
 #pragma unroll
                 for (int k = 0; k < 2; k++) SERVO_ROW(2, k);
             } else {
+                if (PLEN_LA_SERVO) OWN_SYNC();
 #pragma unroll
                 for (int k = 1; k >= 0; k--) SERVO_ROW(2, k);
+                if (PLEN_LA_SERVO) OWN_SYNC();
 #pragma unroll
                 for (int k = 7; k >= 0; k--) SERVO_ROW(1, k);
+                if (PLEN_LA_SERVO) OWN_SYNC();
 #pragma unroll
                 for (int k = 7; k >= 0; k--) SERVO_ROW(0, k);
             }
@@ -305,43 +378,66 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
             for (int p = 0; p < 8; p++) {
                 if ((p & 3) >= ((p >> 2) ? nmax1 : nmax0)) continue;
                 const int f = p >> 2, k = p & 3;
-                const float r_ = fmaf(s[2], py[p], fmaf(-s[3], px[p], s[7]));
+                if (PLEN_LA_NORMAL && k == 0) OWN_SYNC6();
+                const float(&on)[8] = PLEN_LA_NORMAL ? o : s;
+                const float r_ = fmaf(on[2], py[p], fmaf(-on[3], px[p], on[7]));
                 const float x_ = fmaf(-r_, c_dinv[k][2], c_rhs[k][2]);
                 const float dl_ = fmaxf(x_, -c_lam[k][5]);
+                const vec4 ca_ = g_ld(Gl, PLEN_SCOL(f, 5) * 8), cb_ = g_ld(Gl, PLEN_SCOL(f, 5) * 8 + 1);
+                if (PLEN_LA_NORMAL) {
+                    apply_reg6(o, A[f][0], py[p] * dl_);
+                    apply_reg6(o, A[f][1], -px[p] * dl_);
+                    apply_vec6(o, ca_, cb_, dl_);
+                }
                 const float db_ = GSH(dl_, 2 + f);
                 if (g == 2 + f) { c_lam[k][5] += dl_; resF = fmaxf(resF, fabsf(dl_ * c_d[k][2])); }
-                NORMAL_COLUMN(p, f, db_);
+                apply_reg(s, A[f][0], py[p] * db_);
+                apply_reg(s, A[f][1], -px[p] * db_);
+                apply_vec(s, ca_, cb_, db_);
             }
             // ---- all spinning rows, then the rolling rows point by point (t1, t2)
 #pragma unroll
             for (int p = 0; p < 8; p++) {
                 if ((p & 3) >= ((p >> 2) ? nmax1 : nmax0)) continue;
-                TORSION_ROW((p & 3), (p >> 2), 2, cfg.mu_spinning);
+                if (PLEN_LA_TORSION && (p & 3) == 0) OWN_SYNC6();
+                TORSION_ROW((p & 3), (p >> 2), 2, mu_spin);
             }
 #pragma unroll
             for (int p = 0; p < 8; p++) {
                 if ((p & 3) >= ((p >> 2) ? nmax1 : nmax0)) continue;
-                TORSION_ROW((p & 3), (p >> 2), 1, cfg.mu_rolling);
-                TORSION_ROW((p & 3), (p >> 2), 0, cfg.mu_rolling);
+                if (PLEN_LA_TORSION && (p & 3) == 0) OWN_SYNC6();
+                TORSION_ROW((p & 3), (p >> 2), 1, mu_roll);
+                TORSION_ROW((p & 3), (p >> 2), 0, mu_roll);
             }
             // ---- lateral pairs with the implicit friction cone (resolveConeFrictionConstraintRows)
 #pragma unroll
             for (int p = 0; p < 8; p++) {
                 if ((p & 3) >= ((p >> 2) ? nmax1 : nmax0)) continue;
                 const int f = p >> 2, k = p & 3;
-                const float rA = fmaf(s[4], px[p], fmaf(-s[2], pz[p], s[6]));     // row A: own = vy
-                const float rB = fmaf(s[3], pz[p], fmaf(-s[4], py[p], s[5]));     // row B: own = vx
+                if (PLEN_LA_LATERAL && k == 0) OWN_SYNC6();
+                const float(&ol)[8] = PLEN_LA_LATERAL ? o : s;
+                const float rA = fmaf(ol[4], px[p], fmaf(-ol[2], pz[p], ol[6]));     // row A: own = vy
+                const float rB = fmaf(ol[3], pz[p], fmaf(-ol[4], py[p], ol[5]));     // row B: own = vx
                 const float sumA = c_lam[k][4] + fmaf(-rA, c_dinv[k][1], c_rhs[k][1]);
                 const float sumB = c_lam[k][3] + fmaf(-rB, c_dinv[k][0], c_rhs[k][0]);
-                const float lim = cfg.mu_lateral * c_lam[k][5];
-                float nA = sumA, nB = sumB;
-                if (fabsf(sumA) > lim || fabsf(sumB) > lim) {
-                    const float inv = rsqrtf(sumA * sumA + sumB * sumB);
-                    const float cA = fabsf(lim * sumA * inv), cB = fabsf(lim * sumB * inv);
-                    nA = clampf(sumA, -cA, cA);
-                    nB = clampf(sumB, -cB, cB);
-                }
+                const float lim = mu_lat * c_lam[k][5];
+                // branch free: the projection is always evaluated and selected by the cone test (inside the cone the
+                // operands may be 0 * inf = NaN; fminf / fmaxf return the other operand and the select drops the result)
+                const bool outside = fmaxf(fabsf(sumA), fabsf(sumB)) > lim;
+                const float inv = rsqrt_fast(fmaf(sumA, sumA, sumB * sumB));
+                const float cA = fabsf(lim * sumA * inv), cB = fabsf(lim * sumB * inv);
+                const float nA = outside ? clampf(sumA, -cA, cA) : sumA;
+                const float nB = outside ? clampf(sumB, -cB, cB) : sumB;
                 const float dlA = nA - c_lam[k][4], dlB = nB - c_lam[k][3];
+                const vec4 xa_ = g_ld(Gl, PLEN_SCOL(f, 3) * 8), xb_ = g_ld(Gl, PLEN_SCOL(f, 3) * 8 + 1);
+                const vec4 ya_ = g_ld(Gl, PLEN_SCOL(f, 4) * 8), yb_ = g_ld(Gl, PLEN_SCOL(f, 4) * 8 + 1);
+                if (PLEN_LA_LATERAL) {
+                    apply_reg6(o, A[f][0], -pz[p] * dlA);
+                    apply_reg6(o, A[f][1], pz[p] * dlB);
+                    apply_reg6(o, A[f][2], px[p] * dlA - py[p] * dlB);
+                    apply_vec6(o, xa_, xb_, dlB);
+                    apply_vec6(o, ya_, yb_, dlA);
+                }
                 const float dA = GSH(dlA, 2 + f), dB = GSH(dlB, 2 + f);
                 if (g == 2 + f) {
                     c_lam[k][4] = nA; c_lam[k][3] = nB;
@@ -350,19 +446,21 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
                 apply_reg(s, A[f][0], -pz[p] * dA);
                 apply_reg(s, A[f][1], pz[p] * dB);
                 apply_reg(s, A[f][2], px[p] * dA - py[p] * dB);
-                apply_col(s, Gl, PLEN_SCOL(f, 3), dB);
-                apply_col(s, Gl, PLEN_SCOL(f, 4), dA);
+                apply_vec(s, xa_, xb_, dB);
+                apply_vec(s, ya_, yb_, dA);
             }
         }
         // ---- residual of this iteration, per robot: servo / limit part is already robot-uniform, the contact part
         //      lives in the two foot lanes
+        // spinning / rolling rows of a foot share one d per twist component (t_d), so |dl * d| is scaled once here
+        resF = fmaxf(resF, fmaxf(resT[0] * fabsf(t_d[0]), fmaxf(resT[1] * fabsf(t_d[1]), resT[2] * fabsf(t_d[2]))));
         float rf = (g >= 2) ? resF : 0.0f;
         rf = fmaxf(rf, shfl_xor(rf, 1));
         rf = fmaxf(rf, shfl_xor(rf, 2));
         const float rr = fmaxf(res, rf);
         if (alive) {
             my_iters = it + 1;
-            if (rr * rr <= cfg.residual_threshold) {
+            if (rr * rr <= res_thr) {
                 alive = false;      // freeze: every later row update of this robot is exactly zero
 #pragma unroll
                 for (int k = 0; k < 8; k++) {     // park the accumulated servo row value in m_rhs, close the bounds
@@ -481,6 +579,8 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
         }
     }
 #undef GSH
+#undef OWN_SYNC
+#undef OWN_SYNC6
 #undef SERVO_ROW
 #undef LIMIT_ROW
 #undef L_LAM

@@ -33,6 +33,7 @@ static int td3_fail(int code, const char *msg, const char *detail = "") {
     snprintf(g_td3_err, sizeof g_td3_err, "%s%s", msg, detail);
     return code;
 }
+extern "C" int plen_td3_set_error(int code, const char *msg, const char *detail) { return td3_fail(code, msg, detail); }
 #define TCK(call)                                                                          \
     do {                                                                                   \
         cudaError_t e_ = (call);                                                           \

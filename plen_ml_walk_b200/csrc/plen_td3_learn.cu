@@ -1,0 +1,504 @@
+// plen_td3_learn.cu -- TD3Agent.train (plen_ros/src/plen_ros_helpers/td3.py:259-356) as hand-written CUDA, part of
+// libplen_b200.so (C ABI in include/plen_b200.h).  sm_100a only, no CPU path, no cuBLAS / autograd.
+//
+// One update = sample -> target Q (actor_target, critic_target, clipped noise) -> critic forward / MSE / backward -> Adam
+// -> every policy_freq-th call: actor forward, Q1 forward, backward through Q1 into the actor, Adam, Polyak targets.
+// The networks are the reference's (Actor 26-256-256-18, Critic 2 x 44-256-256-1, td3.py:19-117) with every parameter of
+// a network in ONE flat float32 vector in state_dict order (fc1.weight, fc1.bias, ...), so an optimiser step or a target
+// update is one launch and a data-parallel learner all-reduces one buffer.
+//
+// At the reference's batch of 100 every matrix product is tiny (100 x 256 x 256): the step is bound by launch and
+// dependency latency, not by FLOPs, so the products run on the FP32 CUDA cores in one strided GEMM kernel with fused
+// epilogues (bias / ReLU / tanh / ReLU-mask / tanh-gradient / bias-gradient) -- 17 launches for a critic-only update, 35
+// with the policy update, all enqueued from C on the caller's stream (no host sync, no allocation).  fp32 keeps the
+// update within 1e-5 of the reference's torch arithmetic (tests/test_td3_gpu.py).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/plen_b200.h"
+
+extern "C" int plen_td3_set_error(int code, const char *msg, const char *detail);      // plen_td3.cu
+
+#define LCK(call)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return plen_td3_set_error(PLEN_E_CUDA, #call ": ", cudaGetErrorString(e_)); \
+    } while (0)
+
+namespace {
+
+constexpr int S = PLEN_OBS, A = PLEN_NJ, SA = PLEN_OBS + PLEN_NJ, H = 256;
+// flat layouts (floats), state_dict order
+constexpr int AW1 = 0, AB1 = AW1 + H * S, AW2 = AB1 + H, AB2 = AW2 + H * H, AW3 = AB2 + H, AB3 = AW3 + A * H, ACTOR_N = AB3 + A;
+constexpr int CW1 = 0, CB1 = CW1 + H * SA, CW2 = CB1 + H, CB2 = CW2 + H * H, CW3 = CB2 + H, CB3 = CW3 + H, TOWER_N = CB3 + 1;
+constexpr int CRITIC_N = 2 * TOWER_N;
+static_assert(ACTOR_N == PLEN_TD3_ACTOR_PARAMS && CRITIC_N == PLEN_TD3_CRITIC_PARAMS, "flat parameter layouts");
+
+enum { EPI_NONE = 0, EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_TANH, EPI_BIAS_TANH_NOISE, EPI_RELUMASK, EPI_TANHGRAD };
+
+struct Gemm {
+    // C[z][m][n] = epi( sum_k A(z, m, k) B(z, k, n) ),  A(z,m,k) = a[z az + m am + k ak],  B(z,k,n) = b[z bz + k bk + n bn]
+    const float *a, *b;
+    float *c;
+    long long az, am, ak, bz, bk, bn, cz, ldc;
+    int M, N, K, nz;
+    int epi;
+    const float *bias; long long bias_z;          // bias[z][n]
+    const float *aux; long long aux_z, ld_aux;     // EPI_RELUMASK: activation; EPI_TANHGRAD: max_action*tanh; EPI_BIAS_TANH_NOISE: noise or NULL
+    float p0, p1, p2;                              // max_action, policy_noise, noise_clip
+    unsigned long long seed;
+    float *rowsum; long long rowsum_z;             // nullable: rowsum[z][m] = sum_k A(z, m, k)   (bias gradient of a dW product)
+};
+
+__device__ __forceinline__ uint32_t mix32(uint64_t x) {     // splitmix64 finaliser
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return (uint32_t)((x ^ (x >> 31)) >> 32);
+}
+
+constexpr int BM = 32, BN = 32, BK = 32, GT = 256;
+
+// 32 x 32 output tile per CTA, 256 threads, 2 x 2 outputs per thread, K in steps of 32 with the next tiles prefetched
+// into registers while the current ones are multiplied.  Strides are arbitrary (row- or column-major operands, strided
+// sub-matrices such as the action columns of fc1), loads are coalesced along whichever operand stride is 1.
+__global__ void __launch_bounds__(GT) k_gemm(const Gemm g) {
+    __shared__ float As[BK][BM + 1], Bs[BK][BN + 1];
+    const int z = blockIdx.z, m0 = blockIdx.y * BM, n0 = blockIdx.x * BN, tid = threadIdx.x;
+    const float *a = g.a + z * g.az, *b = g.b + z * g.bz;
+    const bool a_kfast = g.ak == 1, b_nfast = g.bn == 1;
+    float ra[4], rb[4];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int e = tid + GT * i;
+            const int am = a_kfast ? (e >> 5) : (e & 31), ak = a_kfast ? (e & 31) : (e >> 5);
+            const int bk = b_nfast ? (e >> 5) : (e & 31), bn = b_nfast ? (e & 31) : (e >> 5);
+            ra[i] = (m0 + am < g.M && k0 + ak < g.K) ? a[(m0 + am) * g.am + (k0 + ak) * g.ak] : 0.0f;
+            rb[i] = (k0 + bk < g.K && n0 + bn < g.N) ? b[(k0 + bk) * g.bk + (n0 + bn) * g.bn] : 0.0f;
+        }
+    };
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[2][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}};
+    float rs = 0.0f;                                   // row sum of A for row m0 + tid (threads < 32, first column tile only)
+    const bool do_rs = g.rowsum != nullptr && blockIdx.x == 0;
+    fetch(0);
+    for (int k0 = 0; k0 < g.K; k0 += BK) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int e = tid + GT * i;
+            const int am = a_kfast ? (e >> 5) : (e & 31), ak = a_kfast ? (e & 31) : (e >> 5);
+            const int bk = b_nfast ? (e >> 5) : (e & 31), bn = b_nfast ? (e & 31) : (e >> 5);
+            As[ak][am] = ra[i];
+            Bs[bk][bn] = rb[i];
+        }
+        __syncthreads();
+        if (k0 + BK < g.K) fetch(k0 + BK);
+#pragma unroll
+        for (int k = 0; k < BK; k++) {
+            const float a0 = As[k][2 * ty], a1 = As[k][2 * ty + 1], b0 = Bs[k][2 * tx], b1 = Bs[k][2 * tx + 1];
+            acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+            acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+        }
+        if (do_rs && tid < BM) {
+#pragma unroll
+            for (int k = 0; k < BK; k++) rs += As[k][tid];
+        }
+    }
+    if (do_rs && tid < BM && m0 + tid < g.M) g.rowsum[z * g.rowsum_z + m0 + tid] = rs;
+    float *c = g.c + z * g.cz;
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int m = m0 + 2 * ty + i, n = n0 + 2 * tx + j;
+            if (m >= g.M || n >= g.N) continue;
+            float v = acc[i][j];
+            switch (g.epi) {
+                case EPI_BIAS: v += g.bias[z * g.bias_z + n]; break;
+                case EPI_BIAS_RELU: v = fmaxf(v + g.bias[z * g.bias_z + n], 0.0f); break;
+                case EPI_BIAS_TANH: v = g.p0 * tanhf(v + g.bias[z * g.bias_z + n]); break;
+                case EPI_BIAS_TANH_NOISE: {
+                    // td3.py:303-308: noise = clamp(randn * policy_noise, +-noise_clip); clamp(actor_target(s') + noise, +-max_action)
+                    float nz;
+                    if (g.aux) nz = g.aux[z * g.aux_z + m * g.ld_aux + n];
+                    else {
+                        const uint64_t ctr = g.seed * 0x100000001B3ull + (uint64_t)m * 64u + (uint64_t)n;
+                        const float u1 = (mix32(ctr) + 1.0f) * 2.3283064e-10f, u2 = mix32(ctr ^ 0x5DEECE66D1234567ull) * 2.3283064e-10f;
+                        nz = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+                    }
+                    nz = fminf(fmaxf(nz * g.p1, -g.p2), g.p2);
+                    v = g.p0 * tanhf(v + g.bias[z * g.bias_z + n]) + nz;
+                    v = fminf(fmaxf(v, -g.p0), g.p0);
+                    break;
+                }
+                case EPI_RELUMASK: v = (g.aux[z * g.aux_z + m * g.ld_aux + n] > 0.0f) ? v : 0.0f; break;
+                case EPI_TANHGRAD: {
+                    const float t = g.aux[z * g.aux_z + m * g.ld_aux + n] / g.p0;
+                    v = v * g.p0 * (1.0f - t * t);
+                    break;
+                }
+                default: break;
+            }
+            c[m * g.ldc + n] = v;
+        }
+}
+
+// minibatch rows drawn uniformly with replacement (td3.py:175), written as the concatenated critic inputs:
+// sa = [s | a], s2a = [s' | .] (the action columns are filled by the target actor), spi = [s | .] (filled by the actor)
+__global__ void k_sample_sa(const float *__restrict__ store, long long size, int batch, uint64_t seed, float *__restrict__ sa,
+                            float *__restrict__ s2a, float *__restrict__ spi, float *__restrict__ r, float *__restrict__ nd) {
+    const int bi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (bi >= batch) return;
+    const uint32_t u = mix32(seed * 0x100000001B3ull + (uint64_t)bi);
+    const long long row = (long long)(((uint64_t)u * (uint64_t)size) >> 32);
+    const float *t = store + row * 72;
+    for (int w = lane; w < 72; w += 32) {
+        const float v = t[w];
+        if (w < 44) { sa[(size_t)bi * SA + w] = v; if (w < 26) spi[(size_t)bi * SA + w] = v; }
+        else if (w < 70) s2a[(size_t)bi * SA + (w - 44)] = v;
+        else if (w == 70) r[bi] = v;
+        else nd[bi] = 1.0f - v;
+    }
+}
+
+__global__ void k_set_batch(int batch, const float *__restrict__ s, const float *__restrict__ a, const float *__restrict__ s2,
+                            const float *__restrict__ r_in, const float *__restrict__ nd_in, float *__restrict__ sa,
+                            float *__restrict__ s2a, float *__restrict__ spi, float *__restrict__ r, float *__restrict__ nd) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= batch * SA) return;
+    const int bi = e / SA, w = e - bi * SA;
+    if (w < S) { sa[e] = s[bi * S + w]; spi[e] = s[bi * S + w]; s2a[e] = s2[bi * S + w]; }
+    else sa[e] = a[bi * A + (w - S)];
+    if (w == 0) { r[bi] = r_in[bi]; nd[bi] = nd_in[bi]; }
+}
+
+// y = r + not_done * discount * min(Q1', Q2') (td3.py:311-313); critic_loss = mse(Q1, y) + mse(Q2, y) (:322-323);
+// dq[z] = 2 (Q_z - y) / B.  One CTA, strided over the batch.
+__global__ void k_td_loss(int batch, float discount, const float *__restrict__ qt, const float *__restrict__ q, const float *__restrict__ r,
+                          const float *__restrict__ nd, float *__restrict__ dq, float *__restrict__ loss_out) {
+    __shared__ float red[32];
+    float acc = 0.0f;
+    const float inv = 1.0f / (float)batch;
+    for (int i = threadIdx.x; i < batch; i += blockDim.x) {
+        const float y = r[i] + nd[i] * discount * fminf(qt[i], qt[batch + i]);
+        const float e1 = q[i] - y, e2 = q[batch + i] - y;
+        dq[i] = 2.0f * e1 * inv; dq[batch + i] = 2.0f * e2 * inv;
+        acc += e1 * e1 + e2 * e2;
+    }
+    for (int m = 16; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0f;
+        for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+        if (threadIdx.x == 0 && loss_out) *loss_out = v * inv;
+    }
+}
+
+// actor_loss = -mean(Q1(s, actor(s))) (td3.py:342); dq = -1 / B
+__global__ void k_actor_loss(int batch, const float *__restrict__ q, float *__restrict__ dq, float *__restrict__ loss_out) {
+    __shared__ float red[32];
+    float acc = 0.0f;
+    const float inv = 1.0f / (float)batch;
+    for (int i = threadIdx.x; i < batch; i += blockDim.x) { acc += q[i]; dq[i] = -inv; }
+    for (int m = 16; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0f;
+        for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+        if (threadIdx.x == 0 && loss_out) *loss_out = -v * inv;
+    }
+}
+
+// torch.optim.Adam (td3.py:226-233: lr 3e-4, default betas / eps, no weight decay), same operation order as torch's
+// single-tensor path: m.lerp_(g, 1 - b1); v = v b2 + (1 - b2) g g; p -= (lr / bc1) m / (sqrt(v) / sqrt(bc2) + eps)
+__global__ void k_adam(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, int n,
+                       float one_minus_b1, float b2, float one_minus_b2, float step_size, float inv_bc2_sqrt, float eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gi = g[i];
+    const float mi = m[i] + (gi - m[i]) * one_minus_b1;
+    const float vi = v[i] * b2 + one_minus_b2 * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) * inv_bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+}
+
+// target = tau * param + (1 - tau) * target (td3.py:352-360)
+__global__ void k_soft_update(float *__restrict__ tgt, const float *__restrict__ src, int n, float tau) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tgt[i] = tau * src[i] + (1.0f - tau) * tgt[i];
+}
+
+int launch(const Gemm &g, cudaStream_t st) {
+    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.nz);
+    k_gemm<<<grid, GT, 0, st>>>(g);
+    return 1;
+}
+
+// forward layer: C[z] = epi(X[z] W[z]^T + b[z]),  W in nn.Linear layout [N][K] with row stride ldw (a column sub-range of
+// a wider weight is addressed by offsetting w)
+Gemm fwd(const float *x, long long ldx, long long xz, const float *w, long long ldw, long long wz, const float *bias, float *c,
+         long long ldc, long long cz, int M, int N, int K, int nz, int epi) {
+    Gemm g;
+    memset(&g, 0, sizeof g);
+    g.a = x; g.am = ldx; g.ak = 1; g.az = xz;
+    g.b = w; g.bk = 1; g.bn = ldw; g.bz = wz;
+    g.c = c; g.ldc = ldc; g.cz = cz;
+    g.M = M; g.N = N; g.K = K; g.nz = nz; g.epi = epi; g.bias = bias; g.bias_z = wz;
+    return g;
+}
+// backward-data: dX[z] = epi(dY[z] W[z]),  dY [M][Nout] (ld ldy), W [Nout][Kin] (row stride ldw)
+Gemm bwd_data(const float *dy, long long ldy, long long dyz, const float *w, long long ldw, long long wz, float *dx, long long ldx,
+              long long dxz, int M, int Kin, int Nout, int nz, int epi, const float *aux, long long ld_aux, long long aux_z) {
+    Gemm g;
+    memset(&g, 0, sizeof g);
+    g.a = dy; g.am = ldy; g.ak = 1; g.az = dyz;
+    g.b = w; g.bk = ldw; g.bn = 1; g.bz = wz;
+    g.c = dx; g.ldc = ldx; g.cz = dxz;
+    g.M = M; g.N = Kin; g.K = Nout; g.nz = nz; g.epi = epi; g.aux = aux; g.ld_aux = ld_aux; g.aux_z = aux_z;
+    return g;
+}
+// backward-weight: dW[z] = dY[z]^T X[z] ([Nout][Kin], row stride ldw), db[z] = column sums of dY[z]
+Gemm bwd_weight(const float *dy, long long ldy, long long dyz, const float *x, long long ldx, long long xz, float *dw, long long ldw,
+                float *db, long long gz, int Bt, int Nout, int Kin, int nz) {
+    Gemm g;
+    memset(&g, 0, sizeof g);
+    g.a = dy; g.am = 1; g.ak = ldy; g.az = dyz;
+    g.b = x; g.bk = ldx; g.bn = 1; g.bz = xz;
+    g.c = dw; g.ldc = ldw; g.cz = gz;
+    g.M = Nout; g.N = Kin; g.K = Bt; g.nz = nz; g.epi = EPI_NONE;
+    g.rowsum = db; g.rowsum_z = gz;
+    return g;
+}
+
+}  // namespace
+
+struct plen_td3 {
+    int device, max_batch, batch;
+    float *ws;                          // one allocation, carved below
+    float *sa, *s2a, *spi, *r, *nd;
+    float *at_h1, *at_h2, *ct_h1, *ct_h2, *qt;
+    float *c_h1, *c_h2, *q, *dq, *dh2, *dh1;
+    float *a_h1, *a_h2, *p_h1, *p_h2, *qpi, *dqpi, *dp_h2, *dp_h1, *da3, *da_h2, *da_h1;
+    long long launches;
+};
+
+extern "C" {
+
+int plen_td3_default_hyper(plen_td3_hyper *h) {
+    if (!h) return plen_td3_set_error(PLEN_E_ARG, "plen_td3_default_hyper: NULL", "");
+    // td3.py:211-219 (TD3Agent defaults), :226-233 (Adam lr 3e-4, torch default betas / eps)
+    h->discount = 0.99f; h->tau = 0.005f; h->policy_noise = 0.2f; h->noise_clip = 0.5f; h->max_action = 1.0f;
+    h->lr = 3e-4f; h->beta1 = 0.9f; h->beta2 = 0.999f; h->eps = 1e-8f; h->policy_freq = 2;
+    return PLEN_OK;
+}
+
+plen_td3 *plen_td3_create(int max_batch, int device) {
+    int ndev = 0;
+    if (max_batch <= 0) { plen_td3_set_error(PLEN_E_ARG, "plen_td3_create: max_batch <= 0", ""); return nullptr; }
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        plen_td3_set_error(PLEN_E_CUDA, "plen_td3_create: no usable CUDA device; this library has no CPU fallback", "");
+        return nullptr;
+    }
+    plen_td3 *t = new (std::nothrow) plen_td3();
+    if (!t) return nullptr;
+    memset(t, 0, sizeof *t);
+    t->device = device; t->max_batch = max_batch;
+    const size_t Bm = (size_t)max_batch;
+    const size_t words = 3 * Bm * SA + 2 * Bm + 2 * Bm * H + 4 * Bm * H + 2 * Bm + 4 * Bm * H + 4 * Bm + 4 * Bm * H +
+                         4 * Bm * H + 2 * Bm + 2 * Bm * H + Bm * A + 2 * Bm * H;
+    if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&t->ws, sizeof(float) * words) != cudaSuccess) {
+        plen_td3_set_error(PLEN_E_CUDA, "plen_td3_create: cudaMalloc failed", "");
+        delete t;
+        return nullptr;
+    }
+    cudaMemset(t->ws, 0, sizeof(float) * words);
+    float *p = t->ws;
+    auto take = [&](size_t n) { float *q = p; p += n; return q; };
+    t->sa = take(Bm * SA); t->s2a = take(Bm * SA); t->spi = take(Bm * SA); t->r = take(Bm); t->nd = take(Bm);
+    t->at_h1 = take(Bm * H); t->at_h2 = take(Bm * H);
+    t->ct_h1 = take(2 * Bm * H); t->ct_h2 = take(2 * Bm * H); t->qt = take(2 * Bm);
+    t->c_h1 = take(2 * Bm * H); t->c_h2 = take(2 * Bm * H); t->q = take(2 * Bm); t->dq = take(2 * Bm);
+    t->dh2 = take(2 * Bm * H); t->dh1 = take(2 * Bm * H);
+    t->a_h1 = take(Bm * H); t->a_h2 = take(Bm * H); t->p_h1 = take(Bm * H); t->p_h2 = take(Bm * H);
+    t->qpi = take(Bm); t->dqpi = take(Bm); t->dp_h2 = take(Bm * H); t->dp_h1 = take(Bm * H); t->da3 = take(Bm * A);
+    t->da_h2 = take(Bm * H); t->da_h1 = take(Bm * H);
+    if ((size_t)(p - t->ws) != words) { plen_td3_set_error(PLEN_E_STATE, "plen_td3_create: workspace carve mismatch", ""); cudaFree(t->ws); delete t; return nullptr; }
+    return t;
+}
+
+void plen_td3_destroy(plen_td3 *t) {
+    if (!t) return;
+    cudaSetDevice(t->device);
+    cudaFree(t->ws);
+    delete t;
+}
+
+long long plen_td3_launches(const plen_td3 *t) { return t ? t->launches : 0; }
+
+int plen_td3_sample(plen_td3 *t, plen_replay *rb, int batch, unsigned long long seed, void *stream) {
+    if (!t || !rb || batch <= 0 || batch > t->max_batch) return plen_td3_set_error(PLEN_E_ARG, "plen_td3_sample: bad arguments", "");
+    const long long size = plen_replay_size(rb);
+    if (size <= 0) return plen_td3_set_error(PLEN_E_STATE, "plen_td3_sample: the replay buffer is empty", "");
+    LCK(cudaSetDevice(t->device));
+    k_sample_sa<<<(batch * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(plen_replay_storage(rb), size, batch, seed, t->sa, t->s2a,
+                                                                          t->spi, t->r, t->nd);
+    t->batch = batch; t->launches += 1;
+    LCK(cudaGetLastError());
+    return PLEN_OK;
+}
+
+int plen_td3_set_batch(plen_td3 *t, const float *state_dev, const float *action_dev, const float *next_state_dev,
+                       const float *reward_dev, const float *not_done_dev, int batch, void *stream) {
+    if (!t || !state_dev || !action_dev || !next_state_dev || !reward_dev || !not_done_dev || batch <= 0 || batch > t->max_batch)
+        return plen_td3_set_error(PLEN_E_ARG, "plen_td3_set_batch: bad arguments", "");
+    LCK(cudaSetDevice(t->device));
+    k_set_batch<<<(batch * SA + 255) / 256, 256, 0, (cudaStream_t)stream>>>(batch, state_dev, action_dev, next_state_dev, reward_dev,
+                                                                          not_done_dev, t->sa, t->s2a, t->spi, t->r, t->nd);
+    t->batch = batch; t->launches += 1;
+    LCK(cudaGetLastError());
+    return PLEN_OK;
+}
+
+int plen_td3_critic_grads(plen_td3 *t, const plen_td3_params *P, const plen_td3_hyper *h, const float *noise_dev,
+                          unsigned long long seed, float *critic_loss_dev, void *stream) {
+    if (!t || !P || !h || !P->actor_target || !P->critic || !P->critic_target || !P->critic_grad)
+        return plen_td3_set_error(PLEN_E_ARG, "plen_td3_critic_grads: bad arguments", "");
+    if (t->batch <= 0) return plen_td3_set_error(PLEN_E_STATE, "plen_td3_critic_grads: no minibatch (call plen_td3_sample / plen_td3_set_batch)", "");
+    LCK(cudaSetDevice(t->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = t->batch;
+    const long long BH = (long long)B * H;
+    int n = 0;
+    // ---- target Q (no gradient), td3.py:303-313
+    const float *at = P->actor_target;
+    n += launch(fwd(t->s2a, SA, 0, at + AW1, S, 0, at + AB1, t->at_h1, H, 0, B, H, S, 1, EPI_BIAS_RELU), st);
+    n += launch(fwd(t->at_h1, H, 0, at + AW2, H, 0, at + AB2, t->at_h2, H, 0, B, H, H, 1, EPI_BIAS_RELU), st);
+    {
+        Gemm g = fwd(t->at_h2, H, 0, at + AW3, H, 0, at + AB3, t->s2a + S, SA, 0, B, A, H, 1, EPI_BIAS_TANH_NOISE);
+        g.p0 = h->max_action; g.p1 = h->policy_noise; g.p2 = h->noise_clip; g.seed = seed; g.aux = noise_dev; g.ld_aux = A;
+        n += launch(g, st);
+    }
+    const float *ct = P->critic_target;
+    n += launch(fwd(t->s2a, SA, 0, ct + CW1, SA, TOWER_N, ct + CB1, t->ct_h1, H, BH, B, H, SA, 2, EPI_BIAS_RELU), st);
+    n += launch(fwd(t->ct_h1, H, BH, ct + CW2, H, TOWER_N, ct + CB2, t->ct_h2, H, BH, B, H, H, 2, EPI_BIAS_RELU), st);
+    n += launch(fwd(t->ct_h2, H, BH, ct + CW3, H, TOWER_N, ct + CB3, t->qt, 1, B, B, 1, H, 2, EPI_BIAS), st);
+    // ---- current Q, td3.py:316
+    const float *c = P->critic;
+    n += launch(fwd(t->sa, SA, 0, c + CW1, SA, TOWER_N, c + CB1, t->c_h1, H, BH, B, H, SA, 2, EPI_BIAS_RELU), st);
+    n += launch(fwd(t->c_h1, H, BH, c + CW2, H, TOWER_N, c + CB2, t->c_h2, H, BH, B, H, H, 2, EPI_BIAS_RELU), st);
+    n += launch(fwd(t->c_h2, H, BH, c + CW3, H, TOWER_N, c + CB3, t->q, 1, B, B, 1, H, 2, EPI_BIAS), st);
+    k_td_loss<<<1, 256, 0, st>>>(B, h->discount, t->qt, t->q, t->r, t->nd, t->dq, critic_loss_dev);
+    n += 1;
+    // ---- backward through both towers, td3.py:333 (gradients land in P->critic_grad, flat layout of the critic)
+    float *gr = P->critic_grad;
+    n += launch(bwd_weight(t->dq, 1, B, t->c_h2, H, BH, gr + CW3, H, gr + CB3, TOWER_N, B, 1, H, 2), st);
+    n += launch(bwd_data(t->dq, 1, B, c + CW3, H, TOWER_N, t->dh2, H, BH, B, H, 1, 2, EPI_RELUMASK, t->c_h2, H, BH), st);
+    n += launch(bwd_weight(t->dh2, H, BH, t->c_h1, H, BH, gr + CW2, H, gr + CB2, TOWER_N, B, H, H, 2), st);
+    n += launch(bwd_data(t->dh2, H, BH, c + CW2, H, TOWER_N, t->dh1, H, BH, B, H, H, 2, EPI_RELUMASK, t->c_h1, H, BH), st);
+    n += launch(bwd_weight(t->dh1, H, BH, t->sa, SA, 0, gr + CW1, SA, gr + CB1, TOWER_N, B, H, SA, 2), st);
+    t->launches += n;
+    LCK(cudaGetLastError());
+    return PLEN_OK;
+}
+
+int plen_td3_actor_grads(plen_td3 *t, const plen_td3_params *P, const plen_td3_hyper *h, float *actor_loss_dev, void *stream) {
+    if (!t || !P || !h || !P->actor || !P->critic || !P->actor_grad)
+        return plen_td3_set_error(PLEN_E_ARG, "plen_td3_actor_grads: bad arguments", "");
+    if (t->batch <= 0) return plen_td3_set_error(PLEN_E_STATE, "plen_td3_actor_grads: no minibatch", "");
+    LCK(cudaSetDevice(t->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = t->batch;
+    int n = 0;
+    // ---- actor_loss = -critic.Q1(state, actor(state)).mean(), td3.py:342
+    const float *ac = P->actor, *c = P->critic;
+    n += launch(fwd(t->spi, SA, 0, ac + AW1, S, 0, ac + AB1, t->a_h1, H, 0, B, H, S, 1, EPI_BIAS_RELU), st);
+    n += launch(fwd(t->a_h1, H, 0, ac + AW2, H, 0, ac + AB2, t->a_h2, H, 0, B, H, H, 1, EPI_BIAS_RELU), st);
+    {
+        Gemm g = fwd(t->a_h2, H, 0, ac + AW3, H, 0, ac + AB3, t->spi + S, SA, 0, B, A, H, 1, EPI_BIAS_TANH);
+        g.p0 = h->max_action;
+        n += launch(g, st);
+    }
+    n += launch(fwd(t->spi, SA, 0, c + CW1, SA, 0, c + CB1, t->p_h1, H, 0, B, H, SA, 1, EPI_BIAS_RELU), st);
+    n += launch(fwd(t->p_h1, H, 0, c + CW2, H, 0, c + CB2, t->p_h2, H, 0, B, H, H, 1, EPI_BIAS_RELU), st);
+    n += launch(fwd(t->p_h2, H, 0, c + CW3, H, 0, c + CB3, t->qpi, 1, 0, B, 1, H, 1, EPI_BIAS), st);
+    k_actor_loss<<<1, 256, 0, st>>>(B, t->qpi, t->dqpi, actor_loss_dev);
+    n += 1;
+    // ---- backward: through Q1 down to its action inputs (no critic parameter gradients are needed: the critic
+    //      optimiser zeroes them before its next step, td3.py:328), then through the actor
+    n += launch(bwd_data(t->dqpi, 1, 0, c + CW3, H, 0, t->dp_h2, H, 0, B, H, 1, 1, EPI_RELUMASK, t->p_h2, H, 0), st);
+    n += launch(bwd_data(t->dp_h2, H, 0, c + CW2, H, 0, t->dp_h1, H, 0, B, H, H, 1, EPI_RELUMASK, t->p_h1, H, 0), st);
+    {
+        Gemm g = bwd_data(t->dp_h1, H, 0, c + CW1 + S, SA, 0, t->da3, A, 0, B, A, H, 1, EPI_TANHGRAD, t->spi + S, SA, 0);
+        g.p0 = h->max_action;
+        n += launch(g, st);
+    }
+    float *gr = P->actor_grad;
+    n += launch(bwd_weight(t->da3, A, 0, t->a_h2, H, 0, gr + AW3, H, gr + AB3, 0, B, A, H, 1), st);
+    n += launch(bwd_data(t->da3, A, 0, ac + AW3, H, 0, t->da_h2, H, 0, B, H, A, 1, EPI_RELUMASK, t->a_h2, H, 0), st);
+    n += launch(bwd_weight(t->da_h2, H, 0, t->a_h1, H, 0, gr + AW2, H, gr + AB2, 0, B, H, H, 1), st);
+    n += launch(bwd_data(t->da_h2, H, 0, ac + AW2, H, 0, t->da_h1, H, 0, B, H, H, 1, EPI_RELUMASK, t->a_h1, H, 0), st);
+    n += launch(bwd_weight(t->da_h1, H, 0, t->spi, SA, 0, gr + AW1, S, gr + AB1, 0, B, H, S, 1), st);
+    t->launches += n;
+    LCK(cudaGetLastError());
+    return PLEN_OK;
+}
+
+int plen_td3_adam(float *param_dev, const float *grad_dev, float *m_dev, float *v_dev, int n, long long step,
+                  const plen_td3_hyper *h, int device, void *stream) {
+    if (!param_dev || !grad_dev || !m_dev || !v_dev || n <= 0 || step <= 0 || !h)
+        return plen_td3_set_error(PLEN_E_ARG, "plen_td3_adam: bad arguments", "");
+    LCK(cudaSetDevice(device));
+    // scalars as torch computes them (python doubles, torch/optim/adam.py _single_tensor_adam), then cast to float32
+    const double bc1 = 1.0 - pow((double)h->beta1, (double)step), bc2 = 1.0 - pow((double)h->beta2, (double)step);
+    const float step_size = (float)((double)h->lr / bc1), inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+    k_adam<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(param_dev, grad_dev, m_dev, v_dev, n, 1.0f - h->beta1, h->beta2,
+                                                             1.0f - h->beta2, step_size, inv_bc2_sqrt, h->eps);
+    LCK(cudaGetLastError());
+    return PLEN_OK;
+}
+
+int plen_td3_soft_update(float *target_dev, const float *source_dev, int n, float tau, int device, void *stream) {
+    if (!target_dev || !source_dev || n <= 0) return plen_td3_set_error(PLEN_E_ARG, "plen_td3_soft_update: bad arguments", "");
+    LCK(cudaSetDevice(device));
+    k_soft_update<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(target_dev, source_dev, n, tau);
+    LCK(cudaGetLastError());
+    return PLEN_OK;
+}
+
+int plen_td3_train(plen_td3 *t, const plen_td3_params *P, const plen_td3_hyper *h, plen_replay *rb, int batch, long long total_it,
+                   long long critic_step, long long actor_step, unsigned long long seed, float *losses_dev, void *stream) {
+    if (!t || !P || !h || total_it <= 0 || critic_step <= 0 || h->policy_freq <= 0)
+        return plen_td3_set_error(PLEN_E_ARG, "plen_td3_train: bad arguments", "");
+    int rc;
+    if (rb) { rc = plen_td3_sample(t, rb, batch, seed * 2654435761ull + 1ull, stream); if (rc) return rc; }
+    rc = plen_td3_critic_grads(t, P, h, nullptr, seed, losses_dev ? losses_dev + 1 : nullptr, stream);
+    if (rc) return rc;
+    rc = plen_td3_adam(P->critic, P->critic_grad, P->critic_m, P->critic_v, CRITIC_N, critic_step, h, t->device, stream);
+    if (rc) return rc;
+    t->launches += 1;
+    if (total_it % h->policy_freq == 0) {       // delayed policy update, td3.py:339-360
+        if (actor_step <= 0) return plen_td3_set_error(PLEN_E_ARG, "plen_td3_train: actor_step <= 0 on a policy update", "");
+        rc = plen_td3_actor_grads(t, P, h, losses_dev, stream);
+        if (rc) return rc;
+        rc = plen_td3_adam(P->actor, P->actor_grad, P->actor_m, P->actor_v, ACTOR_N, actor_step, h, t->device, stream);
+        if (rc) return rc;
+        rc = plen_td3_soft_update(P->critic_target, P->critic, CRITIC_N, h->tau, t->device, stream);
+        if (rc) return rc;
+        rc = plen_td3_soft_update(P->actor_target, P->actor, ACTOR_N, h->tau, t->device, stream);
+        if (rc) return rc;
+        t->launches += 3;
+    }
+    return PLEN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,140 @@
+"""Size-independent properties of the batched env step at BASELINE.json's full sizes (configs 2, 3 and 5).
+
+The oracle finishes a few hundred robots in seconds; at 4,096 / 65,536 / 1,048,576 robots parity is carried by
+properties the domain offers: robots are independent, so a robot's result may depend neither on WHERE it sits in the
+batch (k_rank sorts robots by contact load, k_solve packs eight of them per warp), nor on how many other robots the
+context holds, nor on which context / shard owns it -- and all of it must hold BIT FOR BIT, since every robot runs the
+same float32 instruction sequence.  A 64-robot sample of the large batch is then checked against the oracle
+(teacher-forced, the tolerance of test_gpu_parity.py), which ties the whole batch to the checker.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _mk(n, **kw):
+    from plen_ml_walk_b200.vec_env import PlenVecEnv
+    return PlenVecEnv(n, device="cuda:0", **kw)
+
+
+def _rollout(env, steps, seed):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    env.reset()
+    for _ in range(steps):
+        env.step(torch.empty((env.num_envs, 18), device="cuda").uniform_(-1, 1, generator=g))
+
+
+def _snapshot(env):
+    return [t.clone() for t in env.get_state()]
+
+
+def _step_out(env, act):
+    obs, rew, done, info = env.step(act)
+    term = torch.where(done[:, None], info["terminal_obs"], torch.zeros_like(obs))      # only written where done
+    return obs.clone(), rew.clone(), done.clone(), info["timeout"].clone(), term
+
+
+def _same(a, b):
+    # bit-exact, NaN-aware (the cosine-similarity reward term may be 0/0 = NaN in the reference too, plen_env.py:932)
+    return bool(torch.equal(a, b) or torch.equal(torch.nan_to_num(a.float(), nan=1234.5), torch.nan_to_num(b.float(), nan=1234.5)))
+
+
+def test_result_does_not_depend_on_batch_position_config2():
+    """4096 robots in mixed contact phases; a random permutation of the batch permutes the results bit for bit."""
+    n = 4096
+    env = _mk(n)
+    _rollout(env, 37, seed=1)
+    st = _snapshot(env)
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    act = torch.empty((n, 18), device="cuda").uniform_(-1, 1, generator=g)
+    ref = _step_out(env, act)
+    ref_state = _snapshot(env)
+    perm = torch.randperm(n, device="cuda", generator=g)
+    env2 = _mk(n)
+    env2.reset()
+    env2.set_state(*[t[perm] for t in st])
+    got = _step_out(env2, act[perm])
+    for a, b in zip(ref, got):
+        assert _same(a[perm], b)
+    for a, b in zip(ref_state, _snapshot(env2)):
+        assert _same(a[perm], b)
+    assert 0.02 < ref[0][:, 24:26].mean().item() < 0.98      # the sample really mixes flight and contact
+
+
+def test_shards_reproduce_the_single_context_result():
+    """Config 5's sharding: two contexts of N/2 robots give exactly the rows one context of N gives (no cross-robot
+    coupling, no dependence on the batch size or the tile a robot falls in)."""
+    n = 6144 + 8                                              # not a multiple of the 1024-robot sort tile
+    env = _mk(n)
+    _rollout(env, 21, seed=3)
+    st = _snapshot(env)
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    acts = [torch.empty((n, 18), device="cuda").uniform_(-1, 1, generator=g) for _ in range(3)]
+    outs = [_step_out(env, a) for a in acts]
+    lo = 0
+    for size in (n // 2 - 5, n - (n // 2 - 5)):               # ragged split
+        sh = _mk(size)
+        sh.reset()
+        sh.set_state(*[t[lo:lo + size] for t in st])
+        for a, ref in zip(acts, outs):
+            got = _step_out(sh, a[lo:lo + size])
+            for x, y in zip(ref, got):
+                assert _same(x[lo:lo + size], y)
+        lo += size
+
+
+def test_step_is_deterministic_run_to_run():
+    n = 8192
+    res = []
+    for _ in range(2):
+        env = _mk(n)
+        _rollout(env, 25, seed=5)
+        res.append(_snapshot(env) + [env._obs.clone(), env._reward.clone()])
+    for a, b in zip(*res):
+        assert _same(a, b)
+
+
+def test_one_million_robots_config5_full_size():
+    """1,048,576 robots on ONE GPU (6.7 GB of solve records): the first 4096 robots reproduce a 4096-robot context bit
+    for bit over 6 steps with auto-reset, and robots with identical inputs stay identical across the whole batch."""
+    n, m = 1048576, 4096
+    big, small = _mk(n), _mk(m)
+    g = torch.Generator(device="cuda"); g.manual_seed(13)
+    big.reset(); small.reset()
+    for s in range(6):
+        a_small = torch.empty((m, 18), device="cuda").uniform_(-1, 1, generator=g)
+        a_big = a_small.repeat(n // m, 1)                     # robot i of every 4096-block gets the same action
+        ob, rb, db, _ = big.step(a_big)
+        os_, rs, ds, _ = small.step(a_small)
+        assert _same(ob[:m], os_) and _same(rb[:m], rs) and _same(db[:m], ds)
+        assert _same(ob.view(n // m, m, 26)[-1], os_)         # last block too (different tiles, different SMs)
+        assert _same(rb.view(n // m, m).amax(0), rb.view(n // m, m).amin(0)) or torch.isnan(rb).any()
+    big.close(); small.close()
+
+
+def test_sample_of_large_batch_against_oracle_config3_size():
+    """65,536 robots (config 3's size), random actions with auto-reset: a 64-robot sample from the middle of the batch
+    after 30 steps is stepped once more by the oracle from the same state -- same bound as the small teacher-forced test."""
+    from oracle.oracle import PlenOracle
+    from parity_util import oracle_from_abi
+    n, k = 65536, 64
+    env = _mk(n)
+    _rollout(env, 30, seed=17)
+    idx = torch.arange(n // 2 - k // 2, n // 2 + k // 2, device="cuda")
+    st = oracle_from_abi(*[t[idx].cpu().numpy() for t in env.get_state()])
+    g = torch.Generator(device="cuda"); g.manual_seed(19)
+    act = torch.empty((n, 18), device="cuda").uniform_(-1, 1, generator=g)
+    obs, rew, done, info = env.step(act)
+    gobs = torch.where(done[:, None], info["terminal_obs"], obs)[idx].cpu().numpy()      # pre-reset observation where done
+    o = PlenOracle(k, n_threads=4)
+    o.reset()
+    o.set_state(st)
+    oo, orw, od, _ = o.step(act[idx].cpu().numpy().astype(np.float64), auto_reset=False)
+    err = np.abs(gobs[:, :24] - oo[:, :24]).max(axis=1)
+    assert np.median(err) < 1e-4
+    assert (err < 1e-3).mean() >= 0.6
+    assert (gobs[:, 24:26] != oo[:, 24:26]).mean() <= 0.05
+    assert (done[idx].cpu().numpy() != od).mean() <= 0.05
