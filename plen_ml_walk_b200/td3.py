@@ -9,10 +9,12 @@ keys fc1..fc3 / fc1..fc6) load unchanged.  What runs where:
                       (the reference rebuilds O(B^2) host tensors per sample, td3.py:178-191).
   * select_action     hand-written CUDA fused 3-layer MLP (plen_actor_forward), fp32, N observations per launch,
                       optional exploration noise + clip (plen_td3.py:101-104) in the same kernel.
-  * train             the reference's update rule (td3.py:259-356) with torch autograd / Adam on the device: library
-                      GEMMs (cuBLAS), stated as such -- the batch-100 critic GEMMs are not on the env-step critical path.
+  * train             the reference's update rule (td3.py:259-356) as hand-written CUDA (csrc/plen_td3_learn.cu): strided
+                      fp32 GEMM kernel with fused bias / ReLU / tanh / mask / bias-gradient epilogues, fused Adam, fused
+                      Polyak update over flat parameter vectors; 17 launches per critic step, 35 with the policy step,
+                      enqueued from C with no host sync.  train_torch = the same rule in PyTorch (test reference only).
 
-No CPU fallback for the two CUDA pieces.
+No CPU fallback for the CUDA pieces.
 """
 from __future__ import annotations
 
@@ -173,20 +175,82 @@ def _from_device_ptr(ptr, numel, device):
     return torch.as_tensor(h, device=device)
 
 
+def _flatten_module(module):
+    """Move every parameter of `module` into ONE flat float32 vector (state_dict order) and make the parameters views of it,
+    so the CUDA learner (flat layouts of include/plen_b200.h) and the nn.Module / state_dict / checkpoint surface share
+    the same memory."""
+    ps = list(module.parameters())
+    flat = torch.cat([p.detach().reshape(-1).float() for p in ps]).contiguous()
+    off = 0
+    for p in ps:
+        n = p.numel()
+        p.data = flat[off:off + n].view(p.shape)
+        off += n
+    return flat
+
+
 class TD3Agent:                                            # td3.py:196-376
+    """TD3Agent of the reference with the update rule (td3.py:259-356) running in the CUDA library (`train`): strided fp32
+    GEMM kernels with fused epilogues, fused Adam, fused Polyak update -- no autograd, no cuBLAS.  `train_torch` keeps the
+    same rule in plain PyTorch as the fp32 reference the tests compare against (and for CPU-only checkpoint tooling)."""
+
     def __init__(self, state_dim=STATE_DIM, action_dim=ACTION_DIM, max_action=1.0, discount=0.99, tau=0.005,
-                 policy_noise=0.2, noise_clip=0.5, policy_freq=2, device="cuda:0", lr=3e-4):
+                 policy_noise=0.2, noise_clip=0.5, policy_freq=2, device="cuda:0", lr=3e-4, max_batch=4096, seed=0):
         self.device = torch.device(device)
         self.actor = Actor(state_dim, action_dim, max_action).to(self.device)
         self.actor_target = copy.deepcopy(self.actor)
-        self.actor_optimizer = torch.optim.Adam(self.actor.parameters(), lr=lr)
         self.critic = Critic(state_dim, action_dim).to(self.device)
         self.critic_target = copy.deepcopy(self.critic)
-        self.critic_optimizer = torch.optim.Adam(self.critic.parameters(), lr=lr)
         self.max_action, self.discount, self.tau = max_action, discount, tau
         self.policy_noise, self.noise_clip, self.policy_freq = policy_noise, noise_clip, policy_freq
+        self.lr = lr
         self.total_it = 0
+        self.critic_steps = 0      # Adam step counters (torch keeps them in optimizer.state[p]["step"])
+        self.actor_steps = 0
         self._draws = 0
+        self._seed = int(seed)
+        self._flat = {}
+        self._reflatten()
+        z = lambda ref: torch.zeros_like(ref)
+        self._adam = {"actor_m": z(self._flat["actor"]), "actor_v": z(self._flat["actor"]),
+                      "critic_m": z(self._flat["critic"]), "critic_v": z(self._flat["critic"])}
+        self._grad = {"actor": z(self._flat["actor"]), "critic": z(self._flat["critic"])}
+        # torch optimizers exist for the checkpoint surface (save / load of *_optimizer files) and for train_torch
+        self.actor_optimizer = torch.optim.Adam(self.actor.parameters(), lr=lr)
+        self.critic_optimizer = torch.optim.Adam(self.critic.parameters(), lr=lr)
+        self._learner, self._max_batch = None, int(max_batch)
+        self._losses = torch.zeros(2, dtype=torch.float32, device=self.device) if self.device.type == "cuda" else None
+
+    # ---- flat storage shared with the CUDA learner
+    def _reflatten(self):
+        for name in ("actor", "actor_target", "critic", "critic_target"):
+            self._flat[name] = _flatten_module(getattr(self, name))
+        assert self._flat["actor"].numel() == _abi.TD3_ACTOR_PARAMS and self._flat["critic"].numel() == _abi.TD3_CRITIC_PARAMS
+
+    def _cuda_handles(self):
+        if self.device.type != "cuda":
+            raise RuntimeError("TD3Agent.train runs in the CUDA library; there is no CPU fallback (train_torch is the test reference)")
+        lib = _abi.load_library()
+        if self._learner is None:
+            idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            self._learner = lib.plen_td3_create(self._max_batch, idx)
+            if not self._learner:
+                raise RuntimeError("plen_td3_create: %s" % lib.plen_td3_last_error().decode())
+            self._hyper = _abi.PlenTd3HyperC()
+            lib.plen_td3_default_hyper(C.byref(self._hyper))
+        h = self._hyper
+        h.discount, h.tau, h.policy_noise, h.noise_clip = self.discount, self.tau, self.policy_noise, self.noise_clip
+        h.max_action, h.lr, h.policy_freq = self.max_action, self.lr, self.policy_freq
+        P = _abi.PlenTd3ParamsC()
+        for k in ("actor", "actor_target", "critic", "critic_target"):
+            setattr(P, k, self._flat[k].data_ptr())
+        for k in ("actor_m", "actor_v", "critic_m", "critic_v"):
+            setattr(P, k, self._adam[k].data_ptr())
+        P.actor_grad, P.critic_grad = self._grad["actor"].data_ptr(), self._grad["critic"].data_ptr()
+        return lib, P, h
+
+    def _idx(self):
+        return self.device.index if self.device.index is not None else torch.cuda.current_device()
 
     def select_action(self, state, expl_noise=0.0):
         """Batched: state [N,26] on the device -> action [N,18]; expl_noise = plen_td3.py:101-104 (std = max_action * expl_noise)."""
@@ -194,13 +258,74 @@ class TD3Agent:                                            # td3.py:196-376
         return actor_forward(self.actor, torch.as_tensor(state, device=self.device).reshape(-1, STATE_DIM),
                              noise_std=self.max_action * expl_noise, seed=self._draws)
 
-    def train(self, replay_buffer, batch_size=100):
-        """One TD3 update, td3.py:259-356 verbatim semantics."""
+    def train(self, replay_buffer, batch_size=100, batch=None, noise=None, return_losses=False, grad_hook=None):
+        """One TD3 update (td3.py:259-356) in the CUDA library.
+
+        replay_buffer: the device ReplayBuffer (sampled inside the library); or pass an explicit minibatch
+        batch = (state, action, next_state, reward, not_done) -- used by the parity tests together with `noise`
+        ([B,18] standard-normal samples for the target policy smoothing).  grad_hook(flat_grad) runs between the
+        gradient kernels and Adam: a data-parallel learner all-reduces there (NCCL).
+        Returns (actor_loss, critic_loss) device scalars when return_losses (actor_loss is None off the policy step)."""
+        lib, P, h = self._cuda_handles()
         self.total_it += 1
-        state, action, next_state, reward, not_done = replay_buffer.sample(batch_size)
+        self._draws += 1
+        seed = (self._seed * 1000003 + self._draws) & (2 ** 64 - 1)
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        policy = self.total_it % self.policy_freq == 0
+        with torch.cuda.device(self.device):
+            if batch is not None:
+                s, a, s2, r, nd = [torch.as_tensor(x, device=self.device).float().contiguous() for x in batch]
+                rc = lib.plen_td3_set_batch(self._learner, _p(s), _p(a), _p(s2), _p(r.reshape(-1)), _p(nd.reshape(-1)), s.shape[0], st)
+                self._check(lib, rc)
+            if batch is None and noise is None and grad_hook is None:
+                # the whole step in one library call
+                self.critic_steps += 1
+                if policy:
+                    self.actor_steps += 1
+                rc = lib.plen_td3_train(self._learner, C.byref(P), C.byref(h), replay_buffer._rb, int(batch_size), self.total_it,
+                                        self.critic_steps, max(1, self.actor_steps), seed, _p(self._losses), st)
+                self._check(lib, rc)
+            else:
+                if batch is None:
+                    self._check(lib, lib.plen_td3_sample(self._learner, replay_buffer._rb, int(batch_size), seed ^ 0x9E3779B97F4A7C15, st))
+                nz = None if noise is None else torch.as_tensor(noise, device=self.device).float().contiguous()
+                self._check(lib, lib.plen_td3_critic_grads(self._learner, C.byref(P), C.byref(h), _p(nz), seed,
+                                                           C.c_void_p(self._losses.data_ptr() + 4), st))
+                if grad_hook is not None:
+                    grad_hook(self._grad["critic"])
+                self.critic_steps += 1
+                self._check(lib, lib.plen_td3_adam(P.critic, P.critic_grad, P.critic_m, P.critic_v, _abi.TD3_CRITIC_PARAMS,
+                                                   self.critic_steps, C.byref(h), self._idx(), st))
+                if policy:
+                    self._check(lib, lib.plen_td3_actor_grads(self._learner, C.byref(P), C.byref(h), _p(self._losses), st))
+                    if grad_hook is not None:
+                        grad_hook(self._grad["actor"])
+                    self.actor_steps += 1
+                    self._check(lib, lib.plen_td3_adam(P.actor, P.actor_grad, P.actor_m, P.actor_v, _abi.TD3_ACTOR_PARAMS,
+                                                       self.actor_steps, C.byref(h), self._idx(), st))
+                    self._check(lib, lib.plen_td3_soft_update(P.critic_target, P.critic, _abi.TD3_CRITIC_PARAMS, float(self.tau), self._idx(), st))
+                    self._check(lib, lib.plen_td3_soft_update(P.actor_target, P.actor, _abi.TD3_ACTOR_PARAMS, float(self.tau), self._idx(), st))
+        if return_losses:
+            return (self._losses[0].clone() if policy else None), self._losses[1].clone()
+        return None
+
+    @staticmethod
+    def _check(lib, rc):
+        if rc != 0:
+            raise RuntimeError("libplen_b200 TD3 learner: %s" % lib.plen_td3_last_error().decode())
+
+    def kernel_launches(self):
+        return int(_abi.load_library().plen_td3_launches(self._learner)) if self._learner else 0
+
+    def train_torch(self, batch, noise=None):
+        """The same update in plain PyTorch (autograd + torch.optim.Adam): the fp32 reference of the tests.  batch =
+        (state, action, next_state, reward [B,1], not_done [B,1]); noise [B,18] standard normal (None: torch.randn)."""
+        self.total_it += 1
+        state, action, next_state, reward, not_done = batch
         with torch.no_grad():
-            noise = (torch.randn_like(action) * self.policy_noise).clamp(-self.noise_clip, self.noise_clip)
-            next_action = (self.actor_target(next_state) + noise).clamp(-self.max_action, self.max_action)
+            nz = torch.randn_like(action) if noise is None else noise
+            nz = (nz * self.policy_noise).clamp(-self.noise_clip, self.noise_clip)
+            next_action = (self.actor_target(next_state) + nz).clamp(-self.max_action, self.max_action)
             target_Q1, target_Q2 = self.critic_target(next_state, next_action)
             target_Q = reward + not_done * self.discount * torch.min(target_Q1, target_Q2)
         current_Q1, current_Q2 = self.critic(state, action)
@@ -216,22 +341,59 @@ class TD3Agent:                                            # td3.py:196-376
             self.actor_optimizer.step()
             with torch.no_grad():
                 for param, target_param in zip(self.critic.parameters(), self.critic_target.parameters()):
-                    target_param.mul_(1 - self.tau).add_(param, alpha=self.tau)
+                    target_param.copy_(self.tau * param + (1 - self.tau) * target_param)
                 for param, target_param in zip(self.actor.parameters(), self.actor_target.parameters()):
-                    target_param.mul_(1 - self.tau).add_(param, alpha=self.tau)
+                    target_param.copy_(self.tau * param + (1 - self.tau) * target_param)
         return actor_loss, critic_loss
 
-    def save(self, filename):                              # same four files as td3.py:358-365
+    # ---- checkpoints: same four files and formats as td3.py:358-376
+    def _sync_optimizer_state(self, opt, module, m, v, steps):
+        off = 0
+        for p in module.parameters():
+            n = p.numel()
+            opt.state[p] = {"step": torch.tensor(float(steps)), "exp_avg": m[off:off + n].view(p.shape).clone(),
+                            "exp_avg_sq": v[off:off + n].view(p.shape).clone()}
+            off += n
+
+    def _load_optimizer_state(self, opt, module, m, v):
+        off, steps = 0, 0
+        for p in module.parameters():
+            n = p.numel()
+            st = opt.state.get(p, {})
+            if "exp_avg" in st:
+                m[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                v[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                steps = int(float(st["step"]))
+            off += n
+        return steps
+
+    def save(self, filename):
+        self._sync_optimizer_state(self.critic_optimizer, self.critic, self._adam["critic_m"], self._adam["critic_v"], self.critic_steps)
+        self._sync_optimizer_state(self.actor_optimizer, self.actor, self._adam["actor_m"], self._adam["actor_v"], self.actor_steps)
         torch.save(self.critic.state_dict(), filename + "_critic")
         torch.save(self.critic_optimizer.state_dict(), filename + "_critic_optimizer")
         torch.save(self.actor.state_dict(), filename + "_actor")
         torch.save(self.actor_optimizer.state_dict(), filename + "_actor_optimizer")
 
     def load(self, filename, optimizers=True):
+        # load_state_dict copies in place, so the parameters stay views of the flat vectors
         self.critic.load_state_dict(torch.load(filename + "_critic", map_location=self.device))
         self.actor.load_state_dict(torch.load(filename + "_actor", map_location=self.device))
         if optimizers:   # the reference's optimizer files are python-2 pickles that need weights_only=False
             self.critic_optimizer.load_state_dict(torch.load(filename + "_critic_optimizer", map_location=self.device, weights_only=False))
             self.actor_optimizer.load_state_dict(torch.load(filename + "_actor_optimizer", map_location=self.device, weights_only=False))
-        self.actor_target = copy.deepcopy(self.actor)
-        self.critic_target = copy.deepcopy(self.critic)
+            self.critic_steps = self._load_optimizer_state(self.critic_optimizer, self.critic, self._adam["critic_m"], self._adam["critic_v"])
+            self.actor_steps = self._load_optimizer_state(self.actor_optimizer, self.actor, self._adam["actor_m"], self._adam["actor_v"])
+        self._flat["actor_target"].copy_(self._flat["actor"])          # td3.py:372, :376 (targets = deep copies)
+        self._flat["critic_target"].copy_(self._flat["critic"])
+
+    def close(self):
+        if getattr(self, "_learner", None):
+            _abi.load_library().plen_td3_destroy(self._learner)
+            self._learner = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

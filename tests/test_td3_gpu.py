@@ -87,9 +87,85 @@ def test_actor_forward_kernel_vs_reference_checkpoint_and_torch():
     assert not torch.equal(noisy, actor_forward(b, obs, noise_std=0.1, seed=8))
 
 
+def _twin_agents(dev, seed=0):
+    """Two agents with identical parameters: one stepped by the CUDA learner, one by the PyTorch fp32 reference."""
+    from plen_ml_walk_b200.td3 import TD3Agent
+    torch.manual_seed(seed)
+    a, b = TD3Agent(device=dev), TD3Agent(device=dev)
+    for k in ("actor", "actor_target", "critic", "critic_target"):
+        b._flat[k].copy_(a._flat[k])
+    return a, b
+
+
+def test_td3_cuda_update_matches_pytorch_reference():
+    """plen_td3_* (hand-written CUDA forward / backward / Adam / Polyak) against the same update in PyTorch autograd +
+    torch.optim.Adam (the reference's td3.py:259-356 rule), same minibatch and the same policy-smoothing noise, over six
+    consecutive updates (three of them policy updates).  fp32 on both sides: parameters within 2e-5 after every step."""
+    dev = torch.device("cuda:0")
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for B in (100, 37, 256):                                     # the reference's batch, a ragged one, a tile multiple
+            a, b = _twin_agents(dev, seed=B)
+            g = torch.Generator(device=dev); g.manual_seed(B)
+            for it in range(6):
+                s = torch.randn(B, 26, device=dev, generator=g)
+                ac = torch.rand(B, 18, device=dev, generator=g) * 2 - 1
+                s2 = s + 0.05 * torch.randn(B, 26, device=dev, generator=g)
+                r = torch.randn(B, 1, device=dev, generator=g)
+                nd = (torch.rand(B, 1, device=dev, generator=g) > 0.1).float()
+                nz = torch.randn(B, 18, device=dev, generator=g)
+                al_c, cl_c = a.train(None, batch=(s, ac, s2, r, nd), noise=nz, return_losses=True)
+                al_t, cl_t = b.train_torch((s, ac, s2, r, nd), noise=nz)
+                assert abs(float(cl_c) - float(cl_t)) <= 1e-4 * max(1.0, abs(float(cl_t)))
+                assert (al_c is None) == (al_t is None)
+                if al_t is not None:
+                    assert abs(float(al_c) - float(al_t)) <= 1e-4 * max(1.0, abs(float(al_t)))
+                for k in ("critic", "actor", "critic_target", "actor_target"):
+                    d = float((a._flat[k] - b._flat[k]).abs().max())
+                    assert d < 2e-5, (B, it, k, d)
+            # Adam moments agree with torch's optimizer state
+            m_t = torch.cat([b.critic_optimizer.state[p]["exp_avg"].reshape(-1) for p in b.critic.parameters()])
+            v_t = torch.cat([b.critic_optimizer.state[p]["exp_avg_sq"].reshape(-1) for p in b.critic.parameters()])
+            assert float((a._adam["critic_m"] - m_t).abs().max()) < 1e-6 and float((a._adam["critic_v"] - v_t).abs().max()) < 1e-6
+            assert a.kernel_launches() == 6 * (1 + 15) + 3 * 15      # set_batch + critic graph; actor graph on policy steps
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def test_td3_gradients_match_autograd():
+    """critic_grad / actor_grad (the vectors a data-parallel learner all-reduces) against autograd, entry by entry."""
+    import torch.nn.functional as F
+    dev = torch.device("cuda:0")
+    a, b = _twin_agents(dev, seed=3)
+    B = 100
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    s = torch.randn(B, 26, device=dev, generator=g); ac = torch.rand(B, 18, device=dev, generator=g) * 2 - 1
+    s2 = torch.randn(B, 26, device=dev, generator=g); r = torch.randn(B, 1, device=dev, generator=g)
+    nd = torch.ones(B, 1, device=dev); nz = torch.randn(B, 18, device=dev, generator=g)
+    seen = {}
+    a.total_it = 1                                                  # next call is a policy update
+    a.train(None, batch=(s, ac, s2, r, nd), noise=nz, grad_hook=lambda gflat: seen.setdefault(gflat.numel(), gflat.clone()))
+    with torch.no_grad():
+        n2 = (nz * b.policy_noise).clamp(-b.noise_clip, b.noise_clip)
+        a2 = (b.actor_target(s2) + n2).clamp(-1, 1)
+        q1t, q2t = b.critic_target(s2, a2)
+        y = r + nd * b.discount * torch.min(q1t, q2t)
+    q1, q2 = b.critic(s, ac)
+    loss = F.mse_loss(q1, y) + F.mse_loss(q2, y)
+    gc = torch.cat([x.reshape(-1) for x in torch.autograd.grad(loss, list(b.critic.parameters()), retain_graph=True)])
+    assert float((seen[155138] - gc).abs().max()) < 1e-5 * max(1.0, float(gc.abs().max()))
+    # the actor gradient is taken after the critic's Adam step, as in the reference: apply the same step to b first
+    b.critic_optimizer.zero_grad(); loss.backward(); b.critic_optimizer.step()
+    la = -b.critic.Q1(s, b.actor(s)).mean()
+    ga = torch.cat([x.reshape(-1) for x in torch.autograd.grad(la, list(b.actor.parameters()))])
+    assert float((seen[77330] - ga).abs().max()) < 1e-5 * max(1.0, float(ga.abs().max()))
+
+
 def test_td3_update_follows_reference_rule():
-    """TD3Agent.train (td3.py:259-356): critic step every call, actor + Polyak every policy_freq calls; the critic loss on
-    a fixed synthetic buffer goes down."""
+    """TD3Agent.train (td3.py:259-356) sampling from the device replay ring inside the library: critic step every call,
+    actor + Polyak every policy_freq calls; the critic loss on a fixed synthetic buffer goes down; checkpoints round-trip
+    through the reference's four-file format including the Adam state."""
     from plen_ml_walk_b200.td3 import ReplayBuffer, TD3Agent
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
@@ -100,15 +176,23 @@ def test_td3_update_follows_reference_rule():
     rb.add(s, a, s + 0.01, -(a ** 2).sum(1), torch.zeros(5000, dtype=torch.bool, device=dev))
     actor0 = [p.clone() for p in agent.actor.parameters()]
     tgt0 = [p.clone() for p in agent.critic_target.parameters()]
-    al, cl0 = agent.train(rb, 100)
+    al, cl0 = agent.train(rb, 100, return_losses=True)
     assert al is None and all(torch.equal(p, q) for p, q in zip(agent.actor.parameters(), actor0))      # delayed policy update
     assert all(torch.equal(p, q) for p, q in zip(agent.critic_target.parameters(), tgt0))
-    al, _ = agent.train(rb, 100)
+    al, _ = agent.train(rb, 100, return_losses=True)
     assert al is not None and not all(torch.equal(p, q) for p, q in zip(agent.actor.parameters(), actor0))
     d = [float((p - q).abs().max()) for p, q in zip(agent.critic_target.parameters(), tgt0)]
     assert 0 < max(d) < 0.01                                                                              # tau = 0.005
-    losses = [float(agent.train(rb, 100)[1]) for _ in range(300)]
+    losses = [float(agent.train(rb, 100, return_losses=True)[1]) for _ in range(300)]
     assert np.mean(losses[-50:]) < 0.5 * float(cl0)
     act = agent.select_action(s[:1000])
     with torch.no_grad():
         assert float((act - agent.actor(s[:1000])).abs().max()) < 1e-5
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        agent.save(td + "/ck")
+        other = TD3Agent(device=dev)
+        other.load(td + "/ck")
+        assert torch.equal(other._flat["actor"], agent._flat["actor"]) and torch.equal(other._flat["critic"], agent._flat["critic"])
+        assert other.critic_steps == agent.critic_steps == 302 and other.actor_steps == agent.actor_steps == 151
+        assert torch.equal(other._adam["critic_v"], agent._adam["critic_v"])
