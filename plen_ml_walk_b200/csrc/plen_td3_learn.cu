@@ -62,12 +62,16 @@ __device__ __forceinline__ uint32_t mix32(uint64_t x) {     // splitmix64 finali
     return (uint32_t)((x ^ (x >> 31)) >> 32);
 }
 
-constexpr int BM = 32, BN = 32, BK = 32, GT = 256;
+constexpr int GT = 256;
 
-// 32 x 32 output tile per CTA, 256 threads, 2 x 2 outputs per thread, K in steps of 32 with the next tiles prefetched
-// into registers while the current ones are multiplied.  Strides are arbitrary (row- or column-major operands, strided
-// sub-matrices such as the action columns of fc1), loads are coalesced along whichever operand stride is 1.
+// BM x BN output tile per CTA, 256 threads as 16 x 16, TM x TN outputs per thread (register tile), K in steps of BK with
+// the next tiles prefetched into registers while the current ones are multiplied.  Strides are arbitrary (row- or
+// column-major operands, strided sub-matrices such as the action columns of fc1); loads are coalesced along whichever
+// operand stride is 1.  Two instances: 32 x 32 x 32 (2 x 2 per thread) for the reference's batch of 100, where the grid
+// must be as wide as possible, and 64 x 64 x 16 (4 x 4 per thread) once the batch fills the device.
+template <int BM, int BN, int BK, int TM, int TN>
 __global__ void __launch_bounds__(GT) k_gemm(const Gemm g) {
+    static_assert(BM == 16 * TM && BN == 16 * TN && BM * BK == 4 * GT && BN * BK == 4 * GT, "tile shape");
     __shared__ float As[BK][BM + 1], Bs[BK][BN + 1];
     const int z = blockIdx.z, m0 = blockIdx.y * BM, n0 = blockIdx.x * BN, tid = threadIdx.x;
     const float *a = g.a + z * g.az, *b = g.b + z * g.bz;
@@ -77,15 +81,19 @@ __global__ void __launch_bounds__(GT) k_gemm(const Gemm g) {
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int e = tid + GT * i;
-            const int am = a_kfast ? (e >> 5) : (e & 31), ak = a_kfast ? (e & 31) : (e >> 5);
-            const int bk = b_nfast ? (e >> 5) : (e & 31), bn = b_nfast ? (e & 31) : (e >> 5);
+            const int am = a_kfast ? (e / BK) : (e % BM), ak = a_kfast ? (e % BK) : (e / BM);
+            const int bk = b_nfast ? (e / BN) : (e % BK), bn = b_nfast ? (e % BN) : (e / BK);
             ra[i] = (m0 + am < g.M && k0 + ak < g.K) ? a[(m0 + am) * g.am + (k0 + ak) * g.ak] : 0.0f;
             rb[i] = (k0 + bk < g.K && n0 + bn < g.N) ? b[(k0 + bk) * g.bk + (n0 + bn) * g.bn] : 0.0f;
         }
     };
     const int tx = tid & 15, ty = tid >> 4;
-    float acc[2][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}};
-    float rs = 0.0f;                                   // row sum of A for row m0 + tid (threads < 32, first column tile only)
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) acc[i][j] = 0.0f;
+    float rs = 0.0f;                                   // row sum of A for row m0 + tid (threads < BM, first column tile only)
     const bool do_rs = g.rowsum != nullptr && blockIdx.x == 0;
     fetch(0);
     for (int k0 = 0; k0 < g.K; k0 += BK) {
@@ -93,8 +101,8 @@ __global__ void __launch_bounds__(GT) k_gemm(const Gemm g) {
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int e = tid + GT * i;
-            const int am = a_kfast ? (e >> 5) : (e & 31), ak = a_kfast ? (e & 31) : (e >> 5);
-            const int bk = b_nfast ? (e >> 5) : (e & 31), bn = b_nfast ? (e & 31) : (e >> 5);
+            const int am = a_kfast ? (e / BK) : (e % BM), ak = a_kfast ? (e % BK) : (e / BM);
+            const int bk = b_nfast ? (e / BN) : (e % BK), bn = b_nfast ? (e % BN) : (e / BK);
             As[ak][am] = ra[i];
             Bs[bk][bn] = rb[i];
         }
@@ -102,9 +110,15 @@ __global__ void __launch_bounds__(GT) k_gemm(const Gemm g) {
         if (k0 + BK < g.K) fetch(k0 + BK);
 #pragma unroll
         for (int k = 0; k < BK; k++) {
-            const float a0 = As[k][2 * ty], a1 = As[k][2 * ty + 1], b0 = Bs[k][2 * tx], b1 = Bs[k][2 * tx + 1];
-            acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
-            acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+            float av[TM], bv[TN];
+#pragma unroll
+            for (int i = 0; i < TM; i++) av[i] = As[k][TM * ty + i];
+#pragma unroll
+            for (int j = 0; j < TN; j++) bv[j] = Bs[k][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < TM; i++)
+#pragma unroll
+                for (int j = 0; j < TN; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
         if (do_rs && tid < BM) {
 #pragma unroll
@@ -114,10 +128,10 @@ __global__ void __launch_bounds__(GT) k_gemm(const Gemm g) {
     if (do_rs && tid < BM && m0 + tid < g.M) g.rowsum[z * g.rowsum_z + m0 + tid] = rs;
     float *c = g.c + z * g.cz;
 #pragma unroll
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < TM; i++)
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const int m = m0 + 2 * ty + i, n = n0 + 2 * tx + j;
+        for (int j = 0; j < TN; j++) {
+            const int m = m0 + TM * ty + i, n = n0 + tx + 16 * j;
             if (m >= g.M || n >= g.N) continue;
             float v = acc[i][j];
             switch (g.epi) {
@@ -239,8 +253,14 @@ __global__ void k_soft_update(float *__restrict__ tgt, const float *__restrict__
 }
 
 int launch(const Gemm &g, cudaStream_t st) {
-    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.nz);
-    k_gemm<<<grid, GT, 0, st>>>(g);
+    // wide tiles only when they still give every SM a CTA
+    if ((long long)((g.N + 63) / 64) * ((g.M + 63) / 64) * g.nz >= 148) {
+        dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, g.nz);
+        k_gemm<64, 64, 16, 4, 4><<<grid, GT, 0, st>>>(g);
+    } else {
+        dim3 grid((g.N + 31) / 32, (g.M + 31) / 32, g.nz);
+        k_gemm<32, 32, 32, 2, 2><<<grid, GT, 0, st>>>(g);
+    }
     return 1;
 }
 
