@@ -166,7 +166,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: one JSON line only
+        os.environ.pop("NCCL_DEBUG", None)               # any NCCL_DEBUG level prints the version banner on stdout: one JSON line only
         import torch.distributed as dist_mod
         dist_mod.init_process_group("nccl", device_id=dev)
         dist = dist_mod

@@ -69,8 +69,11 @@ def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def actor_forward(actor: Actor, obs: torch.Tensor, noise_std: float = 0.0, seed: int = 0, out: torch.Tensor | None = None):
-    """Actor.forward for obs [N,26] (float32, CUDA) through the fused CUDA kernel; optional exploration noise + clip."""
+def actor_forward(actor: Actor, obs: torch.Tensor, noise_std: float = 0.0, seed: int = 0, out: torch.Tensor | None = None,
+                  precision: str = "fp32"):
+    """Actor.forward for obs [N,26] (float32, CUDA) through the fused CUDA kernel; optional exploration noise + clip.
+    precision "fp32": CUDA-core kernel, 1e-5 parity with the reference; "bf16": tcgen05 tensor-core kernel (BF16 operands,
+    FP32 accumulation), actions within ~2e-2 of fp32 -- the throughput path for rollouts."""
     if not obs.is_cuda:
         raise RuntimeError("plen_actor_forward needs CUDA tensors; there is no CPU fallback")
     lib = _abi.load_library()
@@ -84,7 +87,10 @@ def actor_forward(actor: Actor, obs: torch.Tensor, noise_std: float = 0.0, seed:
         raise ValueError("plen_actor_forward implements the reference architecture 26-256-256-18 (td3.py:37-41)")
     dev = obs.device
     with torch.cuda.device(dev):
-        rc = lib.plen_actor_forward(dev.index if dev.index is not None else torch.cuda.current_device(), *[_p(t) for t in w],
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        fn = lib.plen_actor_forward if precision == "fp32" else lib.plen_actor_forward_bf16
+        rc = fn(dev.index if dev.index is not None else torch.cuda.current_device(), *[_p(t) for t in w],
                                     _p(obs), n, float(actor.max_action), float(noise_std), int(seed) & (2 ** 64 - 1), _p(out),
                                     C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
     if rc != 0:
@@ -252,11 +258,11 @@ class TD3Agent:                                            # td3.py:196-376
     def _idx(self):
         return self.device.index if self.device.index is not None else torch.cuda.current_device()
 
-    def select_action(self, state, expl_noise=0.0):
+    def select_action(self, state, expl_noise=0.0, precision="fp32"):
         """Batched: state [N,26] on the device -> action [N,18]; expl_noise = plen_td3.py:101-104 (std = max_action * expl_noise)."""
         self._draws += 1
         return actor_forward(self.actor, torch.as_tensor(state, device=self.device).reshape(-1, STATE_DIM),
-                             noise_std=self.max_action * expl_noise, seed=self._draws)
+                             noise_std=self.max_action * expl_noise, seed=self._draws, precision=precision)
 
     def train(self, replay_buffer, batch_size=100, batch=None, noise=None, return_losses=False, grad_hook=None):
         """One TD3 update (td3.py:259-356) in the CUDA library.

@@ -198,3 +198,33 @@ def test_td3_update_follows_reference_rule():
         assert torch.equal(other._flat["actor"], agent._flat["actor"]) and torch.equal(other._flat["critic"], agent._flat["critic"])
         assert other.critic_steps == agent.critic_steps == 302 and other.actor_steps == agent.actor_steps == 151
         assert torch.equal(other._adam["critic_v"], agent._adam["critic_v"])
+
+
+def test_actor_forward_tensor_core_path_vs_fp32_kernel():
+    """plen_actor_forward_bf16 (tcgen05.mma, BF16 operands, FP32 accumulation in TMEM) against the fp32 CUDA-core kernel on
+    the reference's shipped checkpoint: BF16 operand rounding (2^-9 relative per operand, three layers) moves an action by
+    at most 3e-2 and by 3e-3 on average; ragged N (not a multiple of the 128-row tile), more tiles than SMs, and the
+    exploration-noise stream is the same as the fp32 kernel's."""
+    from plen_ml_walk_b200 import _abi
+    from plen_ml_walk_b200.td3 import Actor, actor_forward
+    dev = torch.device("cuda:0")
+    g = np.load(GOLD)
+    a = Actor().to(dev)
+    a.load_state_dict({k: torch.from_numpy(g["actor_" + k.replace(".", "_")]).to(dev) for k in a.state_dict().keys()})
+    gen = torch.Generator(device=dev); gen.manual_seed(3)
+    for n in (1, 127, 1000, 148 * 128 * 2 + 77):
+        obs = torch.randn(n, 26, device=dev, generator=gen) * 0.5
+        ref = actor_forward(a, obs)
+        got = actor_forward(a, obs, precision="bf16")
+        torch.cuda.synchronize()
+        assert _abi.load_library().plen_actor_tc_timed_out() == 0
+        d = (got - ref).abs()
+        assert float(d.max()) < 3e-2 and float(d.mean()) < 3e-3, (n, float(d.max()), float(d.mean()))
+    obs = torch.from_numpy(g["obs"]).to(dev)
+    got = actor_forward(a, obs, precision="bf16")
+    assert float((got - torch.from_numpy(g["actor_out"]).to(dev)).abs().max()) < 3e-2         # reference td3.py outputs
+    obs = torch.randn(4096, 26, device=dev, generator=gen) * 0.1
+    c32, n32 = actor_forward(a, obs), actor_forward(a, obs, noise_std=0.1, seed=11)
+    c16, n16 = actor_forward(a, obs, precision="bf16"), actor_forward(a, obs, noise_std=0.1, seed=11, precision="bf16")
+    inside = (n32.abs() < 0.999) & (n16.abs() < 0.999)
+    assert float(((n16 - c16) - (n32 - c32))[inside].abs().max()) < 1e-5
