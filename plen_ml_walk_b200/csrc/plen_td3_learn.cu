@@ -53,6 +53,8 @@ struct Gemm {
     float p0, p1, p2;                              // max_action, policy_noise, noise_clip
     unsigned long long seed;
     float *rowsum; long long rowsum_z;             // nullable: rowsum[z][m] = sum_k A(z, m, k)   (bias gradient of a dW product)
+    int splits, k_chunk;                           // split-K (dW products of large minibatches): blockIdx.z = z + nz * split; results are
+                                                   // accumulated with atomicAdd into a zeroed C / rowsum
 };
 
 __device__ __forceinline__ uint32_t mix32(uint64_t x) {     // splitmix64 finaliser
@@ -73,7 +75,8 @@ template <int BM, int BN, int BK, int TM, int TN>
 __global__ void __launch_bounds__(GT) k_gemm(const Gemm g) {
     static_assert(BM == 16 * TM && BN == 16 * TN && BM * BK == 4 * GT && BN * BK == 4 * GT, "tile shape");
     __shared__ float As[BK][BM + 1], Bs[BK][BN + 1];
-    const int z = blockIdx.z, m0 = blockIdx.y * BM, n0 = blockIdx.x * BN, tid = threadIdx.x;
+    const int z = blockIdx.z % g.nz, split = blockIdx.z / g.nz, m0 = blockIdx.y * BM, n0 = blockIdx.x * BN, tid = threadIdx.x;
+    const int k_lo = split * g.k_chunk, k_hi = min(g.K, k_lo + g.k_chunk);
     const float *a = g.a + z * g.az, *b = g.b + z * g.bz;
     const bool a_kfast = g.ak == 1, b_nfast = g.bn == 1;
     float ra[4], rb[4];
@@ -83,8 +86,8 @@ __global__ void __launch_bounds__(GT) k_gemm(const Gemm g) {
             const int e = tid + GT * i;
             const int am = a_kfast ? (e / BK) : (e % BM), ak = a_kfast ? (e % BK) : (e / BM);
             const int bk = b_nfast ? (e / BN) : (e % BK), bn = b_nfast ? (e % BN) : (e / BK);
-            ra[i] = (m0 + am < g.M && k0 + ak < g.K) ? a[(m0 + am) * g.am + (k0 + ak) * g.ak] : 0.0f;
-            rb[i] = (k0 + bk < g.K && n0 + bn < g.N) ? b[(k0 + bk) * g.bk + (n0 + bn) * g.bn] : 0.0f;
+            ra[i] = (m0 + am < g.M && k0 + ak < k_hi) ? a[(m0 + am) * g.am + (k0 + ak) * g.ak] : 0.0f;
+            rb[i] = (k0 + bk < k_hi && n0 + bn < g.N) ? b[(k0 + bk) * g.bk + (n0 + bn) * g.bn] : 0.0f;
         }
     };
     const int tx = tid & 15, ty = tid >> 4;
@@ -95,8 +98,8 @@ __global__ void __launch_bounds__(GT) k_gemm(const Gemm g) {
         for (int j = 0; j < TN; j++) acc[i][j] = 0.0f;
     float rs = 0.0f;                                   // row sum of A for row m0 + tid (threads < BM, first column tile only)
     const bool do_rs = g.rowsum != nullptr && blockIdx.x == 0;
-    fetch(0);
-    for (int k0 = 0; k0 < g.K; k0 += BK) {
+    fetch(k_lo);
+    for (int k0 = k_lo; k0 < k_hi; k0 += BK) {
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(GT) k_gemm(const Gemm g) {
             Bs[bk][bn] = rb[i];
         }
         __syncthreads();
-        if (k0 + BK < g.K) fetch(k0 + BK);
+        if (k0 + BK < k_hi) fetch(k0 + BK);
 #pragma unroll
         for (int k = 0; k < BK; k++) {
             float av[TM], bv[TN];
@@ -125,7 +128,10 @@ __global__ void __launch_bounds__(GT) k_gemm(const Gemm g) {
             for (int k = 0; k < BK; k++) rs += As[k][tid];
         }
     }
-    if (do_rs && tid < BM && m0 + tid < g.M) g.rowsum[z * g.rowsum_z + m0 + tid] = rs;
+    if (do_rs && tid < BM && m0 + tid < g.M) {
+        if (g.splits > 1) atomicAdd(&g.rowsum[z * g.rowsum_z + m0 + tid], rs);
+        else g.rowsum[z * g.rowsum_z + m0 + tid] = rs;
+    }
     float *c = g.c + z * g.cz;
 #pragma unroll
     for (int i = 0; i < TM; i++)
@@ -160,7 +166,8 @@ __global__ void __launch_bounds__(GT) k_gemm(const Gemm g) {
                 }
                 default: break;
             }
-            c[m * g.ldc + n] = v;
+            if (g.splits > 1) atomicAdd(&c[m * g.ldc + n], v);      // epilogue is EPI_NONE on split products
+            else c[m * g.ldc + n] = v;
         }
 }
 
@@ -252,13 +259,22 @@ __global__ void k_soft_update(float *__restrict__ tgt, const float *__restrict__
     if (i < n) tgt[i] = tau * src[i] + (1.0f - tau) * tgt[i];
 }
 
-int launch(const Gemm &g, cudaStream_t st) {
+// minibatch size from which the dW products are split along K (= the minibatch) and accumulated atomically
+constexpr int SPLIT_K_MIN_BATCH = 512;
+
+int launch(Gemm g, cudaStream_t st) {
+    g.splits = 1; g.k_chunk = g.K;
+    if (g.epi == EPI_NONE && g.rowsum != nullptr && g.K >= SPLIT_K_MIN_BATCH) {      // dW = dY^T X of a large minibatch
+        g.splits = g.K / 256 < 16 ? g.K / 256 : 16;
+        g.k_chunk = ((g.K + g.splits - 1) / g.splits + 31) / 32 * 32;
+        g.splits = (g.K + g.k_chunk - 1) / g.k_chunk;
+    }
     // wide tiles only when they still give every SM a CTA
-    if ((long long)((g.N + 63) / 64) * ((g.M + 63) / 64) * g.nz >= 148) {
-        dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, g.nz);
+    if ((long long)((g.N + 63) / 64) * ((g.M + 63) / 64) * g.nz * g.splits >= 148) {
+        dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, g.nz * g.splits);
         k_gemm<64, 64, 16, 4, 4><<<grid, GT, 0, st>>>(g);
     } else {
-        dim3 grid((g.N + 31) / 32, (g.M + 31) / 32, g.nz);
+        dim3 grid((g.N + 31) / 32, (g.M + 31) / 32, g.nz * g.splits);
         k_gemm<32, 32, 32, 2, 2><<<grid, GT, 0, st>>>(g);
     }
     return 1;
@@ -421,6 +437,7 @@ int plen_td3_critic_grads(plen_td3 *t, const plen_td3_params *P, const plen_td3_
     n += 1;
     // ---- backward through both towers, td3.py:333 (gradients land in P->critic_grad, flat layout of the critic)
     float *gr = P->critic_grad;
+    if (B >= SPLIT_K_MIN_BATCH) { LCK(cudaMemsetAsync(gr, 0, sizeof(float) * CRITIC_N, st)); n += 1; }      // split-K accumulates
     n += launch(bwd_weight(t->dq, 1, B, t->c_h2, H, BH, gr + CW3, H, gr + CB3, TOWER_N, B, 1, H, 2), st);
     n += launch(bwd_data(t->dq, 1, B, c + CW3, H, TOWER_N, t->dh2, H, BH, B, H, 1, 2, EPI_RELUMASK, t->c_h2, H, BH), st);
     n += launch(bwd_weight(t->dh2, H, BH, t->c_h1, H, BH, gr + CW2, H, gr + CB2, TOWER_N, B, H, H, 2), st);
@@ -463,6 +480,7 @@ int plen_td3_actor_grads(plen_td3 *t, const plen_td3_params *P, const plen_td3_h
         n += launch(g, st);
     }
     float *gr = P->actor_grad;
+    if (B >= SPLIT_K_MIN_BATCH) { LCK(cudaMemsetAsync(gr, 0, sizeof(float) * ACTOR_N, st)); n += 1; }
     n += launch(bwd_weight(t->da3, A, 0, t->a_h2, H, 0, gr + AW3, H, gr + AB3, 0, B, A, H, 1), st);
     n += launch(bwd_data(t->da3, A, 0, ac + AW3, H, 0, t->da_h2, H, 0, B, H, A, 1, EPI_RELUMASK, t->a_h2, H, 0), st);
     n += launch(bwd_weight(t->da_h2, H, 0, t->a_h1, H, 0, gr + AW2, H, gr + AB2, 0, B, H, H, 1), st);

@@ -24,7 +24,7 @@ from plen_ml_walk_b200.vec_env import PlenVecEnv
 
 
 def run(n_envs, total_env_steps, updates_per_step, start_timesteps=10000, expl_noise=0.1, batch_size=100, seed=0,
-        device="cuda:0", replay_size=1000000, learner=True):
+        device="cuda:0", replay_size=1000000, learner=True, actor_precision="fp32"):
     dev = torch.device(device)
     torch.manual_seed(seed)
     env = PlenVecEnv(n_envs, device=dev, seed=seed)
@@ -42,7 +42,7 @@ def run(n_envs, total_env_steps, updates_per_step, start_timesteps=10000, expl_n
         if t < start_timesteps:
             action = torch.empty((n_envs, 18), device=dev).uniform_(-1, 1, generator=gen)        # action_space.sample()
         else:
-            action = agent.select_action(state, expl_noise=expl_noise)                           # plen_td3.py:101-104
+            action = agent.select_action(state, expl_noise=expl_noise, precision=actor_precision)  # plen_td3.py:101-104
         obs, reward, done, info = env.step(action)
         done_bool = done & ~info["timeout"]                                                      # plen_td3.py:109-110
         next_state = torch.where(done[:, None], info["terminal_obs"], obs)
@@ -63,7 +63,8 @@ def run(n_envs, total_env_steps, updates_per_step, start_timesteps=10000, expl_n
     return {"envs": n_envs, "env_steps": vec_steps * n_envs, "vector_steps": vec_steps, "updates": updates,
             "update_to_data": updates / max(1, vec_steps * n_envs), "seconds": dt, "env_steps_per_s": vec_steps * n_envs / dt,
             "episodes": done_count, "mean_episode_return": ret_sum / max(1, done_count), "replay_len": len(rb),
-            "learner": learner}
+            "learner": learner, "batch_size": batch_size, "actor_precision": actor_precision,
+            "td3_kernel_launches": agent.kernel_launches()}
 
 
 if __name__ == "__main__":
@@ -72,5 +73,9 @@ if __name__ == "__main__":
     ap.add_argument("--env-steps", type=int, default=1048576)
     ap.add_argument("--updates-per-step", type=int, default=8)
     ap.add_argument("--no-learner", action="store_true")
+    ap.add_argument("--batch-size", type=int, default=100)
+    ap.add_argument("--start-timesteps", type=int, default=10000)
+    ap.add_argument("--actor-precision", default="fp32", choices=["fp32", "bf16"])
     a = ap.parse_args()
-    print(json.dumps(run(a.envs, a.env_steps, a.updates_per_step, learner=not a.no_learner)))
+    print(json.dumps(run(a.envs, a.env_steps, a.updates_per_step, learner=not a.no_learner, batch_size=a.batch_size,
+                         start_timesteps=a.start_timesteps, actor_precision=a.actor_precision)))
