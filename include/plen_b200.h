@@ -194,11 +194,11 @@ int plen_replay_sample(plen_replay *rb, int batch, unsigned long long seed, floa
 int plen_actor_forward(int device, const float *w1, const float *b1, const float *w2, const float *b2, const float *w3,
                        const float *b3, const float *obs_dev, int n, float max_action, float noise_std,
                        unsigned long long seed, float *action_dev, void *stream);
-/* The same forward pass on the 5th-generation tensor cores (tcgen05.mma kind::f16: BF16 operands, FP32 accumulation in
+/* The same forward pass on the 5th-generation tensor cores (tcgen05.mma kind::f16: FP16 operands, FP32 accumulation in
  * TMEM; weights resident in shared memory, one persistent CTA per SM, 128 observations per tile).  Throughput path for
- * rollouts with large N; BF16 operand rounding moves an action by up to ~2e-2 (bound tested), so plen_actor_forward
- * stays the parity path.  Same arguments and noise stream as plen_actor_forward. */
-int plen_actor_forward_bf16(int device, const float *w1, const float *b1, const float *w2, const float *b2, const float *w3,
+ * rollouts with large N (8-13x the fp32 kernel); FP16 operand rounding (2^-12 relative) moves an action by ~5e-4 on
+ * average (bound tested), so plen_actor_forward stays the parity path.  Same arguments and noise stream. */
+int plen_actor_forward_tc(int device, const float *w1, const float *b1, const float *w2, const float *b2, const float *w3,
                             const float *b3, const float *obs_dev, int n, float max_action, float noise_std,
                             unsigned long long seed, float *action_dev, void *stream);
 int plen_actor_tc_timed_out(void);   /* diagnostic: 1 if a tensor-core actor launch ever abandoned an mbarrier wait */

@@ -74,7 +74,7 @@ EXPORTS = (
     "plen_reset", "plen_step", "plen_step_host", "plen_get_state", "plen_set_state", "plen_tick",
     "plen_debug_dynamics", "plen_debug_records", "plen_gait_ik", "plen_profile_enable", "plen_profile_read", "plen_measure_fp32_peak",
     "plen_replay_create", "plen_replay_destroy", "plen_replay_size", "plen_replay_ptr", "plen_replay_storage",
-    "plen_replay_add", "plen_replay_sample", "plen_actor_forward", "plen_actor_forward_bf16", "plen_actor_tc_timed_out", "plen_td3_last_error",
+    "plen_replay_add", "plen_replay_sample", "plen_actor_forward", "plen_actor_forward_tc", "plen_actor_tc_timed_out", "plen_td3_last_error",
     "plen_td3_default_hyper", "plen_td3_create", "plen_td3_destroy", "plen_td3_launches", "plen_td3_sample",
     "plen_td3_set_batch", "plen_td3_critic_grads", "plen_td3_actor_grads", "plen_td3_adam", "plen_td3_soft_update",
     "plen_td3_train",
@@ -140,7 +140,7 @@ def load_library(path: str = LIB_PATH):
     L.plen_replay_add.argtypes = [vp] * 6 + [ip, vp]
     L.plen_replay_sample.argtypes = [vp, ip, ull] + [vp] * 7
     L.plen_actor_forward.argtypes = [ip] + [vp] * 7 + [ip, C.c_float, C.c_float, ull, vp, vp]
-    L.plen_actor_forward_bf16.argtypes = [ip] + [vp] * 7 + [ip, C.c_float, C.c_float, ull, vp, vp]
+    L.plen_actor_forward_tc.argtypes = [ip] + [vp] * 7 + [ip, C.c_float, C.c_float, ull, vp, vp]
     L.plen_td3_last_error.restype = C.c_char_p
     hp, pp = C.POINTER(PlenTd3HyperC), C.POINTER(PlenTd3ParamsC)
     L.plen_td3_default_hyper.argtypes = [hp]

@@ -1,21 +1,22 @@
 // plen_actor_tc.cu -- Actor.forward (plen_ros/src/plen_ros_helpers/td3.py:45-57) for N observations on the 5th-generation
-// tensor cores: tcgen05.mma (kind::f16, BF16 operands, FP32 accumulators in TMEM), part of libplen_b200.so.  sm_100a only.
+// tensor cores: tcgen05.mma (kind::f16, FP16 operands, FP32 accumulators in TMEM), part of libplen_b200.so.  sm_100a only.
 //
 // This is the one place on the path where the work is a dense contraction with a large M (N observations x 26-256-256-18,
 // N = 16k .. 1M robots), so it goes to the tensor cores; the fp32 CUDA-core kernel (plen_actor_forward) stays the
 // parity path (1e-5 against the reference's fp32 checkpoints), this one is the throughput path for rollouts
-// (BF16 operands: actions within ~2e-2 of fp32, bound stated and tested in tests/test_td3_gpu.py).
+// (FP16 operands, 11-bit significands: mean action error ~5e-4 against fp32, bound stated and tested in
+// tests/test_td3_gpu.py; BF16 operands were measured 8x worse on the shipped checkpoint and dropped).
 //
 // One persistent CTA per SM, 128 threads, M = 128 observations per tile:
-//   * all three weight matrices live in shared memory as BF16 for the whole kernel (W2 128 KB, W1 / W3 16 KB each, K
+//   * all three weight matrices live in shared memory as FP16 for the whole kernel (W2 128 KB, W1 / W3 16 KB each, K
 //     padded 26 -> 32, N padded 18 -> 32), in the canonical K-major no-swizzle UMMA layout (8 x 16 B core matrices);
-//   * the activations of the tile (128 x 256 BF16, 64 KB) are the A operand, rewritten in place by every epilogue;
+//   * the activations of the tile (128 x 256 FP16, 64 KB) are the A operand, rewritten in place by every epilogue;
 //   * per layer ONE thread issues K / 16 tcgen05.mma (128 x N x 16) into TMEM and commits to an mbarrier; the four warps
-//     then read their 32 TMEM lanes with tcgen05.ld (32x32b.x32), add the bias, apply ReLU, convert to BF16 and store
+//     then read their 32 TMEM lanes with tcgen05.ld (32x32b.x32), add the bias, apply ReLU, convert to FP16 and store
 //     the next A operand (layer 3: tanh, exploration noise, clip, store the actions).
-// No TMA: the operands are produced by the threads themselves (fp32 -> bf16 conversion), so they are written with
+// No TMA: the operands are produced by the threads themselves (fp32 -> fp16 conversion), so they are written with
 // ordinary stores followed by fence.proxy.async.
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -32,7 +33,7 @@ constexpr uint32_t OFF_W2 = 0, OFF_W1 = OFF_W2 + HID * HID * 2, OFF_W3 = OFF_W1 
 static_assert(TC_SMEM <= 232448, "shared memory budget of one CTA");
 
 // byte offset of element (row, k) of an R-row K-major operand in the canonical no-swizzle layout:
-// core matrix = 8 rows x 16 bytes (8 bf16 of K), contiguous; core matrices of consecutive row groups are adjacent
+// core matrix = 8 rows x 16 bytes (8 fp16 of K), contiguous; core matrices of consecutive row groups are adjacent
 // (SBO = 128 B), core matrices of consecutive K groups are R * 16 B apart (LBO)
 __device__ __forceinline__ uint32_t canon(int row, int k, int R) {
     return (uint32_t)((k >> 3) * (R * 16) + (row >> 3) * 128 + (row & 7) * 16 + (k & 7) * 2);
@@ -44,13 +45,13 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
 
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = BF16 (1 << 7, 1 << 10), both K-major,
-// N >> 3 at [17,23), M >> 4 at [24,29)
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = F16 (format 0 at [7,10) and [10,13)), both
+// K-major, N >> 3 at [17,23), M >> 4 at [24,29)
 __device__ __forceinline__ uint32_t instr_desc(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
@@ -88,8 +89,9 @@ __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::be
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+// two fp32 -> packed FP16 (saturating: a hidden activation beyond +-65504 would otherwise become inf)
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+    __half2 v = __floats2half2_rn(fminf(fmaxf(lo, -65504.0f), 65504.0f), fminf(fmaxf(hi, -65504.0f), 65504.0f));
     return *reinterpret_cast<uint32_t *>(&v);
 }
 __device__ __forceinline__ uint32_t mixh(uint64_t x) {     // splitmix64 finaliser (same generator as plen_actor_forward)
@@ -104,7 +106,7 @@ __device__ __forceinline__ void stage_chunk(unsigned char *dst, const float *src
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) v[i] = (row_ok && k0 + i < kmax) ? src_row[k0 + i] : 0.0f;
-    uint4 q = {pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7])};
+    uint4 q = {pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]), pack_f16(v[6], v[7])};
     *reinterpret_cast<uint4 *>(dst) = q;
 }
 
@@ -120,7 +122,7 @@ k_actor_forward_tc(const float *__restrict__ w1, const float *__restrict__ b1, c
     float *bias = reinterpret_cast<float *>(sm + OFF_BIAS);
     volatile uint32_t *tptr = reinterpret_cast<volatile uint32_t *>(sm + OFF_TPTR);
 
-    // ---- one-time set-up: weights -> BF16 canonical operands, biases, mbarrier, TMEM (512 columns: two 256-wide accumulators)
+    // ---- one-time set-up: weights -> FP16 canonical operands, biases, mbarrier, TMEM (512 columns: two 256-wide accumulators)
     for (int e = tid; e < HID * (HID / 8); e += 128) {          // W2 [256][256]
         const int nrow = e & (HID - 1), kg = e >> 8;
         stage_chunk(sm + OFF_W2 + canon(nrow, kg * 8, HID), w2 + (size_t)nrow * HID, kg * 8, HID, true);
@@ -168,13 +170,13 @@ k_actor_forward_tc(const float *__restrict__ w1, const float *__restrict__ b1, c
             fence_after();
 #pragma unroll
             for (int ks = 0; ks < K1 / 16; ks++)
-                mma_bf16(tmem, smem_desc(sbase + OFF_A + ks * 2 * (TM * 16), TM * 16, 128),
+                mma_f16(tmem, smem_desc(sbase + OFF_A + ks * 2 * (TM * 16), TM * 16, 128),
                          smem_desc(sbase + OFF_W1 + ks * 2 * (HID * 16), HID * 16, 128), idesc256, ks > 0);
             mma_commit(bar);
         }
         mbar_wait(bar, parity); parity ^= 1;
         fence_after();
-        // ---- epilogue 1: A <- bf16(relu(D1 + b1))
+        // ---- epilogue 1: A <- fp16(relu(D1 + b1))
 #pragma unroll 1
         for (int c = 0; c < HID / 32; c++) {
             uint32_t r[32];
@@ -184,7 +186,7 @@ k_actor_forward_tc(const float *__restrict__ w1, const float *__restrict__ b1, c
                 float v[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) v[i] = fmaxf(__uint_as_float(r[8 * q + i]) + bias[32 * c + 8 * q + i], 0.0f);
-                uint4 o = {pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7])};
+                uint4 o = {pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]), pack_f16(v[6], v[7])};
                 *reinterpret_cast<uint4 *>(sm + OFF_A + canon(row, 32 * c + 8 * q, TM)) = o;
             }
         }
@@ -196,7 +198,7 @@ k_actor_forward_tc(const float *__restrict__ w1, const float *__restrict__ b1, c
             fence_after();
 #pragma unroll
             for (int ks = 0; ks < HID / 16; ks++)
-                mma_bf16(tmem + 256, smem_desc(sbase + OFF_A + ks * 2 * (TM * 16), TM * 16, 128),
+                mma_f16(tmem + 256, smem_desc(sbase + OFF_A + ks * 2 * (TM * 16), TM * 16, 128),
                          smem_desc(sbase + OFF_W2 + ks * 2 * (HID * 16), HID * 16, 128), idesc256, ks > 0);
             mma_commit(bar);
         }
@@ -211,7 +213,7 @@ k_actor_forward_tc(const float *__restrict__ w1, const float *__restrict__ b1, c
                 float v[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) v[i] = fmaxf(__uint_as_float(r[8 * q + i]) + bias[HID + 32 * c + 8 * q + i], 0.0f);
-                uint4 o = {pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7])};
+                uint4 o = {pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]), pack_f16(v[6], v[7])};
                 *reinterpret_cast<uint4 *>(sm + OFF_A + canon(row, 32 * c + 8 * q, TM)) = o;
             }
         }
@@ -223,7 +225,7 @@ k_actor_forward_tc(const float *__restrict__ w1, const float *__restrict__ b1, c
             fence_after();
 #pragma unroll
             for (int ks = 0; ks < HID / 16; ks++)
-                mma_bf16(tmem, smem_desc(sbase + OFF_A + ks * 2 * (TM * 16), TM * 16, 128),
+                mma_f16(tmem, smem_desc(sbase + OFF_A + ks * 2 * (TM * 16), TM * 16, 128),
                          smem_desc(sbase + OFF_W3 + ks * 2 * (N3 * 16), N3 * 16, 128), idesc32, ks > 0);
             mma_commit(bar);
         }
@@ -256,18 +258,18 @@ k_actor_forward_tc(const float *__restrict__ w1, const float *__restrict__ b1, c
 
 }  // namespace
 
-extern "C" int plen_actor_forward_bf16(int device, const float *w1, const float *b1, const float *w2, const float *b2,
+extern "C" int plen_actor_forward_tc(int device, const float *w1, const float *b1, const float *w2, const float *b2,
                                        const float *w3, const float *b3, const float *obs_dev, int n, float max_action,
                                        float noise_std, unsigned long long seed, float *action_dev, void *stream) {
     if (!w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !obs_dev || !action_dev || n <= 0)
-        return plen_td3_set_error(PLEN_E_ARG, "plen_actor_forward_bf16: bad arguments", "");
+        return plen_td3_set_error(PLEN_E_ARG, "plen_actor_forward_tc: bad arguments", "");
     cudaError_t e = cudaSetDevice(device);
-    if (e != cudaSuccess) return plen_td3_set_error(PLEN_E_CUDA, "plen_actor_forward_bf16: ", cudaGetErrorString(e));
+    if (e != cudaSuccess) return plen_td3_set_error(PLEN_E_CUDA, "plen_actor_forward_tc: ", cudaGetErrorString(e));
     static int sm_count[64] = {0};
     const int di = device < 64 ? device : 63;
     if (sm_count[di] == 0) {
         e = cudaFuncSetAttribute(k_actor_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
-        if (e != cudaSuccess) return plen_td3_set_error(PLEN_E_CUDA, "plen_actor_forward_bf16: ", cudaGetErrorString(e));
+        if (e != cudaSuccess) return plen_td3_set_error(PLEN_E_CUDA, "plen_actor_forward_tc: ", cudaGetErrorString(e));
         int c = 0;
         cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, device);
         sm_count[di] = c > 0 ? c : 148;
@@ -277,7 +279,7 @@ extern "C" int plen_actor_forward_bf16(int device, const float *w1, const float 
     k_actor_forward_tc<<<grid, 128, TC_SMEM, (cudaStream_t)stream>>>(w1, b1, w2, b2, w3, b3, obs_dev, n, max_action, noise_std, seed,
                                                                    action_dev);
     e = cudaGetLastError();
-    if (e != cudaSuccess) return plen_td3_set_error(PLEN_E_CUDA, "plen_actor_forward_bf16: ", cudaGetErrorString(e));
+    if (e != cudaSuccess) return plen_td3_set_error(PLEN_E_CUDA, "plen_actor_forward_tc: ", cudaGetErrorString(e));
     return PLEN_OK;
 }
 

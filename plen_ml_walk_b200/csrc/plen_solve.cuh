@@ -266,6 +266,14 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
 #define OWN_SYNC()  { _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++) o[k_] = s[k_]; }
 #define OWN_SYNC6() { _Pragma("unroll") for (int k_ = 2; k_ < 8; k_++) o[k_] = s[k_]; }
 
+    // The active points of either foot occupy slots 0 .. n-1 (compacted), so the walk over a foot stops at the first empty
+    // slot: min(n + 1, 4) warp-uniform tests per foot instead of 4 (k_rank groups robots of similar load into a warp).
+    // Usage: FOR_ACTIVE_POINTS { body }.  p = slot (0..7), f = foot, k = point of the foot, all compile-time after unrolling.
+#define FOR_ACTIVE_POINTS                                                          \
+    _Pragma("unroll") for (int f = 0; f < 2; f++)                                  \
+        _Pragma("unroll") for (int k = 0, p = 4 * f; k < 4; k++, p++)              \
+            if (k >= (f ? nmax1 : nmax0)) break; else
+
 #define NORMAL_COLUMN(p, f, db)                              \
     {                                                        \
         apply_reg(s, A[f][0], py[p] * (db));                 \
@@ -275,12 +283,10 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
 
     // ---- warm start of the normal rows from the cached impulses
     if (man_any) {
-#pragma unroll
-        for (int p = 0; p < 8; p++)
-            if ((p & 3) < ((p >> 2) ? nmax1 : nmax0)) {
-                const float db_ = GSH(c_lam[p & 3][5], 2 + (p >> 2));
-                NORMAL_COLUMN(p, (p >> 2), db_);
-            }
+        FOR_ACTIVE_POINTS {
+            const float db_ = GSH(c_lam[k][5], 2 + f);
+            NORMAL_COLUMN(p, f, db_);
+        }
     }
 
     // servo row of joint 8 b + k (owner lane b)
@@ -374,10 +380,7 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
         }
         if (man_any) {
             // ---- contact normals (lower bound 0; the 1e10 upper bound of the reference never binds)
-#pragma unroll
-            for (int p = 0; p < 8; p++) {
-                if ((p & 3) >= ((p >> 2) ? nmax1 : nmax0)) continue;
-                const int f = p >> 2, k = p & 3;
+            FOR_ACTIVE_POINTS {
                 if (PLEN_LA_NORMAL && k == 0) OWN_SYNC6();
                 const float(&on)[8] = PLEN_LA_NORMAL ? o : s;
                 const float r_ = fmaf(on[2], py[p], fmaf(-on[3], px[p], on[7]));
@@ -396,24 +399,17 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
                 apply_vec(s, ca_, cb_, db_);
             }
             // ---- all spinning rows, then the rolling rows point by point (t1, t2)
-#pragma unroll
-            for (int p = 0; p < 8; p++) {
-                if ((p & 3) >= ((p >> 2) ? nmax1 : nmax0)) continue;
-                if (PLEN_LA_TORSION && (p & 3) == 0) OWN_SYNC6();
-                TORSION_ROW((p & 3), (p >> 2), 2, mu_spin);
+            FOR_ACTIVE_POINTS {
+                if (PLEN_LA_TORSION && k == 0) OWN_SYNC6();
+                TORSION_ROW(k, f, 2, mu_spin);
             }
-#pragma unroll
-            for (int p = 0; p < 8; p++) {
-                if ((p & 3) >= ((p >> 2) ? nmax1 : nmax0)) continue;
-                if (PLEN_LA_TORSION && (p & 3) == 0) OWN_SYNC6();
-                TORSION_ROW((p & 3), (p >> 2), 1, mu_roll);
-                TORSION_ROW((p & 3), (p >> 2), 0, mu_roll);
+            FOR_ACTIVE_POINTS {
+                if (PLEN_LA_TORSION && k == 0) OWN_SYNC6();
+                TORSION_ROW(k, f, 1, mu_roll);
+                TORSION_ROW(k, f, 0, mu_roll);
             }
             // ---- lateral pairs with the implicit friction cone (resolveConeFrictionConstraintRows)
-#pragma unroll
-            for (int p = 0; p < 8; p++) {
-                if ((p & 3) >= ((p >> 2) ? nmax1 : nmax0)) continue;
-                const int f = p >> 2, k = p & 3;
+            FOR_ACTIVE_POINTS {
                 if (PLEN_LA_LATERAL && k == 0) OWN_SYNC6();
                 const float(&ol)[8] = PLEN_LA_LATERAL ? o : s;
                 const float rA = fmaf(ol[4], px[p], fmaf(-ol[2], pz[p], ol[6]));     // row A: own = vy

@@ -72,8 +72,8 @@ def _p(t):
 def actor_forward(actor: Actor, obs: torch.Tensor, noise_std: float = 0.0, seed: int = 0, out: torch.Tensor | None = None,
                   precision: str = "fp32"):
     """Actor.forward for obs [N,26] (float32, CUDA) through the fused CUDA kernel; optional exploration noise + clip.
-    precision "fp32": CUDA-core kernel, 1e-5 parity with the reference; "bf16": tcgen05 tensor-core kernel (BF16 operands,
-    FP32 accumulation), actions within ~2e-2 of fp32 -- the throughput path for rollouts."""
+    precision "fp32": CUDA-core kernel, 1e-5 parity with the reference; "fp16": tcgen05 tensor-core kernel (FP16 operands,
+    FP32 accumulation in TMEM), mean action error ~5e-4 against fp32 -- the throughput path for rollouts."""
     if not obs.is_cuda:
         raise RuntimeError("plen_actor_forward needs CUDA tensors; there is no CPU fallback")
     lib = _abi.load_library()
@@ -87,9 +87,9 @@ def actor_forward(actor: Actor, obs: torch.Tensor, noise_std: float = 0.0, seed:
         raise ValueError("plen_actor_forward implements the reference architecture 26-256-256-18 (td3.py:37-41)")
     dev = obs.device
     with torch.cuda.device(dev):
-        if precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
-        fn = lib.plen_actor_forward if precision == "fp32" else lib.plen_actor_forward_bf16
+        if precision not in ("fp32", "fp16"):
+            raise ValueError("precision must be 'fp32' or 'fp16'")
+        fn = lib.plen_actor_forward if precision == "fp32" else lib.plen_actor_forward_tc
         rc = fn(dev.index if dev.index is not None else torch.cuda.current_device(), *[_p(t) for t in w],
                                     _p(obs), n, float(actor.max_action), float(noise_std), int(seed) & (2 ** 64 - 1), _p(out),
                                     C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))

@@ -1,4 +1,4 @@
-"""Dev tool: Actor.forward for N observations -- fp32 CUDA-core kernel vs tcgen05 BF16 kernel vs torch (cuBLAS) eager.
+"""Dev tool: Actor.forward for N observations -- fp32 CUDA-core kernel vs tcgen05 FP16 kernel vs torch (cuBLAS) eager.
     python scripts/actor_bench.py"""
 import json
 import os
@@ -17,7 +17,7 @@ out = {}
 for n in (16384, 131072, 1048576):
     obs = torch.randn(n, 26, device=dev)
     res = {}
-    for name, fn in (("fp32_kernel", lambda: actor_forward(a, obs)), ("tcgen05_bf16", lambda: actor_forward(a, obs, precision="bf16")),
+    for name, fn in (("fp32_kernel", lambda: actor_forward(a, obs)), ("tcgen05_fp16", lambda: actor_forward(a, obs, precision="fp16")),
                      ("torch_eager_fp32", lambda: a(obs))):
         with torch.no_grad():
             for _ in range(3):
@@ -32,7 +32,7 @@ for n in (16384, 131072, 1048576):
         flop = 2.0 * n * (26 * 256 + 256 * 256 + 256 * 18)
         res[name] = {"us": us, "tflops": flop / us / 1e6}
     with torch.no_grad():
-        res["max_abs_diff_bf16_vs_fp32"] = float((actor_forward(a, obs, precision="bf16") - actor_forward(a, obs)).abs().max())
+        res["max_abs_diff_fp16_vs_fp32"] = float((actor_forward(a, obs, precision="fp16") - actor_forward(a, obs)).abs().max())
     res["timed_out"] = _abi.load_library().plen_actor_tc_timed_out()
     out["n_%d" % n] = res
 print(json.dumps(out))

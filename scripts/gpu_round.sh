@@ -22,7 +22,7 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_a
     python scripts/actor_bench.py > $O/actor_tc.log 2>&1
 ncu -i $O/actor_tc.ncu-rep --page raw --csv > $O/actor_tc_raw.csv 2>/dev/null
 timeout 600 python scripts/plen_td3_batched.py --envs 16384 --env-steps 1048576 --updates-per-step 8 > $O/config4_u8.json 2> $O/config4.err
-timeout 600 python scripts/plen_td3_batched.py --envs 16384 --env-steps 1048576 --updates-per-step 8 --actor-precision bf16 --batch-size 1024 > $O/config4_u8_b1024_bf16.json 2>> $O/config4.err
+timeout 600 python scripts/plen_td3_batched.py --envs 16384 --env-steps 1048576 --updates-per-step 8 --actor-precision fp16 --batch-size 1024 > $O/config4_u8_b1024_fp16.json 2>> $O/config4.err
 timeout 600 python scripts/plen_td3_batched.py --envs 16384 --env-steps 1048576 --no-learner > $O/config4_nolearner.json 2>> $O/config4.err
 timeout 600 python scripts/trajectory_eval_batched.py > $O/config3.json 2> $O/config3.err
 tail -3 $O/pytest_gpu.log; cat $O/smoke.log | tail -2; cat $O/bench.json; cat $O/bench_ref.json

@@ -75,7 +75,7 @@ if __name__ == "__main__":
     ap.add_argument("--no-learner", action="store_true")
     ap.add_argument("--batch-size", type=int, default=100)
     ap.add_argument("--start-timesteps", type=int, default=10000)
-    ap.add_argument("--actor-precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--actor-precision", default="fp32", choices=["fp32", "fp16"])
     a = ap.parse_args()
     print(json.dumps(run(a.envs, a.env_steps, a.updates_per_step, learner=not a.no_learner, batch_size=a.batch_size,
                          start_timesteps=a.start_timesteps, actor_precision=a.actor_precision)))
