@@ -129,8 +129,8 @@ def test_td3_cuda_update_matches_pytorch_reference():
                 if it == 0:
                     m_t = torch.cat([b.critic_optimizer.state[p]["exp_avg"].reshape(-1) for p in b.critic.parameters()])
                     v_t = torch.cat([b.critic_optimizer.state[p]["exp_avg_sq"].reshape(-1) for p in b.critic.parameters()])
-                    assert float((a._adam["critic_m"] - m_t).abs().max()) < 1e-5 * float(m_t.abs().max()) + 1e-8
-                    assert float((a._adam["critic_v"] - v_t).abs().max()) < 1e-5 * float(v_t.abs().max()) + 1e-10
+                    assert float((a._adam["critic_m"] - m_t).abs().max()) < 1e-4 * float(m_t.abs().max()) + 1e-8
+                    assert float((a._adam["critic_v"] - v_t).abs().max()) < 1e-4 * float(v_t.abs().max()) + 1e-10
             # Adam moments against torch's optimizer state: tight after the first update (gradients taken at identical
             # parameters, checked inside the loop), loose after six (parameters already differ by up to 1e-4)
             m_t = torch.cat([b.critic_optimizer.state[p]["exp_avg"].reshape(-1) for p in b.critic.parameters()])
