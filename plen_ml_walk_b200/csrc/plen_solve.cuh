@@ -72,13 +72,29 @@ PLEN_DEV void fma2(float &a0, float &a1, float x0, float x1, float d) {
 #endif
 }
 
-// keep a kernel-parameter constant in a register for the whole loop (ptxas otherwise re-reads it from the constant bank
-// with an LDCU in front of every use and waits for it)
-PLEN_DEV float pin_reg(float v) {
+// Loop constants that come from the kernel parameters (friction coefficients, residual threshold, iteration cap) must sit
+// in registers: ptxas otherwise re-reads each from the constant bank with an LDCU in front of every foot block and waits
+// for it (~35 exposed cycles, eight times per iteration).  Neither an empty asm (only NVVM sees it) nor a SHFL of the
+// value (folded: kernel parameters are warp-uniform) survives to SASS, so the constants take a round trip through shared
+// memory with a volatile load, which cannot be rematerialised.
+struct LoopConsts { float mu_spin, mu_roll, mu_lat, res_thr; int iterations; };
+PLEN_DEV LoopConsts pin_loop_consts(const DevConfig &cfg, int lane) {
+    LoopConsts c;
 #ifndef PLEN_HOST_EMU
-    asm volatile("" : "+f"(v));
+    __shared__ float pins[8];
+    if (lane == 0) {
+        pins[0] = cfg.mu_spinning; pins[1] = cfg.mu_rolling; pins[2] = cfg.mu_lateral; pins[3] = cfg.residual_threshold;
+        pins[4] = __int_as_float(cfg.iterations);
+    }
+    __syncwarp();
+    volatile float *vp = pins;
+    c.mu_spin = vp[0]; c.mu_roll = vp[1]; c.mu_lat = vp[2]; c.res_thr = vp[3]; c.iterations = __float_as_int(vp[4]);
+#else
+    (void)lane;
+    c.mu_spin = cfg.mu_spinning; c.mu_roll = cfg.mu_rolling; c.mu_lat = cfg.mu_lateral; c.res_thr = cfg.residual_threshold;
+    c.iterations = cfg.iterations;
 #endif
-    return v;
+    return c;
 }
 // 1/sqrt(x) as one MUFU.RSQ: rsqrtf() adds a subnormal-input rescue (FSETP + two predicated FMUL on the row chain)
 PLEN_DEV float rsqrt_fast(float x) {
@@ -328,11 +344,12 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
         apply_reg(s, A[f][c], db_);                                                                       \
     }
 
-    const float mu_spin = pin_reg(cfg.mu_spinning), mu_roll = pin_reg(cfg.mu_rolling), mu_lat = pin_reg(cfg.mu_lateral);
-    const float res_thr = pin_reg(cfg.residual_threshold);
+    const LoopConsts lc = pin_loop_consts(cfg, lane);
+    const float mu_spin = lc.mu_spin, mu_roll = lc.mu_roll, mu_lat = lc.mu_lat, res_thr = lc.res_thr;
+    const int n_iterations = lc.iterations;
     bool alive = valid;
     int my_iters = 0;
-    for (int it = 0; it < cfg.iterations; it++) {
+    for (int it = 0; it < n_iterations; it++) {
         res = 0.0f; resF = 0.0f;
         float resT[3] = {0.0f, 0.0f, 0.0f};      // largest |impulse change| of the spinning / rolling rows per twist component
         const bool fwd = (it & 1) != 0;

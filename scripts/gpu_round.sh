@@ -18,11 +18,15 @@ ncu -i $O/full.ncu-rep --page source --csv -k regex:k_solve > $O/solve_sass.csv 
 ncu -i $O/full.ncu-rep --page source --csv -k regex:k_dyn > $O/dyn_sass.csv 2>/dev/null
 timeout 300 python scripts/td3_bench.py 1000 > $O/td3_bench.json 2> $O/td3_bench.err
 timeout 200 python scripts/actor_bench.py > $O/actor_bench.json 2> $O/actor_bench.err
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_actor_forward_tc" -s 3 -c 1 -o $O/actor_tc -f \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_actor_forward_tc" -s 30 -c 1 -o $O/actor_tc -f \
     python scripts/actor_bench.py > $O/actor_tc.log 2>&1
 ncu -i $O/actor_tc.ncu-rep --page raw --csv > $O/actor_tc_raw.csv 2>/dev/null
 timeout 600 python scripts/plen_td3_batched.py --envs 16384 --env-steps 1048576 --updates-per-step 8 > $O/config4_u8.json 2> $O/config4.err
 timeout 600 python scripts/plen_td3_batched.py --envs 16384 --env-steps 1048576 --updates-per-step 8 --actor-precision fp16 --batch-size 1024 > $O/config4_u8_b1024_fp16.json 2>> $O/config4.err
 timeout 600 python scripts/plen_td3_batched.py --envs 16384 --env-steps 1048576 --no-learner > $O/config4_nolearner.json 2>> $O/config4.err
 timeout 600 python scripts/trajectory_eval_batched.py > $O/config3.json 2> $O/config3.err
+timeout 300 python scripts/walk_eval_batched.py > $O/walk_eval_fp32.json 2> $O/walk_eval.err
+timeout 300 python scripts/walk_eval_batched.py --precision fp16 > $O/walk_eval_fp16.json 2>> $O/walk_eval.err
+python scripts/ab_time.py plen_ml_walk_b200/libplen_b200.so 4096 200 > $O/config2_4096.txt 2>&1
+python scripts/ab_time.py plen_ml_walk_b200/libplen_b200.so 1048576 10 > $O/config5_1m.txt 2>&1
 tail -3 $O/pytest_gpu.log; cat $O/smoke.log | tail -2; cat $O/bench.json; cat $O/bench_ref.json
