@@ -23,6 +23,9 @@ using namespace plen;
 
 // warps per CTA of the warp-per-robot kernels (k_dyn, k_post)
 #define DYN_WPC 4
+#ifndef PLEN_DYN_CHUNK
+#define PLEN_DYN_CHUNK 1      // groups of DYN_WPC robots per k_dyn CTA
+#endif
 
 struct plen_ctx {
     int n, device, sm_count;
@@ -86,9 +89,11 @@ k_dyn(const __grid_constant__ DevConfig dc, const __grid_constant__ EnvRanges er
     DynSmem &sm = stage_table(tab_g);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpScratch &ws = sm.ws[warp];
-    // grid-stride walk (one trip at the default grid of one CTA per four robots, see PLEN_DYN_PERSISTENT); warps only
-    // synchronise with themselves from here on
-    for (int env = blockIdx.x * DYN_WPC + warp; env < n; env += gridDim.x * DYN_WPC) {
+    // a CTA walks PLEN_DYN_CHUNK consecutive groups of four robots (the 4 KB model table is staged once per CTA); warps
+    // only synchronise with themselves from here on
+    for (int it = 0; it < PLEN_DYN_CHUNK; it++) {
+        const int env = (blockIdx.x * PLEN_DYN_CHUNK + it) * DYN_WPC + warp;
+        if (env >= n) break;
         LaneState L;
         load_record(state + (size_t)env * PLEN_STATE_WORDS, ws, L, lane);
         if (lane >= 6 && lane < 24) {
@@ -390,16 +395,10 @@ k_fp32_peak(float *out, int iters, int mode, float seed) {
 // ------------------------------------------------------------------------------------------------ C ABI
 static const size_t DYN_SMEM = sizeof(DynSmem);
 static const size_t SOLVE_SMEM = sizeof(float) * PLEN_GS_WORDS * PLEN_SOLVE_ROBOTS;
-#ifndef PLEN_DYN_PERSISTENT
-#define PLEN_DYN_PERSISTENT 0      // k_dyn grid: 0 = one CTA per four robots (measured 3 % FASTER than persistent CTAs: the
-                                   // hardware scheduler balances the SMs better than a grid-stride walk), k = k x resident CTAs
-#endif
 static int dyn_grid(int n) { return (n + DYN_WPC - 1) / DYN_WPC; }
-// k_dyn grid: full by default; PLEN_DYN_PERSISTENT = k caps it at k x the CTAs the device holds at once (5 per SM)
-static int dyn_grid_persistent(const plen_ctx *ctx, int n) {
-    const int full = dyn_grid(n), resident = PLEN_DYN_PERSISTENT * 5 * ctx->sm_count;
-    return (PLEN_DYN_PERSISTENT == 0 || full < resident) ? full : resident;
-}
+// k_dyn: one CTA per PLEN_DYN_CHUNK groups of four CONSECUTIVE robots.  (A persistent grid-stride walk, grid = resident CTAs,
+// was measured 3 % slower than one CTA per group: robots far apart in the arrays at any one time.)
+static int dyn_grid_persistent(const plen_ctx *, int n) { return (dyn_grid(n) + PLEN_DYN_CHUNK - 1) / PLEN_DYN_CHUNK; }
 static int rank_tiles(int n) { return (n + RANK_TILE - 1) / RANK_TILE; }
 
 // n_ticks physics ticks of 1/240 s: (k_dyn, k_solve) per tick.  `actions` (agent space) only on the first tick.

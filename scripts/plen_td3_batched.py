@@ -34,7 +34,9 @@ def run(n_envs, total_env_steps, updates_per_step, start_timesteps=10000, expl_n
     gen.manual_seed(seed)
     state = env.reset().clone()
     ep_ret = torch.zeros(n_envs, device=dev)
-    done_count, ret_sum, updates, t = 0, 0.0, 0, 0
+    done_count = torch.zeros((), device=dev)           # episode statistics stay on the device: no host sync in the loop
+    ret_sum = torch.zeros((), device=dev)
+    updates, t = 0, 0
     vec_steps = (total_env_steps + n_envs - 1) // n_envs
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
@@ -48,11 +50,10 @@ def run(n_envs, total_env_steps, updates_per_step, start_timesteps=10000, expl_n
         next_state = torch.where(done[:, None], info["terminal_obs"], obs)
         rb.add(state, action, next_state, reward, done_bool)
         ep_ret += reward
-        if bool(done.any()):
-            done_count += int(done.sum())
-            ret_sum += float(ep_ret[done].sum())
-            ep_ret[done] = 0
-        state = obs.clone()
+        done_count += done.sum()
+        ret_sum += (ep_ret * done).sum()
+        ep_ret *= ~done
+        state.copy_(obs)
         t += n_envs
         if learner and t >= start_timesteps:
             for _ in range(updates_per_step):
@@ -62,7 +63,7 @@ def run(n_envs, total_env_steps, updates_per_step, start_timesteps=10000, expl_n
     dt = time.perf_counter() - t0
     return {"envs": n_envs, "env_steps": vec_steps * n_envs, "vector_steps": vec_steps, "updates": updates,
             "update_to_data": updates / max(1, vec_steps * n_envs), "seconds": dt, "env_steps_per_s": vec_steps * n_envs / dt,
-            "episodes": done_count, "mean_episode_return": ret_sum / max(1, done_count), "replay_len": len(rb),
+            "episodes": int(done_count), "mean_episode_return": float(ret_sum) / max(1, int(done_count)), "replay_len": len(rb),
             "learner": learner, "batch_size": batch_size, "actor_precision": actor_precision,
             "td3_kernel_launches": agent.kernel_launches()}
 
