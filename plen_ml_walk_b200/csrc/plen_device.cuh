@@ -32,6 +32,8 @@
 namespace plen {
 PLEN_DEV int lane_id() { return threadIdx.x & 31; }
 PLEN_DEV float shfl(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+// broadcast inside every aligned group of four lanes (src = 0..3): the source is an immediate of the SHFL, no lane arithmetic
+PLEN_DEV float shfl4(float v, int src) { return __shfl_sync(0xffffffffu, v, src, 4); }
 PLEN_DEV float shfl_up(float v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 PLEN_DEV float shfl_down(float v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
 PLEN_DEV float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }

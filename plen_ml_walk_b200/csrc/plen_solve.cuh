@@ -77,11 +77,13 @@ PLEN_DEV void fma2(float &a0, float &a1, float x0, float x1, float d) {
 // for it (~35 exposed cycles, eight times per iteration).  Neither an empty asm (only NVVM sees it) nor a SHFL of the
 // value (folded: kernel parameters are warp-uniform) survives to SASS, so the constants take a round trip through shared
 // memory with a volatile load, which cannot be rematerialised.
-struct LoopConsts { float mu_spin, mu_roll, mu_lat, res_thr; int iterations; };
+struct LoopConsts { float mu_spin, mu_roll, mu_lat, res_thr; int iterations, g; };
 PLEN_DEV LoopConsts pin_loop_consts(const DevConfig &cfg, int lane) {
     LoopConsts c;
 #ifndef PLEN_HOST_EMU
     __shared__ float pins[8];
+    __shared__ int gpin[32];
+    gpin[lane] = lane & 3;      // the lane's index inside its robot, too: ptxas otherwise re-derives it (S2R + LOP3) in every row
     if (lane == 0) {
         pins[0] = cfg.mu_spinning; pins[1] = cfg.mu_rolling; pins[2] = cfg.mu_lateral; pins[3] = cfg.residual_threshold;
         pins[4] = __int_as_float(cfg.iterations);
@@ -89,10 +91,12 @@ PLEN_DEV LoopConsts pin_loop_consts(const DevConfig &cfg, int lane) {
     __syncwarp();
     volatile float *vp = pins;
     c.mu_spin = vp[0]; c.mu_roll = vp[1]; c.mu_lat = vp[2]; c.res_thr = vp[3]; c.iterations = __float_as_int(vp[4]);
+    c.g = reinterpret_cast<volatile int *>(gpin)[lane];
 #else
     (void)lane;
     c.mu_spin = cfg.mu_spinning; c.mu_roll = cfg.mu_rolling; c.mu_lat = cfg.mu_lateral; c.res_thr = cfg.residual_threshold;
     c.iterations = cfg.iterations;
+    c.g = lane & 3;
 #endif
     return c;
 }
@@ -170,8 +174,9 @@ PLEN_DEV void load8(const float *p, float (&o)[8]) {
 // PLEN_GS_WORDS shared staging area; state: this robot's 96-word state record (global), updated in place.
 PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, float *Gs, float *__restrict__ state,
                          int lane, bool valid) {
-    const int g = lane & 3, gb = lane & 28;
-#define GSH(v, l) shfl((v), gb | (l))
+    const LoopConsts lc = pin_loop_consts(cfg, lane);
+    const int g = lc.g;      // lane & 3, pinned in a register
+#define GSH(v, l) shfl4((v), (l))
     {
         vec4 *dst4 = reinterpret_cast<vec4 *>(Gs);
         const vec4 *src4 = reinterpret_cast<const vec4 *>(srec + SR_G);
@@ -344,7 +349,6 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
         apply_reg(s, A[f][c], db_);                                                                       \
     }
 
-    const LoopConsts lc = pin_loop_consts(cfg, lane);
     const float mu_spin = lc.mu_spin, mu_roll = lc.mu_roll, mu_lat = lc.mu_lat, res_thr = lc.res_thr;
     const int n_iterations = lc.iterations;
     bool alive = valid;

@@ -42,6 +42,7 @@ static inline void bar() { g_bar->arrive_and_wait(); }
 static inline int lane_id() { return t_lane; }
 static inline float xchg(float v, int src) { g_x[t_lane] = v; bar(); float r = g_x[src & 31]; bar(); return r; }
 static inline float shfl(float v, int src) { return xchg(v, src); }
+static inline float shfl4(float v, int src) { return xchg(v, (t_lane & 28) | (src & 3)); }
 static inline float shfl_up(float v, int d) { return xchg(v, t_lane - d >= 0 ? t_lane - d : t_lane); }
 static inline float shfl_down(float v, int d) { return xchg(v, t_lane + d <= 31 ? t_lane + d : t_lane); }
 static inline float shfl_xor(float v, int m) { return xchg(v, t_lane ^ m); }
