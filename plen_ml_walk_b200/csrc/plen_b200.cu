@@ -23,6 +23,9 @@ using namespace plen;
 
 // warps per CTA of the warp-per-robot kernels (k_dyn, k_post)
 #define DYN_WPC 4
+#ifndef PLEN_HOST_PIPE
+#define PLEN_HOST_PIPE 4      // ranges plen_step_host pipelines (copy of one range under the kernels of the others)
+#endif
 #ifndef PLEN_DYN_CHUNK
 #define PLEN_DYN_CHUNK 1      // groups of DYN_WPC robots per k_dyn CTA
 #endif
@@ -41,6 +44,7 @@ struct plen_ctx {
     float *d_act, *d_obs, *d_rew;
     uint8_t *d_done, *d_tmo;
     cudaStream_t stream;
+    cudaStream_t pipe[PLEN_HOST_PIPE];      // pipe[0] == stream; ranges of plen_step_host
     // optional per-kernel timing of plen_step (plen_profile_enable): 2*substeps+2 events per recorded step
     cudaEvent_t *prof_ev;
     int prof_cap, prof_steps;
@@ -404,16 +408,33 @@ static int rank_tiles(int n) { return (n + RANK_TILE - 1) / RANK_TILE; }
 // n_ticks physics ticks of 1/240 s: (k_dyn, k_solve) per tick.  `actions` (agent space) only on the first tick.
 // ev (nullable): 2*n_ticks events recorded before each kernel.
 static void launch_ticks(plen_ctx *ctx, float *state, int n, const float *actions, float *tgt, int n_ticks, cudaStream_t st,
-                         cudaEvent_t *ev = nullptr) {
+                         cudaEvent_t *ev = nullptr, size_t off = 0) {
+    // off: first robot of the range inside the context's per-robot scratch (solve records, sort keys, permutation);
+    // state / actions / tgt are already offset by the caller.  Ranges start on RANK_TILE boundaries.
+    float *srec = ctx->d_srec + off * SR_WORDS;
+    uint8_t *key = ctx->d_key + off;
+    int *perm = ctx->d_perm + off;
     for (int t = 0; t < n_ticks; t++) {
         if (ev) cudaEventRecord(ev[2 * t], st);
         k_dyn<<<dyn_grid_persistent(ctx, n), DYN_WPC * 32, DYN_SMEM, st>>>(ctx->dc, ctx->er, ctx->d_tab, state, n, t == 0 ? actions : nullptr,
-                                                          tgt, ctx->d_srec, ctx->d_key, nullptr, nullptr, nullptr);
+                                                          tgt, srec, key, nullptr, nullptr, nullptr);
         if (ev) cudaEventRecord(ev[2 * t + 1], st);
         const int nt = rank_tiles(n);
-        k_rank<<<nt, RANK_TILE, 0, st>>>(ctx->d_key, n, ctx->d_perm);
-        k_solve<<<nt * (RANK_TILE / PLEN_SOLVE_ROBOTS), 32, SOLVE_SMEM, st>>>(ctx->dc, ctx->d_srec, ctx->d_perm, state, n, nt);
+        k_rank<<<nt, RANK_TILE, 0, st>>>(key, n, perm);
+        k_solve<<<nt * (RANK_TILE / PLEN_SOLVE_ROBOTS), 32, SOLVE_SMEM, st>>>(ctx->dc, srec, perm, state, n, nt);
     }
+}
+
+// One env step of robots [off, off + cnt) on stream st (all pointers are whole-batch base pointers)
+static void launch_step_range(plen_ctx *ctx, size_t off, int cnt, const float *actions_dev, float *obs_dev, float *reward_dev,
+                              uint8_t *done_dev, uint8_t *timeout_dev, float *terminal_obs_dev, cudaStream_t st, cudaEvent_t *ev, int nev) {
+    float *state = ctx->d_state + off * PLEN_STATE_WORDS;
+    launch_ticks(ctx, state, cnt, actions_dev + off * PLEN_NJ, ctx->d_tgt + off * PLEN_NJ, ctx->cfg.substeps, st, ev, off);
+    if (ev) cudaEventRecord(ev[nev - 2], st);
+    k_post<<<dyn_grid(cnt), DYN_WPC * 32, DYN_SMEM, st>>>(ctx->dc, ctx->d_tab, state, cnt, obs_dev + off * PLEN_OBS, reward_dev + off,
+                                                         done_dev + off, timeout_dev ? timeout_dev + off : nullptr,
+                                                         terminal_obs_dev ? terminal_obs_dev + off * PLEN_OBS : nullptr, ctx->d_snapshot);
+    if (ev) cudaEventRecord(ev[nev - 1], st);
 }
 
 extern "C" {
@@ -433,6 +454,8 @@ void plen_destroy(plen_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_tab); cudaFree(ctx->d_state); cudaFree(ctx->d_snapshot); cudaFree(ctx->d_srec); cudaFree(ctx->d_tgt); cudaFree(ctx->d_key); cudaFree(ctx->d_perm);
     cudaFree(ctx->d_act); cudaFree(ctx->d_obs); cudaFree(ctx->d_rew); cudaFree(ctx->d_done); cudaFree(ctx->d_tmo);
+    for (int k = 1; k < PLEN_HOST_PIPE; k++)
+        if (ctx->pipe[k]) cudaStreamDestroy(ctx->pipe[k]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->prof_ev) {
         for (int i = 0; i < ctx->prof_cap * (2 * ctx->cfg.substeps + 2); i++) cudaEventDestroy(ctx->prof_ev[i]);
@@ -452,6 +475,8 @@ static int create_impl(plen_ctx *ctx) {
     CK(ctx, cudaFuncSetAttribute(k_solve, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(ctx, cudaFuncSetAttribute(k_dyn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->pipe[0] = ctx->stream;
+    for (int k = 1; k < PLEN_HOST_PIPE; k++) CK(ctx, cudaStreamCreateWithFlags(&ctx->pipe[k], cudaStreamNonBlocking));
     float tab[T_ROWS * 32], rec[PLEN_STATE_WORDS];
     build_table(&ctx->model, &ctx->cfg, tab);
     build_devconfig(&ctx->model, &ctx->cfg, &ctx->dc, &ctx->er);
@@ -519,11 +544,8 @@ int plen_step(plen_ctx *ctx, const float *actions_dev, float *obs_dev, float *re
     cudaStream_t st = (cudaStream_t)stream;
     const int nev = 2 * ctx->cfg.substeps + 2;
     cudaEvent_t *ev = (ctx->prof_ev && ctx->prof_steps < ctx->prof_cap) ? ctx->prof_ev + (size_t)nev * ctx->prof_steps : nullptr;
-    launch_ticks(ctx, ctx->d_state, ctx->n, actions_dev, ctx->d_tgt, ctx->cfg.substeps, st, ev);
-    if (ev) cudaEventRecord(ev[nev - 2], st);
-    k_post<<<dyn_grid(ctx->n), DYN_WPC * 32, DYN_SMEM, st>>>(ctx->dc, ctx->d_tab, ctx->d_state, ctx->n, obs_dev, reward_dev,
-                                                            done_dev, timeout_dev, terminal_obs_dev, ctx->d_snapshot);
-    if (ev) { cudaEventRecord(ev[nev - 1], st); ctx->prof_steps++; }
+    launch_step_range(ctx, 0, ctx->n, actions_dev, obs_dev, reward_dev, done_dev, timeout_dev, terminal_obs_dev, st, ev, nev);
+    if (ev) ctx->prof_steps++;
     CK(ctx, cudaGetLastError());
     return PLEN_OK;
 }
@@ -534,14 +556,26 @@ int plen_step_host(plen_ctx *ctx, const float *actions_host, float *obs_host, fl
     if (!actions_host || !obs_host || !reward_host || !done_host) return fail(ctx, PLEN_E_ARG, "plen_step_host: NULL buffer");
     const size_t n = ctx->n;
     CK(ctx, cudaSetDevice(ctx->device));
-    CK(ctx, cudaMemcpyAsync(ctx->d_act, actions_host, sizeof(float) * PLEN_NJ * n, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = plen_step(ctx, ctx->d_act, ctx->d_obs, ctx->d_rew, ctx->d_done, ctx->d_tmo, nullptr, ctx->stream);
-    if (rc != PLEN_OK) return rc;
-    CK(ctx, cudaMemcpyAsync(obs_host, ctx->d_obs, sizeof(float) * PLEN_OBS * n, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(ctx, cudaMemcpyAsync(reward_host, ctx->d_rew, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(ctx, cudaMemcpyAsync(done_host, ctx->d_done, n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (timeout_host) CK(ctx, cudaMemcpyAsync(timeout_host, ctx->d_tmo, n, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    // The batch is cut into PLEN_HOST_PIPE ranges (multiples of the 1024-robot sort tile), each on its own stream:
+    // H2D of the range's actions -> its 13 kernels -> D2H of its obs / reward / done.  Robots are independent, so the
+    // copies of one range overlap the kernels of the others and only the first H2D and the last D2H stay exposed.
+    size_t chunk = (n + PLEN_HOST_PIPE - 1) / PLEN_HOST_PIPE;
+    chunk = (chunk + RANK_TILE - 1) / RANK_TILE * RANK_TILE;
+    int used = 0;
+    for (size_t off = 0; off < n; off += chunk, used++) {
+        const size_t cnt = (n - off < chunk) ? n - off : chunk;
+        cudaStream_t st = ctx->pipe[used];
+        CK(ctx, cudaMemcpyAsync(ctx->d_act + off * PLEN_NJ, actions_host + off * PLEN_NJ, sizeof(float) * PLEN_NJ * cnt,
+                                cudaMemcpyHostToDevice, st));
+        launch_step_range(ctx, off, (int)cnt, ctx->d_act, ctx->d_obs, ctx->d_rew, ctx->d_done, ctx->d_tmo, nullptr, st, nullptr, 0);
+        CK(ctx, cudaMemcpyAsync(obs_host + off * PLEN_OBS, ctx->d_obs + off * PLEN_OBS, sizeof(float) * PLEN_OBS * cnt,
+                                cudaMemcpyDeviceToHost, st));
+        CK(ctx, cudaMemcpyAsync(reward_host + off, ctx->d_rew + off, sizeof(float) * cnt, cudaMemcpyDeviceToHost, st));
+        CK(ctx, cudaMemcpyAsync(done_host + off, ctx->d_done + off, cnt, cudaMemcpyDeviceToHost, st));
+        if (timeout_host) CK(ctx, cudaMemcpyAsync(timeout_host + off, ctx->d_tmo + off, cnt, cudaMemcpyDeviceToHost, st));
+    }
+    CK(ctx, cudaGetLastError());
+    for (int k = 0; k < used; k++) CK(ctx, cudaStreamSynchronize(ctx->pipe[k]));
     return PLEN_OK;
 }
 

@@ -138,3 +138,25 @@ def test_sample_of_large_batch_against_oracle_config3_size():
     assert (err < 1e-3).mean() >= 0.6
     assert (gobs[:, 24:26] != oo[:, 24:26]).mean() <= 0.05
     assert (done[idx].cpu().numpy() != od).mean() <= 0.05
+
+
+def test_host_buffer_step_equals_device_step():
+    """plen_step_host (pinned host buffers, the batch pipelined in ranges over several streams so the copies hide under
+    the kernels) returns exactly what plen_step returns for the same robots: ragged N (ranges of 2048 + 2048 + 904)."""
+    n = 5000
+    a, b = _mk(n), _mk(n)
+    _rollout(a, 12, seed=23)
+    b.reset(); b.set_state(*_snapshot(a))
+    g = torch.Generator(device="cuda"); g.manual_seed(29)
+    for _ in range(3):
+        act = torch.empty((n, 18), device="cuda").uniform_(-1, 1, generator=g)
+        obs, rew, done, info = a.step(act)
+        torch.cuda.synchronize()
+        h_act = act.cpu().pin_memory()
+        h_obs = torch.empty((n, 26)).pin_memory(); h_rew = torch.empty(n).pin_memory()
+        h_done = torch.empty(n, dtype=torch.uint8).pin_memory(); h_tmo = torch.empty(n, dtype=torch.uint8).pin_memory()
+        b.step_host(h_act, h_obs, h_rew, h_done, h_tmo)
+        assert _same(obs.cpu(), h_obs) and _same(rew.cpu(), h_rew)
+        assert torch.equal(done.cpu(), h_done.bool()) and torch.equal(info["timeout"].cpu(), h_tmo.bool())
+    for x, y in zip(_snapshot(a), _snapshot(b)):
+        assert _same(x, y)
