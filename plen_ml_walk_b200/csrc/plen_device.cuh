@@ -43,7 +43,21 @@ PLEN_DEV unsigned redux_or(unsigned v) { return __reduce_or_sync(0xffffffffu, v)
 PLEN_DEV void warp_sync() { __syncwarp(); }
 PLEN_DEV float f_as_u_max(float v) { return __uint_as_float(redux_max(__float_as_uint(v))); }
 PLEN_DEV void sincos_(float x, float *s, float *c) { sincosf(x, s, c); }
-PLEN_DEV float rcp_(float x) { return 1.0f / x; }
+#ifndef PLEN_FAST_RCP
+#define PLEN_FAST_RCP 1
+#endif
+// 1 / x as one MUFU.RCP (rcp.approx.ftz, <= 1 ulp: the same order as any fp32 rounding on this path) instead of the IEEE
+// division, whose denormal / special-case slow path puts a CALL behind each of the ~20 reciprocals of a tick: -2 % of the
+// step (PLEN_FAST_RCP = 0 restores the division)
+PLEN_DEV float rcp_(float x) {
+#if PLEN_FAST_RCP
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
 PLEN_DEV int lowest_bit(unsigned m) { return __ffs((int)m) - 1; }
 PLEN_DEV int highest_bit(unsigned m) { return 31 - __clz((int)m); }
 PLEN_DEV int popc_(unsigned m) { return __popc(m); }

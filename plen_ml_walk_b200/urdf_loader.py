@@ -110,6 +110,7 @@ class _Link:
     inertia_diag: np.ndarray
     aabb_disc: float
     hull: np.ndarray | None
+    hull_margin: float = 0.0     # collision margin the contact surface is inflated by (convex hulls: SHAPE_MARGIN, boxes: 0)
 
 
 @dataclass
@@ -127,6 +128,7 @@ class PlenModel:
     foot_lane: np.ndarray = field(default_factory=lambda: np.zeros(2, dtype=np.int32))
     foot_pts: np.ndarray = field(default_factory=lambda: np.zeros((2, 4, 3)))
     foot_break: np.ndarray = field(default_factory=lambda: np.zeros(2))
+    foot_margin: float = 0.001     # collision margin of the foot shape (convex hull: 1 mm, box: 0) -> plen_config.hull_margin
     body_links: list = field(default_factory=list)     # names of the URDF links folded into each lane's body
     total_mass: float = 0.0
 
@@ -155,16 +157,20 @@ def _read_links(root, mesh_dir):
         iR, com = _origin(ine)
         if not np.allclose(iR, np.eye(3)):
             raise NotImplementedError("rotated inertial frames are not used by plen.urdf")
-        lo, hi, hull = None, None, None
+        lo, hi, hull, margin = None, None, None, 0.0
         for col in le.findall("collision"):
             cR, cx = _origin(col)
             g = col.find("geometry")[0]
             if g.tag == "box":
-                ext = np.abs(cR) @ (_floats(g.get("size")) / 2)
+                half = _floats(g.get("size")) / 2
+                ext = np.abs(cR) @ half
                 a, b = cx - ext, cx + ext
+                if hull is None:      # box feet (plen_new.urdf): the 8 corners stand in for the hull; Bullet boxes keep their size
+                    corners = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)]) * half
+                    hull, margin = corners @ cR.T + cx, 0.0
             elif g.tag == "mesh":
                 pts = _stl_points(os.path.join(mesh_dir, os.path.basename(g.get("filename"))))
-                hull = (pts * _floats(g.get("scale", "1 1 1"))) @ cR.T + cx
+                hull, margin = (pts * _floats(g.get("scale", "1 1 1"))) @ cR.T + cx, SHAPE_MARGIN
                 a, b = hull.min(0) - SHAPE_MARGIN, hull.max(0) + SHAPE_MARGIN
             else:
                 raise NotImplementedError(g.tag)
@@ -174,7 +180,7 @@ def _read_links(root, mesh_dir):
         e = hi - lo
         diag = mass / 12.0 * np.array([e[1] ** 2 + e[2] ** 2, e[0] ** 2 + e[2] ** 2, e[0] ** 2 + e[1] ** 2])
         disc = float(np.linalg.norm((lo + hi) / 2 - com) + np.linalg.norm(e) / 2)
-        out[le.get("name")] = _Link(le.get("name"), mass, com, diag, disc, hull)
+        out[le.get("name")] = _Link(le.get("name"), mass, com, diag, disc, hull, margin)
     return out
 
 
@@ -266,12 +272,19 @@ def load_plen_model(urdf_path, mesh_dir) -> PlenModel:
         model.foot_lane[f] = lane
         model.foot_pts[f] = quad
         model.foot_break[f] = BREAKING_FACTOR * link.aabb_disc
+        model.foot_margin = float(link.hull_margin)     # -> plen_config.hull_margin (PlenVecEnv applies it)
     return model
 
 
-def packaged_model() -> PlenModel:
-    """The tables shipped with the package (generated from the reference URDF by this module's __main__)."""
-    return PlenModel.from_json(_DATA_JSON)
+def packaged_model(name: str = "plen") -> PlenModel:
+    """The tables shipped with the package (generated from the reference URDFs by this module's __main__):
+    "plen" = plen_bullet/src/plen.urdf (the one plen_env.py:312 loads; convex-hull feet from the STL meshes),
+    "plen_new" = plen_bullet/src/plen_new.urdf (box feet, +-1.0 rad joint limits; unused by the reference's env)."""
+    if name == "plen":
+        return PlenModel.from_json(_DATA_JSON)
+    if name == "plen_new":
+        return PlenModel.from_json(_DATA_JSON.replace("plen_model.json", "plen_new_model.json"))
+    raise ValueError("unknown packaged model %r" % name)
 
 
 if __name__ == "__main__":
@@ -279,6 +292,8 @@ if __name__ == "__main__":
     ref = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     mdl = load_plen_model(os.path.join(ref, "plen_bullet/src/plen.urdf"), os.path.join(ref, "plen_ros/meshes_bin"))
     mdl.to_json()
+    load_plen_model(os.path.join(ref, "plen_bullet/src/plen_new.urdf"), os.path.join(ref, "plen_ros/meshes_bin")).to_json(
+        _DATA_JSON.replace("plen_model.json", "plen_new_model.json"))
     print("total mass %.6f kg, bodies:" % mdl.total_mass)
     for lane in [0] + list(range(6, N_LANES)):
         print(lane, "%.6f" % mdl.mass[lane], mdl.body_links[lane])

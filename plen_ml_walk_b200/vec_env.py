@@ -78,6 +78,8 @@ class PlenVecEnv:
         self.cfg = _abi.PlenConfigC()
         self.lib.plen_default_config(C.byref(self.cfg), int(joint_act))
         self.cfg.auto_reset = int(auto_reset)
+        if model is not None:
+            self.cfg.hull_margin = float(getattr(model, "foot_margin", self.cfg.hull_margin))      # box feet carry no margin
         for k, v in (config_overrides or {}).items():
             setattr(self.cfg, k, v)
         self._ctx = self.lib.plen_create(C.byref(self.cfg), C.byref(self._cmodel), self.num_envs, self.device_index)

@@ -93,3 +93,22 @@ def test_settle_height_and_standing(oracle_lib):
         assert not d[0]
         z.append(ob[0, 18])
     assert abs(np.mean(z[20:]) - 0.160178937611) < 1e-3
+
+
+def test_loader_handles_the_box_foot_variant():
+    """plen_new.urdf (box feet, +-1.0 rad limits): same 33-link tree and mass, sole = bottom face of the
+    foot box with no collision margin.  Regenerated from the reference checkout when it is present, else the packaged copy."""
+    import os
+    import numpy as np
+    from plen_ml_walk_b200.urdf_loader import load_plen_model, packaged_model
+    new, old = packaged_model("plen_new"), packaged_model("plen")
+    assert abs(new.total_mass - old.total_mass) < 1e-9 and new.foot_margin == 0.0 and old.foot_margin == 1e-3
+    assert np.allclose(new.upper[6:24], 1.0) and np.allclose(old.upper[6:24], 1.7)
+    for f in range(2):
+        q = new.foot_pts[f]
+        assert np.allclose(q[:, 2], q[0, 2])                                   # a flat rectangle ...
+        assert np.allclose(q[0] + q[2], q[1] + q[3], atol=1e-9)                # ... (diagonals share their midpoint)
+    ref = "/root/reference"
+    if os.path.exists(os.path.join(ref, "plen_bullet/src/plen_new.urdf")):
+        m = load_plen_model(os.path.join(ref, "plen_bullet/src/plen_new.urdf"), os.path.join(ref, "plen_ros/meshes_bin"))
+        assert np.allclose(m.foot_pts, new.foot_pts) and np.allclose(m.inertia, new.inertia)
