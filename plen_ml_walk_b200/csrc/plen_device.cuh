@@ -514,7 +514,10 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
     }
     // note: red[0..20] is written by lanes < 21 while other lanes may still read red[j*21 + lane] for j >= 6 only
     warp_sync();
-    float Si[6][6];
+    // ---- S^-1 by Gauss-Jordan ACROSS lanes 0..5 (lane r owns row r; the pivot row is broadcast with six SHFL per step)
+    //      instead of every lane inverting the full 6 x 6 redundantly: ~150 warp instructions instead of ~450.  Same
+    //      elimination order and operations per entry as a serial in-place Gauss-Jordan without pivoting (S is SPD).
+    float R[6];     // lanes 0..5: row `lane` of S, then of S^-1 (other lanes: scratch)
     {
         // M00 = [[Ibar, hx],[hx^T, m 1]] of the whole robot
         float M00[6][6] = {{It[0], It[3], It[4], 0.0f, -ht[2], ht[1]},
@@ -523,57 +526,82 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
                            {0.0f, ht[2], -ht[1], mt, 0.0f, 0.0f},
                            {-ht[2], 0.0f, ht[0], 0.0f, mt, 0.0f},
                            {ht[1], -ht[0], 0.0f, 0.0f, 0.0f, mt}};
+        float S[6][6];
         int idx = 0;
 #pragma unroll
         for (int r = 0; r < 6; r++)
 #pragma unroll
             for (int c = r; c < 6; c++) {
                 const float v = M00[r][c] - ws.red[idx];
-                Si[r][c] = v; Si[c][r] = v; idx++;
+                S[r][c] = v; S[c][r] = v; idx++;
             }
-        inv6_inplace(Si);
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            float v = S[0][c];
+#pragma unroll
+            for (int r = 1; r < 6; r++) v = (lane == r) ? S[r][c] : v;
+            R[c] = v;
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const float inv = rcp_(R[k]);
+            float P[6];     // row k after scaling: [.. R[j] inv .., inv at j = k, ..]
+#pragma unroll
+            for (int j = 0; j < 6; j++) P[j] = shfl((j == k) ? inv : R[j] * inv, k);
+            const float f = R[k];
+            const bool piv = lane == k;
+#pragma unroll
+            for (int j = 0; j < 6; j++) {
+                const float elim = (j == k) ? -(f * P[k]) : R[j] - f * P[j];
+                R[j] = piv ? P[j] : elim;
+            }
+        }
     }
+    // S^-1 to every lane through shared memory (gg is free until the G rows are stored below)
+    warp_sync();
+    if (lane < 6) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) ws.gg[lane][k] = R[k];
+    }
+    warp_sync();
     // G = K S^-1
     float G[6];
+    {
+        float Si[6][6];
 #pragma unroll
-    for (int c = 0; c < 6; c++) {
-        float s = 0.0f;
+        for (int b = 0; b < 6; b++)
 #pragma unroll
-        for (int b = 0; b < 6; b++) s += Krow[b] * Si[b][c];
-        G[c] = is_joint ? s : 0.0f;
+            for (int c = 0; c < 6; c++) Si[b][c] = ws.gg[b][c];
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            float s = 0.0f;
+#pragma unroll
+            for (int b = 0; b < 6; b++) s += Krow[b] * Si[b][c];
+            G[c] = is_joint ? s : 0.0f;
+        }
     }
+    warp_sync();
     if (lane < 24) {
 #pragma unroll
         for (int k = 0; k < 6; k++) { ws.kk[lane][k] = is_joint ? Krow[k] : 0.0f; ws.gg[lane][k] = G[k]; }
     }
     warp_sync();
-    // ---- assemble M^-1 (this lane's row), stored column-major so later reads are conflict free
+    // ---- assemble M^-1 (this lane's row), stored column-major so later reads are conflict free.  One branch-free loop:
+    //      joint lanes take G . K_j (+ the limb block), base lanes (G = 0) the transposed -G entries and their row of S^-1
     if (lane < 24) {
-        if (is_joint) {
 #pragma unroll
-            for (int k = 0; k < 6; k++) ws.minv[k][lane] = -G[k];
-            for (int j = 6; j < 24; j++) {
-                float s = G[0] * ws.kk[j][0] + G[1] * ws.kk[j][1] + G[2] * ws.kk[j][2] + G[3] * ws.kk[j][3] +
-                          G[4] * ws.kk[j][4] + G[5] * ws.kk[j][5];
-                ws.minv[j][lane] = s;
-            }
+        for (int k = 0; k < 6; k++) ws.minv[k][lane] = is_joint ? -G[k] : R[k];
+        const float *ggl = &ws.gg[0][is_joint ? 0 : lane];
+#pragma unroll 6
+        for (int j = 6; j < 24; j++) {
+            const float s = G[0] * ws.kk[j][0] + G[1] * ws.kk[j][1] + G[2] * ws.kk[j][2] + G[3] * ws.kk[j][3] +
+                            G[4] * ws.kk[j][4] + G[5] * ws.kk[j][5];
+            ws.minv[j][lane] = is_joint ? s : -ggl[j * 8];
+        }
+        if (is_joint) {
 #pragma unroll
             for (int d = 0; d < 6; d++)
                 if (cs + d <= ce) ws.minv[cs + d][lane] += Mrow[d];
-        } else {
-#pragma unroll
-            for (int k = 0; k < 6; k++) {
-                float v = Si[0][k];
-#pragma unroll
-                for (int r = 1; r < 6; r++) v = (lane == r) ? Si[r][k] : v;
-                ws.minv[k][lane] = v;
-            }
-            for (int j = 6; j < 24; j++) {
-                float v = ws.gg[j][0];
-#pragma unroll
-                for (int r = 1; r < 6; r++) v = (lane == r) ? ws.gg[j][r] : v;
-                ws.minv[j][lane] = -v;
-            }
         }
     }
     warp_sync();

@@ -164,11 +164,12 @@ def test_host_buffer_step_equals_device_step():
 
 def test_box_foot_model_variant_stands_and_steps():
     """plen_new.urdf (box feet, no collision margin, +-1.0 rad limits) through the same kernels: the robot settles on its
-    soles at reset (both feet in contact, torso height within 5 mm of the stock model's) and a zero action holds it up."""
+    soles at reset (both feet in contact, torso height within 5 mm of the stock model's) and zero joint targets
+    (joint_act: raw radians, the standing pose) hold it up."""
     from plen_ml_walk_b200.urdf_loader import packaged_model
     from plen_ml_walk_b200.vec_env import PlenVecEnv
-    env = PlenVecEnv(64, device="cuda:0", auto_reset=False, model=packaged_model("plen_new"))
-    ref = PlenVecEnv(64, device="cuda:0", auto_reset=False)
+    env = PlenVecEnv(64, device="cuda:0", auto_reset=False, joint_act=True, model=packaged_model("plen_new"))
+    ref = PlenVecEnv(64, device="cuda:0", auto_reset=False, joint_act=True)
     o, r = env.reset().clone(), ref.reset().clone()
     assert torch.isfinite(o).all() and abs(float(o[0, 18]) - float(r[0, 18])) < 5e-3
     zero = torch.zeros((64, 18), device="cuda")
