@@ -178,13 +178,25 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
     const int g = lc.g;      // lane & 3, pinned in a register
 #define GSH(v, l) shfl4((v), (l))
     {
+        // stage the 24 columns: 48 16-byte pieces per lane, all in flight at once through cp.async (global -> shared without
+        // a register round trip); the pieces are waited for after the register-resident parts of the record are requested
         vec4 *dst4 = reinterpret_cast<vec4 *>(Gs);
         const vec4 *src4 = reinterpret_cast<const vec4 *>(srec + SR_G);
         const vec4 z4 = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll 8
-        for (int k = g; k < 8 * PLEN_GS_COLS; k += 4) {
-            const int col = k >> 3, scol = (col < 18) ? col : ((col < 21) ? col + 3 : col + 6);      // skip the angular columns
+#pragma unroll
+        for (int k0 = 0; k0 < 8 * PLEN_GS_COLS; k0 += 4) {
+            const int k = k0 + g;
+            const int col = k0 >> 3, scol = (col < 18) ? col : ((col < 21) ? col + 3 : col + 6);      // skip the angular columns
+#ifndef PLEN_HOST_EMU
+            if (valid) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(dst4 + k)),
+                             "l"(src4 + 8 * scol + (k & 7)) : "memory");
+            } else {
+                dst4[k] = z4;
+            }
+#else
             dst4[k] = valid ? src4[8 * scol + (k & 7)] : z4;
+#endif
         }
     }
     float A[2][3][8];      // this lane's 8 rows of the angular columns (wx wy wz) of either foot
@@ -196,8 +208,6 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
             for (int k = 0; k < 8; k++) A[f][c][k] = 0.0f;
             if (valid) load8(srec + SR_G + 32 * PLEN_COL(f, c) + 8 * g, A[f][c]);
         }
-    warp_sync();
-    const GSlice Gl = g_slice(Gs, g);      // this lane's 8 rows of column c: vec4 8 c and 8 c + 1 of the slice
 
     // ---- servo rows of this lane (entries >= 18 carry zeros): velocity-unit rhs and bounds
     float m_rhs[8], m_lo[8], m_hi[8];
@@ -301,6 +311,13 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
         apply_reg(s, A[f][1], -px[p] * (db));                \
         apply_col(s, Gl, PLEN_SCOL(f, 5), (db));             \
     }
+
+    // ---- the staged columns must have landed before the first row update
+#ifndef PLEN_HOST_EMU
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+    warp_sync();
+    const GSlice Gl = g_slice(Gs, g);      // this lane's 8 rows of column c: vec4 8 c and 8 c + 1 of the slice
 
     // ---- warm start of the normal rows from the cached impulses
     if (man_any) {
