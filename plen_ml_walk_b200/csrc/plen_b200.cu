@@ -26,9 +26,6 @@ using namespace plen;
 #ifndef PLEN_HOST_PIPE
 #define PLEN_HOST_PIPE 4      // ranges plen_step_host pipelines (copy of one range under the kernels of the others)
 #endif
-#ifndef PLEN_DYN_CHUNK
-#define PLEN_DYN_CHUNK 1      // groups of DYN_WPC robots per k_dyn CTA
-#endif
 
 struct plen_ctx {
     int n, device, sm_count;
@@ -90,26 +87,37 @@ __global__ void __launch_bounds__(DYN_WPC * 32, 5)
 k_dyn(const __grid_constant__ DevConfig dc, const __grid_constant__ EnvRanges er, const float *__restrict__ tab_g,
       const float *__restrict__ state, int n, const float *__restrict__ actions, float *__restrict__ tgt,
       float *__restrict__ srec, uint8_t *__restrict__ keys, float *dbg_minv, float *dbg_pos, float *dbg_rot) {
-    DynSmem &sm = stage_table(tab_g);
+    // The 4 KB model table is staged with cp.async while every warp already fetches its robot's state record and targets:
+    // the two latencies overlap instead of adding up (the table wait used to sit in front of everything).
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DynSmem &sm = *reinterpret_cast<DynSmem *>(smem_raw);
+    for (int i = threadIdx.x; i < T_ROWS * 32 / 4; i += blockDim.x)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(sm.tab + 4 * i)),
+                     "l"(tab_g + 4 * i) : "memory");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpScratch &ws = sm.ws[warp];
-    // a CTA walks PLEN_DYN_CHUNK consecutive groups of four robots (the 4 KB model table is staged once per CTA); warps
-    // only synchronise with themselves from here on
-    for (int it = 0; it < PLEN_DYN_CHUNK; it++) {
-        const int env = (blockIdx.x * PLEN_DYN_CHUNK + it) * DYN_WPC + warp;
-        if (env >= n) break;
-        LaneState L;
-        load_record(state + (size_t)env * PLEN_STATE_WORDS, ws, L, lane);
-        if (lane >= 6 && lane < 24) {
-            const size_t o = (size_t)env * PLEN_NJ + lane - 6;
-            if (actions) { L.tgt = agent_target(dc, er, lane - 6, actions[o]); tgt[o] = L.tgt; }
-            else L.tgt = tgt ? tgt[o] : 0.0f;
-        }
-        DebugOut dbg{dbg_minv ? dbg_minv + (size_t)env * 576 : nullptr, dbg_pos ? dbg_pos + (size_t)env * 72 : nullptr,
-                     dbg_rot ? dbg_rot + (size_t)env * 216 : nullptr};
-        tick_dynamics(dc, sm.tab, ws, L, lane, srec + (size_t)env * SR_WORDS, keys + env, (dbg_minv || dbg_pos || dbg_rot) ? &dbg : nullptr);
-        warp_sync();
+    const int env = blockIdx.x * DYN_WPC + warp;
+    const bool has = env < n;
+    float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f, a_in = 0.0f;
+    const bool jl = lane >= 6 && lane < 24;
+    const size_t o = (size_t)(has ? env : 0) * PLEN_NJ + (jl ? lane - 6 : 0);
+    if (has) {
+        const float *rec = state + (size_t)env * PLEN_STATE_WORDS;
+        r0 = rec[lane]; r1 = rec[32 + lane]; r2 = rec[64 + lane];
+        if (jl) a_in = actions ? actions[o] : (tgt ? tgt[o] : 0.0f);
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    if (!has) return;
+    LaneState L;
+    unpack_record(r0, r1, r2, ws, L, lane);
+    if (jl) {
+        if (actions) { L.tgt = agent_target(dc, er, lane - 6, a_in); tgt[o] = L.tgt; }
+        else L.tgt = a_in;
+    }
+    DebugOut dbg{dbg_minv ? dbg_minv + (size_t)env * 576 : nullptr, dbg_pos ? dbg_pos + (size_t)env * 72 : nullptr,
+                 dbg_rot ? dbg_rot + (size_t)env * 216 : nullptr};
+    tick_dynamics(dc, sm.tab, ws, L, lane, srec + (size_t)env * SR_WORDS, keys + env, (dbg_minv || dbg_pos || dbg_rot) ? &dbg : nullptr);
 }
 
 // Robots are grouped by contact load before the solve: k_rank counting-sorts the keys k_dyn wrote inside tiles of
@@ -400,9 +408,9 @@ k_fp32_peak(float *out, int iters, int mode, float seed) {
 static const size_t DYN_SMEM = sizeof(DynSmem);
 static const size_t SOLVE_SMEM = sizeof(float) * PLEN_GS_WORDS * PLEN_SOLVE_ROBOTS;
 static int dyn_grid(int n) { return (n + DYN_WPC - 1) / DYN_WPC; }
-// k_dyn: one CTA per PLEN_DYN_CHUNK groups of four CONSECUTIVE robots.  (A persistent grid-stride walk, grid = resident CTAs,
-// was measured 3 % slower than one CTA per group: robots far apart in the arrays at any one time.)
-static int dyn_grid_persistent(const plen_ctx *, int n) { return (dyn_grid(n) + PLEN_DYN_CHUNK - 1) / PLEN_DYN_CHUNK; }
+// k_dyn: one CTA per four robots.  (Measured slower: a persistent grid-stride walk, grid = resident CTAs, 3 %; CTAs that walk
+// 2 / 4 / 8 consecutive groups, 1.7 / 3.6 / 4.4 % -- many short CTAs overlap their load phases best.)
+static int dyn_grid_persistent(const plen_ctx *, int n) { return dyn_grid(n); }
 static int rank_tiles(int n) { return (n + RANK_TILE - 1) / RANK_TILE; }
 
 // n_ticks physics ticks of 1/240 s: (k_dyn, k_solve) per tick.  `actions` (agent space) only on the first tick.

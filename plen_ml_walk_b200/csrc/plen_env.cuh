@@ -8,10 +8,15 @@
 namespace plen {
 
 // ---- state record <-> lane registers ---------------------------------------------------------------------------
+// r0..r2: this lane's words lane, 32 + lane, 64 + lane of the record (already fetched, so the fetch can overlap other loads)
+PLEN_DEV void unpack_record(float r0, float r1, float r2, WarpScratch &ws, LaneState &L, int lane);
 PLEN_DEV void load_record(const float *rec, WarpScratch &ws, LaneState &L, int lane) {
-    ws.st[lane] = rec[lane];
-    ws.st[32 + lane] = rec[32 + lane];
-    ws.st[64 + lane] = rec[64 + lane];
+    unpack_record(rec[lane], rec[32 + lane], rec[64 + lane], ws, L, lane);
+}
+PLEN_DEV void unpack_record(float r0, float r1, float r2, WarpScratch &ws, LaneState &L, int lane) {
+    ws.st[lane] = r0;
+    ws.st[32 + lane] = r1;
+    ws.st[64 + lane] = r2;
     warp_sync();
     L.u = (lane < 24) ? ws.st[W_U + lane] : 0.0f;
     L.lam = (lane >= 24) ? ws.st[W_U + lane] : 0.0f;
