@@ -34,14 +34,14 @@ UNIT = "env-steps/s"
 # obs 26 f32, reward f32, done + timeout bytes
 BYTES_PER_ENV_STEP = 2 * 96 * 4 + 18 * 4 + 26 * 4 + 4 + 2
 TICKS_PER_STEP = 4
-# measured DRAM traffic of one k_solve launch per robot (ncu --set full, profiles/r1_v8_summary.md): it reads the
+# measured DRAM traffic of one k_solve launch per robot (ncu --set full, profiles/r1_v9_summary.md): it reads the
 # 6.4 KB solve record k_dyn wrote for the tick -- a deliberate trade of HBM bytes for issue slots
-SOLVE_DRAM_BYTES_PER_ROBOT = (207.08e6 + 10.24e6) / 32768
+SOLVE_DRAM_BYTES_PER_ROBOT = (207.09e6 + 7.93e6) / 32768
 # executed FP32 work per robot-tick, counted by ncu (smsp__sass_thread_inst_executed_op_{fadd,fmul,ffma}_pred_on, FFMA = 2
-# flop; 32768-robot capture, profiles/r1_v8_summary.md): k_dyn 56.8 kflop + k_solve 58.2 kflop.  It replaces SURVEY 8d's
+# flop; 32768-robot capture, profiles/r1_v9_summary.md): k_dyn 46.8 kflop + k_solve 58.2 kflop.  It replaces SURVEY 8d's
 # estimate (0.65-1.6 Mflop per env-step for Bullet's ABA + velocity-space PGS): this solver iterates in the 30-dim
 # operational space, so a row update is 30 FMAs instead of a Jacobian-wide one.
-FLOP_PER_ENV_STEP = 4 * (56.8e3 + 58.2e3)
+FLOP_PER_ENV_STEP = 4 * (46.8e3 + 58.2e3)
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 
 
@@ -258,7 +258,7 @@ def main():
                               "peak": fp32_peak, "unit": "TFLOP/s", "frac": FLOP_PER_ENV_STEP * value / world / 1e12 / fp32_peak,
                               "peak_source": fp32_src, "flop_per_env_step": FLOP_PER_ENV_STEP,
                               "note": "per GPU; executed FADD + FMUL + 2 FFMA thread operations per env-step counted by ncu "
-                                      "(profiles/r1_v8_summary.md) x measured env-steps/s; the limiter is the dependency "
+                                      "(profiles/r1_v9_summary.md) x measured env-steps/s; the limiter is the dependency "
                                       "latency of the Gauss-Seidel row chain at 2 warps per scheduler, not the pipe"},
             "kernel_ms_per_step": {"k_dyn": prof["ms_dyn"] / max(1, prof["steps"]), "k_solve": prof["ms_solve"] / max(1, prof["steps"]),
                                    "k_post": prof["ms_post"] / max(1, prof["steps"])},
