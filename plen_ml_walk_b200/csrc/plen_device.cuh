@@ -131,8 +131,41 @@ PLEN_DEV int nth_bit4(unsigned m, int k) {
     return r;
 }
 
-// per-warp shared scratch of k_dyn (floats)
-struct WarpScratch {
+#ifndef PLEN_HOST_EMU
+struct __align__(16) vec4 { float x, y, z, w; };
+struct __align__(8) vec2 { float x, y; };
+#define PLEN_ALIGN16 __align__(16)
+#else
+struct vec4 { float x, y, z, w; };
+struct vec2 { float x, y; };
+#define PLEN_ALIGN16
+#endif
+
+// Loads of data another kernel of the step produced (state records, solve records, targets, permutation): L2 only
+// (ld.global.cg), never the non-coherent L1 / read-only path.  Every such word is read once, so nothing is lost, and the
+// step stays correct when ranges of the batch run on several streams at once (plen_step_host) and kernels of different
+// ranges share an SM.
+#ifndef PLEN_HOST_EMU
+PLEN_DEV float gld(const float *p) { return __ldcg(p); }
+PLEN_DEV vec4 gld4(const float *p) {
+    const float4 v = __ldcg(reinterpret_cast<const float4 *>(p));
+    vec4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+    return r;
+}
+#else
+PLEN_DEV float gld(const float *p) { return *p; }
+PLEN_DEV vec4 gld4(const float *p) { return *reinterpret_cast<const vec4 *>(p); }
+#endif
+
+// six consecutive floats of a 32-byte-aligned row (tw / kk / gg rows of WarpScratch) as LDS.128 + LDS.64
+PLEN_DEV void load6(const float *row, float (&o)[6]) {
+    const vec4 a = *reinterpret_cast<const vec4 *>(row);
+    const vec2 b = *reinterpret_cast<const vec2 *>(row + 4);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y;
+}
+
+// per-warp shared scratch of k_dyn (floats); 16-byte aligned so that the 8-float rows can be read as vectors
+struct PLEN_ALIGN16 WarpScratch {
     float st[96];
     float tw[24][8];      // joint twists s_j = [a(3), m(3)] about the base origin, world axes
     float kk[24][8];      // K rows = A_c M_c0, later Y_right = M^-1 Jfoot_right^T
@@ -457,12 +490,13 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
             const int j = cs + d;
             float v = (d == off) ? 1.0f : 0.0f;   // identity padding for short chains / non-joint lanes
             if (is_joint && j <= ce) {
+                float r6[6];
                 if (d <= off) {  // ancestor-or-self j: M = s_j . f_lane
-                    v = ws.tw[j][0] * fM[0] + ws.tw[j][1] * fM[1] + ws.tw[j][2] * fM[2] + ws.tw[j][3] * fM[3] +
-                        ws.tw[j][4] * fM[4] + ws.tw[j][5] * fM[5];
+                    load6(ws.tw[j], r6);
+                    v = r6[0] * fM[0] + r6[1] * fM[1] + r6[2] * fM[2] + r6[3] * fM[3] + r6[4] * fM[4] + r6[5] * fM[5];
                 } else {         // descendant j: M = s_lane . f_j
-                    v = a[0] * ws.kk[j][0] + a[1] * ws.kk[j][1] + a[2] * ws.kk[j][2] + m[0] * ws.kk[j][3] +
-                        m[1] * ws.kk[j][4] + m[2] * ws.kk[j][5];
+                    load6(ws.kk[j], r6);
+                    v = a[0] * r6[0] + a[1] * r6[1] + a[2] * r6[2] + m[0] * r6[3] + m[1] * r6[4] + m[2] * r6[5];
                 }
             }
             Mrow[d] = v;
@@ -594,8 +628,9 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
         const float *ggl = &ws.gg[0][is_joint ? 0 : lane];
 #pragma unroll 6
         for (int j = 6; j < 24; j++) {
-            const float s = G[0] * ws.kk[j][0] + G[1] * ws.kk[j][1] + G[2] * ws.kk[j][2] + G[3] * ws.kk[j][3] +
-                            G[4] * ws.kk[j][4] + G[5] * ws.kk[j][5];
+            float r6[6];
+            load6(ws.kk[j], r6);
+            const float s = G[0] * r6[0] + G[1] * r6[1] + G[2] * r6[2] + G[3] * r6[3] + G[4] * r6[4] + G[5] * r6[5];
             ws.minv[j][lane] = is_joint ? s : -ggl[j * 8];
         }
         if (is_joint) {
@@ -648,13 +683,10 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
     warp_sync();
 
     // ---- masked twists and operational columns Y_f = M^-1 Jfoot_f^T per foot with active contacts
-    float aF[2][3], mF[2][3], Y[2][6];
+    float Y[2][6];
 #pragma unroll
     for (int f = 0; f < 2; f++) {
         const int fl = cfg.foot_lane[f], fcs = fl - 5;
-        const bool mine = (lane < 6) || (lane >= fcs && lane <= fl);
-#pragma unroll
-        for (int k = 0; k < 3; k++) { aF[f][k] = mine ? a[k] : 0.0f; mF[f][k] = mine ? m[k] : 0.0f; }
 #pragma unroll
         for (int k = 0; k < 6; k++) Y[f][k] = 0.0f;
         if (((man_new >> (4 * f)) & 0xFu) && lane < 24) {
@@ -662,8 +694,10 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
             for (int k = 0; k < 6; k++) Y[f][k] = ws.minv[k][lane];
             for (int j = fcs; j <= fl; j++) {
                 const float w = ws.minv[j][lane];
+                float r6[6];
+                load6(ws.tw[j], r6);
 #pragma unroll
-                for (int k = 0; k < 6; k++) Y[f][k] += w * ws.tw[j][k];
+                for (int k = 0; k < 6; k++) Y[f][k] += w * r6[k];
             }
         }
     }
@@ -691,25 +725,23 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
         }
     }
     // ---- foot twists at v*: Vs_f = Jfoot_f v*;  Y stash;  Lambda^-1 = Jfoot M^-1 Jfoot^T (12 x 12)
-    float Vs[2][6];
-#pragma unroll
-    for (int f = 0; f < 2; f++)
-#pragma unroll
-        for (int k = 0; k < 6; k++) Vs[f][k] = 0.0f;
+    //      Vs is computed by lanes 0..11 (one twist component each: 12 terms from shared memory) and read back by the
+    //      contact-row lanes through ws.st[W_SPARE ..]; it used to be twelve full-warp butterfly reductions (60 SHFL).
+    ws.obs[lane] = vstar;                           // obs is free scratch in k_dyn (lanes >= 24 hold 0)
     if (lane < 24) {
 #pragma unroll
         for (int k = 0; k < 6; k++) { ws.kk[lane][k] = Y[0][k]; ws.gg[lane][k] = Y[1][k]; }
     }
     warp_sync();
     if (man_new) {
+        if (lane < 12) {
+            const int f = (lane >= 6) ? 1 : 0, k = lane - 6 * f, fl = cfg.foot_lane[f];
+            float acc = 0.0f;
 #pragma unroll
-        for (int f = 0; f < 2; f++) {
+            for (int l = 0; l < 6; l++) acc += ws.tw[l][k] * ws.obs[l];
 #pragma unroll
-            for (int k = 0; k < 3; k++) { Vs[f][k] = aF[f][k] * vstar; Vs[f][3 + k] = mF[f][k] * vstar; }
-#pragma unroll
-            for (int mm = 16; mm > 0; mm >>= 1)
-#pragma unroll
-                for (int k = 0; k < 6; k++) Vs[f][k] += shfl_xor(Vs[f][k], mm);
+            for (int l = 0; l < 6; l++) acc += ws.tw[fl - 5 + l][k] * ws.obs[fl - 5 + l];
+            ws.st[W_SPARE + lane] = acc;
         }
         // Lambda^-1[fa*6+a][fb*6+b] = Y_fb[a][b] + sum_{j in leg fa} s_j[a] Y_fb[j][b]
         for (int e = lane; e < 144; e += 32) {
@@ -841,12 +873,8 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
                 c1 * (c0 * ws.lin[o + i1][o + i0] + c1 * ws.lin[o + i1][o + i1] + c2 * ws.lin[o + i1][o + i2]) +
                 c2 * (c0 * ws.lin[o + i2][o + i0] + c1 * ws.lin[o + i2][o + i1] + c2 * ws.lin[o + i2][o + i2]);
             dinv = (d > 1.1920929e-7f) ? rcp_(d) : 0.0f;
-            float vs[6];
-#pragma unroll
-            for (int k = 0; k < 6; k++) vs[k] = f ? Vs[1][k] : Vs[0][k];
-            float v0 = vs[0], v1 = vs[0], v2 = vs[0];
-#pragma unroll
-            for (int k = 1; k < 6; k++) { v0 = (i0 == k) ? vs[k] : v0; v1 = (i1 == k) ? vs[k] : v1; v2 = (i2 == k) ? vs[k] : v2; }
+            const float *vsf = &ws.st[W_SPARE + 6 * f];      // foot twist at v* (written above, before the Lambda^-1 sync)
+            const float v0 = vsf[i0], v1 = vsf[i1], v2 = vsf[i2];
             const float rel = c0 * v0 + c1 * v1 + c2 * v2;
             if (comp == 5) {
                 const float pdist = ws.cp[p][3] + cfg.linear_slop;

@@ -11,7 +11,7 @@ namespace plen {
 // r0..r2: this lane's words lane, 32 + lane, 64 + lane of the record (already fetched, so the fetch can overlap other loads)
 PLEN_DEV void unpack_record(float r0, float r1, float r2, WarpScratch &ws, LaneState &L, int lane);
 PLEN_DEV void load_record(const float *rec, WarpScratch &ws, LaneState &L, int lane) {
-    unpack_record(rec[lane], rec[32 + lane], rec[64 + lane], ws, L, lane);
+    unpack_record(gld(rec + lane), gld(rec + 32 + lane), gld(rec + 64 + lane), ws, L, lane);
 }
 PLEN_DEV void unpack_record(float r0, float r1, float r2, WarpScratch &ws, LaneState &L, int lane) {
     ws.st[lane] = r0;

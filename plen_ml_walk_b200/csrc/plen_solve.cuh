@@ -25,16 +25,14 @@
 
 namespace plen {
 
-#ifndef PLEN_HOST_EMU
-struct __align__(16) vec4 { float x, y, z, w; };
-#else
-struct vec4 { float x, y, z, w; };
-#endif
 
 // Owner look-ahead (see solve_tick) per row family; each costs extra FFMA2 issue slots and removes one SHFL round trip
 // from the dependency chain of the family.  Chosen by A/B timing on B200 (profiles/r1_v6_summary.md).
 #ifndef PLEN_LA_SERVO
 #define PLEN_LA_SERVO 1
+#endif
+#ifndef PLEN_REDUX_CONV
+#define PLEN_REDUX_CONV 0      // convergence test: one partitioned redux.sync instead of two SHFL + FMNMX
 #endif
 #ifndef PLEN_LA_NORMAL
 #define PLEN_LA_NORMAL 0
@@ -166,7 +164,7 @@ PLEN_DEV void apply_vec6(float (&o)[8], const vec4 &a, const vec4 &b, float d) {
 }
 
 PLEN_DEV void load8(const float *p, float (&o)[8]) {
-    const vec4 a = *reinterpret_cast<const vec4 *>(p), b = *reinterpret_cast<const vec4 *>(p + 4);
+    const vec4 a = gld4(p), b = gld4(p + 4);      // solve-record / state words: L2 only
     o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
 }
 
@@ -226,7 +224,7 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
             m_lo[k] = -m_hi[k];
             limbits |= (ld[k] != 0.0f) ? (1u << k) : 0u;
         }
-        man = (unsigned)srec[SR_BASE + 13];
+        man = (unsigned)gld(srec + SR_BASE + 13);
     }
     // active-point counts per foot: this robot's and the largest among the robots of the warp
     const int n0 = popc_(man & 15u), n1 = popc_((man >> 4) & 15u);
@@ -259,7 +257,7 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
     if (man_any && valid) {
 #pragma unroll
         for (int p = 0; p < 8; p++) {
-            const vec4 t = *reinterpret_cast<const vec4 *>(srec + SR_PT + 4 * p);
+            const vec4 t = gld4(srec + SR_PT + 4 * p);
             px[p] = t.x; py[p] = t.y; pz[p] = t.z;
         }
         if (g >= 2) {
@@ -267,18 +265,18 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 const int o = 8 * (4 * f) + 2 + c;       // an empty foot has zeros here
-                t_rhs[c] = srec[SR_CRHS + o]; t_dinv[c] = srec[SR_CDINV + o]; t_d[c] = srec[SR_CD + o];
+                t_rhs[c] = gld(srec + SR_CRHS + o); t_dinv[c] = gld(srec + SR_CDINV + o); t_d[c] = gld(srec + SR_CD + o);
             }
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int o = 8 * (4 * f + k) + 2 + 3;
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
-                    c_rhs[k][c] = srec[SR_CRHS + o + c];
-                    c_dinv[k][c] = srec[SR_CDINV + o + c];
-                    c_d[k][c] = srec[SR_CD + o + c];
+                    c_rhs[k][c] = gld(srec + SR_CRHS + o + c);
+                    c_dinv[k][c] = gld(srec + SR_CDINV + o + c);
+                    c_d[k][c] = gld(srec + SR_CD + o + c);
                 }
-                c_lam[k][5] = srec[SR_LAMC + 4 * f + k] * cfg.warm;      // zero for unused slots
+                c_lam[k][5] = gld(srec + SR_LAMC + 4 * f + k) * cfg.warm;      // zero for unused slots
             }
         }
     }
@@ -342,8 +340,8 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
     // joint-limit row of joint 8 b + k (rare: the joint is beyond +-1.7 rad); lower bound 0, upper bound 100 (impulse units)
 #define LIMIT_ROW(b, k)                                                                  \
     {                                                                                    \
-        const float ldir_ = srec[SR_LDIR + 8 * g + (k)], up_ = 100.0f * srec[SR_MD + 8 * g + (k)]; \
-        const float x_ = srec[SR_LRHS + 8 * g + (k)] - ldir_ * s[k];                     \
+        const float ldir_ = gld(srec + SR_LDIR + 8 * g + (k)), up_ = 100.0f * gld(srec + SR_MD + 8 * g + (k)); \
+        const float x_ = gld(srec + SR_LRHS + 8 * g + (k)) - ldir_ * s[k];                     \
         const float ol_ = L_LAM(8 * g + (k));                                            \
         const float nl_ = alive ? clampf(ol_ + x_, 0.0f, up_) : ol_;                     \
         const float dl_ = (nl_ - ol_) * ldir_;                                           \
@@ -489,8 +487,13 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
         // spinning / rolling rows of a foot share one d per twist component (t_d), so |dl * d| is scaled once here
         resF = fmaxf(resF, fmaxf(resT[0] * fabsf(t_d[0]), fmaxf(resT[1] * fabsf(t_d[1]), resT[2] * fabsf(t_d[2]))));
         float rf = (g >= 2) ? resF : 0.0f;
+#if PLEN_REDUX_CONV && !defined(PLEN_HOST_EMU)
+        // max over the robot's four lanes with ONE partitioned redux.sync (non-negative floats order like their bit patterns)
+        rf = __uint_as_float(__reduce_max_sync(0xFu << (lane & 28), __float_as_uint(rf)));
+#else
         rf = fmaxf(rf, shfl_xor(rf, 1));
         rf = fmaxf(rf, shfl_xor(rf, 2));
+#endif
         const float rr = fmaxf(res, rf);
         if (alive) {
             my_iters = it + 1;
@@ -519,7 +522,7 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
     for (int k = 0; k < 8; k++) z[k] = alive ? -0.5f * (m_lo[k] + m_hi[k]) : m_rhs[k];
     if (lim_any && valid) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) z[k] += (g < 3) ? srec[SR_LDIR + 8 * g + k] * L_LAM(8 * g + k) : 0.0f;
+        for (int k = 0; k < 8; k++) z[k] += (g < 3) ? gld(srec + SR_LDIR + 8 * g + k) * L_LAM(8 * g + k) : 0.0f;
     }
     if (man_any) {
         // wrench of this lane's foot (lanes 0, 1 hold zero rows): normal (py,-px,0 | vz), lateral A (-pz,0,px | vy),
@@ -587,10 +590,10 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
         if (g == 0) {
             float ub[6];
 #pragma unroll
-            for (int k = 0; k < 6; k++) { ub[k] = clampf(srec[SR_BASE + k] + dvb[k], -cfg.vmax, cfg.vmax); state[W_U + k] = ub[k]; }
+            for (int k = 0; k < 6; k++) { ub[k] = clampf(gld(srec + SR_BASE + k) + dvb[k], -cfg.vmax, cfg.vmax); state[W_U + k] = ub[k]; }
 
 #pragma unroll
-            for (int k = 0; k < 3; k++) state[W_POS + k] = srec[SR_BASE + 6 + k] + ub[3 + k] * cfg.dt;
+            for (int k = 0; k < 3; k++) state[W_POS + k] = gld(srec + SR_BASE + 6 + k) + ub[3 + k] * cfg.dt;
             float fa = sqrtf(ub[0] * ub[0] + ub[1] * ub[1] + ub[2] * ub[2]);
             if (fa * cfg.dt > 0.78539816339f) fa = 0.78539816339f * cfg.inv_dt;
             float sc, cw;
@@ -603,7 +606,7 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
                 sc = sn / fa;
             }
             const float dx = ub[0] * sc, dy = ub[1] * sc, dz = ub[2] * sc;
-            const float qx = srec[SR_BASE + 9], qy = srec[SR_BASE + 10], qz = srec[SR_BASE + 11], qw = srec[SR_BASE + 12];
+            const float qx = gld(srec + SR_BASE + 9), qy = gld(srec + SR_BASE + 10), qz = gld(srec + SR_BASE + 11), qw = gld(srec + SR_BASE + 12);
             const float rx = cw * qx + dx * qw + dy * qz - dz * qy;
             const float ry = cw * qy - dx * qz + dy * qw + dz * qx;
             const float rz = cw * qz + dx * qy - dy * qx + dz * qw;
