@@ -133,7 +133,7 @@ k_rank(const uint8_t *__restrict__ keys, int n, int *__restrict__ perm) {
     if (t < 128) s_cnt[t] = 0;
     __syncthreads();
     // class 0 = heaviest; robots beyond n sort last
-    const int cls = (r < n) ? 126 - min((int)__ldcg(keys + r), 126) : 127;
+    const int cls = (r < n) ? 126 - min(gld_u8(keys + r), 126) : 127;
     const int pos = atomicAdd(&s_cnt[cls], 1);
     __syncthreads();
     if (t < 32) {            // exclusive scan of the 128 class counts: 4 per lane
@@ -164,7 +164,7 @@ k_solve(const __grid_constant__ DevConfig dc, const float *__restrict__ srec, co
     float *Gs = reinterpret_cast<float *>(smem_raw);
     const int lane = threadIdx.x;
     const int tile = blockIdx.x % n_tiles, grp = blockIdx.x / n_tiles;
-    const int robot = __ldcg(perm + tile * RANK_TILE + grp * PLEN_SOLVE_ROBOTS + (lane >> 2));
+    const int robot = gld_i(perm + tile * RANK_TILE + grp * PLEN_SOLVE_ROBOTS + (lane >> 2));
     const bool valid = robot < n;
     const size_t r = valid ? (size_t)robot : 0;
     solve_tick(dc, srec + r * SR_WORDS, Gs + (size_t)(lane >> 2) * PLEN_GS_WORDS, state + r * PLEN_STATE_WORDS, lane, valid);

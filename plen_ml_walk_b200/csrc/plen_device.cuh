@@ -141,20 +141,36 @@ struct vec2 { float x, y; };
 #define PLEN_ALIGN16
 #endif
 
-// Loads of data another kernel of the step produced (state records, solve records, targets, permutation): L2 only
-// (ld.global.cg), never the non-coherent L1 / read-only path.  Every such word is read once, so nothing is lost, and the
-// step stays correct when ranges of the batch run on several streams at once (plen_step_host) and kernels of different
-// ranges share an SM.
+// Loads of data another kernel of the step produced (state records, solve records, targets, permutation, sort keys) go
+// through plain coherent ld.global, never the non-coherent read-only path (LDG.E.CONSTANT) that `const __restrict__`
+// pointers invite: plen_step_host runs ranges of the batch on several streams, so kernels of different ranges share an SM
+// and its L1 while these buffers are rewritten tick after tick.  (ld.global.cg -- L2 only -- was measured 6 % slower.)
 #ifndef PLEN_HOST_EMU
-PLEN_DEV float gld(const float *p) { return __ldcg(p); }
+PLEN_DEV float gld(const float *p) {
+    float v;
+    asm("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
 PLEN_DEV vec4 gld4(const float *p) {
-    const float4 v = __ldcg(reinterpret_cast<const float4 *>(p));
-    vec4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+    vec4 r;
+    asm("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
+}
+PLEN_DEV int gld_i(const int *p) {
+    int v;
+    asm("ld.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+PLEN_DEV int gld_u8(const uint8_t *p) {
+    unsigned v;
+    asm("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return (int)v;
 }
 #else
 PLEN_DEV float gld(const float *p) { return *p; }
 PLEN_DEV vec4 gld4(const float *p) { return *reinterpret_cast<const vec4 *>(p); }
+PLEN_DEV int gld_i(const int *p) { return *p; }
+PLEN_DEV int gld_u8(const uint8_t *p) { return *p; }
 #endif
 
 // six consecutive floats of a 32-byte-aligned row (tw / kk / gg rows of WarpScratch) as LDS.128 + LDS.64
