@@ -155,7 +155,7 @@ k_rank(const uint8_t *__restrict__ keys, int n, int *__restrict__ perm) {
 // A CTA is ONE warp = 8 robots (30.1 KB of G in shared memory, 7 CTAs per SM).  CTA b takes group b / n_tiles of tile
 // b % n_tiles, so the heavy groups of all tiles run first and the tail of the grid is made of light ones.
 #ifndef PLEN_SOLVE_MAXREG
-#define PLEN_SOLVE_MAXREG 240
+#define PLEN_SOLVE_MAXREG 255
 #endif
 __global__ void __maxnreg__(PLEN_SOLVE_MAXREG)
 k_solve(const __grid_constant__ DevConfig dc, const float *__restrict__ srec, const int *__restrict__ perm,

@@ -292,7 +292,9 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
     // order, so they agree bit for bit; in the other lanes o is scratch.  This takes the SHFL round trip (the longest
     // link of the Gauss-Seidel dependency chain) off the critical path except once per block, where o is refreshed from s.
     float o[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-#define OWN_SYNC()  { _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++) o[k_] = s[k_]; }
+    // servo blocks keep the private copy as the row ERROR u = x - rhs (so the candidate is clamp(-u): the subtraction of
+    // the right-hand side leaves the row-to-row chain, FMNMX -> FMNMX -> FFMA2 instead of FADD -> FMNMX -> FMNMX -> FFMA2)
+#define OWN_SYNC()  { _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++) o[k_] = s[k_] - m_rhs[k_]; }
 #define OWN_SYNC6() { _Pragma("unroll") for (int k_ = 2; k_ < 8; k_++) o[k_] = s[k_]; }
 
     // The active points of either foot occupy slots 0 .. n-1 (compacted), so the walk over a foot stops at the first empty
@@ -328,7 +330,7 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
     // servo row of joint 8 b + k (owner lane b)
 #define SERVO_ROW(b, k)                                                \
     {                                                                  \
-        const float dl_ = fminf(fmaxf(m_rhs[k] - (PLEN_LA_SERVO ? o[k] : s[k]), m_lo[k]), m_hi[k]); \
+        const float dl_ = fminf(fmaxf(PLEN_LA_SERVO ? -o[k] : m_rhs[k] - s[k], m_lo[k]), m_hi[k]); \
         const vec4 ca_ = g_ld(Gl, (8 * (b) + (k)) * 8), cb_ = g_ld(Gl, (8 * (b) + (k)) * 8 + 1); \
         if (PLEN_LA_SERVO) apply_vec(o, ca_, cb_, dl_);                \
         const float db_ = GSH(dl_, b);                                 \
@@ -356,8 +358,11 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
     {                                                                                                     \
         const float x_ = fmaf(-(PLEN_LA_TORSION ? o[2 + (c)] : s[2 + (c)]), t_dinv[c], t_rhs[c]);                                        \
         const float lim_ = (mu) * c_lam[k][5];                                                            \
-        float dl_ = fminf(fmaxf(x_, -lim_ - c_lam[k][c]), lim_ - c_lam[k][c]);                            \
-        dl_ = (c_lam[k][5] > 0.0f) ? dl_ : 0.0f;   /* row skipped while the normal impulse is not positive */ \
+        /* row skipped while the normal impulse is not positive: its bounds collapse to [0, 0] (the selects sit on the  \
+           bounds, which do not depend on the row chain, instead of on the candidate) */                    \
+        const bool on_ = c_lam[k][5] > 0.0f;                                                              \
+        const float lo_ = on_ ? -lim_ - c_lam[k][c] : 0.0f, hi_ = on_ ? lim_ - c_lam[k][c] : 0.0f;        \
+        const float dl_ = fminf(fmaxf(x_, lo_), hi_);                                                     \
         if (PLEN_LA_TORSION) apply_reg6(o, A[f][c], dl_);                                                 \
         const float db_ = GSH(dl_, 2 + (f));                                                              \
         if (g == 2 + (f)) { c_lam[k][c] += dl_; resT[c] = fmaxf(resT[c], fabsf(dl_)); }                   \
