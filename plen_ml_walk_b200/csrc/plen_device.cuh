@@ -64,10 +64,6 @@ PLEN_DEV int popc_(unsigned m) { return __popc(m); }
 }  // namespace plen
 #endif
 
-#ifndef PLEN_DYN_EMIT_FLAT
-#define PLEN_DYN_EMIT_FLAT 1
-#endif
-
 namespace plen {
 
 // ---- model table rows (each row is 32 floats, one per lane), staged in shared memory per CTA
@@ -279,25 +275,6 @@ PLEN_DEV void forward_kinematics(const float *tab, int lane, float q, const floa
     quat_to_mat(quat, R0);
     mat3_mul(R0, R, Rw);
     mat3_vec(R0, p, pw);
-}
-
-// In-place Gauss-Jordan inverse (no pivoting, SPD) of a full 6x6 held redundantly by every lane.
-PLEN_DEV void inv6_inplace(float (*A)[6]) {
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
-        const float inv = rcp_(A[k][k]);
-        A[k][k] = 1.0f;
-#pragma unroll
-        for (int j = 0; j < 6; j++) A[k][j] *= inv;
-#pragma unroll
-        for (int i = 0; i < 6; i++) {
-            if (i == k) continue;
-            const float f = A[i][k];
-            A[i][k] = 0.0f;
-#pragma unroll
-            for (int j = 0; j < 6; j++) A[i][j] -= f * A[k][j];
-        }
-    }
 }
 
 PLEN_DEV float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
@@ -774,7 +751,6 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
 
     // ---- G (30 columns x 32 words) and B (6 rows x 32 words): word w of a column = entry i = w; joint columns are
     //      divided by their diagonal entry (velocity-unit servo rows, see the SR_ enum)
-#if PLEN_DYN_EMIT_FLAT
     {
         // Branch free: every lane reads its entries through ONE base pointer + a stride fixed per lane class (joint rows
         // from M^-1 / Y, foot-twist rows from Y^T / Lambda^-1, the two unused words zero), so the 30 column stores are
@@ -822,41 +798,6 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
 #pragma unroll
             for (int k = 0; k < 6; k++) Bm[k * 32 + lane] = (ij || ic) ? b3[k * st3] * sc3 : 0.0f;
         }
-#else
-    {
-        const int i = lane;
-        const bool ij = i < 18, ic = (i >= 18 && i < 24) || i >= 26;
-        const int fa = (i >= 26) ? 1 : 0, a6 = fa ? i - 26 : i - 18;
-        const float(*Ya)[8] = fa ? ws.gg : ws.kk;
-        float *G = srec + SR_G;
-        for (int c = 0; c < 18; c++) {
-            float v = 0.0f;
-            if (ij) v = ws.minv[6 + c][6 + i];
-            else if (ic) v = Ya[6 + c][a6];
-            G[c * 32 + lane] = v * shfl(m_dinv, 6 + c);
-        }
-        for (int c = 18; c < 30; c++) {
-            const int fb = (c >= 24) ? 1 : 0, b6 = c - 18 - 6 * fb;
-            const float(*Yb)[8] = fb ? ws.gg : ws.kk;
-            float v = 0.0f;
-            if (ij) v = Yb[6 + i][b6];
-            else if (ic && man_new) v = ws.lin[fa * 6 + a6][c - 18];
-            G[c * 32 + lane] = v;
-        }
-        // per-joint scalars in the same word order (entries >= 18 are zero)
-        const int src = ij ? 6 + i : 0;
-        const float s_rhs = shfl(m_rhs, src), s_dinv = shfl(m_dinv, src), s_ldir = shfl(l_dir, src),
-                    s_lrhs = shfl(l_rhs, src), s_vs = shfl(vstar, src), s_q = shfl(L.q, src),
-                    s_d = shfl(is_joint ? ws.minv[lane][lane] : 0.0f, src);
-        float *Bm = srec + SR_B;
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-            float v = 0.0f;
-            if (ij) v = ws.minv[6 + i][k] * s_dinv;
-            else if (ic) v = Ya[k][a6];
-            Bm[k * 32 + lane] = v;
-        }
-#endif
         srec[SR_MRHS + lane] = ij ? s_rhs : 0.0f;
         srec[SR_MD + lane] = (ij && s_dinv > 0.0f) ? s_d : 0.0f;
         srec[SR_LDIR + lane] = ij ? s_ldir : 0.0f;
