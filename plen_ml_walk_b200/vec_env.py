@@ -191,6 +191,18 @@ class PlenVecEnv:
         with torch.cuda.device(self.device):
             self._check(self.lib.plen_set_state(self._ctx, self._p(qpos), self._p(qvel), self._p(aux), self._stream()))
 
+    def save_state(self, path):
+        """Snapshot of every env (pose, velocities, contact cache, env bookkeeping) to one .pt file."""
+        qpos, qvel, aux = self.get_state()
+        torch.save({"num_envs": self.num_envs, "joint_act": self.joint_act, "qpos": qpos.cpu(), "qvel": qvel.cpu(), "aux": aux.cpu()}, path)
+
+    def load_state(self, path):
+        """Restore a save_state snapshot; stepping on from it reproduces the original run bit for bit."""
+        d = torch.load(path, map_location="cpu")
+        if int(d["num_envs"]) != self.num_envs or bool(d["joint_act"]) != self.joint_act:
+            raise ValueError("snapshot is for %d envs (joint_act=%s)" % (d["num_envs"], d["joint_act"]))
+        self.set_state(d["qpos"], d["qvel"], d["aux"])
+
     def tick(self, targets, n_ticks=1):
         """Raw physics: n_ticks of 1/240 s with joint targets in radians, no env logic (move_joints + stepSimulation)."""
         t = self._dev_f32(targets, (self.num_envs, ACT_DIM))

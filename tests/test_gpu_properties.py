@@ -179,3 +179,23 @@ def test_box_foot_model_variant_stands_and_steps():
         o, rew, done, _ = env.step(zero)
     assert torch.isfinite(o).all() and not bool(done.any())
     assert float(o[0, 24]) == 1.0 and float(o[0, 25]) == 1.0 and float(o[0, 18]) > 0.14
+
+
+def test_snapshot_to_disk_and_back_continues_bit_exact(tmp_path):
+    """save_state / load_state: a run restored from disk into a fresh context continues exactly."""
+    n = 3000
+    a = _mk(n)
+    _rollout(a, 15, seed=31)
+    path = str(tmp_path / "plen_state.pt")
+    a.save_state(path)
+    b = _mk(n)
+    b.reset()
+    b.load_state(path)
+    g = torch.Generator(device="cuda"); g.manual_seed(37)
+    for _ in range(4):
+        act = torch.empty((n, 18), device="cuda").uniform_(-1, 1, generator=g)
+        ra, rb = _step_out(a, act), _step_out(b, act)
+        for x, y in zip(ra, rb):
+            assert _same(x, y)
+    with pytest.raises(ValueError):
+        _mk(n + 1).load_state(path)
