@@ -133,3 +133,35 @@ def test_reward_on_same_state(mods):
             env.reset(mask=torch.from_numpy(gd).cuda())
     print("worst relative reward error %.2e" % worst)
     assert worst < 1e-5
+
+
+def test_joint_limit_rows_free_flight(mods):
+    """The rare limit-row path of k_solve on the GPU: airborne robots with joints beyond the +-1.7 rad URDF limits (rows that
+    only exist while violated, ERP 0.2), mixed into a batch whose other robots have none -- so warps carry limit rows for
+    some of their eight robots only.  One env step against the oracle, free-flight tolerance."""
+    oracle, PlenVecEnv = mods
+    n = 64
+    rng = np.random.default_rng(7)
+    o = oracle.PlenOracle(n, n_threads=8)
+    env = PlenVecEnv(n, auto_reset=False)
+    st = o.get_state()
+    st["qpos"], st["qvel"] = random_flight_state(rng, n)
+    st["qvel"][:, 6:] *= 0.25
+    viol = rng.random((n, 18)) < 0.08                         # ~1.4 violated joints per robot on average, many robots with none
+    viol[::4] = False
+    sign = np.where(rng.random((n, 18)) < 0.5, -1.0, 1.0)
+    st["qpos"][:, 7:] = np.where(viol, sign * (1.7 + rng.uniform(0.005, 0.2, (n, 18))), st["qpos"][:, 7:])
+    o.set_state(st)
+    env.set_state(*abi_from_oracle(o.get_state()))
+    act = rng.uniform(-1, 1, (n, 18)).astype(np.float32)
+    o.step(act.astype(np.float64))
+    env.step(torch.from_numpy(act).cuda())
+    qpos, qvel, aux = (t.cpu().numpy() for t in env.get_state())
+    ref = o.get_state()
+    assert viol.sum() > 40 and (~viol.any(1)).sum() >= 16
+    assert np.abs(qpos[:, 7:] - ref["qpos"][:, 7:]).max() < 1e-4
+    assert np.abs(qpos[:, 0:7] - ref["qpos"][:, 0:7]).max() < 1e-4
+    assert np.abs(qvel - ref["qvel"]).max() < 5e-3
+    # the limit rows did something: violated joints were pushed back towards the limit
+    back = (np.abs(qpos[:, 7:]) < np.abs(st["qpos"][:, 7:]))[viol]
+    assert back.mean() > 0.9
