@@ -132,6 +132,13 @@ int plen_step_host(plen_ctx *ctx, const float *actions_host, float *obs_host, fl
 int plen_get_state(plen_ctx *ctx, float *qpos_dev, float *qvel_dev, float *aux_dev, void *stream);
 int plen_set_state(plen_ctx *ctx, const float *qpos_dev, const float *qvel_dev, const float *aux_dev, void *stream);
 
+/* Per-env domain randomisation (the reference lists it as future work, README.md:75-76): scale factors of
+ * the three foot friction coefficients (plen_env.py:309, 439-452), of the servo force limit (setJointMotorControlArray
+ * forces=0.15, plen_env.py:753) and of the servo position gain (POSITION_CONTROL kp 0.1).  Arrays are [N] device floats;
+ * NULL leaves a column as it is; every scale is 1 after plen_create.  Takes effect from the next tick. */
+int plen_set_env_scales(plen_ctx *ctx, const float *friction_scale_dev, const float *motor_force_scale_dev,
+                        const float *motor_gain_scale_dev, void *stream);
+
 /* Advance every env by n_ticks physics ticks with raw joint targets [N,18] (radians) and no env logic.
  * Replaces move_joints + p.stepSimulation (plen_env.py:746-753, :665-667); used by the parity tests. */
 int plen_tick(plen_ctx *ctx, const float *targets_dev, int n_ticks, void *stream);

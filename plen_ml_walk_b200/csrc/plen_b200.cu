@@ -36,6 +36,7 @@ struct plen_ctx {
     float *d_tab, *d_state, *d_snapshot;
     float *d_srec;   // [n][SR_WORDS] solve records (k_dyn -> k_solve)
     float *d_tgt;    // [n][18] servo targets of the current env step
+    float *d_scale;  // [n][4] per-robot scales: friction, servo force limit, servo gain, reserved (plen_set_env_scales; all 1)
     uint8_t *d_key;  // [n] contact-load sort key of the current tick (k_dyn -> k_rank)
     int *d_perm;     // [n_tiles * RANK_TILE] robots ordered by contact load inside each tile (k_rank -> k_solve)
     float *d_act, *d_obs, *d_rew;
@@ -86,7 +87,8 @@ __device__ __forceinline__ DynSmem &stage_table(const float *tab_g) {
 __global__ void __launch_bounds__(DYN_WPC * 32, 5)
 k_dyn(const __grid_constant__ DevConfig dc, const __grid_constant__ EnvRanges er, const float *__restrict__ tab_g,
       const float *__restrict__ state, int n, const float *__restrict__ actions, float *__restrict__ tgt,
-      float *__restrict__ srec, uint8_t *__restrict__ keys, float *dbg_minv, float *dbg_pos, float *dbg_rot) {
+      float *__restrict__ srec, uint8_t *__restrict__ keys, float *dbg_minv, float *dbg_pos, float *dbg_rot,
+      const float *__restrict__ scale) {
     // The 4 KB model table is staged with cp.async while every warp already fetches its robot's state record and targets:
     // the two latencies overlap instead of adding up (the table wait used to sit in front of everything).
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -106,11 +108,14 @@ k_dyn(const __grid_constant__ DevConfig dc, const __grid_constant__ EnvRanges er
         r0 = gld(rec + lane); r1 = gld(rec + 32 + lane); r2 = gld(rec + 64 + lane);
         if (jl) a_in = actions ? gld(actions + o) : (tgt ? gld(tgt + o) : 0.0f);
     }
+    vec4 sc; sc.x = sc.y = sc.z = sc.w = 1.0f;
+    if (has && scale) sc = gld4(scale + 4 * (size_t)env);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     if (!has) return;
     LaneState L;
     unpack_record(r0, r1, r2, ws, L, lane);
+    L.fric_s = sc.x; L.motor_s = sc.y; L.kp_s = sc.z;
     if (jl) {
         if (actions) { L.tgt = agent_target(dc, er, lane - 6, a_in); tgt[o] = L.tgt; }
         else L.tgt = a_in;
@@ -168,6 +173,17 @@ k_solve(const __grid_constant__ DevConfig dc, const float *__restrict__ srec, co
     const bool valid = robot < n;
     const size_t r = valid ? (size_t)robot : 0;
     solve_tick(dc, srec + r * SR_WORDS, Gs + (size_t)(lane >> 2) * PLEN_GS_WORDS, state + r * PLEN_STATE_WORDS, lane, valid);
+}
+
+// per-robot scales (domain randomisation): column c of d_scale <- the given array, or 1 when `init`
+__global__ void k_set_scales(float *__restrict__ scale, int n, const float *fric, const float *motor, const float *kp, int init) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    float *s = scale + 4 * (size_t)e;
+    if (init) { s[0] = s[1] = s[2] = s[3] = 1.0f; }
+    if (fric) s[0] = fric[e];
+    if (motor) s[1] = motor[e];
+    if (kp) s[2] = kp[e];
 }
 
 // After the last tick of an env step, one warp per robot: observation, done, reward, counters, auto-reset.
@@ -425,7 +441,8 @@ static void launch_ticks(plen_ctx *ctx, float *state, int n, const float *action
     for (int t = 0; t < n_ticks; t++) {
         if (ev) cudaEventRecord(ev[2 * t], st);
         k_dyn<<<dyn_grid_persistent(ctx, n), DYN_WPC * 32, DYN_SMEM, st>>>(ctx->dc, ctx->er, ctx->d_tab, state, n, t == 0 ? actions : nullptr,
-                                                          tgt, srec, key, nullptr, nullptr, nullptr);
+                                                          tgt, srec, key, nullptr, nullptr, nullptr,
+                                                          (state == ctx->d_snapshot || !ctx->d_scale) ? nullptr : ctx->d_scale + 4 * off);
         if (ev) cudaEventRecord(ev[2 * t + 1], st);
         const int nt = rank_tiles(n);
         k_rank<<<nt, RANK_TILE, 0, st>>>(key, n, perm);
@@ -460,7 +477,7 @@ int plen_num_envs(const plen_ctx *ctx) { return ctx ? ctx->n : 0; }
 void plen_destroy(plen_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->d_tab); cudaFree(ctx->d_state); cudaFree(ctx->d_snapshot); cudaFree(ctx->d_srec); cudaFree(ctx->d_tgt); cudaFree(ctx->d_key); cudaFree(ctx->d_perm);
+    cudaFree(ctx->d_tab); cudaFree(ctx->d_state); cudaFree(ctx->d_snapshot); cudaFree(ctx->d_srec); cudaFree(ctx->d_tgt); cudaFree(ctx->d_key); cudaFree(ctx->d_perm); cudaFree(ctx->d_scale);
     cudaFree(ctx->d_act); cudaFree(ctx->d_obs); cudaFree(ctx->d_rew); cudaFree(ctx->d_done); cudaFree(ctx->d_tmo);
     for (int k = 1; k < PLEN_HOST_PIPE; k++)
         if (ctx->pipe[k]) cudaStreamDestroy(ctx->pipe[k]);
@@ -495,6 +512,8 @@ static int create_impl(plen_ctx *ctx) {
     CK(ctx, cudaMalloc(&ctx->d_tgt, sizeof(float) * PLEN_NJ * (size_t)n));
     CK(ctx, cudaMalloc(&ctx->d_key, (size_t)n));
     CK(ctx, cudaMalloc(&ctx->d_perm, sizeof(int) * (size_t)rank_tiles(n) * RANK_TILE));
+    CK(ctx, cudaMalloc(&ctx->d_scale, sizeof(float) * 4 * (size_t)n));
+    k_set_scales<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_scale, n, nullptr, nullptr, nullptr, 1);
     CK(ctx, cudaMalloc(&ctx->d_act, sizeof(float) * PLEN_NJ * (size_t)n));
     CK(ctx, cudaMalloc(&ctx->d_obs, sizeof(float) * PLEN_OBS * (size_t)n));
     CK(ctx, cudaMalloc(&ctx->d_rew, sizeof(float) * (size_t)n));
@@ -587,6 +606,16 @@ int plen_step_host(plen_ctx *ctx, const float *actions_host, float *obs_host, fl
     return PLEN_OK;
 }
 
+int plen_set_env_scales(plen_ctx *ctx, const float *friction_scale_dev, const float *motor_force_scale_dev,
+                        const float *motor_gain_scale_dev, void *stream) {
+    if (!ctx) return fail(nullptr, PLEN_E_ARG, "ctx is NULL");
+    CK(ctx, cudaSetDevice(ctx->device));
+    k_set_scales<<<(ctx->n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ctx->d_scale, ctx->n, friction_scale_dev, motor_force_scale_dev,
+                                                                       motor_gain_scale_dev, 0);
+    CK(ctx, cudaGetLastError());
+    return PLEN_OK;
+}
+
 int plen_get_state(plen_ctx *ctx, float *qpos_dev, float *qvel_dev, float *aux_dev, void *stream) {
     if (!ctx) return fail(nullptr, PLEN_E_ARG, "ctx is NULL");
     CK(ctx, cudaSetDevice(ctx->device));
@@ -619,7 +648,7 @@ int plen_debug_dynamics(plen_ctx *ctx, float *minv_dev, float *pos_dev, float *r
     if (!ctx) return fail(nullptr, PLEN_E_ARG, "ctx is NULL");
     CK(ctx, cudaSetDevice(ctx->device));
     k_dyn<<<dyn_grid_persistent(ctx, ctx->n), DYN_WPC * 32, DYN_SMEM, (cudaStream_t)stream>>>(ctx->dc, ctx->er, ctx->d_tab, ctx->d_state, ctx->n,
-                                                                            nullptr, nullptr, ctx->d_srec, ctx->d_key, minv_dev, pos_dev, rot_dev);
+                                                                            nullptr, nullptr, ctx->d_srec, ctx->d_key, minv_dev, pos_dev, rot_dev, ctx->d_scale);
     CK(ctx, cudaGetLastError());
     return PLEN_OK;
 }

@@ -111,7 +111,7 @@ enum {
     SR_CRHS = 1344, SR_CDINV = 1408, SR_CD = 1472,   // 64 words each: [contact slot q = 4 foot + k][solver lane g]
     SR_PT = 1536,      // 8 x (x, y, z, distance): k-th ACTIVE contact point of each foot, relative to the base origin
     SR_LAMC = 1568,    // 8 cached normal impulses, same slot order
-    SR_BASE = 1576,    // v* of the base (6), base position (3), quaternion (4), manifold bits (1)
+    SR_BASE = 1576,    // v* of the base (6), base position (3), quaternion (4), manifold bits (1), friction / servo-force scale (2)
     SR_WORDS = 1600
 };
 
@@ -201,6 +201,8 @@ struct LaneState {
     float quat[4];    // base orientation xyzw (uniform)
     unsigned man;     // manifold bits (uniform)
     int iters;        // PGS iterations of the last tick (diagnostic, uniform)
+    float fric_s, motor_s, kp_s;   // per-robot scales of the friction coefficients, the servo force limit and the servo
+                                   // gain (domain randomisation, plen_set_env_scales; 1 = the reference's constants)
 };
 
 PLEN_DEV void mat3_mul(const float *A, const float *B, float *C) {
@@ -708,7 +710,7 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
     if (is_joint) {
         const float m_d = ws.minv[lane][lane];
         m_dinv = (m_d > 1.1920929e-7f) ? rcp_(m_d) : 0.0f;
-        const float desired = cfg.kp_over_dt * (L.tgt - L.q) + cfg.one_minus_kd * vstar;
+        const float desired = cfg.kp_over_dt * L.kp_s * (L.tgt - L.q) + cfg.one_minus_kd * vstar;
         m_rhs = (m_dinv > 0.0f) ? (desired - vstar) : 0.0f;          // velocity units
         const float lo = tab[T_LOWER * 32 + lane], hi = tab[T_UPPER * 32 + lane];
         const float pen_lo = L.q - lo, pen_hi = hi - L.q;
@@ -864,6 +866,8 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
     if (lane < 4) srec[SR_BASE + 9 + lane] = L.quat[lane];
     if (lane == 0) {
         srec[SR_BASE + 13] = (float)man_new;
+        srec[SR_BASE + 14] = L.fric_s;            // k_solve scales mu_lateral / mu_spinning / mu_rolling ...
+        srec[SR_BASE + 15] = L.motor_s;           // ... and the servo impulse bound of this robot
         // k_solve groups robots of similar contact load into the same warp (tile-local sort by this key)
         const int n0 = popc_(man_new & 15u), n1 = popc_((man_new >> 4) & 15u);
         if (sort_key) *sort_key = (uint8_t)((n0 > n1 ? n0 : n1) * 25 + n0 * 5 + n1);

@@ -28,6 +28,7 @@ PLEN_DEV void unpack_record(float r0, float r1, float r2, WarpScratch &ws, LaneS
     for (int k = 0; k < 4; k++) L.quat[k] = ws.st[W_QUAT + k];
     L.man = (unsigned)ws.st[W_MAN];
     L.iters = 0;
+    L.fric_s = L.motor_s = L.kp_s = 1.0f;
 }
 
 PLEN_DEV void store_record(float *rec, WarpScratch &ws, const LaneState &L, int lane) {

@@ -211,16 +211,19 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
     float m_rhs[8], m_lo[8], m_hi[8];
     unsigned limbits = 0;          // bit k: joint 8 g + k is beyond a URDF limit (its limit row exists this tick)
     unsigned man = 0;
+    float fric_s = 1.0f;           // per-robot scale of the three friction coefficients (plen_set_env_scales)
 #pragma unroll
     for (int k = 0; k < 8; k++) m_rhs[k] = m_lo[k] = m_hi[k] = 0.0f;
     if (valid) {
         float d[8], ld[8];
+        fric_s = gld(srec + SR_BASE + 14);
+        const float motor_s = gld(srec + SR_BASE + 15);
         load8(srec + SR_MRHS + 8 * g, m_rhs);
         load8(srec + SR_MD + 8 * g, d);
         load8(srec + SR_LDIR + 8 * g, ld);
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            m_hi[k] = cfg.motor_imp * d[k];
+            m_hi[k] = cfg.motor_imp * motor_s * d[k];
             m_lo[k] = -m_hi[k];
             limbits |= (ld[k] != 0.0f) ? (1u << k) : 0u;
         }
@@ -369,7 +372,7 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
         apply_reg(s, A[f][c], db_);                                                                       \
     }
 
-    const float mu_spin = lc.mu_spin, mu_roll = lc.mu_roll, mu_lat = lc.mu_lat, res_thr = lc.res_thr;
+    const float mu_spin = lc.mu_spin * fric_s, mu_roll = lc.mu_roll * fric_s, mu_lat = lc.mu_lat * fric_s, res_thr = lc.res_thr;
     const int n_iterations = lc.iterations;
     bool alive = valid;
     int my_iters = 0;

@@ -191,6 +191,13 @@ class PlenVecEnv:
         with torch.cuda.device(self.device):
             self._check(self.lib.plen_set_state(self._ctx, self._p(qpos), self._p(qvel), self._p(aux), self._stream()))
 
+    def set_env_scales(self, friction=None, motor_force=None, motor_gain=None):
+        """Per-env domain randomisation: scale factors [N] of the foot friction coefficients, the servo force
+        limit and the servo position gain; None leaves a quantity unchanged, 1.0 is the reference's constant."""
+        arr = [None if x is None else self._dev_f32(x, (self.num_envs,)) for x in (friction, motor_force, motor_gain)]
+        with torch.cuda.device(self.device):
+            self._check(self.lib.plen_set_env_scales(self._ctx, *[self._p(x) for x in arr], self._stream()))
+
     def save_state(self, path):
         """Snapshot of every env (pose, velocities, contact cache, env bookkeeping) to one .pt file."""
         qpos, qvel, aux = self.get_state()

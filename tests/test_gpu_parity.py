@@ -165,3 +165,53 @@ def test_joint_limit_rows_free_flight(mods):
     # the limit rows did something: violated joints were pushed back towards the limit
     back = (np.abs(qpos[:, 7:]) < np.abs(st["qpos"][:, 7:]))[viol]
     assert back.mean() > 0.9
+
+
+def test_per_env_scales_against_oracles_with_scaled_constants(mods):
+    """plen_set_env_scales: one batch whose first half runs with friction x 0.5, servo force limit x 1.5 and
+    servo gain x 0.7 is checked, teacher-forced through contact, against TWO oracles -- one built with those constants
+    scaled in its config, one stock.  Scales of 1 must leave the step bit-identical."""
+    oracle, PlenVecEnv = mods
+    n, h, steps = 64, 32, 25
+    rng = np.random.default_rng(11)
+    oa, ob = oracle.PlenOracle(h, n_threads=4), oracle.PlenOracle(h, n_threads=4)
+    for k in ("mu_lateral", "mu_spinning", "mu_rolling"):
+        setattr(oa.cfg, k, getattr(oa.cfg, k) * 0.5)
+    oa.cfg.motor_max_force *= 1.5
+    oa.cfg.motor_kp *= 0.7
+    env = PlenVecEnv(n, auto_reset=False)
+    one = PlenVecEnv(n, auto_reset=False)
+    fr = torch.ones(n, device="cuda"); mf = torch.ones(n, device="cuda"); kp = torch.ones(n, device="cuda")
+    one.set_env_scales(fr, mf, kp)
+    fr[:h] = 0.5; mf[:h] = 1.5; kp[:h] = 0.7
+    env.set_env_scales(friction=fr, motor_force=mf, motor_gain=kp)
+    oa.reset(); ob.reset(); env.reset(); one.reset()
+    stock = PlenVecEnv(n, auto_reset=False); stock.reset()
+    errs = []
+    for t in range(steps):
+        sa, sb = oa.get_state(), ob.get_state()
+        merged = {k: np.concatenate([sa[k], sb[k]]) for k in sa}
+        env.set_state(*abi_from_oracle(merged))
+        act = rng.uniform(-1, 1, (n, 18)).astype(np.float32)
+        xa, _, da, _ = oa.step(act[:h].astype(np.float64))
+        xb, _, db, _ = ob.step(act[h:].astype(np.float64))
+        go, _, _, _ = env.step(torch.from_numpy(act).cuda())
+        errs.append(np.abs(go.cpu().numpy()[:, :24] - np.concatenate([xa, xb])[:, :24]).max(1))
+        for e in np.where(da)[0]:
+            oa.reset_one(int(e))
+        for e in np.where(db)[0]:
+            ob.reset_one(int(e))
+        # scales of one: bit-identical to a context that never set them
+        a1 = torch.from_numpy(act).cuda()
+        o1, r1, _, _ = one.step(a1)
+        o0, r0, _, _ = stock.step(a1)
+        assert torch.equal(o1, o0) and torch.equal(torch.nan_to_num(r1, nan=7.0), torch.nan_to_num(r0, nan=7.0))
+    errs = np.stack(errs)
+    assert np.median(errs[:, :h]) < 1e-4 and np.median(errs[:, h:]) < 1e-4
+    assert np.mean(errs < 1e-3) > 0.6
+    # and the scaled constants really change the dynamics: same state, same action, scaled vs stock robots differ
+    env.set_state(*abi_from_oracle({k: np.concatenate([sb[k], sb[k]]) for k in sb}))
+    act2 = np.concatenate([act[h:], act[h:]])
+    g2, _, _, _ = env.step(torch.from_numpy(act2).cuda())
+    g2 = g2.cpu().numpy()
+    assert np.abs(g2[:h, :18] - g2[h:, :18]).max() > 1e-3
