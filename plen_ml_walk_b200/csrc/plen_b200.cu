@@ -128,23 +128,34 @@ k_dyn(const __grid_constant__ DevConfig dc, const __grid_constant__ EnvRanges er
 // Robots are grouped by contact load before the solve: k_rank counting-sorts the keys k_dyn wrote inside tiles of
 // RANK_TILE robots (heaviest first) and writes the permutation k_solve reads, so that the eight robots of a solver warp
 // have similar active-point counts (mean per-foot loop length 2.6 -> 1.9 slots on the bench workload) and the heavy
-// warps of every tile are dispatched first.  The order inside a key class is arbitrary (shared-memory atomics); results
-// do not depend on it (a robot's solve never reads another robot's data).
+// warps of every tile are dispatched first.  The sort is stable, so the grouping is reproducible.
 #define RANK_TILE 1024
 __global__ void __launch_bounds__(RANK_TILE)
 k_rank(const uint8_t *__restrict__ keys, int n, int *__restrict__ perm) {
-    __shared__ int s_cnt[128], s_base[128];
-    const int t = threadIdx.x, r = blockIdx.x * RANK_TILE + t;
-    if (t < 128) s_cnt[t] = 0;
+    // STABLE counting sort (robots of a class keep their index order), so the grouping of robots into solver warps -- and
+    // with it every bit of the step -- is reproducible run to run: rank inside the warp from match_any, warps of a class
+    // in warp order through a [warp][class] count table.
+    __shared__ unsigned short s_wcnt[RANK_TILE / 32][128];
+    __shared__ int s_base[128];
+    const int t = threadIdx.x, r = blockIdx.x * RANK_TILE + t, w = t >> 5, lane = t & 31;
+    for (int i = t; i < (RANK_TILE / 32) * 128; i += RANK_TILE) (&s_wcnt[0][0])[i] = 0;
     __syncthreads();
     // class 0 = heaviest; robots beyond n sort last
     const int cls = (r < n) ? 126 - min(gld_u8(keys + r), 126) : 127;
-    const int pos = atomicAdd(&s_cnt[cls], 1);
+    const unsigned peers = __match_any_sync(0xffffffffu, cls);
+    const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+    if (rank_in_warp == 0) s_wcnt[w][cls] = (unsigned short)__popc(peers);
+    __syncthreads();
+    if (t < 128) {           // class totals, then (below) their exclusive scan
+        int tot = 0;
+        for (int k = 0; k < RANK_TILE / 32; k++) tot += s_wcnt[k][t];
+        s_base[t] = tot;
+    }
     __syncthreads();
     if (t < 32) {            // exclusive scan of the 128 class counts: 4 per lane
         int c[4], sum = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) { c[k] = s_cnt[4 * t + k]; sum += c[k]; }
+        for (int k = 0; k < 4; k++) { c[k] = s_base[4 * t + k]; sum += c[k]; }
         int incl = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (t >= d) incl += o; }
@@ -153,6 +164,8 @@ k_rank(const uint8_t *__restrict__ keys, int n, int *__restrict__ perm) {
         for (int k = 0; k < 4; k++) { s_base[4 * t + k] = run; run += c[k]; }
     }
     __syncthreads();
+    int pos = rank_in_warp;
+    for (int k = 0; k < w; k++) pos += s_wcnt[k][cls];
     perm[blockIdx.x * RANK_TILE + s_base[cls] + pos] = r;
 }
 

@@ -372,7 +372,8 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
         apply_reg(s, A[f][c], db_);                                                                       \
     }
 
-    const float mu_spin = lc.mu_spin * fric_s, mu_roll = lc.mu_roll * fric_s, mu_lat = lc.mu_lat * fric_s, res_thr = lc.res_thr;
+    float mu_spin = lc.mu_spin * fric_s, mu_roll = lc.mu_roll * fric_s, mu_lat = lc.mu_lat * fric_s;      // opened at the freeze
+    const float res_thr = lc.res_thr;
     const int n_iterations = lc.iterations;
     bool alive = valid;
     int my_iters = 0;
@@ -518,6 +519,11 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
                     for (int c = 0; c < 3; c++) { c_rhs[k][c] = 0.0f; c_dinv[k][c] = 0.0f; }
 #pragma unroll
                 for (int c = 0; c < 3; c++) { t_rhs[c] = 0.0f; t_dinv[c] = 0.0f; }
+                // ... and open the friction bounds: an impulse sitting ON its bound can exceed it by an ulp (lam + (lim - lam)
+                // != lim in fp32), and the next clamp would then move it again.  With the rows' right-hand sides zeroed and
+                // the bounds wide, every later candidate of this robot is exactly its current impulse (dl = 0), so a frozen
+                // robot does not depend on how long the other robots of its warp keep iterating.
+                mu_spin = mu_roll = mu_lat = 1.0e30f;
             }
         }
         if (!ballot(alive)) break;
