@@ -36,7 +36,7 @@ BYTES_PER_ENV_STEP = 2 * 96 * 4 + 18 * 4 + 26 * 4 + 4 + 2
 TICKS_PER_STEP = 4
 # measured DRAM traffic of one k_solve launch per robot (ncu --set full, profiles/r1_v9_summary.md): it reads the
 # 6.4 KB solve record k_dyn wrote for the tick -- a deliberate trade of HBM bytes for issue slots
-SOLVE_DRAM_BYTES_PER_ROBOT = (207.10e6 + 8.47e6) / 32768
+SOLVE_DRAM_BYTES_PER_ROBOT = (207.10e6 + 9.92e6) / 32768
 # executed FP32 work per robot-tick, counted by ncu (smsp__sass_thread_inst_executed_op_{fadd,fmul,ffma}_pred_on, FFMA = 2
 # flop; 32768-robot capture, profiles/r1_v9_summary.md): k_dyn 44.8 kflop + k_solve 58.1 kflop.  It replaces SURVEY 8d's
 # estimate (0.65-1.6 Mflop per env-step for Bullet's ABA + velocity-space PGS): this solver iterates in the 30-dim
