@@ -442,16 +442,34 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
         for (int k = 0; k < 6; k++) { t = shfl_down(Fc[k], d); if (take) Fc[k] += t; }
     }
     // whole robot: torso (lane 0) + the four chain roots
+    //      (one shared-memory gather: the <= 5 root lanes store their 16 composite values, every lane adds them up -- it used
+    //      to be 16 full-warp butterfly reductions, 80 SHFL)
     float mt, ht[3], It[6], Ft[6];
     {
         const bool root = (lane == 0) || (is_joint && lane == cs);
-        mt = warp_sum(root ? mc : 0.0f);
+        const unsigned roots = ballot(root);
+        const int ord = popc_(roots & ((1u << lane) - 1u)), n_roots = popc_(roots);
+        if (root) {
+            float *dst = ws.red + 16 * ord;            // red is free until the Schur-complement products below
+            dst[0] = mc; dst[1] = hc[0]; dst[2] = hc[1]; dst[3] = hc[2];
 #pragma unroll
-        for (int k = 0; k < 3; k++) ht[k] = warp_sum(root ? hc[k] : 0.0f);
+            for (int k = 0; k < 6; k++) { dst[4 + k] = Ic[k]; dst[10 + k] = Fc[k]; }
+        }
+        warp_sync();
+        float acc[16];
 #pragma unroll
-        for (int k = 0; k < 6; k++) It[k] = warp_sum(root ? Ic[k] : 0.0f);
+        for (int v = 0; v < 16; v++) acc[v] = 0.0f;
+        for (int r = 0; r < n_roots; r++) {
 #pragma unroll
-        for (int k = 0; k < 6; k++) Ft[k] = warp_sum(root ? Fc[k] : 0.0f);
+            for (int q = 0; q < 4; q++) {
+                const vec4 x = *reinterpret_cast<const vec4 *>(ws.red + 16 * r + 4 * q);
+                acc[4 * q] += x.x; acc[4 * q + 1] += x.y; acc[4 * q + 2] += x.z; acc[4 * q + 3] += x.w;
+            }
+        }
+        mt = acc[0]; ht[0] = acc[1]; ht[1] = acc[2]; ht[2] = acc[3];
+#pragma unroll
+        for (int k = 0; k < 6; k++) { It[k] = acc[4 + k]; Ft[k] = acc[10 + k]; }
+        warp_sync();
     }
 
     // ---- bias force of this lane's coordinate and f = Ic s (column of M restricted to ancestors)
