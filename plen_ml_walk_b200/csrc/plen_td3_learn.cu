@@ -9,8 +9,9 @@
 //
 // At the reference's batch of 100 every matrix product is tiny (100 x 256 x 256): the step is bound by launch and
 // dependency latency, not by FLOPs, so the products run on the FP32 CUDA cores in one strided GEMM kernel with fused
-// epilogues (bias / ReLU / tanh / ReLU-mask / tanh-gradient / bias-gradient) -- 17 launches for a critic-only update, 35
-// with the policy update, all enqueued from C on the caller's stream (no host sync, no allocation).  fp32 keeps the
+// epilogues (bias / ReLU / tanh / ReLU-mask / tanh-gradient / bias-gradient) -- 18 kernels for a critic-only update, 36
+// with the policy update, captured once as a CUDA graph by plen_td3_train and replayed with one launch per update on
+// the caller's stream (no host sync, no allocation).  fp32 keeps the
 // update within 1e-5 of the reference's torch arithmetic (tests/test_td3_gpu.py).
 #include <cuda_runtime.h>
 #include <math.h>
@@ -41,6 +42,14 @@ static_assert(ACTOR_N == PLEN_TD3_ACTOR_PARAMS && CRITIC_N == PLEN_TD3_CRITIC_PA
 
 enum { EPI_NONE = 0, EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_TANH, EPI_BIAS_TANH_NOISE, EPI_RELUMASK, EPI_TANHGRAD };
 
+// Per-call scalars of plen_td3_train live in device memory, so that the captured CUDA graph of an update never changes:
+// the draw seed, the current size of the replay ring, and the bias-corrected Adam step sizes of the two optimisers.
+struct CallParams {
+    unsigned long long seed;
+    long long size;
+    float adam_c[2], adam_a[2];      // {lr / (1 - b1^t), 1 / sqrt(1 - b2^t)} of the critic / actor step
+};
+
 struct Gemm {
     // C[z][m][n] = epi( sum_k A(z, m, k) B(z, k, n) ),  A(z,m,k) = a[z az + m am + k ak],  B(z,k,n) = b[z bz + k bk + n bn]
     const float *a, *b;
@@ -53,6 +62,7 @@ struct Gemm {
     float p0, p1, p2;                              // max_action, policy_noise, noise_clip
     unsigned long long seed;
     float *rowsum; long long rowsum_z;             // nullable: rowsum[z][m] = sum_k A(z, m, k)   (bias gradient of a dW product)
+    const CallParams *cp;                          // nullable: seed read from device memory (graph replay) instead of `seed`
     int splits, k_chunk;                           // split-K (dW products of large minibatches): blockIdx.z = z + nz * split; results are
                                                    // accumulated with atomicAdd into a zeroed C / rowsum
 };
@@ -149,7 +159,8 @@ __global__ void __launch_bounds__(GT) k_gemm(const Gemm g) {
                     float nz;
                     if (g.aux) nz = g.aux[z * g.aux_z + m * g.ld_aux + n];
                     else {
-                        const uint64_t ctr = g.seed * 0x100000001B3ull + (uint64_t)m * 64u + (uint64_t)n;
+                        const uint64_t sd = g.cp ? g.cp->seed : g.seed;
+                        const uint64_t ctr = sd * 0x100000001B3ull + (uint64_t)m * 64u + (uint64_t)n;
                         const float u1 = (mix32(ctr) + 1.0f) * 2.3283064e-10f, u2 = mix32(ctr ^ 0x5DEECE66D1234567ull) * 2.3283064e-10f;
                         nz = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
                     }
@@ -174,9 +185,11 @@ __global__ void __launch_bounds__(GT) k_gemm(const Gemm g) {
 // minibatch rows drawn uniformly with replacement (td3.py:175), written as the concatenated critic inputs:
 // sa = [s | a], s2a = [s' | .] (the action columns are filled by the target actor), spi = [s | .] (filled by the actor)
 __global__ void k_sample_sa(const float *__restrict__ store, long long size, int batch, uint64_t seed, float *__restrict__ sa,
-                            float *__restrict__ s2a, float *__restrict__ spi, float *__restrict__ r, float *__restrict__ nd) {
+                            float *__restrict__ s2a, float *__restrict__ spi, float *__restrict__ r, float *__restrict__ nd,
+                            const CallParams *cp) {
     const int bi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (bi >= batch) return;
+    if (cp) { size = cp->size; seed = cp->seed * 2654435761ull + 1ull; }      // plen_td3_train's draw, from device memory
     const uint32_t u = mix32(seed * 0x100000001B3ull + (uint64_t)bi);
     const long long row = (long long)(((uint64_t)u * (uint64_t)size) >> 32);
     const float *t = store + row * 72;
@@ -242,9 +255,11 @@ __global__ void k_actor_loss(int batch, const float *__restrict__ q, float *__re
 // torch.optim.Adam (td3.py:226-233: lr 3e-4, default betas / eps, no weight decay), same operation order as torch's
 // single-tensor path: m.lerp_(g, 1 - b1); v = v b2 + (1 - b2) g g; p -= (lr / bc1) m / (sqrt(v) / sqrt(bc2) + eps)
 __global__ void k_adam(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, int n,
-                       float one_minus_b1, float b2, float one_minus_b2, float step_size, float inv_bc2_sqrt, float eps) {
+                       float one_minus_b1, float b2, float one_minus_b2, float step_size, float inv_bc2_sqrt, float eps,
+                       const float *sc) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (sc) { step_size = sc[0]; inv_bc2_sqrt = sc[1]; }      // graph replay: the step-dependent scalars come from device memory
     const float gi = g[i];
     const float mi = m[i] + (gi - m[i]) * one_minus_b1;
     const float vi = v[i] * b2 + one_minus_b2 * gi * gi;
@@ -326,6 +341,13 @@ struct plen_td3 {
     float *c_h1, *c_h2, *q, *dq, *dh2, *dh1;
     float *a_h1, *a_h2, *p_h1, *p_h2, *qpi, *dqpi, *dp_h2, *dp_h1, *da3, *da_h2, *da_h1;
     long long launches;
+    // plen_td3_train: per-call scalars in device memory + one captured CUDA graph per update kind (critic only / with policy)
+    CallParams *d_cp;
+    bool use_cp;                        // the piecewise entry points read seed / ring size / Adam scalars from d_cp
+    cudaStream_t cap;                   // capture stream
+    cudaGraphExec_t exec[2];
+    unsigned long long key[2];          // hash of everything a captured graph bakes in (pointers, batch, hyper-parameters)
+    int nodes[2];
 };
 
 extern "C" {
@@ -368,6 +390,11 @@ plen_td3 *plen_td3_create(int max_batch, int device) {
     t->a_h1 = take(Bm * H); t->a_h2 = take(Bm * H); t->p_h1 = take(Bm * H); t->p_h2 = take(Bm * H);
     t->qpi = take(Bm); t->dqpi = take(Bm); t->dp_h2 = take(Bm * H); t->dp_h1 = take(Bm * H); t->da3 = take(Bm * A);
     t->da_h2 = take(Bm * H); t->da_h1 = take(Bm * H);
+    if (cudaMalloc(&t->d_cp, sizeof(CallParams)) != cudaSuccess || cudaStreamCreateWithFlags(&t->cap, cudaStreamNonBlocking) != cudaSuccess) {
+        plen_td3_set_error(PLEN_E_CUDA, "plen_td3_create: call-parameter buffer / capture stream", "");
+        cudaFree(t->ws); delete t;
+        return nullptr;
+    }
     if ((size_t)(p - t->ws) != words) { plen_td3_set_error(PLEN_E_STATE, "plen_td3_create: workspace carve mismatch", ""); cudaFree(t->ws); delete t; return nullptr; }
     return t;
 }
@@ -375,6 +402,10 @@ plen_td3 *plen_td3_create(int max_batch, int device) {
 void plen_td3_destroy(plen_td3 *t) {
     if (!t) return;
     cudaSetDevice(t->device);
+    for (int k = 0; k < 2; k++)
+        if (t->exec[k]) cudaGraphExecDestroy(t->exec[k]);
+    if (t->cap) cudaStreamDestroy(t->cap);
+    cudaFree(t->d_cp);
     cudaFree(t->ws);
     delete t;
 }
@@ -387,7 +418,7 @@ int plen_td3_sample(plen_td3 *t, plen_replay *rb, int batch, unsigned long long 
     if (size <= 0) return plen_td3_set_error(PLEN_E_STATE, "plen_td3_sample: the replay buffer is empty", "");
     LCK(cudaSetDevice(t->device));
     k_sample_sa<<<(batch * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(plen_replay_storage(rb), size, batch, seed, t->sa, t->s2a,
-                                                                          t->spi, t->r, t->nd);
+                                                                          t->spi, t->r, t->nd, t->use_cp ? t->d_cp : nullptr);
     t->batch = batch; t->launches += 1;
     LCK(cudaGetLastError());
     return PLEN_OK;
@@ -421,7 +452,7 @@ int plen_td3_critic_grads(plen_td3 *t, const plen_td3_params *P, const plen_td3_
     n += launch(fwd(t->at_h1, H, 0, at + AW2, H, 0, at + AB2, t->at_h2, H, 0, B, H, H, 1, EPI_BIAS_RELU), st);
     {
         Gemm g = fwd(t->at_h2, H, 0, at + AW3, H, 0, at + AB3, t->s2a + S, SA, 0, B, A, H, 1, EPI_BIAS_TANH_NOISE);
-        g.p0 = h->max_action; g.p1 = h->policy_noise; g.p2 = h->noise_clip; g.seed = seed; g.aux = noise_dev; g.ld_aux = A;
+        g.p0 = h->max_action; g.p1 = h->policy_noise; g.p2 = h->noise_clip; g.seed = seed; g.aux = noise_dev; g.ld_aux = A; g.cp = t->use_cp ? t->d_cp : nullptr;
         n += launch(g, st);
     }
     const float *ct = P->critic_target;
@@ -491,18 +522,30 @@ int plen_td3_actor_grads(plen_td3 *t, const plen_td3_params *P, const plen_td3_h
     return PLEN_OK;
 }
 
+// scalars as torch computes them (python doubles, torch/optim/adam.py _single_tensor_adam), then cast to float32
+static void adam_scalars(const plen_td3_hyper *h, long long step, float out[2]) {
+    const double bc1 = 1.0 - pow((double)h->beta1, (double)step), bc2 = 1.0 - pow((double)h->beta2, (double)step);
+    out[0] = (float)((double)h->lr / bc1);
+    out[1] = (float)(1.0 / sqrt(bc2));
+}
+
+// sc (nullable): device pointer to {step size, 1 / sqrt(bias correction 2)}; overrides the values computed from `step`
+static int adam_launch(float *param_dev, const float *grad_dev, float *m_dev, float *v_dev, int n, long long step,
+                       const plen_td3_hyper *h, int device, cudaStream_t st, const float *sc) {
+    LCK(cudaSetDevice(device));
+    float s2[2];
+    adam_scalars(h, step, s2);
+    k_adam<<<(n + 255) / 256, 256, 0, st>>>(param_dev, grad_dev, m_dev, v_dev, n, 1.0f - h->beta1, h->beta2, 1.0f - h->beta2, s2[0],
+                                           s2[1], h->eps, sc);
+    LCK(cudaGetLastError());
+    return PLEN_OK;
+}
+
 int plen_td3_adam(float *param_dev, const float *grad_dev, float *m_dev, float *v_dev, int n, long long step,
                   const plen_td3_hyper *h, int device, void *stream) {
     if (!param_dev || !grad_dev || !m_dev || !v_dev || n <= 0 || step <= 0 || !h)
         return plen_td3_set_error(PLEN_E_ARG, "plen_td3_adam: bad arguments", "");
-    LCK(cudaSetDevice(device));
-    // scalars as torch computes them (python doubles, torch/optim/adam.py _single_tensor_adam), then cast to float32
-    const double bc1 = 1.0 - pow((double)h->beta1, (double)step), bc2 = 1.0 - pow((double)h->beta2, (double)step);
-    const float step_size = (float)((double)h->lr / bc1), inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
-    k_adam<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(param_dev, grad_dev, m_dev, v_dev, n, 1.0f - h->beta1, h->beta2,
-                                                             1.0f - h->beta2, step_size, inv_bc2_sqrt, h->eps);
-    LCK(cudaGetLastError());
-    return PLEN_OK;
+    return adam_launch(param_dev, grad_dev, m_dev, v_dev, n, step, h, device, (cudaStream_t)stream, nullptr);
 }
 
 int plen_td3_soft_update(float *target_dev, const float *source_dev, int n, float tau, int device, void *stream) {
@@ -513,29 +556,83 @@ int plen_td3_soft_update(float *target_dev, const float *source_dev, int n, floa
     return PLEN_OK;
 }
 
+// the whole update enqueued on st, every per-call scalar read from t->d_cp (so the sequence can be captured once)
+static int enqueue_train(plen_td3 *t, const plen_td3_params *P, const plen_td3_hyper *h, plen_replay *rb, int batch, bool policy,
+                         float *losses_dev, cudaStream_t st) {
+    int rc;
+    t->use_cp = true;
+    do {
+        if (rb) { rc = plen_td3_sample(t, rb, batch, 0, st); if (rc) break; }
+        rc = plen_td3_critic_grads(t, P, h, nullptr, 0, losses_dev ? losses_dev + 1 : nullptr, st);
+        if (rc) break;
+        rc = adam_launch(P->critic, P->critic_grad, P->critic_m, P->critic_v, CRITIC_N, 1, h, t->device, st, t->d_cp->adam_c);
+        if (rc) break;
+        t->launches += 1;
+        if (policy) {       // delayed policy update, td3.py:339-360
+            rc = plen_td3_actor_grads(t, P, h, losses_dev, st);
+            if (rc) break;
+            rc = adam_launch(P->actor, P->actor_grad, P->actor_m, P->actor_v, ACTOR_N, 1, h, t->device, st, t->d_cp->adam_a);
+            if (rc) break;
+            rc = plen_td3_soft_update(P->critic_target, P->critic, CRITIC_N, h->tau, t->device, st);
+            if (rc) break;
+            rc = plen_td3_soft_update(P->actor_target, P->actor, ACTOR_N, h->tau, t->device, st);
+            if (rc) break;
+            t->launches += 3;
+        }
+    } while (0);
+    t->use_cp = false;
+    return rc;
+}
+
+static unsigned long long mix_key(unsigned long long k, unsigned long long v) {
+    k ^= v + 0x9E3779B97F4A7C15ull + (k << 6) + (k >> 2);
+    return k;
+}
+
 int plen_td3_train(plen_td3 *t, const plen_td3_params *P, const plen_td3_hyper *h, plen_replay *rb, int batch, long long total_it,
                    long long critic_step, long long actor_step, unsigned long long seed, float *losses_dev, void *stream) {
     if (!t || !P || !h || total_it <= 0 || critic_step <= 0 || h->policy_freq <= 0)
         return plen_td3_set_error(PLEN_E_ARG, "plen_td3_train: bad arguments", "");
-    int rc;
-    if (rb) { rc = plen_td3_sample(t, rb, batch, seed * 2654435761ull + 1ull, stream); if (rc) return rc; }
-    rc = plen_td3_critic_grads(t, P, h, nullptr, seed, losses_dev ? losses_dev + 1 : nullptr, stream);
-    if (rc) return rc;
-    rc = plen_td3_adam(P->critic, P->critic_grad, P->critic_m, P->critic_v, CRITIC_N, critic_step, h, t->device, stream);
-    if (rc) return rc;
-    t->launches += 1;
-    if (total_it % h->policy_freq == 0) {       // delayed policy update, td3.py:339-360
-        if (actor_step <= 0) return plen_td3_set_error(PLEN_E_ARG, "plen_td3_train: actor_step <= 0 on a policy update", "");
-        rc = plen_td3_actor_grads(t, P, h, losses_dev, stream);
-        if (rc) return rc;
-        rc = plen_td3_adam(P->actor, P->actor_grad, P->actor_m, P->actor_v, ACTOR_N, actor_step, h, t->device, stream);
-        if (rc) return rc;
-        rc = plen_td3_soft_update(P->critic_target, P->critic, CRITIC_N, h->tau, t->device, stream);
-        if (rc) return rc;
-        rc = plen_td3_soft_update(P->actor_target, P->actor, ACTOR_N, h->tau, t->device, stream);
-        if (rc) return rc;
-        t->launches += 3;
+    const bool policy = total_it % h->policy_freq == 0;
+    if (policy && actor_step <= 0) return plen_td3_set_error(PLEN_E_ARG, "plen_td3_train: actor_step <= 0 on a policy update", "");
+    if (rb && (batch <= 0 || batch > t->max_batch)) return plen_td3_set_error(PLEN_E_ARG, "plen_td3_train: bad batch", "");
+    if (rb && plen_replay_size(rb) <= 0) return plen_td3_set_error(PLEN_E_STATE, "plen_td3_train: the replay buffer is empty", "");
+    LCK(cudaSetDevice(t->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // per-call scalars -> device memory (a small pageable copy is staged before the call returns)
+    CallParams cp;
+    cp.seed = seed; cp.size = rb ? plen_replay_size(rb) : 0;
+    adam_scalars(h, critic_step, cp.adam_c);
+    adam_scalars(h, policy ? actor_step : 1, cp.adam_a);
+    LCK(cudaMemcpyAsync(t->d_cp, &cp, sizeof cp, cudaMemcpyHostToDevice, st));
+    // One CUDA graph per update kind: 18 / 36 kernel nodes replayed with one launch.  Everything the graph bakes in is
+    // hashed; a change (new buffers, batch, hyper-parameters) re-captures.
+    unsigned long long key = 0x1234;
+    const void *ptrs[] = {P->actor, P->actor_target, P->critic, P->critic_target, P->actor_m, P->actor_v, P->critic_m, P->critic_v,
+                          P->actor_grad, P->critic_grad, losses_dev, rb ? (const void *)plen_replay_storage(rb) : nullptr};
+    for (const void *q : ptrs) key = mix_key(key, (unsigned long long)(uintptr_t)q);
+    const float hf[] = {h->discount, h->tau, h->policy_noise, h->noise_clip, h->max_action, h->beta1, h->beta2, h->eps};
+    for (float f : hf) { unsigned u; memcpy(&u, &f, 4); key = mix_key(key, u); }
+    key = mix_key(key, (unsigned long long)(rb ? batch : t->batch));
+    const int kind = policy ? 1 : 0;
+    if (!t->exec[kind] || t->key[kind] != key) {
+        if (t->exec[kind]) { cudaGraphExecDestroy(t->exec[kind]); t->exec[kind] = nullptr; }
+        cudaGraph_t graph = nullptr;
+        LCK(cudaStreamBeginCapture(t->cap, cudaStreamCaptureModeRelaxed));
+        const long long l0 = t->launches;
+        const int rc = enqueue_train(t, P, h, rb, batch, policy, losses_dev, t->cap);
+        const cudaError_t ce = cudaStreamEndCapture(t->cap, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return plen_td3_set_error(PLEN_E_CUDA, "plen_td3_train: graph capture: ", cudaGetErrorString(ce));
+        t->nodes[kind] = (int)(t->launches - l0);
+        t->launches = l0;
+        const cudaError_t ie = cudaGraphInstantiate(&t->exec[kind], graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { t->exec[kind] = nullptr; return plen_td3_set_error(PLEN_E_CUDA, "plen_td3_train: graph instantiate: ", cudaGetErrorString(ie)); }
+        t->key[kind] = key;
     }
+    LCK(cudaGraphLaunch(t->exec[kind], st));
+    t->launches += t->nodes[kind];
     return PLEN_OK;
 }
 

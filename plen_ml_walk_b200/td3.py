@@ -11,8 +11,8 @@ keys fc1..fc3 / fc1..fc6) load unchanged.  What runs where:
                       optional exploration noise + clip (plen_td3.py:101-104) in the same kernel.
   * train             the reference's update rule (td3.py:259-356) as hand-written CUDA (csrc/plen_td3_learn.cu): strided
                       fp32 GEMM kernel with fused bias / ReLU / tanh / mask / bias-gradient epilogues, fused Adam, fused
-                      Polyak update over flat parameter vectors; 17 launches per critic step, 35 with the policy step,
-                      enqueued from C with no host sync.  train_torch = the same rule in PyTorch (test reference only).
+                      Polyak update over flat parameter vectors; 18 kernels per critic step, 36 with the policy step,
+                      replayed as one CUDA graph per update, no host sync.  train_torch = the same rule in PyTorch (test reference only).
 
 No CPU fallback for the CUDA pieces.
 """
