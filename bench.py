@@ -65,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -74,9 +74,19 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def wait_first(self, timeout=4.0):
+        """nvidia-smi takes a while to print its first line (longer on an 8-GPU box): block until it does."""
+        t0 = time.time()
+        while self.proc and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
+    def count_in(self, t0, t1):
+        return sum(1 for ts, _ in self.rows if t0 <= ts <= t1)
+
+    def stop(self, t0=None, t1=None):
+        """Median SM clock / throttle reasons of the samples taken in [t0, t1] (all samples when no window is given)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -86,7 +96,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for ts, r in self.rows if t0 is None or t0 <= ts <= t1]
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for k, nme in enumerate(names):
@@ -190,18 +201,32 @@ def main():
     # ---- device-resident leg: K steps, each bracketed by CUDA events on the launching stream, L2 flushed in between
     env.profile_enable(K)
     sampler = ClockSampler(local_rank)
+    sampler.start()
+    sampler.wait_first()              # nvidia-smi needs a moment before its first sample: do not let it eat the timed region
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     launches0 = env.launches
     barrier()
-    sampler.start()
+    t_w0 = time.time()
     for k in range(K):
         flush.zero_()
         ev[k][0].record()
         env.step(acts[k % 8])
         ev[k][1].record()
     barrier()
-    clocks = sampler.stop()
-    gpu_launches = env.launches - launches0
+    t_w1 = time.time()
+    launches1 = env.launches
+    # a short timed region (K x 7 ms) spans only a few 50 ms sampling periods: keep the SAME load on, untimed, until at
+    # least five samples under load exist, and say so
+    extra = 0
+    while sampler.proc and sampler.count_in(t_w0, time.time()) < 5 and time.time() - t_w1 < 2.0:
+        env.step(acts[extra % 8])
+        torch.cuda.synchronize(dev)
+        extra += 1
+    clocks = sampler.stop(t_w0, time.time())
+    clocks["samples_in_timed_region"] = sampler.count_in(t_w0, t_w1)
+    if extra:
+        clocks["note"] = "%d untimed steps of the same workload appended to collect samples under load" % extra
+    gpu_launches = launches1 - launches0
     prof = env.profile_read()
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     total_ms = max_over_ranks(total_ms, dist, dev)
