@@ -288,6 +288,25 @@ def main():
             "kernel_ms_per_step": {"k_dyn": prof["ms_dyn"] / max(1, prof["steps"]), "k_solve": prof["ms_solve"] / max(1, prof["steps"]),
                                    "k_post": prof["ms_post"] / max(1, prof["steps"])},
         }
+        if world == 1:
+            # BASELINE config 2 (4,096 robots on one GPU) in the same run, device-resident, CUDA events: the grid of this size
+            # under-fills 148 SMs (one wave of solver warps), so it is reported next to the headline, not instead of it
+            e2 = PlenVecEnv(4096, device=dev)
+            a2 = [torch.empty((4096, 18), device=dev).uniform_(-1, 1, generator=gen) for _ in range(8)]
+            e2.reset()
+            for w in range(10):
+                e2.step(a2[w % 8])
+            torch.cuda.synchronize(dev)
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for k in range(200):
+                e2.step(a2[k % 8])
+            s1.record()
+            torch.cuda.synchronize(dev)
+            ms2 = s0.elapsed_time(s1) / 200
+            line["other_configs"] = {"config2_4096_envs": {"value": 4096 / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2, "steps": 200,
+                                                          "note": "BASELINE configs[1]; back-to-back steps, no L2 flush (working set 28 MB)"}}
+            e2.close()
         if not args.no_cpu_baseline and world == 1:
             cores = len(os.sched_getaffinity(0))
             probe, _, _ = cpu_port_throughput(cores, 8, 4, seed=1)
