@@ -70,7 +70,7 @@ def model_to_c(model: PlenModel) -> PlenModelC:
 
 
 EXPORTS = (
-    "plen_version", "plen_default_config", "plen_create", "plen_destroy", "plen_last_error", "plen_num_envs",
+    "plen_version", "plen_default_config", "plen_create", "plen_destroy", "plen_last_error", "plen_num_envs", "plen_kernel_launches",
     "plen_reset", "plen_step", "plen_step_host", "plen_get_state", "plen_set_state", "plen_set_env_scales", "plen_tick",
     "plen_debug_dynamics", "plen_debug_records", "plen_gait_ik", "plen_profile_enable", "plen_profile_read", "plen_measure_fp32_peak",
     "plen_replay_create", "plen_replay_destroy", "plen_replay_size", "plen_replay_ptr", "plen_replay_storage",
@@ -116,6 +116,8 @@ def load_library(path: str = LIB_PATH):
     L.plen_last_error.argtypes = [vp]
     L.plen_last_error.restype = C.c_char_p
     L.plen_num_envs.argtypes = [vp]
+    L.plen_kernel_launches.argtypes = [vp]
+    L.plen_kernel_launches.restype = C.c_ulonglong
     L.plen_reset.argtypes = [vp, vp, vp, vp]
     L.plen_step.argtypes = [vp] * 8
     L.plen_step_host.argtypes = [vp] * 6

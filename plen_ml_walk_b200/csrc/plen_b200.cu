@@ -23,6 +23,9 @@ using namespace plen;
 
 // warps per CTA of the warp-per-robot kernels (k_dyn, k_post)
 #define DYN_WPC 4
+#ifndef PLEN_FAN_MAX_N
+#define PLEN_FAN_MAX_N 4096     // plen_step of at most this many robots runs as PLEN_HOST_PIPE concurrent ranges (0: never)
+#endif
 #ifndef PLEN_HOST_PIPE
 #define PLEN_HOST_PIPE 4      // ranges plen_step_host pipelines (copy of one range under the kernels of the others)
 #endif
@@ -42,7 +45,9 @@ struct plen_ctx {
     float *d_act, *d_obs, *d_rew;
     uint8_t *d_done, *d_tmo;
     cudaStream_t stream;
-    cudaStream_t pipe[PLEN_HOST_PIPE];      // pipe[0] == stream; ranges of plen_step_host
+    cudaStream_t pipe[PLEN_HOST_PIPE];      // pipe[0] == stream; ranges of plen_step_host / of a fanned-out small plen_step
+    cudaEvent_t fan_fork, fan_join[PLEN_HOST_PIPE];
+    unsigned long long launches;            // kernels launched by plen_reset / plen_step / plen_step_host / plen_tick (plen_kernel_launches)
     // optional per-kernel timing of plen_step (plen_profile_enable): 2*substeps+2 events per recorded step
     cudaEvent_t *prof_ev;
     int prof_cap, prof_steps;
@@ -460,6 +465,7 @@ static void launch_ticks(plen_ctx *ctx, float *state, int n, const float *action
         const int nt = rank_tiles(n);
         k_rank<<<nt, RANK_TILE, 0, st>>>(key, n, perm);
         k_solve<<<nt * (RANK_TILE / PLEN_SOLVE_ROBOTS), 32, SOLVE_SMEM, st>>>(ctx->dc, srec, perm, state, n, nt);
+        ctx->launches += 3;
     }
 }
 
@@ -472,6 +478,7 @@ static void launch_step_range(plen_ctx *ctx, size_t off, int cnt, const float *a
     k_post<<<dyn_grid(cnt), DYN_WPC * 32, DYN_SMEM, st>>>(ctx->dc, ctx->d_tab, state, cnt, obs_dev + off * PLEN_OBS, reward_dev + off,
                                                          done_dev + off, timeout_dev ? timeout_dev + off : nullptr,
                                                          terminal_obs_dev ? terminal_obs_dev + off * PLEN_OBS : nullptr, ctx->d_snapshot);
+    ctx->launches += 1;
     if (ev) cudaEventRecord(ev[nev - 1], st);
 }
 
@@ -486,6 +493,7 @@ int plen_default_config(plen_config *cfg, int joint_act) {
 
 const char *plen_last_error(const plen_ctx *ctx) { return ctx ? ctx->err : g_err; }
 int plen_num_envs(const plen_ctx *ctx) { return ctx ? ctx->n : 0; }
+unsigned long long plen_kernel_launches(const plen_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 void plen_destroy(plen_ctx *ctx) {
     if (!ctx) return;
@@ -494,6 +502,9 @@ void plen_destroy(plen_ctx *ctx) {
     cudaFree(ctx->d_act); cudaFree(ctx->d_obs); cudaFree(ctx->d_rew); cudaFree(ctx->d_done); cudaFree(ctx->d_tmo);
     for (int k = 1; k < PLEN_HOST_PIPE; k++)
         if (ctx->pipe[k]) cudaStreamDestroy(ctx->pipe[k]);
+    if (ctx->fan_fork) cudaEventDestroy(ctx->fan_fork);
+    for (int k = 0; k < PLEN_HOST_PIPE; k++)
+        if (ctx->fan_join[k]) cudaEventDestroy(ctx->fan_join[k]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->prof_ev) {
         for (int i = 0; i < ctx->prof_cap * (2 * ctx->cfg.substeps + 2); i++) cudaEventDestroy(ctx->prof_ev[i]);
@@ -515,6 +526,8 @@ static int create_impl(plen_ctx *ctx) {
     CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ctx->pipe[0] = ctx->stream;
     for (int k = 1; k < PLEN_HOST_PIPE; k++) CK(ctx, cudaStreamCreateWithFlags(&ctx->pipe[k], cudaStreamNonBlocking));
+    CK(ctx, cudaEventCreateWithFlags(&ctx->fan_fork, cudaEventDisableTiming));
+    for (int k = 0; k < PLEN_HOST_PIPE; k++) CK(ctx, cudaEventCreateWithFlags(&ctx->fan_join[k], cudaEventDisableTiming));
     float tab[T_ROWS * 32], rec[PLEN_STATE_WORDS];
     build_table(&ctx->model, &ctx->cfg, tab);
     build_devconfig(&ctx->model, &ctx->cfg, &ctx->dc, &ctx->er);
@@ -572,6 +585,7 @@ int plen_reset(plen_ctx *ctx, const uint8_t *mask_dev, float *obs_dev, void *str
     if (!ctx) return fail(nullptr, PLEN_E_ARG, "ctx is NULL");
     CK(ctx, cudaSetDevice(ctx->device));
     k_reset<<<(ctx->n * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->d_state, ctx->n, mask_dev, ctx->d_snapshot, obs_dev);
+    ctx->launches += 1;
     CK(ctx, cudaGetLastError());
     return PLEN_OK;
 }
@@ -584,7 +598,26 @@ int plen_step(plen_ctx *ctx, const float *actions_dev, float *obs_dev, float *re
     cudaStream_t st = (cudaStream_t)stream;
     const int nev = 2 * ctx->cfg.substeps + 2;
     cudaEvent_t *ev = (ctx->prof_ev && ctx->prof_steps < ctx->prof_cap) ? ctx->prof_ev + (size_t)nev * ctx->prof_steps : nullptr;
-    launch_step_range(ctx, 0, ctx->n, actions_dev, obs_dev, reward_dev, done_dev, timeout_dev, terminal_obs_dev, st, ev, nev);
+    if (!ev && PLEN_FAN_MAX_N > 0 && ctx->n <= PLEN_FAN_MAX_N && ctx->n >= 2 * RANK_TILE) {
+        // A small batch under-fills the device (4,096 robots = 512 solver warps for 1,184 slots) and k_solve is bound by its
+        // row chain, not by throughput: cut the batch into ranges of whole sort tiles on the context's private streams, so
+        // that the k_dyn of one range runs under the k_solve of the others.  Fork / join with events on the caller's stream;
+        // robots are independent, so the results are bit-identical to the single-stream order.
+        size_t chunk = ((size_t)ctx->n + PLEN_HOST_PIPE - 1) / PLEN_HOST_PIPE;
+        chunk = (chunk + RANK_TILE - 1) / RANK_TILE * RANK_TILE;
+        CK(ctx, cudaEventRecord(ctx->fan_fork, st));
+        int used = 0;
+        for (size_t off = 0; off < (size_t)ctx->n; off += chunk, used++) {
+            const size_t cnt = ((size_t)ctx->n - off < chunk) ? (size_t)ctx->n - off : chunk;
+            cudaStream_t s = ctx->pipe[used];
+            CK(ctx, cudaStreamWaitEvent(s, ctx->fan_fork, 0));
+            launch_step_range(ctx, off, (int)cnt, actions_dev, obs_dev, reward_dev, done_dev, timeout_dev, terminal_obs_dev, s, nullptr, 0);
+            CK(ctx, cudaEventRecord(ctx->fan_join[used], s));
+            CK(ctx, cudaStreamWaitEvent(st, ctx->fan_join[used], 0));
+        }
+    } else {
+        launch_step_range(ctx, 0, ctx->n, actions_dev, obs_dev, reward_dev, done_dev, timeout_dev, terminal_obs_dev, st, ev, nev);
+    }
     if (ev) ctx->prof_steps++;
     CK(ctx, cudaGetLastError());
     return PLEN_OK;

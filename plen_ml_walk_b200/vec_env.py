@@ -95,7 +95,6 @@ class PlenVecEnv:
         self._reward = torch.empty(n, dtype=torch.float32, device=dev)
         self._done = torch.empty(n, dtype=torch.uint8, device=dev)
         self._timeout = torch.empty(n, dtype=torch.uint8, device=dev)
-        self.launches = 0          # kernels of ours launched by step()/reset()/tick() (bench.py reports it)
 
     # ---- plumbing
     def _check(self, rc):
@@ -128,8 +127,12 @@ class PlenVecEnv:
             m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
         with torch.cuda.device(self.device):
             self._check(self.lib.plen_reset(self._ctx, self._p(m), self._p(self._obs), self._stream()))
-        self.launches += 1
         return self._obs
+
+    @property
+    def launches(self):
+        """Kernels of ours launched by step()/step_host()/reset()/tick() so far, counted where they are launched (bench.py reports it)."""
+        return int(self.lib.plen_kernel_launches(self._ctx))
 
     def step(self, actions):
         """PlenWalkEnv.step (plen_env.py:638-692) for all N envs in one launch.  Returned tensors are reused buffers."""
@@ -138,7 +141,6 @@ class PlenVecEnv:
             self._check(self.lib.plen_step(self._ctx, self._p(a), self._p(self._obs), self._p(self._reward),
                                            self._p(self._done), self._p(self._timeout), self._p(self._terminal_obs),
                                            self._stream()))
-        self.launches += 3 * int(self.cfg.substeps) + 1
         info = {"terminal_obs": self._terminal_obs, "timeout": self._timeout.bool()}
         return self._obs, self._reward, self._done.bool(), info
 
@@ -150,7 +152,6 @@ class PlenVecEnv:
             return C.c_void_p(x.data_ptr() if isinstance(x, torch.Tensor) else x.ctypes.data)
         self._check(self.lib.plen_step_host(self._ctx, hp(actions_host), hp(obs_host), hp(reward_host), hp(done_host),
                                             hp(timeout_host)))
-        self.launches += 3 * int(self.cfg.substeps) + 1
 
     def profile_enable(self, max_steps):
         """Record CUDA events around every kernel of the next max_steps step() calls (bench.py's roofline leg)."""
@@ -215,7 +216,6 @@ class PlenVecEnv:
         t = self._dev_f32(targets, (self.num_envs, ACT_DIM))
         with torch.cuda.device(self.device):
             self._check(self.lib.plen_tick(self._ctx, self._p(t), int(n_ticks), self._stream()))
-        self.launches += 3 * int(n_ticks)
 
     def debug_records(self):
         """Raw per-env state records [N,96] (word 79 = PGS iterations of the last tick)."""
