@@ -217,3 +217,33 @@ def test_long_permuted_rollout_stays_bit_exact_config5_shard():
         ra, rb = a.debug_records()[perm, :80], b.debug_records()[:, :80]
         same = (ra.view(torch.int32) == rb.view(torch.int32)).all(1)
         assert bool(same.all()), "step %d: %d robots differ from their permuted twins" % (s, int((~same).sum()))
+
+
+@pytest.mark.parametrize("n", [1024, 4096])
+def test_step_captured_in_a_cuda_graph_replays_bit_exact(n):
+    """plen_step launches only kernels on the caller's stream (and, for 2,048-4,096 robots, on the context's streams behind
+    an event fork / join), so a caller may capture it in a CUDA graph: 20 replays equal 20 direct calls bit for bit."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(11)
+    acts = [torch.empty((n, 18), device="cuda").uniform_(-1, 1, generator=g) for _ in range(20)]
+    a, b = _mk(n), _mk(n)
+    _rollout(a, 30, 5)
+    _rollout(b, 30, 5)
+    direct = [_step_out(a, x) for x in acts]
+    static_act = acts[0].clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    state0 = _snapshot(b)
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            out = b.step(static_act)
+    torch.cuda.current_stream().wait_stream(side)
+    b.set_state(*state0)                                        # capture runs nothing, but keep the start state explicit
+    for k, x in enumerate(acts):
+        static_act.copy_(x)
+        graph.replay()
+        obs, rew, done, info = out
+        term = torch.where(done[:, None], info["terminal_obs"], torch.zeros_like(obs))
+        for u, v in zip(direct[k], (obs, rew, done, b._timeout.bool(), term)):
+            assert _same(u, v), "graph replay %d differs from the direct call" % k
