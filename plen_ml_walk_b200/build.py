@@ -30,7 +30,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if p.returncode != 0:
         raise RuntimeError("nvcc failed building libplen_b200.so")
     with open(os.path.join(HERE, "csrc", "ptxas_info.txt"), "w") as f:
-        f.write(p.stderr)
+        # register / spill report of every kernel (tracked: reviewable without a build); compile times would only be noise
+        f.write("".join(l for l in p.stderr.splitlines(True) if "Compile time" not in l))
     return OUT
 
 
