@@ -106,7 +106,7 @@ void plen_destroy(plen_ctx *ctx);
 const char *plen_last_error(const plen_ctx *ctx);
 int plen_num_envs(const plen_ctx *ctx);
 /* Kernels launched so far by plen_reset / plen_step / plen_step_host / plen_tick on this context (13 per step and range:
- * plen_step_host runs up to four ranges, plen_step of 2,048-4,096 robots too); bench.py's gpu_launches reads it. */
+ * plen_step_host runs up to four ranges, plen_step of 2,048 robots or more runs two); bench.py's gpu_launches reads it. */
 unsigned long long plen_kernel_launches(const plen_ctx *ctx);
 
 /* Replaces PlenWalkEnv.reset (plen_env.py:558-614) for the envs whose mask byte is non-zero (NULL = all).

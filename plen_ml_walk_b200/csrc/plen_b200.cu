@@ -24,7 +24,10 @@ using namespace plen;
 // warps per CTA of the warp-per-robot kernels (k_dyn, k_post)
 #define DYN_WPC 4
 #ifndef PLEN_FAN_MAX_N
-#define PLEN_FAN_MAX_N 4096     // plen_step of at most this many robots runs as PLEN_HOST_PIPE concurrent ranges (0: never)
+#define PLEN_FAN_MAX_N (1 << 30)     // plen_step of at most this many (and at least two sort tiles of) robots runs as concurrent ranges (0: never)
+#endif
+#ifndef PLEN_FAN_RANGES
+#define PLEN_FAN_RANGES 2   // ... this many (<= PLEN_HOST_PIPE); measured: 2 beats 3 / 4 at every batch size (profiles/r1_v9_summary.md)
 #endif
 #ifndef PLEN_HOST_PIPE
 #define PLEN_HOST_PIPE 4      // ranges plen_step_host pipelines (copy of one range under the kernels of the others)
@@ -599,11 +602,11 @@ int plen_step(plen_ctx *ctx, const float *actions_dev, float *obs_dev, float *re
     const int nev = 2 * ctx->cfg.substeps + 2;
     cudaEvent_t *ev = (ctx->prof_ev && ctx->prof_steps < ctx->prof_cap) ? ctx->prof_ev + (size_t)nev * ctx->prof_steps : nullptr;
     if (!ev && PLEN_FAN_MAX_N > 0 && ctx->n <= PLEN_FAN_MAX_N && ctx->n >= 2 * RANK_TILE) {
-        // A small batch under-fills the device (4,096 robots = 512 solver warps for 1,184 slots) and k_solve is bound by its
-        // row chain, not by throughput: cut the batch into ranges of whole sort tiles on the context's private streams, so
-        // that the k_dyn of one range runs under the k_solve of the others.  Fork / join with events on the caller's stream;
-        // robots are independent, so the results are bit-identical to the single-stream order.
-        size_t chunk = ((size_t)ctx->n + PLEN_HOST_PIPE - 1) / PLEN_HOST_PIPE;
+        // Cut the batch into two ranges of whole sort tiles on the context's private streams: the k_dyn of one range runs
+        // under the k_solve of the other and each kernel's last partial wave is filled by the other range's work (+4-6 % from
+        // 8,192 to 32,768 robots, +2 % at 65,536, +0.5 % at 131,072).  Fork / join with events on the caller's stream; robots
+        // are independent, so the results are bit-identical to the single-stream order.
+        size_t chunk = ((size_t)ctx->n + PLEN_FAN_RANGES - 1) / PLEN_FAN_RANGES;
         chunk = (chunk + RANK_TILE - 1) / RANK_TILE * RANK_TILE;
         CK(ctx, cudaEventRecord(ctx->fan_fork, st));
         int used = 0;
