@@ -287,8 +287,9 @@ def main():
                                       "latency of the Gauss-Seidel row chain at 2 warps per scheduler, not the pipe"},
             "kernel_ms_per_step": {"k_dyn": prof["ms_dyn"] / max(1, prof["steps"]), "k_solve": prof["ms_solve"] / max(1, prof["steps"]),
                                    "k_post": prof["ms_post"] / max(1, prof["steps"])},
-            "kernel_ms_note": "CUDA-event brackets inside the library on the single-stream order of the step; the timed steps run "
-                              "plen_step as two concurrent ranges (26 launches per step), whose kernels overlap",
+            "kernel_ms_note": "CUDA-event brackets written by the library around every kernel of the timed steps; bracketed steps "
+                              "run in the single-stream order (13 launches per step), an unbracketed plen_step runs as two "
+                              "concurrent ranges (26 launches, +0.5 % at this size, +6 % at 32,768 robots: DESIGN.md)",
         }
         if world == 1:
             # BASELINE config 2 (4,096 robots on one GPU) in the same run, device-resident, CUDA events: the grid of this size
