@@ -126,9 +126,21 @@ int plen_step(plen_ctx *ctx, const float *actions_dev, float *obs_dev, float *re
               uint8_t *timeout_dev, float *terminal_obs_dev, void *stream);
 
 /* Same call with HOST buffers (pinned memory recommended): H2D of the actions, the step, D2H of obs / reward / done,
- * and a stream synchronise.  This is the end-to-end path a PyBullet user would see. */
+ * and a stream synchronise.  This is the end-to-end path a PyBullet user would see.
+ * Ordering contract: the call runs on the context's PRIVATE streams (the batch is pipelined in ranges).  It first waits
+ * (cudaStreamWaitEvent) for the work the last plen_reset / plen_step / plen_set_state / plen_set_env_scales / plen_tick
+ * call queued on its caller stream, so `plen_reset(...); plen_step_host(...)` needs no synchronisation in between; it
+ * returns after its own streams have drained, so whatever the caller queues next is ordered after it.  (Work the caller
+ * queued on a stream WITHOUT going through this library -- e.g. a torch kernel still writing the state through
+ * plen_set_state's source buffer -- is the caller's to order.) */
 int plen_step_host(plen_ctx *ctx, const float *actions_host, float *obs_host, float *reward_host,
                    uint8_t *done_host, uint8_t *timeout_host);
+
+/* Numeric guard (the reference's Bullet env has none, its Gazebo twin shuts ROS down on a NaN
+ * reward, robot_gazebo_env.py:180-185): a robot whose physical state is non-finite after a step is reported done with
+ * reward -100 and reset from the snapshot (even when auto_reset is off).  Returns how many robots that has happened to
+ * since plen_create; synchronises the device. */
+int plen_fault_count(plen_ctx *ctx, unsigned long long *count_host);
 
 /* Replaces getBasePositionAndOrientation / getJointStates / getBaseVelocity (plen_env.py:771-773) and
  * resetBasePositionAndOrientation / resetJointState (plen_env.py:561-565) for all envs; any pointer may be NULL. */

@@ -71,7 +71,7 @@ def model_to_c(model: PlenModel) -> PlenModelC:
 
 EXPORTS = (
     "plen_version", "plen_default_config", "plen_create", "plen_destroy", "plen_last_error", "plen_num_envs", "plen_kernel_launches",
-    "plen_reset", "plen_step", "plen_step_host", "plen_get_state", "plen_set_state", "plen_set_env_scales", "plen_tick",
+    "plen_reset", "plen_step", "plen_step_host", "plen_fault_count", "plen_get_state", "plen_set_state", "plen_set_env_scales", "plen_tick",
     "plen_debug_dynamics", "plen_debug_records", "plen_gait_ik", "plen_profile_enable", "plen_profile_read", "plen_measure_fp32_peak",
     "plen_replay_create", "plen_replay_destroy", "plen_replay_size", "plen_replay_ptr", "plen_replay_storage",
     "plen_replay_add", "plen_replay_sample", "plen_actor_forward", "plen_actor_forward_tc", "plen_actor_tc_timed_out", "plen_td3_last_error",
@@ -121,6 +121,7 @@ def load_library(path: str = LIB_PATH):
     L.plen_reset.argtypes = [vp, vp, vp, vp]
     L.plen_step.argtypes = [vp] * 8
     L.plen_step_host.argtypes = [vp] * 6
+    L.plen_fault_count.argtypes = [vp, C.POINTER(C.c_ulonglong)]
     L.plen_get_state.argtypes = [vp] * 5
     L.plen_set_state.argtypes = [vp] * 5
     L.plen_set_env_scales.argtypes = [vp] * 5

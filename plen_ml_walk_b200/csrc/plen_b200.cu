@@ -47,9 +47,11 @@ struct plen_ctx {
     int *d_perm;     // [n_tiles * RANK_TILE] robots ordered by contact load inside each tile (k_rank -> k_solve)
     float *d_act, *d_obs, *d_rew;
     uint8_t *d_done, *d_tmo;
+    unsigned long long *d_faults;   // robots retired by the numeric guard of k_post (plen_fault_count)
     cudaStream_t stream;
     cudaStream_t pipe[PLEN_HOST_PIPE];      // pipe[0] == stream; ranges of plen_step_host / of a fanned-out small plen_step
     cudaEvent_t fan_fork, fan_join[PLEN_HOST_PIPE];
+    cudaEvent_t last_work;                  // recorded by every entry point that queues work on a caller stream; plen_step_host waits for it
     unsigned long long launches;            // kernels launched by plen_reset / plen_step / plen_step_host / plen_tick (plen_kernel_launches)
     // optional per-kernel timing of plen_step (plen_profile_enable): 2*substeps+2 events per recorded step
     cudaEvent_t *prof_ev;
@@ -211,7 +213,7 @@ __global__ void k_set_scales(float *__restrict__ scale, int n, const float *fric
 __global__ void __launch_bounds__(DYN_WPC * 32)
 k_post(const __grid_constant__ DevConfig dc, const float *__restrict__ tab_g, float *__restrict__ state, int n,
        float *__restrict__ obs, float *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ timeout,
-       float *__restrict__ terminal_obs, const float *__restrict__ snapshot) {
+       float *__restrict__ terminal_obs, const float *__restrict__ snapshot, unsigned long long *__restrict__ faults) {
     DynSmem &sm = stage_table(tab_g);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * DYN_WPC + warp;
@@ -220,7 +222,7 @@ k_post(const __grid_constant__ DevConfig dc, const float *__restrict__ tab_g, fl
     LaneState L;
     load_record(state + (size_t)env * PLEN_STATE_WORDS, ws, L, lane);
     StepIO io{nullptr, obs + (size_t)env * PLEN_OBS, reward + env, done + env, timeout ? timeout + env : nullptr,
-              terminal_obs ? terminal_obs + (size_t)env * PLEN_OBS : nullptr, snapshot};
+              terminal_obs ? terminal_obs + (size_t)env * PLEN_OBS : nullptr, snapshot, faults};
     env_post(dc, sm.tab, ws, L, lane, io);
     store_record(state + (size_t)env * PLEN_STATE_WORDS, ws, L, lane);
 }
@@ -444,10 +446,9 @@ k_fp32_peak(float *out, int iters, int mode, float seed) {
 // ------------------------------------------------------------------------------------------------ C ABI
 static const size_t DYN_SMEM = sizeof(DynSmem);
 static const size_t SOLVE_SMEM = sizeof(float) * PLEN_GS_WORDS * PLEN_SOLVE_ROBOTS;
-static int dyn_grid(int n) { return (n + DYN_WPC - 1) / DYN_WPC; }
 // k_dyn: one CTA per four robots.  (Measured slower: a persistent grid-stride walk, grid = resident CTAs, 3 %; CTAs that walk
 // 2 / 4 / 8 consecutive groups, 1.7 / 3.6 / 4.4 % -- many short CTAs overlap their load phases best.)
-static int dyn_grid_persistent(const plen_ctx *, int n) { return dyn_grid(n); }
+static int dyn_grid(int n) { return (n + DYN_WPC - 1) / DYN_WPC; }
 static int rank_tiles(int n) { return (n + RANK_TILE - 1) / RANK_TILE; }
 
 // n_ticks physics ticks of 1/240 s: (k_dyn, k_solve) per tick.  `actions` (agent space) only on the first tick.
@@ -461,7 +462,7 @@ static void launch_ticks(plen_ctx *ctx, float *state, int n, const float *action
     int *perm = ctx->d_perm + off;
     for (int t = 0; t < n_ticks; t++) {
         if (ev) cudaEventRecord(ev[2 * t], st);
-        k_dyn<<<dyn_grid_persistent(ctx, n), DYN_WPC * 32, DYN_SMEM, st>>>(ctx->dc, ctx->er, ctx->d_tab, state, n, t == 0 ? actions : nullptr,
+        k_dyn<<<dyn_grid(n), DYN_WPC * 32, DYN_SMEM, st>>>(ctx->dc, ctx->er, ctx->d_tab, state, n, t == 0 ? actions : nullptr,
                                                           tgt, srec, key, nullptr, nullptr, nullptr,
                                                           (state == ctx->d_snapshot || !ctx->d_scale) ? nullptr : ctx->d_scale + 4 * off);
         if (ev) cudaEventRecord(ev[2 * t + 1], st);
@@ -480,14 +481,25 @@ static void launch_step_range(plen_ctx *ctx, size_t off, int cnt, const float *a
     if (ev) cudaEventRecord(ev[nev - 2], st);
     k_post<<<dyn_grid(cnt), DYN_WPC * 32, DYN_SMEM, st>>>(ctx->dc, ctx->d_tab, state, cnt, obs_dev + off * PLEN_OBS, reward_dev + off,
                                                          done_dev + off, timeout_dev ? timeout_dev + off : nullptr,
-                                                         terminal_obs_dev ? terminal_obs_dev + off * PLEN_OBS : nullptr, ctx->d_snapshot);
+                                                         terminal_obs_dev ? terminal_obs_dev + off * PLEN_OBS : nullptr, ctx->d_snapshot,
+                                                         ctx->d_faults);
     ctx->launches += 1;
     if (ev) cudaEventRecord(ev[nev - 1], st);
 }
 
+// Remember the last work queued on a caller stream so that plen_step_host (private streams) can order itself after it.
+// A capturing stream is left alone: an event recorded into a graph cannot be waited for from outside the capture.
+static cudaError_t mark_work(plen_ctx *ctx, cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaError_t e = cudaStreamIsCapturing(st, &cs);
+    if (e != cudaSuccess) return e;
+    if (cs != cudaStreamCaptureStatusNone) return cudaSuccess;
+    return cudaEventRecord(ctx->last_work, st);
+}
+
 extern "C" {
 
-const char *plen_version(void) { return "plen_b200 0.2 (sm_100a)"; }
+const char *plen_version(void) { return "plen_b200 0.3 (sm_100a)"; }
 
 int plen_default_config(plen_config *cfg, int joint_act) {
     if (!cfg) return fail(nullptr, PLEN_E_ARG, "cfg is NULL");
@@ -502,10 +514,11 @@ void plen_destroy(plen_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_tab); cudaFree(ctx->d_state); cudaFree(ctx->d_snapshot); cudaFree(ctx->d_srec); cudaFree(ctx->d_tgt); cudaFree(ctx->d_key); cudaFree(ctx->d_perm); cudaFree(ctx->d_scale);
-    cudaFree(ctx->d_act); cudaFree(ctx->d_obs); cudaFree(ctx->d_rew); cudaFree(ctx->d_done); cudaFree(ctx->d_tmo);
+    cudaFree(ctx->d_act); cudaFree(ctx->d_obs); cudaFree(ctx->d_rew); cudaFree(ctx->d_done); cudaFree(ctx->d_tmo); cudaFree(ctx->d_faults);
     for (int k = 1; k < PLEN_HOST_PIPE; k++)
         if (ctx->pipe[k]) cudaStreamDestroy(ctx->pipe[k]);
     if (ctx->fan_fork) cudaEventDestroy(ctx->fan_fork);
+    if (ctx->last_work) cudaEventDestroy(ctx->last_work);
     for (int k = 0; k < PLEN_HOST_PIPE; k++)
         if (ctx->fan_join[k]) cudaEventDestroy(ctx->fan_join[k]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -530,6 +543,7 @@ static int create_impl(plen_ctx *ctx) {
     ctx->pipe[0] = ctx->stream;
     for (int k = 1; k < PLEN_HOST_PIPE; k++) CK(ctx, cudaStreamCreateWithFlags(&ctx->pipe[k], cudaStreamNonBlocking));
     CK(ctx, cudaEventCreateWithFlags(&ctx->fan_fork, cudaEventDisableTiming));
+    CK(ctx, cudaEventCreateWithFlags(&ctx->last_work, cudaEventDisableTiming));
     for (int k = 0; k < PLEN_HOST_PIPE; k++) CK(ctx, cudaEventCreateWithFlags(&ctx->fan_join[k], cudaEventDisableTiming));
     float tab[T_ROWS * 32], rec[PLEN_STATE_WORDS];
     build_table(&ctx->model, &ctx->cfg, tab);
@@ -548,6 +562,8 @@ static int create_impl(plen_ctx *ctx) {
     CK(ctx, cudaMalloc(&ctx->d_rew, sizeof(float) * (size_t)n));
     CK(ctx, cudaMalloc(&ctx->d_done, (size_t)n));
     CK(ctx, cudaMalloc(&ctx->d_tmo, (size_t)n));
+    CK(ctx, cudaMalloc(&ctx->d_faults, sizeof(unsigned long long)));
+    CK(ctx, cudaMemset(ctx->d_faults, 0, sizeof(unsigned long long)));
     CK(ctx, cudaMemcpy(ctx->d_tab, tab, sizeof tab, cudaMemcpyHostToDevice));
     // post-reset snapshot: teleport to the start pose, zero joints and targets, settle for reset_ticks (plen_env.py:561-574)
     init_record(&ctx->cfg, rec);
@@ -590,6 +606,7 @@ int plen_reset(plen_ctx *ctx, const uint8_t *mask_dev, float *obs_dev, void *str
     k_reset<<<(ctx->n * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->d_state, ctx->n, mask_dev, ctx->d_snapshot, obs_dev);
     ctx->launches += 1;
     CK(ctx, cudaGetLastError());
+    CK(ctx, mark_work(ctx, (cudaStream_t)stream));
     return PLEN_OK;
 }
 
@@ -623,6 +640,7 @@ int plen_step(plen_ctx *ctx, const float *actions_dev, float *obs_dev, float *re
     }
     if (ev) ctx->prof_steps++;
     CK(ctx, cudaGetLastError());
+    CK(ctx, mark_work(ctx, st));
     return PLEN_OK;
 }
 
@@ -641,6 +659,9 @@ int plen_step_host(plen_ctx *ctx, const float *actions_host, float *obs_host, fl
     for (size_t off = 0; off < n; off += chunk, used++) {
         const size_t cnt = (n - off < chunk) ? n - off : chunk;
         cudaStream_t st = ctx->pipe[used];
+        // ordering contract (plen_b200.h): this call runs on the context's private streams, so it first waits for whatever
+        // the last stream-taking entry point (reset / step / set_state / set_env_scales / tick) queued on the caller's stream
+        CK(ctx, cudaStreamWaitEvent(st, ctx->last_work, 0));
         CK(ctx, cudaMemcpyAsync(ctx->d_act + off * PLEN_NJ, actions_host + off * PLEN_NJ, sizeof(float) * PLEN_NJ * cnt,
                                 cudaMemcpyHostToDevice, st));
         launch_step_range(ctx, off, (int)cnt, ctx->d_act, ctx->d_obs, ctx->d_rew, ctx->d_done, ctx->d_tmo, nullptr, st, nullptr, 0);
@@ -662,6 +683,15 @@ int plen_set_env_scales(plen_ctx *ctx, const float *friction_scale_dev, const fl
     k_set_scales<<<(ctx->n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ctx->d_scale, ctx->n, friction_scale_dev, motor_force_scale_dev,
                                                                        motor_gain_scale_dev, 0);
     CK(ctx, cudaGetLastError());
+    CK(ctx, mark_work(ctx, (cudaStream_t)stream));
+    return PLEN_OK;
+}
+
+int plen_fault_count(plen_ctx *ctx, unsigned long long *count_host) {
+    if (!ctx || !count_host) return fail(ctx, PLEN_E_ARG, "plen_fault_count: bad arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaDeviceSynchronize());
+    CK(ctx, cudaMemcpy(count_host, ctx->d_faults, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return PLEN_OK;
 }
 
@@ -678,6 +708,7 @@ int plen_set_state(plen_ctx *ctx, const float *qpos_dev, const float *qvel_dev, 
     CK(ctx, cudaSetDevice(ctx->device));
     k_set_state<<<(ctx->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->d_state, ctx->n, qpos_dev, qvel_dev, aux_dev);
     CK(ctx, cudaGetLastError());
+    CK(ctx, mark_work(ctx, (cudaStream_t)stream));
     return PLEN_OK;
 }
 
@@ -690,13 +721,14 @@ int plen_tick(plen_ctx *ctx, const float *targets_dev, int n_ticks, void *stream
                                 (cudaStream_t)stream));
     launch_ticks(ctx, ctx->d_state, ctx->n, nullptr, targets_dev ? ctx->d_tgt : nullptr, n_ticks, (cudaStream_t)stream);
     CK(ctx, cudaGetLastError());
+    CK(ctx, mark_work(ctx, (cudaStream_t)stream));
     return PLEN_OK;
 }
 
 int plen_debug_dynamics(plen_ctx *ctx, float *minv_dev, float *pos_dev, float *rot_dev, void *stream) {
     if (!ctx) return fail(nullptr, PLEN_E_ARG, "ctx is NULL");
     CK(ctx, cudaSetDevice(ctx->device));
-    k_dyn<<<dyn_grid_persistent(ctx, ctx->n), DYN_WPC * 32, DYN_SMEM, (cudaStream_t)stream>>>(ctx->dc, ctx->er, ctx->d_tab, ctx->d_state, ctx->n,
+    k_dyn<<<dyn_grid(ctx->n), DYN_WPC * 32, DYN_SMEM, (cudaStream_t)stream>>>(ctx->dc, ctx->er, ctx->d_tab, ctx->d_state, ctx->n,
                                                                             nullptr, nullptr, ctx->d_srec, ctx->d_key, minv_dev, pos_dev, rot_dev, ctx->d_scale);
     CK(ctx, cudaGetLastError());
     return PLEN_OK;

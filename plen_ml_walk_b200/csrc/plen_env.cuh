@@ -84,6 +84,7 @@ struct StepIO {
     uint8_t *done, *timeout;  // scalars (timeout nullable)
     float *terminal_obs;      // [26] nullable
     const float *snapshot;    // [96 + 26] post-reset record and its observation
+    unsigned long long *faults;   // device counter of numeric faults (nullable)
 };
 
 // env_ranges of plen_env.py:148-167 are kept in double so that the a = +-1 inset branch (plen_env.py:707-711) takes
@@ -138,8 +139,16 @@ PLEN_DEV void env_post(const DevConfig &cfg, const float *tab, WarpScratch &ws, 
     }
     hist += 1;
 
+    // ---- per-env numeric guard (the reference has none): a robot whose physical state went
+    //      non-finite is retired as a fall -- done, the dead penalty alone as its (finite) reward, forced reset from the
+    //      snapshot whether or not auto_reset is on -- and counted (plen_fault_count).  A NaN REWARD out of the 0/0 cosine
+    //      similarity of a finite state is reference behaviour (E5, plen_env.py:929-945) and is left alone.
+    bool fin = isfinite(L.u) && isfinite(L.q);
+    if (lane == 0) fin = fin && isfinite(L.pos[0] + L.pos[1] + L.pos[2] + L.quat[0] + L.quat[1] + L.quat[2] + L.quat[3]);
+    const bool fault = ballot(!fin) != 0u;
+
     // ---- compute_done (:1072-1093), one-sided
-    const bool dead = (roll > 1.0471975511965976f) || (pitch > 1.0471975511965976f) || (z < 0.08f) || (y > 1.0f);
+    const bool dead = fault || (roll > 1.0471975511965976f) || (pitch > 1.0471975511965976f) || (z < 0.08f) || (y > 1.0f);
 
     // ---- compute_reward (:873-1070)
     float r = 0.0f;                                                        // alive_reward = 0 (:65)
@@ -171,6 +180,7 @@ PLEN_DEV void env_post(const DevConfig &cfg, const float *tab, WarpScratch &ws, 
     if (Lc && flatL) r += 0.1f;                                            // :1014-1023
     if (Rc && flatR) r += 0.1f;                                            // :1027-1036
     if (dead) r -= 100.0f;                                                 // :1057-1059
+    if (fault) r = -100.0f;
     // ---- bookkeeping (:674-678) and the TimeLimit wrapper (:15-19)
     epret += r; ept += 1; cnt += 1;
     const bool timeout = !dead && (ept >= cfg.max_episode_steps);
@@ -183,6 +193,11 @@ PLEN_DEV void env_post(const DevConfig &cfg, const float *tab, WarpScratch &ws, 
         *io.reward = r;
         *io.done = done ? 1 : 0;
         if (io.timeout) *io.timeout = timeout ? 1 : 0;
+#ifndef PLEN_HOST_EMU
+        if (fault && io.faults) atomicAdd(io.faults, 1ull);
+#else
+        if (fault && io.faults) *io.faults += 1ull;
+#endif
     }
     if (lane < 6) ws.st[W_LAST + lane] = cur[lane];
     if (lane >= 6 && lane < 15) {
@@ -192,10 +207,10 @@ PLEN_DEV void env_post(const DevConfig &cfg, const float *tab, WarpScratch &ws, 
         ws.st[W_SUMS + (lane - 6)] = v;
     }
     warp_sync();
-    if (done && cfg.auto_reset) {
+    if ((done && cfg.auto_reset) || fault) {
         // the reference caller resets after a terminal step (plen_td3.py:122-129); the reset is deterministic
         // (fixed pose + 8 ticks, plen_env.py:561-570) so the post-reset record is a constant snapshot
-        if (io.terminal_obs && lane < 26) io.terminal_obs[lane] = ws.obs[lane];
+        if (io.terminal_obs && lane < 26) io.terminal_obs[lane] = fault ? io.snapshot[96 + lane] : ws.obs[lane];
         load_record(io.snapshot, ws, L, lane);
         if (lane < 26) io.obs[lane] = io.snapshot[96 + lane];
     } else {

@@ -153,6 +153,12 @@ class PlenVecEnv:
         self._check(self.lib.plen_step_host(self._ctx, hp(actions_host), hp(obs_host), hp(reward_host), hp(done_host),
                                             hp(timeout_host)))
 
+    def fault_count(self):
+        """Robots retired by the numeric guard (non-finite physical state -> done, reward -100, forced reset) so far."""
+        c = C.c_ulonglong()
+        self._check(self.lib.plen_fault_count(self._ctx, C.byref(c)))
+        return int(c.value)
+
     def profile_enable(self, max_steps):
         """Record CUDA events around every kernel of the next max_steps step() calls (bench.py's roofline leg)."""
         self._check(self.lib.plen_profile_enable(self._ctx, int(max_steps)))

@@ -153,7 +153,7 @@ void emu_step(const plen_model *m, const plen_config *c, float *records, const f
             LaneState L;
             load_record(records + 96 * e, ws, L, lane);
             StepIO io{nullptr, obs + 26 * e, reward + e, done + e, timeout ? timeout + e : nullptr,
-                      terminal_obs ? terminal_obs + 26 * e : nullptr, snapshot};
+                      terminal_obs ? terminal_obs + 26 * e : nullptr, snapshot, nullptr};
             env_post(dc, tab.data(), ws, L, lane, io);
             store_record(records + 96 * e, ws, L, lane);
         }

@@ -164,6 +164,55 @@ def test_host_buffer_step_equals_device_step():
         assert _same(x, y)
 
 
+def test_host_step_orders_itself_after_unsynchronised_device_calls():
+    """Ordering contract of plen_step_host (include/plen_b200.h): it runs on the context's private streams and must wait
+    for whatever reset / set_state / step queued on the caller's stream -- no torch.cuda.synchronize() in between."""
+    n = 9000                                            # ranges of 3072 + 3072 + 2856: two of them beyond plen_step's two ranges
+    a, b = _mk(n), _mk(n)
+    _rollout(a, 6, seed=31)
+    snap = _snapshot(a)
+    g = torch.Generator(device="cuda"); g.manual_seed(37)
+    acts = [torch.empty((n, 18), device="cuda").uniform_(-1, 1, generator=g) for _ in range(3)]
+    h_acts = [x.cpu().pin_memory() for x in acts]
+    torch.cuda.synchronize()
+    h_obs = torch.empty((n, 26)).pin_memory(); h_rew = torch.empty(n).pin_memory()
+    h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
+    for rep in range(5):
+        # reference sequence on ONE stream: reset -> set_state -> step -> step
+        a.reset(); a.set_state(*snap)
+        a.step(acts[0])
+        obs, rew, done, _ = a.step(acts[1])
+        obs, rew, done = obs.clone(), rew.clone(), done.clone()
+        # same thing with the last step through the host path, queued right behind the device calls
+        b.reset(); b.set_state(*snap)
+        b.step(acts[0])
+        b.step_host(h_acts[1], h_obs, h_rew, h_done)
+        torch.cuda.synchronize()
+        assert _same(obs.cpu(), h_obs) and _same(rew.cpu(), h_rew) and torch.equal(done.cpu(), h_done.bool()), rep
+
+
+def test_numeric_guard_retires_a_robot_with_a_non_finite_state():
+    """a robot whose state went NaN / Inf is reported done with reward -100, reset from the snapshot
+    (also with auto_reset off) and counted; its neighbours in the batch / solver warp are untouched."""
+    n = 64
+    a, b = _mk(n, auto_reset=False), _mk(n, auto_reset=False)
+    _rollout(a, 5, seed=41)
+    qpos, qvel, aux = _snapshot(a)
+    b.reset(); b.set_state(qpos, qvel, aux)
+    bad_qvel = qvel.clone(); bad_qvel[9, 7] = float("nan"); bad_qvel[40, 2] = float("inf")
+    a.set_state(qpos, bad_qvel, aux)
+    reset_obs = _mk(1).reset().clone()                   # the post-reset observation (a constant)
+    act = torch.zeros((n, 18), device="cuda")
+    oa, ra, da, _ = a.step(act)
+    ob, rb, db, _ = b.step(act)
+    ok = torch.ones(n, dtype=torch.bool, device="cuda"); ok[9] = ok[40] = False
+    assert _same(oa[ok], ob[ok]) and _same(ra[ok], rb[ok]) and torch.equal(da[ok], db[ok])
+    assert bool(da[9]) and bool(da[40]) and float(ra[9]) == -100.0 and float(ra[40]) == -100.0
+    assert torch.isfinite(oa).all() and _same(oa[9], reset_obs[0]) and _same(oa[40], reset_obs[0])
+    assert a.fault_count() == 2 and b.fault_count() == 0
+    assert torch.isfinite(torch.cat([t.flatten() for t in a.get_state()[:2]])).all()
+
+
 def test_box_foot_model_variant_stands_and_steps():
     """plen_new.urdf (box feet, no collision margin, +-1.0 rad limits) through the same kernels: the robot settles on its
     soles at reset (both feet in contact, torso height within 5 mm of the stock model's) and zero joint targets
