@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- PLEN env-steps/sec on B200 (BASELINE.json metric) with roofline, end-to-end and CPU-baseline legs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs-per-gpu E] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--total-envs T | --envs-per-gpu E] [--impl reference]
 
 A "step" is one vectorised env step (1 action -> 4 physics ticks -> obs/reward/done/auto-reset) of every env of the
-rank: 3 launches per tick (k_dyn, k_rank, k_solve) + k_post.  Workload = BASELINE config 5's shard: E = 131072 envs per GPU (1,048,576 envs at 8
-GPUs), actions U(-1,1)^18 drawn on the device with torch.Generator(seed 0 + rank), auto-reset on.  Envs are
-independent, so ranks share nothing on the data path ("scaling": "weak"); torch.distributed (NCCL) is used only for
-the barrier and the max-over-ranks of the device time.
+rank: 3 launches per tick (k_dyn, k_rank, k_solve) + k_post (+ the rare-path k_solve_x).  Workload = BASELINE config 5
+AS WRITTEN: T = 1,048,576 envs in total, split evenly over the N GPUs of the run (all of them on ONE GPU at N = 1:
+7.1 GB of the 180 GB), actions U(-1,1)^18 drawn on the device with torch.Generator(seed 0 + rank), auto-reset on.  The
+total is fixed, so the 1 -> 8 GPU curve is STRONG scaling ("scaling": "strong"); `--envs-per-gpu E` fixes the per-GPU
+size instead (weak scaling; 131,072 is round 1's shard and is reported under other_configs at N = 1).  Envs are
+independent, so ranks share nothing on the data path; torch.distributed (NCCL) is used only for the barrier and the
+max-over-ranks of the device time.
 
-`--impl reference` times the CPU restatement of the reference path (oracle/, float64 C, one thread per host core):
-PyBullet itself is absent from the reference checkout and from this image, so the reference
-arm is the oracle PORT, labelled as such -- never presented as a PyBullet number.
+`--impl reference` times the reference's CPU implementation of the path on the host cores: the reference's own
+PlenWalkEnv on PyBullet (one process per core, kind "pybullet") when `pybullet` is importable (also probed under
+baseline/_ref) and the reference checkout is present; otherwise -- as in this image, where neither exists (SURVEY.md
+section 8c) -- the float64 oracle PORT (oracle/plen_oracle.c, one thread per core), labelled as such and never
+presented as a PyBullet number.
 """
 from __future__ import annotations
 
@@ -37,11 +42,15 @@ TICKS_PER_STEP = 4
 # measured DRAM traffic of one k_solve launch per robot (ncu --set full, profiles/r1_v9_summary.md): it reads the
 # 6.4 KB solve record k_dyn wrote for the tick -- a deliberate trade of HBM bytes for issue slots
 SOLVE_DRAM_BYTES_PER_ROBOT = (207.10e6 + 9.92e6) / 32768
-# executed FP32 work per robot-tick, counted by ncu (smsp__sass_thread_inst_executed_op_{fadd,fmul,ffma}_pred_on, FFMA = 2
+# FROZEN in BASELINE.md ("Work per env-step"): executed FP32 work per robot-tick, counted by ncu (smsp__sass_thread_inst_executed_op_{fadd,fmul,ffma}_pred_on, FFMA = 2
 # flop; 32768-robot capture, profiles/r1_v9_summary.md): k_dyn 44.8 kflop + k_solve 58.1 kflop.  It replaces SURVEY 8d's
 # estimate (0.65-1.6 Mflop per env-step for Bullet's ABA + velocity-space PGS): this solver iterates in the 30-dim
 # operational space, so a row update is 30 FMAs instead of a Jacobian-wide one.
-FLOP_PER_ENV_STEP = 4 * (44.8e3 + 58.1e3)
+FLOP_DYN_PER_ROBOT_TICK, FLOP_SOLVE_PER_ROBOT_TICK = 44.8e3, 58.1e3
+FLOP_PER_ENV_STEP = 4 * (FLOP_DYN_PER_ROBOT_TICK + FLOP_SOLVE_PER_ROBOT_TICK)
+# the same workload through the REFERENCE ALGORITHM (33-link ABA + velocity-space PGS with 24-wide rows), counted by the
+# oracle's instrumented FLOP counter (plen_oracle_state.flops; scripts/oracle_flops.py): 1.34 Mflop per env-step
+REF_ALGO_FLOP_PER_ENV_STEP = 1.34e6
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 
 
@@ -125,28 +134,68 @@ def cpu_port_throughput(n_threads, envs_per_thread, steps, seed=0):
     return n * steps / dt, dt, n
 
 
+def pybullet_throughput(steps, n_procs):
+    """env-steps/s of the reference's own PlenWalkEnv on PyBullet DIRECT, one process per host core (kind "pybullet");
+    None when PyBullet or the reference checkout is not reachable (the case in this image)."""
+    from oracle import pybullet_ref
+    if not pybullet_ref.available():
+        return None
+    return pybullet_ref.timed_throughput(steps, n_procs)
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
-    # one "step" = one vector step of cores*E envs on all host threads; E sized from a probe so a step is ~0.3 s and
-    # the whole --steps K run stays within a few minutes
-    probe, _, _ = cpu_port_throughput(cores, 8, 4, seed=1)
-    per_step = min(0.3, 150.0 / max(1, args.steps))
-    envs_per_thread = int(max(8, min(4096, probe * per_step / cores)))
-    val, dt, n = cpu_port_throughput(cores, envs_per_thread, args.steps + 0, seed=0)
+    pb = None
+    try:
+        pb = pybullet_throughput(max(200, 20 * args.steps), cores)
+    except Exception as e:                                # a broken PyBullet install must not take the arm down
+        sys.stderr.write("pybullet arm failed (%s); falling back to the oracle port\n" % e)
+    if pb is not None:
+        val, dt, n, kind = pb["value"], pb["seconds"], pb["envs"], "pybullet"
+        sample = "%d processes x 1 env x %d steps of the reference's PlenWalkEnv (PyBullet %s, DIRECT)" % (n, pb["steps"], pb["version"])
+    else:
+        # one "step" = one vector step of cores*E envs on all host threads; E sized from a probe so a step is ~0.3 s and
+        # the whole --steps K run stays within a few minutes
+        probe, _, _ = cpu_port_throughput(cores, 8, 4, seed=1)
+        per_step = min(0.3, 150.0 / max(1, args.steps))
+        envs_per_thread = int(max(8, min(4096, probe * per_step / cores)))
+        val, dt, n = cpu_port_throughput(cores, envs_per_thread, args.steps + 0, seed=0)
+        kind = "port"
+        sample = ("%d envs x %d vector steps, oracle/plen_oracle.c float64, %d threads; PyBullet itself is not "
+                  "installable here (SURVEY.md 8c)" % (n, args.steps, cores))
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "config5 shard workload (random actions U(-1,1)^18, auto-reset) on host cores; "
-                               "sample = %d envs x %d steps" % (n, args.steps)},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d envs x %d vector steps, oracle/plen_oracle.c float64, %d threads; PyBullet "
-                                   "itself is not installable here (SURVEY.md 8c)" % (n, args.steps, cores)},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config5 workload (random actions U(-1,1)^18, auto-reset) on host cores; sample = %s" % sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def time_steps(env, acts, K, dev, flush=None):
+    """K back-to-back env steps bracketed by CUDA events on the current stream -> milliseconds per step."""
+    import torch
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tot = 0.0
+    if flush is None:
+        s0.record()
+        for k in range(K):
+            env.step(acts[k % len(acts)])
+        s1.record()
+        torch.cuda.synchronize(dev)
+        return s0.elapsed_time(s1) / K
+    for k in range(K):
+        flush.zero_()
+        s0.record()
+        env.step(acts[k % len(acts)])
+        s1.record()
+        torch.cuda.synchronize(dev)
+        tot += s0.elapsed_time(s1)
+    return tot / K
 
 
 def main():
@@ -154,9 +203,11 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--envs-per-gpu", type=int, default=131072)
+    ap.add_argument("--total-envs", type=int, default=1048576, help="config 5: envs in total, split over the GPUs (strong scaling)")
+    ap.add_argument("--envs-per-gpu", type=int, default=0, help="fix the per-GPU size instead (weak scaling)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -177,20 +228,23 @@ def main():
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
-        os.environ.pop("NCCL_DEBUG", None)               # any NCCL_DEBUG level prints the version banner on stdout: one JSON line only
+        # NCCL_DEBUG is left as the launcher set it (the driver counts ranks from its INFO lines); the JSON line is the
+        # LAST thing rank 0 prints, after the process group is gone
         import torch.distributed as dist_mod
         dist_mod.init_process_group("nccl", device_id=dev)
         dist = dist_mod
 
-    E, K, W = args.envs_per_gpu, args.steps, max(3, args.warmup)
+    weak = args.envs_per_gpu > 0
+    E = args.envs_per_gpu if weak else args.total_envs // world
+    K, W = args.steps, max(3, args.warmup)
     env = PlenVecEnv(E, device=dev)
     gen = torch.Generator(device=dev)
     gen.manual_seed(env_seed(0, rank))
-    acts = [torch.empty((E, 18), device=dev).uniform_(-1, 1, generator=gen) for _ in range(8)]
+    acts = [torch.empty((E, 18), device=dev).uniform_(-1, 1, generator=gen) for _ in range(4)]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MiB > 126 MB L2
     env.reset()
     for w in range(W):
-        env.step(acts[w % 8])
+        env.step(acts[w % 4])
     torch.cuda.synchronize(dev)
 
     def barrier():
@@ -210,16 +264,16 @@ def main():
     for k in range(K):
         flush.zero_()
         ev[k][0].record()
-        env.step(acts[k % 8])
+        env.step(acts[k % 4])
         ev[k][1].record()
     barrier()
     t_w1 = time.time()
     launches1 = env.launches
-    # a short timed region (K x 7 ms) spans only a few 50 ms sampling periods: keep the SAME load on, untimed, until at
-    # least five samples under load exist, and say so
+    # a short timed region spans only a few 50 ms sampling periods: keep the SAME load on, untimed, until at least five
+    # samples under load exist, and say so
     extra = 0
     while sampler.proc and sampler.count_in(t_w0, time.time()) < 5 and time.time() - t_w1 < 2.0:
-        env.step(acts[extra % 8])
+        env.step(acts[extra % 4])
         torch.cuda.synchronize(dev)
         extra += 1
     clocks = sampler.stop(t_w0, time.time())
@@ -231,6 +285,7 @@ def main():
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     total_ms = max_over_ranks(total_ms, dist, dev)
     value = world * E * K / (total_ms * 1e-3)
+    faults = env.fault_count()
 
     # ---- end-to-end leg: HOST pinned buffers through plen_step_host (H2D actions, step, D2H obs/reward/done)
     Ke = max(3, min(K, 10))
@@ -247,69 +302,80 @@ def main():
     e2e_s = time.perf_counter() - t0
     e2e_val = world * E * Ke / max_over_ranks(e2e_s, dist, dev)
 
+    line = None
     if rank == 0:
         peak, peak_src = _peaks()
         import ctypes as C
         tf, mhz = C.c_float(), C.c_float()
         if env.lib.plen_measure_fp32_peak(local_rank, 1, C.byref(tf), C.byref(mhz)) == 0 and tf.value > 0:
-            fp32_peak, fp32_src = float(tf.value), "measured live (plen_measure_fp32_peak, FFMA2 chains, best of 4)"
+            fp32_peak, fp32_src = float(tf.value), "measured live (plen_measure_fp32_peak, FFMA2 chains, best of 4); not in MEASURED_PEAKS.json"
         else:
             fp32_peak, fp32_src = FP32_NOMINAL_TFLOPS, "nominal 148 SM x 128 lanes x 2 x 1.965 GHz"
         step_ms = total_ms / K
         # dominant kernel = k_solve (one launch per physics tick over all E robots): CUDA events recorded around every
         # launch of the timed region by the library itself (plen_profile_enable), on the launching stream
         solve_ms = prof["ms_solve"] / max(1, prof["steps"] * TICKS_PER_STEP)
-        achieved = E * (BYTES_PER_ENV_STEP / TICKS_PER_STEP) / (solve_ms * 1e-3) / 1e9
+        solve_tf = E * FLOP_SOLVE_PER_ROBOT_TICK / (solve_ms * 1e-3) / 1e12
+        step_tf = FLOP_PER_ENV_STEP * value / world / 1e12
+        hbm_achieved = E * (BYTES_PER_ENV_STEP / TICKS_PER_STEP) / (solve_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config5 shard: %d envs/GPU (1,048,576 envs at 8 GPUs), random actions "
-                                   "U(-1,1)^18, auto-reset, 4 ticks/step" % E,
-                       "envs_per_gpu": E, "l2": "256 MiB flush between timed steps"},
+            "config": {"workload": ("config5: %d envs in total over %d GPU(s) = %d envs/GPU, random actions U(-1,1)^18, "
+                                    "auto-reset, 4 ticks/step" % (E * world, world, E)),
+                       "total_envs": E * world, "envs_per_gpu": E, "l2": "256 MiB flush between timed steps"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": E * 18 * 4,
                     "d2h_bytes_per_step": E * (26 * 4 + 4 + 1), "steps": Ke},
             "gpu_launches": gpu_launches,
+            "numeric_faults": faults,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": SOLVE_DRAM_BYTES_PER_ROBOT * E, "peak_source": peak_src, "kernel": "k_solve",
+            # the path is FP32-issue bound, so the primary roofline is the FP32 FMA pipe; the HBM one follows
+            "roofline": {"bound": "fp32", "achieved": solve_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": solve_tf / fp32_peak,
+                         "traffic": SOLVE_DRAM_BYTES_PER_ROBOT * E, "peak_source": fp32_src, "kernel": "k_solve",
                          "kernel_ms_per_launch": solve_ms, "launches_per_step": TICKS_PER_STEP,
-                         "algorithmic_bytes_per_launch": E * BYTES_PER_ENV_STEP / TICKS_PER_STEP,
-                         "bytes_per_env_step": BYTES_PER_ENV_STEP,
-                         "note": "the path is FP32 instruction-issue / dependency-latency bound inside the projected "
-                                 "Gauss-Seidel (DESIGN.md), neither HBM nor tensor bound; traffic = ncu DRAM bytes per "
-                                 "robot (32768-robot capture) x robots per launch"},
-            "roofline_fp32": {"bound": "fp32 FMA pipe (CUDA cores)", "achieved": FLOP_PER_ENV_STEP * value / world / 1e12,
-                              "peak": fp32_peak, "unit": "TFLOP/s", "frac": FLOP_PER_ENV_STEP * value / world / 1e12 / fp32_peak,
-                              "peak_source": fp32_src, "flop_per_env_step": FLOP_PER_ENV_STEP,
-                              "note": "per GPU; executed FADD + FMUL + 2 FFMA thread operations per env-step counted by ncu "
-                                      "(profiles/r1_v9_summary.md) x measured env-steps/s; the limiter is the dependency "
-                                      "latency of the Gauss-Seidel row chain at 2 warps per scheduler, not the pipe"},
+                         "flop_per_launch": E * FLOP_SOLVE_PER_ROBOT_TICK, "flop_per_robot_tick": FLOP_SOLVE_PER_ROBOT_TICK,
+                         "whole_step": {"achieved": step_tf, "frac": step_tf / fp32_peak, "flop_per_env_step": FLOP_PER_ENV_STEP},
+                         "reference_algorithm": {"flop_per_env_step": REF_ALGO_FLOP_PER_ENV_STEP,
+                                                 "equivalent_tflops": REF_ALGO_FLOP_PER_ENV_STEP * value / world / 1e12,
+                                                 "equivalent_frac": REF_ALGO_FLOP_PER_ENV_STEP * value / world / 1e12 / fp32_peak},
+                         "note": "flop = executed FADD + FMUL + 2 FFMA thread operations counted by ncu (frozen in BASELINE.md); "
+                                 "the limiter is the dependency latency of the Gauss-Seidel row chain at 2 warps per scheduler, "
+                                 "not the pipe; reference_algorithm = the same env-steps/s priced at the oracle's instrumented "
+                                 "flop count of Bullet's ABA + velocity-space PGS (this solver does 3.3x less arithmetic for "
+                                 "the same rows); traffic = ncu DRAM bytes per robot (32768-robot capture) x robots per launch"},
+            "roofline_hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak,
+                             "peak_source": peak_src, "kernel": "k_solve",
+                             "algorithmic_bytes_per_launch": E * BYTES_PER_ENV_STEP / TICKS_PER_STEP,
+                             "bytes_per_env_step": BYTES_PER_ENV_STEP, "note": "not the binding roofline of this path"},
             "kernel_ms_per_step": {"k_dyn": prof["ms_dyn"] / max(1, prof["steps"]), "k_solve": prof["ms_solve"] / max(1, prof["steps"]),
                                    "k_post": prof["ms_post"] / max(1, prof["steps"])},
             "kernel_ms_note": "CUDA-event brackets written by the library around every kernel of the timed steps; bracketed steps "
-                              "run in the single-stream order (13 launches per step), an unbracketed plen_step runs as two "
-                              "concurrent ranges (26 launches, +0.5 % at this size, +6 % at 32,768 robots: DESIGN.md)",
+                              "run in the single-stream order, an unbracketed plen_step runs as two concurrent ranges (DESIGN.md); "
+                              "k_solve includes k_rank and the rare-path k_solve_x of the tick",
         }
-        if world == 1:
-            # BASELINE config 2 (4,096 robots on one GPU) in the same run, device-resident, CUDA events: the grid of this size
-            # under-fills 148 SMs (one wave of solver warps), so it is reported next to the headline, not instead of it
-            e2 = PlenVecEnv(4096, device=dev)
-            a2 = [torch.empty((4096, 18), device=dev).uniform_(-1, 1, generator=gen) for _ in range(8)]
-            e2.reset()
-            for w in range(10):
-                e2.step(a2[w % 8])
-            torch.cuda.synchronize(dev)
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record()
-            for k in range(200):
-                e2.step(a2[k % 8])
-            s1.record()
-            torch.cuda.synchronize(dev)
-            ms2 = s0.elapsed_time(s1) / 200
-            line["other_configs"] = {"config2_4096_envs": {"value": 4096 / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2, "steps": 200,
-                                                          "note": "BASELINE configs[1]; back-to-back steps, no L2 flush (working set 28 MB)"}}
-            e2.close()
+    env.close()
+    del env, acts, h_act, h_obs
+    torch.cuda.empty_cache()
+    if rank == 0:
+        if world == 1 and not args.no_other_configs:
+            # the other BASELINE configs that fit this run, device-resident, CUDA events, same seed discipline: round 1's
+            # 131,072-env shard (weak-scaling unit; 256 MiB L2 flush between steps) and config 2 (4,096 envs, which under-fills
+            # 148 SMs -- one wave of solver warps -- so it is reported next to the headline, not instead of it)
+            other = {}
+            for name, n2, k2, fl, note in (
+                    ("config5_shard_131072_envs", 131072, 30, flush, "one of eight shards of config 5 (weak-scaling unit); L2 flushed between steps"),
+                    ("config2_4096_envs", 4096, 200, None, "BASELINE configs[1]; back-to-back steps, no L2 flush (working set 28 MB)")):
+                e2 = PlenVecEnv(n2, device=dev)
+                a2 = [torch.empty((n2, 18), device=dev).uniform_(-1, 1, generator=gen) for _ in range(4)]
+                e2.reset()
+                for w in range(10):
+                    e2.step(a2[w % 4])
+                torch.cuda.synchronize(dev)
+                ms2 = time_steps(e2, a2, k2, dev, fl)
+                other[name] = {"value": n2 / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2, "steps": k2, "note": note}
+                e2.close()
+            line["other_configs"] = other
         if not args.no_cpu_baseline and world == 1:
             cores = len(os.sched_getaffinity(0))
             probe, _, _ = cpu_port_throughput(cores, 8, 4, seed=1)
@@ -319,9 +385,12 @@ def main():
                                     "sample": "%d envs x 48 vector steps (%.1f s of wall time on %d threads), "
                                               "float64 oracle port (oracle/plen_oracle.c); PyBullet itself is not "
                                               "installable here (SURVEY.md 8c)" % (n, dt, cores)}
-        print(json.dumps(line), flush=True)
     if dist:
+        dist.barrier()
         dist.destroy_process_group()
+    if rank == 0:
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

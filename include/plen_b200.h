@@ -37,6 +37,8 @@ extern "C" {
 #define PLEN_QVEL 24
 #define PLEN_AUX_WORDS 29
 #define PLEN_STATE_WORDS 96    /* per-env state record in HBM: 3 x 128 B lines, one word per lane per line */
+#define PLEN_MAX_BOXES 32      /* box colliders besides the two feet (plen.urdf: torso + 30 links): one per lane of a warp */
+#define PLEN_MAX_BOX_POINTS 4  /* box-vs-ground contact points kept per robot and tick (the deepest ones) */
 
 #define PLEN_OK 0
 #define PLEN_E_ARG (-1)
@@ -57,6 +59,16 @@ typedef struct {
     int32_t foot_lane[2];          /* [0] right foot (Bullet link 11), [1] left foot (link 19) */
     float foot_pts[2][4][3];       /* sole contact vertices in the foot body frame */
     float foot_break[2];           /* contact breaking threshold per foot */
+    /* Box colliders of every link except the feet (plen.urdf:504-1274), for the ground contact of knees, hands, torso ...
+     * (in Bullet every link collider hits plane.urdf; the reference's setCollisionFilterPair loops, plen_env.py:355-434,
+     * only concern self-collision).  Bullet link order; pose in the frame of the body (lane) the link is folded into. */
+    int32_t n_boxes;
+    int32_t box_lane[PLEN_MAX_BOXES];      /* 0 = torso body, 6..23 = limb bodies */
+    float box_center[PLEN_MAX_BOXES][3];
+    float box_rot[PLEN_MAX_BOXES][9];      /* row major */
+    float box_half[PLEN_MAX_BOXES][3];     /* half extents */
+    float box_rest[PLEN_MAX_BOXES];        /* factor on config.restitution: 0 for the base link (its restitution stays 0:
+                                              it is not in the changeDynamics loop, plen_env.py:476-481), 1 otherwise */
 } plen_model;
 
 /* Every constant of the path; defaults = the reference literals (cited) or the PyBullet defaults they rely on. */
@@ -88,6 +100,8 @@ typedef struct {
     float max_coord_velocity;  /* 100 */
     int32_t auto_reset;        /* 1: plen_step resets finished envs in the same launch (the reference leaves it to
                                   the caller, plen_td3.py:122-129) */
+    int32_t link_contacts;     /* 1: the box colliders of the non-foot links collide with the ground (default); 0: soles only */
+    float mu_link;             /* 0.5*0.8: URDF default lateral friction of a link x the plane's, plen_env.py:309 */
 } plen_config;
 
 typedef struct plen_ctx plen_ctx;

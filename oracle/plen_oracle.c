@@ -468,10 +468,10 @@ void plen_oracle_tick(const plen_oracle_model *m, const plen_oracle_config *cfg,
     double acc[ORC_NDOF], vstar[ORC_NDOF], dv[ORC_NDOF];
     const double dt = cfg->dt;
     row_t nc[3 * ORC_NJ];                         /* non-contact: limits then motors */
-    row_t nrm[ORC_NFEET * ORC_NPTS];              /* normals */
     row_t spin[ORC_NFEET * ORC_NPTS];             /* spinning (about normal) */
     row_t roll[2 * ORC_NFEET * ORC_NPTS];         /* rolling (about the two tangents) */
-    row_t fric[2 * ORC_NFEET * ORC_NPTS];         /* lateral */
+    static _Thread_local row_t nrm[ORC_NFEET * ORC_NPTS + ORC_MAXXP];        /* normals: soles first, then the link boxes */
+    static _Thread_local row_t fric[2 * (ORC_NFEET * ORC_NPTS + ORC_MAXXP)]; /* lateral pairs in the same order */
     int n_nc = 0, n_nrm = 0, n_spin = 0, n_roll = 0, n_fric = 0;
     int nrm_foot[ORC_NFEET * ORC_NPTS], nrm_pt[ORC_NFEET * ORC_NPTS];
 
@@ -578,6 +578,87 @@ void plen_oracle_tick(const plen_oracle_model *m, const plen_oracle_config *cfg,
         }
     }
 
+    /* (d2) ground contact of the link BOXES (everything but the two foot hulls), restating btBoxBoxDetector for a small
+     * box on the big ground box of plane.urdf: the separating axis is the ground normal, the incident face is the face of
+     * the link box whose outward normal points most downward, and its (up to four) vertices that PENETRATE (depth >= 0)
+     * become contact points.  No manifold hysteresis and no warm start for these points (documented simplification: a
+     * cached point only adds a speculative row while it hovers within ~1 mm above the ground).  Friction: lateral only
+     * (links carry no spinning / rolling friction, plen_env.py:438-467 sets those on the feet alone). */
+    const int n_foot_nrm = n_nrm;
+    s->last_box_points = 0; s->last_boxes_touching = 0;
+    if (cfg->link_contacts && m->n_boxes > 0) {
+        double bp[ORC_MAXBOX][4][3], bdepth[ORC_MAXBOX][4], bmax[ORC_MAXBOX];
+        int bn[ORC_MAXBOX], keep[ORC_MAXBOX], touching = 0;
+        for (int b = 0; b < m->n_boxes; b++) {
+            const int body = m->box_link[b] + 1;
+            double Rb[9], cb[3], t[3];
+            mat3_mul(w.Rw[body], m->box_rot[b], Rb);
+            mat3_vec(w.Rw[body], m->box_center[b], t);
+            for (int c = 0; c < 3; c++) cb[c] = w.pw[body][c] + t[c];
+            int ks = 0;                                       /* box axis most aligned with the ground normal (first max) */
+            for (int k = 1; k < 3; k++) if (fabs(Rb[6 + k]) > fabs(Rb[6 + ks])) ks = k;
+            const int ki = (ks + 1) % 3, kj = (ks + 2) % 3;
+            const double sgn = Rb[6 + ks] > 0 ? -1.0 : 1.0;   /* walk along the axis towards the ground */
+            bn[b] = 0; bmax[b] = -1.0; keep[b] = 0;
+            for (int v = 0; v < 4; v++) {
+                const double si = (v & 1) ? 1.0 : -1.0, sj = (v & 2) ? 1.0 : -1.0;
+                double pt[3];
+                for (int c = 0; c < 3; c++)
+                    pt[c] = cb[c] + sgn * m->box_half[b][ks] * Rb[3 * c + ks] + si * m->box_half[b][ki] * Rb[3 * c + ki] +
+                            sj * m->box_half[b][kj] * Rb[3 * c + kj];
+                const double depth = -pt[2];
+                if (depth >= 0.0) {
+                    memcpy(bp[b][bn[b]], pt, sizeof pt);
+                    bdepth[b][bn[b]] = depth;
+                    if (depth > bmax[b]) bmax[b] = depth;
+                    bn[b]++;
+                }
+            }
+            if (bn[b]) touching++;
+        }
+        s->last_boxes_touching = touching;
+        /* the cap: keep the max_contact_points points of deepest penetration (ties: lower box index, then lower vertex
+         * index); the kept points then enter the solver in (box, vertex) order */
+        int total = 0, taken[ORC_MAXBOX][4];
+        for (int b = 0; b < m->n_boxes; b++) { total += bn[b]; for (int v = 0; v < 4; v++) taken[b][v] = 0; }
+        int quota = (cfg->max_contact_points < 0 || cfg->max_contact_points > total) ? total : cfg->max_contact_points;
+        for (int q = 0; q < quota; q++) {
+            int bb = -1, bv = -1;
+            for (int b = 0; b < m->n_boxes; b++)
+                for (int v = 0; v < bn[b]; v++)
+                    if (!taken[b][v] && (bb < 0 || bdepth[b][v] > bdepth[bb][bv])) { bb = b; bv = v; }
+            taken[bb][bv] = 1; keep[bb] = 1;
+        }
+        for (int b = 0; b < m->n_boxes; b++) {
+            if (!keep[b]) continue;
+            const int L = m->box_link[b];
+            const double rest_coeff = (L < 0) ? cfg->restitution_base : cfg->restitution;
+            for (int v = 0; v < bn[b]; v++) {
+                if (!taken[b][v]) continue;
+                int ni = n_nrm++;
+                row_t *r = &nrm[ni];
+                point_jacobian(m, &w, L, bp[b][v], nrmdir, 0, r->J);
+                finish_row(m, s, &w, r);
+                double rel = dotn(r->J, vstar);
+                double rest = (fabs(rel) < cfg->restitution_vel_threshold) ? 0.0 : rest_coeff * -rel;
+                if (rest <= 0) rest = 0;
+                double dist = -bdepth[b][v] + cfg->linear_slop;
+                double velerr = rest - rel, poserr = 0;
+                if (dist > 0) velerr -= dist / dt; else poserr = -dist * cfg->erp_contact / dt;
+                r->rhs = (poserr + velerr) * r->dinv;
+                r->lo = 0; r->hi = 1e10;
+                for (int a = 0; a < 2; a++) {
+                    row_t *q = &fric[n_fric++];
+                    point_jacobian(m, &w, L, bp[b][v], a ? t2 : t1, 0, q->J);
+                    finish_row(m, s, &w, q);
+                    q->rhs = -dotn(q->J, vstar) * q->dinv;
+                    q->mu = cfg->mu_link; q->normal_index = ni; q->lo = -q->mu; q->hi = q->mu;
+                }
+                s->last_box_points++;
+            }
+        }
+    }
+
     /* (e) projected Gauss-Seidel, btMultiBodyConstraintSolver::solveSingleIteration order */
     int it;
     for (it = 0; it < cfg->solver_iterations; it++) {
@@ -615,7 +696,7 @@ void plen_oracle_tick(const plen_oracle_model *m, const plen_oracle_config *cfg,
     }
     s->last_iterations = it;
     s->last_rows = n_nc + n_nrm + n_spin + n_roll + n_fric;
-    for (int j = 0; j < n_nrm; j++) s->lam_n[nrm_foot[j]][nrm_pt[j]] = nrm[j].lam;
+    for (int j = 0; j < n_foot_nrm; j++) s->lam_n[nrm_foot[j]][nrm_pt[j]] = nrm[j].lam;
 
     /* (f) apply delta v (clamped like applyDeltaVeeMultiDof) and integrate (stepPositionsMultiDof) */
     for (int k = 0; k < ORC_NDOF; k++) vstar[k] = clampd(vstar[k] + dv[k], -cfg->max_coord_velocity, cfg->max_coord_velocity);
@@ -657,6 +738,7 @@ void plen_oracle_default_config(plen_oracle_config *c, int joint_act) {
     c->motor_kp = 0.1; c->motor_kd = 1.0; c->solver_iterations = 50; c->residual_threshold = 1e-7;
     c->erp_contact = 0.08; c->erp_joint = 0.2; c->linear_slop = 1e-5; c->warmstart_factor = 0.1;
     c->restitution_vel_threshold = 0.2; c->hull_margin = 0.001; c->max_coord_velocity = 100.0; c->implicit_cone = 1;
+    c->link_contacts = 1; c->mu_link = 0.5 * 0.8; c->restitution_base = 0.0 * 0.5; c->max_contact_points = -1;
 }
 
 void plen_oracle_init_state(const plen_oracle_config *cfg, plen_oracle_state *s) {

@@ -29,7 +29,9 @@ extern "C" {
 #define ORC_NJ 18
 #define ORC_NFEET 2
 #define ORC_NPTS 4       /* contact points per foot (persistent-manifold capacity) */
-#define ORC_MAXROWS (2 * ORC_NJ + ORC_NJ + ORC_NFEET * ORC_NPTS * 6)
+#define ORC_MAXBOX 32    /* box colliders besides the two foot hulls (plen.urdf: torso + 30 links) */
+#define ORC_MAXXP (ORC_MAXBOX * 4)   /* contact points they can produce: <= 4 per box (btBoxBoxDetector's manifold) */
+#define ORC_MAXROWS (2 * ORC_NJ + ORC_NJ + ORC_NFEET * ORC_NPTS * 6 + 3 * ORC_MAXXP)
 
 typedef struct {
     int n_links;
@@ -47,6 +49,12 @@ typedef struct {
     int foot_link[ORC_NFEET];                   /* [0]=right (11), [1]=left (19) */
     double foot_pts[ORC_NFEET][ORC_NPTS][3];    /* sole contact vertices, link frame */
     double foot_break[ORC_NFEET];               /* contact breaking threshold per foot */
+    /* box colliders of every link except the feet (plen.urdf:504-1274), for ground contact of knees / hands / torso ... */
+    int n_boxes;
+    int box_link[ORC_MAXBOX];                   /* Bullet link index, -1 = base (torso) */
+    double box_center[ORC_MAXBOX][3];           /* collision origin in the link frame */
+    double box_rot[ORC_MAXBOX][9];              /* collision rpy as a rotation, link frame (row major) */
+    double box_half[ORC_MAXBOX][3];             /* half extents */
 } plen_oracle_model;
 
 typedef struct {
@@ -78,6 +86,12 @@ typedef struct {
     double hull_margin;        /* 0.001: convex hull inflation */
     double max_coord_velocity; /* 100 */
     int implicit_cone;         /* 1: implicit cone friction (multibody default) */
+    /* --- ground contact of the 31 non-foot colliders (every link collider hits plane.urdf in Bullet) --- */
+    int link_contacts;         /* 1: on (default); 0: only the soles collide (round-1 behaviour) */
+    double mu_link;            /* lateral friction link 0.5 (URDF default, [RECALL]) * plane 0.8, plen_env.py:309 */
+    double restitution_base;   /* torso 0 (not in the changeDynamics loop, plen_env.py:476-481) * plane 0.5 */
+    int max_contact_points;    /* at most this many box contact points per tick, deepest first (-1: no cap = Bullet; the CUDA
+                                  path keeps 4 and the parity tests give the oracle the same cap) */
 } plen_oracle_config;
 
 typedef struct {
@@ -90,7 +104,7 @@ typedef struct {
     int cnt, ds, hist_len, ep_t, dead;
     double last[6], sums[9], ep_ret;
     /* diagnostics of the last tick */
-    int last_iterations, last_rows;
+    int last_iterations, last_rows, last_box_points, last_boxes_touching;
     long long flops;                     /* instrumented FLOP counter (adds+muls), whole life */
 } plen_oracle_state;
 

@@ -101,7 +101,7 @@ def sole_corner_points(verts_link):
     return pts, sole
 
 
-def build_tree(urdf_path, mesh_dir):
+def build_tree(urdf_path, mesh_dir, inertia_from_urdf=False):
     root = ET.parse(urdf_path).getroot()
     links = {l.get("name"): l for l in root.findall("link")}
     joints = root.findall("joint")
@@ -137,9 +137,10 @@ def build_tree(urdf_path, mesh_dir):
         co = cols[0].find("origin")
         c_xyz, c_R = _vec(co.get("xyz")), rpy_to_matrix(_vec(co.get("rpy")))
         geom = cols[0].find("geometry")[0]
-        hull = None
+        hull, box = None, None
         if geom.tag == "box":
             half = _vec(geom.get("size")) * 0.5          # box keeps its size (margin is inside)
+            box = dict(center=c_xyz.tolist(), rot=c_R.tolist(), half=half.tolist())
             ext = np.abs(c_R) @ half                     # AABB half extents in the link frame
             lo, hi = c_xyz - ext, c_xyz + ext
         elif geom.tag == "mesh":
@@ -153,10 +154,14 @@ def build_tree(urdf_path, mesh_dir):
         lo, hi = lo - COMPOUND_MARGIN, hi + COMPOUND_MARGIN
         lx, ly, lz = hi - lo
         inertia = mass / 12.0 * np.array([ly * ly + lz * lz, lx * lx + lz * lz, lx * lx + ly * ly])
+        if inertia_from_urdf:      # the URDF_USE_INERTIA_FROM_FILE behaviour (NOT what the reference's loadURDF call asks for):
+            it = inertial.find("inertia")      # only for the sensitivity table (scripts/sensitivity_table.py)
+            assert all(abs(float(it.get(k))) < 1e-12 for k in ("ixy", "ixz", "iyz")), "off-diagonal URDF inertia"
+            inertia = np.array([float(it.get(k)) for k in ("ixx", "iyy", "izz")])
         # compound AABB expressed in the inertial frame (origin = com) for the breaking threshold
         centre = 0.5 * (lo + hi) - com
         radius = 0.5 * np.linalg.norm(hi - lo)
-        return dict(name=name, mass=mass, com=com, inertia=inertia, hull=hull,
+        return dict(name=name, mass=mass, com=com, inertia=inertia, hull=hull, box=box,
                     angular_motion_disc=float(np.linalg.norm(centre) + radius))
 
     base = link_props(base_name)
@@ -200,6 +205,12 @@ def build_tree(urdf_path, mesh_dir):
         feet.append(dict(link=link, name=pr["name"], points=pts.tolist(), n_sole_vertices=int(len(sole)),
                          breaking_threshold=CONTACT_BREAKING_FACTOR * pr["angular_motion_disc"]))
     tree["feet"] = feet
+    # box colliders of every link but the feet, Bullet link index (-1 = base), for the link-vs-ground contacts
+    boxes = [dict(link=-1, name=base_name, **base["box"])]
+    for i, pr in enumerate(props):
+        if pr["box"] is not None:
+            boxes.append(dict(link=i, name=pr["name"], **pr["box"]))
+    tree["boxes"] = boxes
     tree["total_mass"] = float(base["mass"] + sum(tree["mass"]))
     return tree
 
@@ -220,4 +231,6 @@ if __name__ == "__main__":  # regenerate oracle/data/plen_tree33.json from the r
     ref = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     t = build_tree(os.path.join(ref, "plen_bullet/src/plen.urdf"), os.path.join(ref, "plen_ros/meshes_bin"))
     save_tree(t)
+    save_tree(build_tree(os.path.join(ref, "plen_bullet/src/plen.urdf"), os.path.join(ref, "plen_ros/meshes_bin"), inertia_from_urdf=True),
+              os.path.join(HERE, "data", "plen_tree33_urdf_inertia.json"))
     print("links", t["n_links"], "mass", t["total_mass"], "feet", [(f["name"], f["breaking_threshold"]) for f in t["feet"]])

@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-from .urdf_loader import N_LANES, PlenModel
+from .urdf_loader import MAX_BOXES, N_LANES, PlenModel
 
 NJ = 18
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -28,6 +28,8 @@ class PlenModelC(C.Structure):
         ("mass", C.c_float * N_LANES), ("com", (C.c_float * 3) * N_LANES), ("inertia", (C.c_float * 6) * N_LANES),
         ("lower", C.c_float * N_LANES), ("upper", C.c_float * N_LANES), ("chain_start", C.c_int32 * N_LANES),
         ("foot_lane", C.c_int32 * 2), ("foot_pts", ((C.c_float * 3) * 4) * 2), ("foot_break", C.c_float * 2),
+        ("n_boxes", C.c_int32), ("box_lane", C.c_int32 * MAX_BOXES), ("box_center", (C.c_float * 3) * MAX_BOXES),
+        ("box_rot", (C.c_float * 9) * MAX_BOXES), ("box_half", (C.c_float * 3) * MAX_BOXES), ("box_rest", C.c_float * MAX_BOXES),
     ]
 
 
@@ -42,6 +44,7 @@ class PlenConfigC(C.Structure):
         ("residual_threshold", C.c_float), ("erp_contact", C.c_float), ("erp_joint", C.c_float),
         ("linear_slop", C.c_float), ("warmstart_factor", C.c_float), ("restitution_vel_threshold", C.c_float),
         ("hull_margin", C.c_float), ("max_coord_velocity", C.c_float), ("auto_reset", C.c_int32),
+        ("link_contacts", C.c_int32), ("mu_link", C.c_float),
     ]
 
 
@@ -66,6 +69,15 @@ def model_to_c(model: PlenModel) -> PlenModelC:
         for p in range(4):
             for k in range(3):
                 m.foot_pts[f][p][k] = float(model.foot_pts[f][p][k])
+    m.n_boxes = int(model.n_boxes)
+    for b in range(int(model.n_boxes)):
+        m.box_lane[b] = int(model.box_lane[b])
+        m.box_rest[b] = float(model.box_rest[b])
+        for k in range(3):
+            m.box_center[b][k] = float(model.box_center[b][k])
+            m.box_half[b][k] = float(model.box_half[b][k])
+        for k in range(9):
+            m.box_rot[b][k] = float(np.asarray(model.box_rot[b]).reshape(9)[k])
     return m
 
 

@@ -41,6 +41,8 @@ struct plen_ctx {
     EnvRanges er;
     float *d_tab, *d_state, *d_snapshot;
     float *d_srec;   // [n][SR_WORDS] solve records (k_dyn -> k_solve)
+    float *d_srx;    // [n][XR_WORDS] extension records: box-contact rows of the robots whose link boxes touch the ground (rare)
+    int *d_xgroups;  // [n_tiles] leading solver groups of every tile that hold such a robot (k_rank -> k_solve / k_solve_x)
     float *d_tgt;    // [n][18] servo targets of the current env step
     float *d_scale;  // [n][4] per-robot scales: friction, servo force limit, servo gain, reserved (plen_set_env_scales; all 1)
     uint8_t *d_key;  // [n] contact-load sort key of the current tick (k_dyn -> k_rank)
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(DYN_WPC * 32, 5)
 k_dyn(const __grid_constant__ DevConfig dc, const __grid_constant__ EnvRanges er, const float *__restrict__ tab_g,
       const float *__restrict__ state, int n, const float *__restrict__ actions, float *__restrict__ tgt,
       float *__restrict__ srec, uint8_t *__restrict__ keys, float *dbg_minv, float *dbg_pos, float *dbg_rot,
-      const float *__restrict__ scale) {
+      const float *__restrict__ scale, float *__restrict__ srx) {
     // The 4 KB model table is staged with cp.async while every warp already fetches its robot's state record and targets:
     // the two latencies overlap instead of adding up (the table wait used to sit in front of everything).
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -132,7 +134,8 @@ k_dyn(const __grid_constant__ DevConfig dc, const __grid_constant__ EnvRanges er
     }
     DebugOut dbg{dbg_minv ? dbg_minv + (size_t)env * 576 : nullptr, dbg_pos ? dbg_pos + (size_t)env * 72 : nullptr,
                  dbg_rot ? dbg_rot + (size_t)env * 216 : nullptr};
-    tick_dynamics(dc, sm.tab, ws, L, lane, srec + (size_t)env * SR_WORDS, keys + env, (dbg_minv || dbg_pos || dbg_rot) ? &dbg : nullptr);
+    tick_dynamics(dc, sm.tab, ws, L, lane, srec + (size_t)env * SR_WORDS, keys + env, (dbg_minv || dbg_pos || dbg_rot) ? &dbg : nullptr,
+                  srx ? srx + (size_t)env * XR_WORDS : nullptr);
 }
 
 // Robots are grouped by contact load before the solve: k_rank counting-sorts the keys k_dyn wrote inside tiles of
@@ -141,7 +144,7 @@ k_dyn(const __grid_constant__ DevConfig dc, const __grid_constant__ EnvRanges er
 // warps of every tile are dispatched first.  The sort is stable, so the grouping is reproducible.
 #define RANK_TILE 1024
 __global__ void __launch_bounds__(RANK_TILE)
-k_rank(const uint8_t *__restrict__ keys, int n, int *__restrict__ perm) {
+k_rank(const uint8_t *__restrict__ keys, int n, int *__restrict__ perm, int *__restrict__ xgroups) {
     // STABLE counting sort (robots of a class keep their index order), so the grouping of robots into solver warps -- and
     // with it every bit of the step -- is reproducible run to run: rank inside the warp from match_any, warps of a class
     // in warp order through a [warp][class] count table.
@@ -177,6 +180,8 @@ k_rank(const uint8_t *__restrict__ keys, int n, int *__restrict__ perm) {
     int pos = rank_in_warp;
     for (int k = 0; k < w; k++) pos += s_wcnt[k][cls];
     perm[blockIdx.x * RANK_TILE + s_base[cls] + pos] = r;
+    // class 0 = robots with box contacts (key PLEN_KEY_EXT): they lead the tile; so many solver groups hold one
+    if (t == 0 && xgroups) xgroups[blockIdx.x] = (s_base[1] + PLEN_SOLVE_ROBOTS - 1) / PLEN_SOLVE_ROBOTS;
 }
 
 // Second half of a tick, 4 lanes per robot: PGS + delta-v + integration, state record updated in place.
@@ -187,15 +192,42 @@ k_rank(const uint8_t *__restrict__ keys, int n, int *__restrict__ perm) {
 #endif
 __global__ void __maxnreg__(PLEN_SOLVE_MAXREG)
 k_solve(const __grid_constant__ DevConfig dc, const float *__restrict__ srec, const int *__restrict__ perm,
-        float *__restrict__ state, int n, int n_tiles) {
+        float *__restrict__ state, int n, int n_tiles, const int *__restrict__ xgroups) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *Gs = reinterpret_cast<float *>(smem_raw);
     const int lane = threadIdx.x;
     const int tile = blockIdx.x % n_tiles, grp = blockIdx.x / n_tiles;
+    if (xgroups && grp < gld_i(xgroups + tile)) return;      // a group with a box-contact robot: k_solve_x takes it
     const int robot = gld_i(perm + tile * RANK_TILE + grp * PLEN_SOLVE_ROBOTS + (lane >> 2));
     const bool valid = robot < n;
     const size_t r = valid ? (size_t)robot : 0;
-    solve_tick(dc, srec + r * SR_WORDS, Gs + (size_t)(lane >> 2) * PLEN_GS_WORDS, state + r * PLEN_STATE_WORDS, lane, valid);
+    solve_tick<false>(dc, srec + r * SR_WORDS, Gs + (size_t)(lane >> 2) * PLEN_GS_WORDS, state + r * PLEN_STATE_WORDS, lane, valid);
+}
+
+// The same solve for the groups that hold a robot whose link boxes touch the ground (the first xgroups[tile] groups of a
+// tile): EXT instance, with the box-contact rows of the extension records staged behind G.  XS_SPLIT CTAs per tile walk the
+// tile's groups, so the grid does not grow with the (unknown to the host) number of such groups; most CTAs find none.
+#define XS_SPLIT 8
+__global__ void __maxnreg__(255)
+k_solve_x(const __grid_constant__ DevConfig dc, const float *__restrict__ srec, const float *__restrict__ srx,
+          const uint8_t *__restrict__ keys, const int *__restrict__ perm, float *__restrict__ state, int n, int n_tiles,
+          const int *__restrict__ xgroups) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *Gs = reinterpret_cast<float *>(smem_raw);
+    float *Xs = Gs + PLEN_SOLVE_ROBOTS * PLEN_GS_WORDS;
+    const int lane = threadIdx.x;
+    const int tile = blockIdx.x % n_tiles;
+    const int ng = gld_i(xgroups + tile);
+    for (int grp = blockIdx.x / n_tiles; grp < ng; grp += XS_SPLIT) {
+        const int robot = gld_i(perm + tile * RANK_TILE + grp * PLEN_SOLVE_ROBOTS + (lane >> 2));
+        const bool valid = robot < n;
+        const size_t r = valid ? (size_t)robot : 0;
+        const bool isx = valid && gld_u8(keys + r) == PLEN_KEY_EXT;
+        const int nx = isx ? (int)gld(srx + r * XR_WORDS + XR_NX) : 0;
+        solve_tick<true>(dc, srec + r * SR_WORDS, Gs + (size_t)(lane >> 2) * PLEN_GS_WORDS, state + r * PLEN_STATE_WORDS, lane, valid,
+                         srx + r * XR_WORDS, Xs + (size_t)(lane >> 2) * PLEN_XS_WORDS, nx);
+        __syncwarp();
+    }
 }
 
 // per-robot scales (domain randomisation): column c of d_scale <- the given array, or 1 when `init`
@@ -446,6 +478,7 @@ k_fp32_peak(float *out, int iters, int mode, float seed) {
 // ------------------------------------------------------------------------------------------------ C ABI
 static const size_t DYN_SMEM = sizeof(DynSmem);
 static const size_t SOLVE_SMEM = sizeof(float) * PLEN_GS_WORDS * PLEN_SOLVE_ROBOTS;
+static const size_t SOLVE_X_SMEM = sizeof(float) * (PLEN_GS_WORDS + PLEN_XS_WORDS) * PLEN_SOLVE_ROBOTS;
 // k_dyn: one CTA per four robots.  (Measured slower: a persistent grid-stride walk, grid = resident CTAs, 3 %; CTAs that walk
 // 2 / 4 / 8 consecutive groups, 1.7 / 3.6 / 4.4 % -- many short CTAs overlap their load phases best.)
 static int dyn_grid(int n) { return (n + DYN_WPC - 1) / DYN_WPC; }
@@ -460,16 +493,23 @@ static void launch_ticks(plen_ctx *ctx, float *state, int n, const float *action
     float *srec = ctx->d_srec + off * SR_WORDS;
     uint8_t *key = ctx->d_key + off;
     int *perm = ctx->d_perm + off;
+    const bool boxes = ctx->dc.link_contacts != 0;
+    float *srx = boxes ? ctx->d_srx + off * XR_WORDS : nullptr;
+    int *xg = boxes ? ctx->d_xgroups + off / RANK_TILE : nullptr;
     for (int t = 0; t < n_ticks; t++) {
         if (ev) cudaEventRecord(ev[2 * t], st);
         k_dyn<<<dyn_grid(n), DYN_WPC * 32, DYN_SMEM, st>>>(ctx->dc, ctx->er, ctx->d_tab, state, n, t == 0 ? actions : nullptr,
                                                           tgt, srec, key, nullptr, nullptr, nullptr,
-                                                          (state == ctx->d_snapshot || !ctx->d_scale) ? nullptr : ctx->d_scale + 4 * off);
+                                                          (state == ctx->d_snapshot || !ctx->d_scale) ? nullptr : ctx->d_scale + 4 * off, srx);
         if (ev) cudaEventRecord(ev[2 * t + 1], st);
         const int nt = rank_tiles(n);
-        k_rank<<<nt, RANK_TILE, 0, st>>>(key, n, perm);
-        k_solve<<<nt * (RANK_TILE / PLEN_SOLVE_ROBOTS), 32, SOLVE_SMEM, st>>>(ctx->dc, srec, perm, state, n, nt);
+        k_rank<<<nt, RANK_TILE, 0, st>>>(key, n, perm, xg);
+        k_solve<<<nt * (RANK_TILE / PLEN_SOLVE_ROBOTS), 32, SOLVE_SMEM, st>>>(ctx->dc, srec, perm, state, n, nt, xg);
         ctx->launches += 3;
+        if (boxes) {
+            k_solve_x<<<nt * XS_SPLIT, 32, SOLVE_X_SMEM, st>>>(ctx->dc, srec, srx, key, perm, state, n, nt, xg);
+            ctx->launches += 1;
+        }
     }
 }
 
@@ -513,7 +553,7 @@ unsigned long long plen_kernel_launches(const plen_ctx *ctx) { return ctx ? ctx-
 void plen_destroy(plen_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->d_tab); cudaFree(ctx->d_state); cudaFree(ctx->d_snapshot); cudaFree(ctx->d_srec); cudaFree(ctx->d_tgt); cudaFree(ctx->d_key); cudaFree(ctx->d_perm); cudaFree(ctx->d_scale);
+    cudaFree(ctx->d_tab); cudaFree(ctx->d_state); cudaFree(ctx->d_snapshot); cudaFree(ctx->d_srec); cudaFree(ctx->d_srx); cudaFree(ctx->d_xgroups); cudaFree(ctx->d_tgt); cudaFree(ctx->d_key); cudaFree(ctx->d_perm); cudaFree(ctx->d_scale);
     cudaFree(ctx->d_act); cudaFree(ctx->d_obs); cudaFree(ctx->d_rew); cudaFree(ctx->d_done); cudaFree(ctx->d_tmo); cudaFree(ctx->d_faults);
     for (int k = 1; k < PLEN_HOST_PIPE; k++)
         if (ctx->pipe[k]) cudaStreamDestroy(ctx->pipe[k]);
@@ -536,6 +576,8 @@ static int create_impl(plen_ctx *ctx) {
     CK(ctx, cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DYN_SMEM));
     CK(ctx, cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DYN_SMEM));
     CK(ctx, cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
+    CK(ctx, cudaFuncSetAttribute(k_solve_x, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_X_SMEM));
+    CK(ctx, cudaFuncSetAttribute(k_solve_x, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     // both hot kernels are occupancy-limited by shared memory: ask for the largest carve-out (7 k_solve CTAs per SM)
     CK(ctx, cudaFuncSetAttribute(k_solve, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(ctx, cudaFuncSetAttribute(k_dyn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -552,6 +594,10 @@ static int create_impl(plen_ctx *ctx) {
     CK(ctx, cudaMalloc(&ctx->d_state, sizeof(float) * PLEN_STATE_WORDS * (size_t)n));
     CK(ctx, cudaMalloc(&ctx->d_snapshot, sizeof(float) * (PLEN_STATE_WORDS + 32)));
     CK(ctx, cudaMalloc(&ctx->d_srec, sizeof(float) * SR_WORDS * (size_t)n));
+    if (ctx->dc.link_contacts) {
+        CK(ctx, cudaMalloc(&ctx->d_srx, sizeof(float) * XR_WORDS * ((size_t)n + 1)));      // + 1: the snapshot robot's record
+        CK(ctx, cudaMalloc(&ctx->d_xgroups, sizeof(int) * ((size_t)rank_tiles(n) + 1)));
+    }
     CK(ctx, cudaMalloc(&ctx->d_tgt, sizeof(float) * PLEN_NJ * (size_t)n));
     CK(ctx, cudaMalloc(&ctx->d_key, (size_t)n));
     CK(ctx, cudaMalloc(&ctx->d_perm, sizeof(int) * (size_t)rank_tiles(n) * RANK_TILE));
@@ -729,7 +775,7 @@ int plen_debug_dynamics(plen_ctx *ctx, float *minv_dev, float *pos_dev, float *r
     if (!ctx) return fail(nullptr, PLEN_E_ARG, "ctx is NULL");
     CK(ctx, cudaSetDevice(ctx->device));
     k_dyn<<<dyn_grid(ctx->n), DYN_WPC * 32, DYN_SMEM, (cudaStream_t)stream>>>(ctx->dc, ctx->er, ctx->d_tab, ctx->d_state, ctx->n,
-                                                                            nullptr, nullptr, ctx->d_srec, ctx->d_key, minv_dev, pos_dev, rot_dev, ctx->d_scale);
+                                                                            nullptr, nullptr, ctx->d_srec, ctx->d_key, minv_dev, pos_dev, rot_dev, ctx->d_scale, ctx->d_srx);
     CK(ctx, cudaGetLastError());
     return PLEN_OK;
 }

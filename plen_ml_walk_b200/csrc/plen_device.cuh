@@ -58,6 +58,7 @@ PLEN_DEV float rcp_(float x) {
     return 1.0f / x;
 #endif
 }
+PLEN_DEV unsigned f_bits(float v) { return __float_as_uint(v); }
 PLEN_DEV int lowest_bit(unsigned m) { return __ffs((int)m) - 1; }
 PLEN_DEV int highest_bit(unsigned m) { return 31 - __clz((int)m); }
 PLEN_DEV int popc_(unsigned m) { return __popc(m); }
@@ -69,7 +70,10 @@ namespace plen {
 // ---- model table rows (each row is 32 floats, one per lane), staged in shared memory per CTA
 enum {
     T_RPJ = 0, T_PPJ = 9, T_AXIS = 12, T_COM = 15, T_MASS = 18, T_INERTIA = 19, T_LOWER = 25, T_UPPER = 26,
-    T_CS = 27, T_CE = 28, T_ENVLO = 29, T_ENVHI = 30, T_ROWS = 31
+    T_CS = 27, T_CE = 28, T_ENVLO = 29, T_ENVHI = 30,
+    // box collider b of the model in word b of a row (lane b tests box b against the ground): owning body lane, centre (3),
+    // rotation (9, row major) and half extents (3) in the body frame, restitution factor
+    T_BOX_LANE = 31, T_BOX_C = 32, T_BOX_R = 35, T_BOX_H = 44, T_BOX_REST = 47, T_ROWS = 48
 };
 
 // ---- per-env state record in HBM / smem: 96 words, word w = 32*k + lane
@@ -90,12 +94,12 @@ enum {
 struct DevConfig {
     float dt, inv_dt, gravity_z, motor_imp, kp_over_dt, one_minus_kd, linear_damping;
     float mu_lateral, mu_spinning, mu_rolling, restitution, rest_thresh, erp_contact_over_dt, erp_joint_over_dt;
-    float linear_slop, warm, hull_margin, vmax, residual_threshold;
+    float linear_slop, warm, hull_margin, vmax, residual_threshold, mu_link;
     float foot_break[2];
     float foot_pts[2][4][3];
     float start_pos[3];
     int foot_lane[2];
-    int substeps, reset_ticks, iterations, joint_act, max_episode_steps, auto_reset;
+    int substeps, reset_ticks, iterations, joint_act, max_episode_steps, auto_reset, link_contacts, n_boxes;
 };
 
 // ---- solve record: per robot, per tick, written by k_dyn and consumed by k_solve (global memory, words)
@@ -114,6 +118,20 @@ enum {
     SR_BASE = 1576,    // v* of the base (6), base position (3), quaternion (4), manifold bits (1), friction / servo-force scale (2)
     SR_WORDS = 1600
 };
+
+// ---- extension record: per robot, per tick, written by k_dyn only for a robot whose link boxes touch the ground and read by
+// the EXT instance of k_solve.  Up to PLEN_MAX_BOX_POINTS contact points (the deepest), three rows each (normal, lateral t1,
+// lateral t2), every row as explicit vectors in the operational space x of the solve record:
+//   Jx (32)  row velocity = Jx . x        Bx (32)  x += Bx * impulse        Bb (6)  base delta-v = Bb * impulse
+// (a box sits on an arbitrary body, whose twist is NOT a slot of x; but the base twist is the right-foot twist minus the
+// right leg's joint motion, so any body twist -- and with it any row -- is a linear functional of x: see box_rows below).
+enum {
+    XR_NX = 0,           // number of points (float)
+    XR_ROWS = 16,        // row (3 q + r) at XR_ROWS + (3 q + r) * XR_ROW_WORDS
+    XR_J = 0, XR_B = 32, XR_BB = 64, XR_RHS = 70, XR_DINV = 71, XR_D = 72, XR_ROW_WORDS = 80,
+    XR_WORDS = XR_ROWS + 3 * PLEN_MAX_BOX_POINTS * XR_ROW_WORDS
+};
+#define PLEN_KEY_EXT 126     // sort key of a robot with box contacts: its own (heaviest) class, first in every tile of k_rank
 
 // index (0..3) of the k-th set bit of a 4-bit mask, -1 if there are fewer
 PLEN_DEV int nth_bit4(unsigned m, int k) {
@@ -190,6 +208,7 @@ struct PLEN_ALIGN16 WarpScratch {
         float red[32 * 21];   // Schur complement partial products (dead before lin is built)
     };
     float obs[32];
+    float xp[PLEN_MAX_BOX_POINTS][8];   // selected box contact points: x y z (rel. base origin), depth, body lane, restitution factor
 };
 
 struct LaneState {
@@ -299,8 +318,10 @@ PLEN_DEV void row_entries(int type, const float *a, const float *m, const float 
 // First half of a physics tick for the robot owned by this warp: dynamics + constraint set-up (k_dyn).
 struct DebugOut { float *minv, *pos, *rot; };   // [24*24], [24*3], [24*9] of one env; all nullable
 
+PLEN_DEV_NOINLINE void box_rows(const DevConfig &cfg, const float *tab, WarpScratch &ws, int lane, float vstar, int nx, float *srx);
+
 PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch &ws, LaneState &L, int lane,
-                            float *srec, uint8_t *sort_key, const DebugOut *dbg = nullptr) {
+                            float *srec, uint8_t *sort_key, const DebugOut *dbg = nullptr, float *srx = nullptr) {
     const bool is_joint = lane >= 6 && lane < 24;
     const int cs = (int)tab[T_CS * 32 + lane], ce = (int)tab[T_CE * 32 + lane];
     float Rw[9], pw[3];
@@ -695,6 +716,102 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
     }
     warp_sync();
 
+    // ---- ground contact of the link BOXES (every collider but the two foot hulls): lane b tests box b.
+    //      Hot path = one quick test per lane (lowest point of the box above the ground?) and a ballot; the rest is the rare
+    //      branch.  Contact model (restates btBoxBoxDetector for a small box on the ground box of plane.urdf, as the oracle
+    //      does): the incident face is the box face whose normal points most downward, its vertices that PENETRATE are the
+    //      contact points; the PLEN_MAX_BOX_POINTS deepest of a robot are kept (ties: lower box, lower vertex) and enter the
+    //      solver in (box, vertex) order.  No manifold hysteresis and no warm start for these points.
+    int nx = 0;
+    if (cfg.link_contacts && srx != nullptr) {
+        const int bl = (int)tab[T_BOX_LANE * 32 + lane];
+        const float r20 = shfl(Rw[6], bl), r21 = shfl(Rw[7], bl), r22 = shfl(Rw[8], bl), pz = shfl(pw[2], bl);
+        float rz[3], az[3];      // z component of each box axis (world), and times its half extent
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            rz[k] = r20 * tab[(T_BOX_R + k) * 32 + lane] + r21 * tab[(T_BOX_R + 3 + k) * 32 + lane] + r22 * tab[(T_BOX_R + 6 + k) * 32 + lane];
+            az[k] = rz[k] * tab[(T_BOX_H + k) * 32 + lane];
+        }
+        const float cz = L.pos[2] + pz + r20 * tab[(T_BOX_C + 0) * 32 + lane] + r21 * tab[(T_BOX_C + 1) * 32 + lane] +
+                         r22 * tab[(T_BOX_C + 2) * 32 + lane];
+        const bool touch = lane < cfg.n_boxes && cz - (fabsf(az[0]) + fabsf(az[1]) + fabsf(az[2])) <= 0.0f;
+        if (ballot(touch)) {
+            // incident face: axis ks most aligned with the ground normal (first maximum), walked towards the ground;
+            // vertex v = (+-) along ki = ks + 1, (+-) along kj = ks + 2 (mod 3), bit 0 / bit 1 of v
+            const int ks = (fabsf(rz[1]) > fabsf(rz[0])) ? ((fabsf(rz[2]) > fabsf(rz[1])) ? 2 : 1) : ((fabsf(rz[2]) > fabsf(rz[0])) ? 2 : 0);
+            const float zs = (ks == 0) ? az[0] : ((ks == 1) ? az[1] : az[2]);
+            const float zi = (ks == 0) ? az[1] : ((ks == 1) ? az[2] : az[0]);
+            const float zj = (ks == 0) ? az[2] : ((ks == 1) ? az[0] : az[1]);
+            float depth[4];
+            unsigned cand = 0;
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const float vz = cz - fabsf(zs) + ((v & 1) ? zi : -zi) + ((v & 2) ? zj : -zj);
+                depth[v] = -vz;
+                if (touch && depth[v] >= 0.0f) cand |= 1u << v;
+            }
+            unsigned mine = 0;
+            for (int q = 0; q < PLEN_MAX_BOX_POINTS; q++) {
+                float bd = -1.0f;
+                int bv = 0;
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+                    if (((cand & ~mine) >> v) & 1u) { if (depth[v] > bd) { bd = depth[v]; bv = v; } }
+                const unsigned key = (bd >= 0.0f) ? f_bits(bd) + 1u : 0u;     // depth >= 0: the bit pattern orders like the value
+                const unsigned best = redux_max(key);
+                if (best == 0u) break;
+                if (lane == lowest_bit(ballot(key == best))) mine |= 1u << bv;
+                nx++;
+            }
+            if (nx) {
+                // slots in (box, vertex) order; the owning lane publishes point, depth, body lane and restitution factor
+                int below = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) below += popc_(ballot((mine >> b) & 1u) & ((1u << lane) - 1u));
+                float Rb[9], pb[3];
+#pragma unroll
+                for (int k = 0; k < 9; k++) Rb[k] = shfl(Rw[k], bl);
+#pragma unroll
+                for (int k = 0; k < 3; k++) pb[k] = shfl(pw[k], bl);
+                if (mine) {
+                    float ax[3][3], c[3];     // ax[k] = box axis k in world axes times its half extent; c = box centre rel. base origin
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        const float h = tab[(T_BOX_H + k) * 32 + lane];
+#pragma unroll
+                        for (int r = 0; r < 3; r++)
+                            ax[k][r] = (Rb[3 * r] * tab[(T_BOX_R + k) * 32 + lane] + Rb[3 * r + 1] * tab[(T_BOX_R + 3 + k) * 32 + lane] +
+                                        Rb[3 * r + 2] * tab[(T_BOX_R + 6 + k) * 32 + lane]) * h;
+                    }
+#pragma unroll
+                    for (int r = 0; r < 3; r++)
+                        c[r] = pb[r] + Rb[3 * r] * tab[(T_BOX_C + 0) * 32 + lane] + Rb[3 * r + 1] * tab[(T_BOX_C + 1) * 32 + lane] +
+                               Rb[3 * r + 2] * tab[(T_BOX_C + 2) * 32 + lane];
+                    const float sg = (zs > 0.0f) ? -1.0f : 1.0f;
+                    int slot = below;
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+                        if (!((mine >> v) & 1u)) continue;
+                        const float si = (v & 1) ? 1.0f : -1.0f, sj = (v & 2) ? 1.0f : -1.0f;
+#pragma unroll
+                        for (int r = 0; r < 3; r++) {
+                            const float as_ = (ks == 0) ? ax[0][r] : ((ks == 1) ? ax[1][r] : ax[2][r]);
+                            const float ai_ = (ks == 0) ? ax[1][r] : ((ks == 1) ? ax[2][r] : ax[0][r]);
+                            const float aj_ = (ks == 0) ? ax[2][r] : ((ks == 1) ? ax[0][r] : ax[1][r]);
+                            ws.xp[slot][r] = c[r] + sg * as_ + si * ai_ + sj * aj_;
+                        }
+                        ws.xp[slot][3] = depth[v];
+                        ws.xp[slot][4] = (float)bl;
+                        ws.xp[slot][5] = tab[T_BOX_REST * 32 + lane];
+                        slot++;
+                    }
+                }
+                warp_sync();
+            }
+        }
+    }
+    const bool ext = nx > 0;
+
     // ---- masked twists and operational columns Y_f = M^-1 Jfoot_f^T per foot with active contacts
     float Y[2][6];
 #pragma unroll
@@ -702,7 +819,8 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
         const int fl = cfg.foot_lane[f], fcs = fl - 5;
 #pragma unroll
         for (int k = 0; k < 6; k++) Y[f][k] = 0.0f;
-        if (((man_new >> (4 * f)) & 0xFu) && lane < 24) {
+        // (a robot with box contacts always carries the right-foot twist: the box rows are expressed through it)
+        if ((((man_new >> (4 * f)) & 0xFu) || (f == 0 && ext)) && lane < 24) {
 #pragma unroll
             for (int k = 0; k < 6; k++) Y[f][k] = ws.minv[k][lane];
             for (int j = fcs; j <= fl; j++) {
@@ -746,7 +864,7 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
         for (int k = 0; k < 6; k++) { ws.kk[lane][k] = Y[0][k]; ws.gg[lane][k] = Y[1][k]; }
     }
     warp_sync();
-    if (man_new) {
+    if (man_new || ext) {
         if (lane < 12) {
             const int f = (lane >= 6) ? 1 : 0, k = lane - 6 * f, fl = cfg.foot_lane[f];
             float acc = 0.0f;
@@ -795,7 +913,7 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
         {
             // column c = 18 + 6 fb + b6:  joint rows Y_fb[6 + i][b6] (kk / gg are adjacent [24][8] arrays), twist rows
             // Lambda^-1[fa 6 + a6][c - 18] when any contact is active
-            const bool on2 = ij || (ic && man_new);
+            const bool on2 = ij || (ic && (man_new || ext));
             const float *b2 = ij ? &ws.kk[6 + i][0] : (on2 ? &ws.lin[fa * 6 + a6][0] : &ws.cb[0]);
             const int jump = ij ? (int)(&ws.gg[0][0] - &ws.kk[0][0]) - 6 : 0, st2 = on2 ? 1 : 0;
 #pragma unroll
@@ -888,7 +1006,100 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
         srec[SR_BASE + 15] = L.motor_s;           // ... and the servo impulse bound of this robot
         // k_solve groups robots of similar contact load into the same warp (tile-local sort by this key)
         const int n0 = popc_(man_new & 15u), n1 = popc_((man_new >> 4) & 15u);
-        if (sort_key) *sort_key = (uint8_t)((n0 > n1 ? n0 : n1) * 25 + n0 * 5 + n1);
+        if (sort_key) *sort_key = ext ? (uint8_t)PLEN_KEY_EXT : (uint8_t)((n0 > n1 ? n0 : n1) * 25 + n0 * 5 + n1);
+    }
+    warp_sync();
+    if (ext) box_rows(cfg, tab, ws, lane, vstar, nx, srx);
+}
+
+// Rare path of tick_dynamics: the rows of the nx selected box contact points (ws.xp), as explicit operational-space vectors.
+// For a unit impulse along direction d at point p of body b, with generalized Jacobian Jg (support: base lanes 0..5 and the
+// chain of b) and response Bg = M^-1 Jg^T:
+//   Jx: base twist = right-foot twist - sum_{j in right leg} s_j qd_j   =>   slots of the right-foot twist carry Jg_base,
+//       a right-leg joint carries Jg_j - Jg_base . s_j, any other joint Jg_j
+//   Bx = [Bg_joints; Jfoot_right Bg; Jfoot_left Bg],   Bb = Bg_base
+// Scratch: ws.red (free after the solve record is out).  Not inlined: keeps the rare path's registers out of k_dyn's hot path.
+PLEN_DEV_NOINLINE void box_rows(const DevConfig &cfg, const float *tab, WarpScratch &ws, int lane, float vstar, int nx, float *srx) {
+    float *Jg = ws.red, *Bg = ws.red + 96;      // [3][32] each
+    const int flR = cfg.foot_lane[0], flL = cfg.foot_lane[1];
+    if (lane == 0) srx[XR_NX] = (float)nx;
+    for (int q = 0; q < nx; q++) {
+        const float px = ws.xp[q][0], py = ws.xp[q][1], pz = ws.xp[q][2], depth = ws.xp[q][3];
+        const int bl = (int)ws.xp[q][4];
+        const float restf = ws.xp[q][5];
+        const int bcs = (int)tab[T_CS * 32 + bl];
+        const bool sup = lane < 6 || (bl >= 6 && lane >= bcs && lane <= bl);
+        float a[3] = {0, 0, 0}, m[3] = {0, 0, 0};
+        if (lane < 24) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) { a[k] = ws.tw[lane][k]; m[k] = ws.tw[lane][3 + k]; }
+        }
+        // r = 0: normal +z; r = 1: t1 = (0,-1,0); r = 2: t2 = (1,0,0)  (btPlaneSpace1 of +z, the oracle's order)
+        float jg[3];
+        jg[0] = a[0] * py - a[1] * px + m[2];
+        jg[1] = a[0] * pz - a[2] * px - m[1];
+        jg[2] = a[1] * pz - a[2] * py + m[0];
+        warp_sync();
+#pragma unroll
+        for (int r = 0; r < 3; r++) { jg[r] = (sup && lane < 24) ? jg[r] : 0.0f; Jg[32 * r + lane] = jg[r]; }
+        warp_sync();
+        float bg[3] = {0, 0, 0};
+        if (lane < 24) {
+            for (int j = 0; j < 6; j++) {
+                const float w = ws.minv[j][lane];
+#pragma unroll
+                for (int r = 0; r < 3; r++) bg[r] += w * Jg[32 * r + j];
+            }
+            if (bl >= 6)
+                for (int j = bcs; j <= bl; j++) {
+                    const float w = ws.minv[j][lane];
+#pragma unroll
+                    for (int r = 0; r < 3; r++) bg[r] += w * Jg[32 * r + j];
+                }
+        }
+#pragma unroll
+        for (int r = 0; r < 3; r++) Bg[32 * r + lane] = bg[r];
+        warp_sync();
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            float d = jg[r] * bg[r], rel = jg[r] * vstar;
+            warp_sum2(d, rel);
+            const float dinv = (d > 1.1920929e-7f) ? rcp_(d) : 0.0f;
+            float rhs;
+            if (r == 0) {
+                const float pdist = -depth + cfg.linear_slop;
+                float rest = (fabsf(rel) < cfg.rest_thresh) ? 0.0f : cfg.restitution * restf * -rel;
+                rest = fmaxf(rest, 0.0f);
+                float velerr = rest - rel, poserr = 0.0f;
+                if (pdist > 0.0f) velerr -= pdist * cfg.inv_dt; else poserr = -pdist * cfg.erp_contact_over_dt;
+                rhs = (poserr + velerr) * dinv;
+            } else {
+                rhs = -rel * dinv;
+            }
+            // operational-space vectors, word i = lane
+            const int i = lane;
+            float jx = 0.0f, bx = 0.0f;
+            const float *jr = Jg + 32 * r, *br = Bg + 32 * r;
+            if (i < 18) {
+                const int j = 6 + i;
+                jx = jr[j];
+                if (j >= flR - 5 && j <= flR) {
+#pragma unroll
+                    for (int k = 0; k < 6; k++) jx -= jr[k] * ws.tw[j][k];
+                }
+                bx = br[j];
+            } else if (i < 24 || i >= 26) {
+                const int c = (i < 24) ? i - 18 : i - 26, fl = (i < 24) ? flR : flL;
+                jx = (i < 24) ? jr[c] : 0.0f;
+                bx = br[c];
+                for (int j = fl - 5; j <= fl; j++) bx += ws.tw[j][c] * br[j];
+            }
+            float *row = srx + XR_ROWS + (3 * q + r) * XR_ROW_WORDS;
+            row[XR_J + lane] = jx;
+            row[XR_B + lane] = bx;
+            if (lane < 6) row[XR_BB + lane] = br[lane];
+            if (lane == 0) { row[XR_RHS] = rhs; row[XR_DINV] = dinv; row[XR_D] = d; }
+        }
     }
     warp_sync();
 }

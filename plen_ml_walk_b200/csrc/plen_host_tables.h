@@ -32,6 +32,15 @@ inline void build_table(const plen_model *m, const plen_config *c, float *tab /*
         tab[T_CE * 32 + l] = (float)ce;
         tab[T_ENVLO * 32 + l] = joint ? (float)c->env_lo[l - 6] : 0.0f;
         tab[T_ENVHI * 32 + l] = joint ? (float)c->env_hi[l - 6] : 0.0f;
+        // box collider `l` (lane l tests box l against the ground; lanes >= n_boxes test nothing)
+        const bool has = l < m->n_boxes && l < PLEN_MAX_BOXES;
+        tab[T_BOX_LANE * 32 + l] = has ? (float)m->box_lane[l] : 0.0f;
+        for (int k = 0; k < 3; k++) {
+            tab[(T_BOX_C + k) * 32 + l] = has ? m->box_center[l][k] : 0.0f;
+            tab[(T_BOX_H + k) * 32 + l] = has ? m->box_half[l][k] : 0.0f;
+        }
+        for (int k = 0; k < 9; k++) tab[(T_BOX_R + k) * 32 + l] = has ? m->box_rot[l][k] : ((k % 4 == 0) ? 1.0f : 0.0f);
+        tab[T_BOX_REST * 32 + l] = has ? m->box_rest[l] : 0.0f;
     }
 }
 
@@ -46,6 +55,8 @@ inline void build_devconfig(const plen_model *m, const plen_config *c, DevConfig
     d->erp_contact_over_dt = c->erp_contact / c->dt; d->erp_joint_over_dt = c->erp_joint / c->dt;
     d->linear_slop = c->linear_slop; d->warm = c->warmstart_factor; d->hull_margin = c->hull_margin;
     d->vmax = c->max_coord_velocity; d->residual_threshold = c->residual_threshold;
+    d->link_contacts = (c->link_contacts && m->n_boxes > 0) ? 1 : 0; d->mu_link = c->mu_link;
+    d->n_boxes = m->n_boxes < PLEN_MAX_BOXES ? m->n_boxes : PLEN_MAX_BOXES;
     for (int f = 0; f < 2; f++) {
         d->foot_break[f] = m->foot_break[f];
         d->foot_lane[f] = m->foot_lane[f];
@@ -83,6 +94,7 @@ inline int default_config(plen_config *c, int joint_act) {
     c->erp_contact = 0.08f; c->erp_joint = 0.2f; c->linear_slop = 1e-5f; c->warmstart_factor = 0.1f;
     c->restitution_vel_threshold = 0.2f; c->hull_margin = 0.001f; c->max_coord_velocity = 100.0f;
     c->auto_reset = 1;
+    c->link_contacts = 1; c->mu_link = 0.5f * 0.8f;
     return 0;
 }
 

@@ -54,6 +54,9 @@ namespace plen {
 #define PLEN_GS_COLS 24
 #define PLEN_GS_WORDS (PLEN_GS_COLS * 32 + 4)
 #define PLEN_SOLVE_ROBOTS 8      // robots per warp
+// EXT instance only: the Jx / Bx vectors of the 3 x PLEN_MAX_BOX_POINTS box-contact rows of a robot (plen_device.cuh, XR_*),
+// [row][Jx 32 | Bx 32] plus the same one-float4 skew between robots
+#define PLEN_XS_WORDS (3 * PLEN_MAX_BOX_POINTS * 64 + 4)
 
 // column of twist component k of foot f in the solve record (30 columns) / in the shared staging area (k >= 3 only)
 #define PLEN_COL(f, k) (18 + 6 * (f) + (k))
@@ -170,8 +173,12 @@ PLEN_DEV void load8(const float *p, float (&o)[8]) {
 
 // One robot = lanes (lane & 28) .. +3 of the warp.  srec: this robot's solve record (global); Gs: this robot's
 // PLEN_GS_WORDS shared staging area; state: this robot's 96-word state record (global), updated in place.
+// EXT: the instance that also iterates the box-contact rows of the extension record srx (nx points of this robot, 0 for a
+// robot without any; Xs = this robot's PLEN_XS_WORDS staging area).  Only warps that hold such a robot run it (k_rank puts
+// them first in every tile), so the plain instance keeps its registers and its shared-memory footprint.
+template <bool EXT>
 PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, float *Gs, float *__restrict__ state,
-                         int lane, bool valid) {
+                         int lane, bool valid, const float *__restrict__ srx = nullptr, float *Xs = nullptr, int nx = 0) {
     const LoopConsts lc = pin_loop_consts(cfg, lane);
     const int g = lc.g;      // lane & 3, pinned in a register
 #define GSH(v, l) shfl4((v), (l))
@@ -284,6 +291,41 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
         }
     }
 
+    // ---- box-contact rows (EXT): lane q of the robot owns point q (its three impulses and row scalars live in that lane's
+    //      registers); the 64-word Jx | Bx vectors of every row are staged in shared memory
+    int nxmax = 0;
+    float x_rhs[3] = {0.0f, 0.0f, 0.0f}, x_dinv[3] = {0.0f, 0.0f, 0.0f}, x_d[3] = {0.0f, 0.0f, 0.0f}, x_lam[3] = {0.0f, 0.0f, 0.0f};
+    float resX = 0.0f;
+    if (EXT) {
+        nxmax = (int)redux_max((unsigned)nx);
+        for (int q = 0; q < nxmax; q++) {
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const float *row = srx + XR_ROWS + (3 * q + r) * XR_ROW_WORDS;
+                vec4 *dst = reinterpret_cast<vec4 *>(Xs + (3 * q + r) * 64);
+                const vec4 z4 = {0.0f, 0.0f, 0.0f, 0.0f};
+                const bool on = valid && q < nx;
+                // this lane's slices: words 8 g .. 8 g + 7 of Jx and of Bx
+                dst[2 * g] = on ? gld4(row + XR_J + 8 * g) : z4;
+                dst[2 * g + 1] = on ? gld4(row + XR_J + 8 * g + 4) : z4;
+                dst[8 + 2 * g] = on ? gld4(row + XR_B + 8 * g) : z4;
+                dst[8 + 2 * g + 1] = on ? gld4(row + XR_B + 8 * g + 4) : z4;
+                if (on && g == q) { x_rhs[r] = gld(row + XR_RHS); x_dinv[r] = gld(row + XR_DINV); x_d[r] = gld(row + XR_D); }
+            }
+        }
+    }
+#define X_VEC(row, part, half) (reinterpret_cast<const vec4 *>(Xs + (row) * 64 + 32 * (part))[2 * g + (half)])
+#define X_DOT(row, out)                                                                                     \
+    {                                                                                                       \
+        const vec4 xja_ = X_VEC(row, 0, 0), xjb_ = X_VEC(row, 0, 1);                                          \
+        float xr_ = xja_.x * s[0];                                                                            \
+        xr_ = fmaf(xja_.y, s[1], xr_); xr_ = fmaf(xja_.z, s[2], xr_); xr_ = fmaf(xja_.w, s[3], xr_);                 \
+        xr_ = fmaf(xjb_.x, s[4], xr_); xr_ = fmaf(xjb_.y, s[5], xr_); xr_ = fmaf(xjb_.z, s[6], xr_); xr_ = fmaf(xjb_.w, s[7], xr_); \
+        xr_ += shfl_xor(xr_, 1);                                                                              \
+        xr_ += shfl_xor(xr_, 2);                                                                              \
+        out = xr_;                                                                                           \
+    }
+
     float s[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) s[k] = 0.0f;
@@ -373,6 +415,7 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
     }
 
     float mu_spin = lc.mu_spin * fric_s, mu_roll = lc.mu_roll * fric_s, mu_lat = lc.mu_lat * fric_s;      // opened at the freeze
+    float mu_link = EXT ? cfg.mu_link * fric_s : 0.0f;
     const float res_thr = lc.res_thr;
     const int n_iterations = lc.iterations;
     bool alive = valid;
@@ -443,6 +486,20 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
                 apply_reg(s, A[f][1], -px[p] * db_);
                 apply_vec(s, ca_, cb_, db_);
             }
+        }
+        if (EXT && nxmax) {
+            // ---- normals of the box contact points (after the soles', as in the oracle's row list)
+            for (int q = 0; q < nxmax; q++) {
+                float r_;
+                X_DOT(3 * q, r_);
+                const float x_ = fmaf(-r_, x_dinv[0], x_rhs[0]);
+                const float dl_ = fmaxf(x_, -x_lam[0]);
+                const float db_ = GSH(dl_, q);
+                if (g == q) { x_lam[0] += dl_; resX = fmaxf(resX, fabsf(dl_ * x_d[0])); }
+                apply_vec(s, X_VEC(3 * q, 1, 0), X_VEC(3 * q, 1, 1), db_);
+            }
+        }
+        if (man_any) {
             // ---- all spinning rows, then the rolling rows point by point (t1, t2)
             FOR_ACTIVE_POINTS {
                 if (PLEN_LA_TORSION && k == 0) OWN_SYNC6();
@@ -491,11 +548,36 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
                 apply_vec(s, ya_, yb_, dA);
             }
         }
+        if (EXT && nxmax) {
+            // ---- lateral pairs of the box contact points with the implicit cone (A = t1 row, B = t2 row)
+            for (int q = 0; q < nxmax; q++) {
+                float rA, rB;
+                X_DOT(3 * q + 1, rA);
+                X_DOT(3 * q + 2, rB);
+                const float sumA = x_lam[1] + fmaf(-rA, x_dinv[1], x_rhs[1]);
+                const float sumB = x_lam[2] + fmaf(-rB, x_dinv[2], x_rhs[2]);
+                const float lim = mu_link * x_lam[0];
+                const bool outside = fmaxf(fabsf(sumA), fabsf(sumB)) > lim;
+                const float inv = rsqrt_fast(fmaf(sumA, sumA, sumB * sumB));
+                const float cA = fabsf(lim * sumA * inv), cB = fabsf(lim * sumB * inv);
+                const float nA = outside ? clampf(sumA, -cA, cA) : sumA;
+                const float nB = outside ? clampf(sumB, -cB, cB) : sumB;
+                const float dlA = nA - x_lam[1], dlB = nB - x_lam[2];
+                const float dA = GSH(dlA, q), dB = GSH(dlB, q);
+                if (g == q) {
+                    x_lam[1] = nA; x_lam[2] = nB;
+                    resX = fmaxf(resX, fabsf(dlA * x_d[1] + dlB * x_d[2]));
+                }
+                apply_vec(s, X_VEC(3 * q + 1, 1, 0), X_VEC(3 * q + 1, 1, 1), dA);
+                apply_vec(s, X_VEC(3 * q + 2, 1, 0), X_VEC(3 * q + 2, 1, 1), dB);
+            }
+        }
         // ---- residual of this iteration, per robot: servo / limit part is already robot-uniform, the contact part
         //      lives in the two foot lanes
         // spinning / rolling rows of a foot share one d per twist component (t_d), so |dl * d| is scaled once here
         resF = fmaxf(resF, fmaxf(resT[0] * fabsf(t_d[0]), fmaxf(resT[1] * fabsf(t_d[1]), resT[2] * fabsf(t_d[2]))));
         float rf = (g >= 2) ? resF : 0.0f;
+        if (EXT) { rf = fmaxf(rf, resX); resX = 0.0f; }
 #if PLEN_REDUX_CONV && !defined(PLEN_HOST_EMU)
         // max over the robot's four lanes with ONE partitioned redux.sync (non-negative floats order like their bit patterns)
         rf = __uint_as_float(__reduce_max_sync(0xFu << (lane & 28), __float_as_uint(rf)));
@@ -524,6 +606,11 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
                 // the bounds wide, every later candidate of this robot is exactly its current impulse (dl = 0), so a frozen
                 // robot does not depend on how long the other robots of its warp keep iterating.
                 mu_spin = mu_roll = mu_lat = 1.0e30f;
+                if (EXT) {
+                    mu_link = 1.0e30f;
+#pragma unroll
+                    for (int r = 0; r < 3; r++) { x_rhs[r] = 0.0f; x_dinv[r] = 0.0f; }
+                }
             }
         }
         if (!ballot(alive)) break;
@@ -567,6 +654,17 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
             for (int m = 0; m < 8; m++) acc = fmaf(b[m], z[m], acc);
         }
         dvb[k] = acc;
+    }
+    if (EXT && nxmax) {
+        // box rows act on the base through Bb = (M^-1 Jg^T) base entries; lane q adds its point's three rows
+        if (valid && g < nx) {
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const float *row = srx + XR_ROWS + (3 * g + r) * XR_ROW_WORDS + XR_BB;
+#pragma unroll
+                for (int k = 0; k < 6; k++) dvb[k] = fmaf(gld(row + k), x_lam[r], dvb[k]);
+            }
+        }
     }
 #pragma unroll
     for (int m = 1; m < 4; m <<= 1)
@@ -629,6 +727,8 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
             state[W_QUAT + 0] = rx * nn; state[W_QUAT + 1] = ry * nn; state[W_QUAT + 2] = rz * nn; state[W_QUAT + 3] = rw * nn;
         }
     }
+#undef X_VEC
+#undef X_DOT
 #undef GSH
 #undef OWN_SYNC
 #undef OWN_SYNC6

@@ -50,6 +50,7 @@ FOOT_JOINTS = ("r_ankle_r_foot", "l_ankle_l_foot")          # Bullet links 11 an
 SHAPE_MARGIN = 1.0e-3        # collision margin of every URDF shape; convex hulls are inflated by it
 COMPOUND_MARGIN = 1.0e-3     # margin of the per-link compound shape, added once more to its AABB
 BREAKING_FACTOR = 0.02       # contact breaking threshold = factor * (|aabb centre| + aabb radius)
+MAX_BOXES = 32               # box colliders besides the feet (plen.urdf: torso + 30 links), one per lane of the warp
 
 _DATA_JSON = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "plen_model.json")
 
@@ -111,6 +112,7 @@ class _Link:
     aabb_disc: float
     hull: np.ndarray | None
     hull_margin: float = 0.0     # collision margin the contact surface is inflated by (convex hulls: SHAPE_MARGIN, boxes: 0)
+    boxes: list = field(default_factory=list)     # (rotation, centre, half extents) of every box collider, link frame
 
 
 @dataclass
@@ -129,6 +131,16 @@ class PlenModel:
     foot_pts: np.ndarray = field(default_factory=lambda: np.zeros((2, 4, 3)))
     foot_break: np.ndarray = field(default_factory=lambda: np.zeros(2))
     foot_margin: float = 0.001     # collision margin of the foot shape (convex hull: 1 mm, box: 0) -> plen_config.hull_margin
+    # box colliders of every link except the feet (ground contact of knees / hands / torso ...), in Bullet's
+    # link order (base first, then DFS pre-order over the joints in file order); pose in the frame of the BODY (lane) the
+    # link is folded into
+    n_boxes: int = 0
+    box_lane: np.ndarray = field(default_factory=lambda: np.zeros(MAX_BOXES, dtype=np.int32))
+    box_center: np.ndarray = field(default_factory=lambda: np.zeros((MAX_BOXES, 3)))
+    box_rot: np.ndarray = field(default_factory=lambda: np.tile(np.eye(3), (MAX_BOXES, 1, 1)))
+    box_half: np.ndarray = field(default_factory=lambda: np.zeros((MAX_BOXES, 3)))
+    box_rest: np.ndarray = field(default_factory=lambda: np.zeros(MAX_BOXES))   # 0: the base link (restitution 0), 1: any other
+    box_names: list = field(default_factory=list)
     body_links: list = field(default_factory=list)     # names of the URDF links folded into each lane's body
     total_mass: float = 0.0
 
@@ -157,12 +169,13 @@ def _read_links(root, mesh_dir):
         iR, com = _origin(ine)
         if not np.allclose(iR, np.eye(3)):
             raise NotImplementedError("rotated inertial frames are not used by plen.urdf")
-        lo, hi, hull, margin = None, None, None, 0.0
+        lo, hi, hull, margin, boxes = None, None, None, 0.0, []
         for col in le.findall("collision"):
             cR, cx = _origin(col)
             g = col.find("geometry")[0]
             if g.tag == "box":
                 half = _floats(g.get("size")) / 2
+                boxes.append((cR, cx, half))
                 ext = np.abs(cR) @ half
                 a, b = cx - ext, cx + ext
                 if hull is None:      # box feet (plen_new.urdf): the 8 corners stand in for the hull; Bullet boxes keep their size
@@ -180,7 +193,7 @@ def _read_links(root, mesh_dir):
         e = hi - lo
         diag = mass / 12.0 * np.array([e[1] ** 2 + e[2] ** 2, e[0] ** 2 + e[2] ** 2, e[0] ** 2 + e[1] ** 2])
         disc = float(np.linalg.norm((lo + hi) / 2 - com) + np.linalg.norm(e) / 2)
-        out[le.get("name")] = _Link(le.get("name"), mass, com, diag, disc, hull, margin)
+        out[le.get("name")] = _Link(le.get("name"), mass, com, diag, disc, hull, margin, boxes)
     return out
 
 
@@ -257,6 +270,30 @@ def load_plen_model(urdf_path, mesh_dir) -> PlenModel:
         for n in poses[lane]:
             body_of_link[n] = lane
     assert len(body_of_link) == len(links), "unreached links"
+
+    # ---- box colliders of the non-foot links, Bullet link order (base, then DFS pre-order, children in joint-file order)
+    foot_links = {joints[jn].find("child").get("link") for jn in FOOT_JOINTS}
+    dfs = []
+
+    def walk(name):
+        dfs.append(name)
+        for j in by_parent.get(name, []):
+            walk(j.find("child").get("link"))
+
+    walk("torso")
+    for name in dfs:
+        if name in foot_links:
+            continue
+        lane = body_of_link[name]
+        R, p = poses[lane][name]
+        for cR, cx, half in links[name].boxes:
+            b = model.n_boxes
+            if b >= MAX_BOXES:
+                raise ValueError("more than %d box colliders" % MAX_BOXES)
+            model.box_lane[b], model.box_center[b], model.box_rot[b], model.box_half[b] = lane, p + R @ cx, R @ cR, half
+            model.box_rest[b] = 0.0 if name == "torso" else 1.0
+            model.box_names.append(name)
+            model.n_boxes += 1
 
     for f, jn in enumerate(FOOT_JOINTS):
         lane = 6 + JOINT_NAMES.index(jn)

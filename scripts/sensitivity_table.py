@@ -1,0 +1,185 @@
+#!/usr/bin/env python
+"""Sensitivity of the oracle's behaviour to every [RECALL] Bullet constant, against the three Bullet-measured fixtures the
+reference holds for its physics (VERDICT r1 "pin the physics, or quantify exactly how unpinned it is"):
+
+  1. `init_height = 0.160178937611  # measured in bullet` (plen_env.py:70) -- torso height standing at zero targets;
+  2. `plen_bullet/trajectories/*_cmd.npy` -- one full 500-step episode of the shipped policy recorded in Bullet, replayed
+     open loop (deterministic + an ensemble of noisy copies -> survival);
+  3. the shipped policy itself (`plen_bullet/models/plen_walk_gazebo_3229999_actor`; weights in tests/golden/td3_golden.npz)
+     closed loop in this physics: its training return in Bullet over the last 500 episodes was +68 with exploration
+     noise 0.1 (plen_bullet/results/plen_walk_gazebo_.npy).
+
+One row per variant (one constant changed from the default), written as a Markdown table.  CPU only (oracle/), runs here:
+
+    python scripts/sensitivity_table.py [--envs 128] [--out profiles/r2_sensitivity.md] [--only name,...]
+"""
+import argparse
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+from oracle.oracle import PlenOracle
+from oracle import urdf_tree
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+INIT_HEIGHT = 0.160178937611
+# quantiles (5/25/50/75/95 %) of the last 500 training-episode returns of the shipped policy in Bullet, exploration noise 0.1
+# (plen_bullet/results/plen_walk_gazebo_.npy; mean +68.4)
+REF_Q = np.array([-88.7, -4.4, 71.1, 140.2, 216.6])
+
+
+def actor_np(g):
+    W1, b1, W2, b2, W3, b3 = (g["actor_fc%d_%s" % (i, k)].astype(np.float64) for i in (1, 2, 3) for k in ("weight", "bias"))
+
+    def f(s):
+        h = np.maximum(s @ W1.T + b1, 0)
+        h = np.maximum(h @ W2.T + b2, 0)
+        return np.tanh(h @ W3.T + b3)
+    return f
+
+
+def make(n, tweak, tree=None):
+    o = PlenOracle(n, n_threads=min(8, os.cpu_count() or 1), tree=tree, max_contact_points=-1)
+    for k, v in tweak.items():
+        if k == "foot_break_scale":
+            for f in range(2):
+                o.model.foot_break[f] *= v
+        else:
+            setattr(o.cfg, k, v)
+    return o
+
+
+def settle(tweak, tree):
+    o = make(1, tweak, tree)
+    o.reset()
+    lo, hi = np.array(o.cfg.env_lo[:]), np.array(o.cfg.env_hi[:])
+    a0 = (-(hi + lo) / (hi - lo))[None]
+    z = []
+    for _ in range(60):
+        ob, _, d, _ = o.step(a0)
+        z.append(ob[0, 18])
+        if d[0]:
+            return z[0], float("nan")
+    return z[0], float(np.mean(z[20:]))
+
+
+def cmd_replay(tweak, tree, n, sigma, cmd):
+    o = make(n, tweak, tree)
+    o.reset()
+    rng = np.random.default_rng(0)
+    alive = np.ones(n, bool)
+    length = np.zeros(n)
+    for t in range(500):
+        a = np.repeat(cmd[t][None].astype(np.float64), n, 0)
+        a[1:] = np.clip(a[1:] + rng.normal(0, sigma, (n - 1, 18)), -1, 1)
+        _, _, d, _ = o.step(a)
+        length += alive
+        alive &= ~d
+        if not alive.any():
+            break
+    return length
+
+
+def policy_rollout(tweak, tree, n, sigma, actor):
+    o = make(n, tweak, tree)
+    s = o.reset()
+    rng = np.random.default_rng(1)
+    alive = np.ones(n, bool)
+    length, ret = np.zeros(n), np.zeros(n)
+    x = np.zeros(n)
+    for t in range(500):
+        a = actor(s)
+        a[1:] = np.clip(a[1:] + rng.normal(0, sigma, (n - 1, 18)), -1, 1)     # plen_td3.py:101-104, expl_noise 0.1
+        s, r, d, _ = o.step(a)
+        length += alive
+        ret += np.where(alive, np.nan_to_num(r), 0.0)
+        x = np.where(alive, o.get_state()["qpos"][:, 0], x) if t % 25 == 24 or not alive.any() else x
+        alive &= ~d
+        if not alive.any():
+            break
+    return length, ret
+
+
+VARIANTS = [
+    ("default", {}),
+    ("link_contacts off (round 1: soles only)", {"link_contacts": 0}),
+    ("max_contact_points 4 (CUDA cap)", {"max_contact_points": 4}),
+    ("erp_contact 0.08 -> 0.2", {"erp_contact": 0.2}),
+    ("erp_contact 0.08 -> 0.04", {"erp_contact": 0.04}),
+    ("linear_slop 1e-5 -> 0", {"linear_slop": 0.0}),
+    ("linear_slop 1e-5 -> 1e-3", {"linear_slop": 1e-3}),
+    ("warmstart 0.1 -> 0", {"warmstart_factor": 0.0}),
+    ("warmstart 0.1 -> 0.85", {"warmstart_factor": 0.85}),
+    ("restitution threshold 0.2 -> 0.05", {"restitution_vel_threshold": 0.05}),
+    ("restitution threshold 0.2 -> 1.0", {"restitution_vel_threshold": 1.0}),
+    ("hull_margin 1 mm -> 0", {"hull_margin": 0.0}),
+    ("hull_margin 1 mm -> 2 mm", {"hull_margin": 0.002}),
+    ("foot breaking threshold x0.25", {"foot_break_scale": 0.25}),
+    ("foot breaking threshold x4", {"foot_break_scale": 4.0}),
+    ("pyramid friction (implicit_cone 0)", {"implicit_cone": 0}),
+    ("solver iterations 50 -> 10", {"solver_iterations": 10}),
+    ("solver iterations 50 -> 200", {"solver_iterations": 200}),
+    ("residual threshold 1e-7 -> 0", {"residual_threshold": 0.0}),
+    ("motor kp 0.1 -> 0.2", {"motor_kp": 0.2}),
+    ("motor kd 1.0 -> 0.5", {"motor_kd": 0.5}),
+    ("mu_rolling 0.08 -> 0.008", {"mu_rolling": 0.008}),
+    ("mu_rolling / mu_spinning -> 0", {"mu_rolling": 0.0, "mu_spinning": 0.0}),
+    ("mu_lateral 0.64 -> 0.4 (plane 0.5)", {"mu_lateral": 0.4}),
+    ("mu_link 0.4 -> 0.8", {"mu_link": 0.8}),
+    ("inertia from the URDF tensors instead of the collision AABB", {"__tree__": "urdf_inertia"}),
+]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs", type=int, default=128)
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r2_sensitivity.md"))
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    g = np.load(os.path.join(GOLD, "td3_golden.npz"))
+    cmd = np.load(os.path.join(GOLD, "gait_golden.npz"))["shipped_cmd"]
+    actor = actor_np(g)
+    only = [s for s in a.only.split(",") if s]
+    rows = []
+    for name, tweak in VARIANTS:
+        if only and not any(o in name for o in only):
+            continue
+        tweak = dict(tweak)
+        tree = None
+        if tweak.pop("__tree__", None) == "urdf_inertia":
+            tree = urdf_tree.load_tree()
+            alt = os.path.join(ROOT, "oracle", "data", "plen_tree33_urdf_inertia.json")
+            if not os.path.exists(alt):
+                print("skip", name, "(needs", alt, ")")
+                continue
+            tree = urdf_tree.load_tree(alt)
+        t0 = time.time()
+        z0, zs = settle(tweak, tree)
+        L = cmd_replay(tweak, tree, max(16, a.envs // 2), 0.02, cmd)
+        PL, PR = policy_rollout(tweak, tree, a.envs, 0.1, actor)
+        qs = np.percentile(PR[1:], [5, 25, 50, 75, 95])
+        qdist = float(np.abs(qs - REF_Q).mean())
+        rows.append((name, z0, zs, L[0], np.median(L[1:]), (L[1:] >= 500).mean(), PL[0], PR[0], PL[1:].mean(), PR[1:].mean(),
+                     (PL[1:] >= 500).mean(), qdist, "/".join("%.0f" % q for q in qs)))
+        print("%-58s z0 %.6f zs %.6f | cmd det %3d med %3d surv %.2f | policy det len %3d ret %7.1f | noisy len %5.1f ret %7.1f surv %.2f  (%.0f s)"
+              % ((name,) + rows[-1][1:11] + (time.time() - t0,)), rows[-1][11:], flush=True)
+    with open(a.out, "w") as f:
+        f.write("# Oracle sensitivity to the [RECALL] Bullet constants (scripts/sensitivity_table.py, %d envs)\n\n" % a.envs)
+        f.write("Targets measured in Bullet by the reference: standing height **0.160179 m** (`plen_env.py:70`); the recorded\n"
+                "episode `*_cmd.npy` lasted **500** steps; the shipped policy's last 500 training episodes (exploration noise 0.1)\n"
+                "returned **+68** on average (`plen_bullet/results/plen_walk_gazebo_.npy`).\n\n")
+        f.write("| variant | z first step | z settled (steps 20-60) | settled - 0.160179 | cmd replay: det. length | noisy median | noisy survive 500 | "
+                "policy det. length | det. return | noisy mean length | noisy mean return | noisy survive 500 | return quantiles 5/25/50/75/95 | mean abs quantile gap to Bullet's -89/-4/71/140/217 |\n")
+        f.write("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
+        for r in rows:
+            f.write("| %s | %.6f | %.6f | %+.1e | %d | %d | %.2f | %d | %.1f | %.1f | %.1f | %.2f | %s | %.0f |\n"
+                    % (r[0], r[1], r[2], r[2] - INIT_HEIGHT, r[3], r[4], r[5], r[6], r[7], r[8], r[9], r[10], r[12], r[11]))
+    print("wrote", a.out)
+
+
+if __name__ == "__main__":
+    main()

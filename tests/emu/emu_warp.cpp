@@ -11,6 +11,7 @@
 
 #include "../../include/plen_b200.h"   // C ABI structs stay float32 in both builds
 
+typedef float float32_t_;      // a real float even in the float64 build below
 #ifdef PLEN_EMU_DOUBLE
 // Algorithm check: the same device source evaluated in float64 (every `float` below this line becomes double and
 // the f-suffixed libm calls are redirected), so that any disagreement with the oracle that survives is a logic
@@ -69,6 +70,7 @@ static inline float f_as_u_max(float v) {   // max over lanes of a non-negative 
 }
 static inline void sincos_(float x, float *s, float *c) { *s = sinf(x); *c = cosf(x); }
 static inline float rcp_(float x) { return 1.0f / x; }
+static inline unsigned f_bits(float v) { const float32_t_ f = (float32_t_)v; unsigned u; std::memcpy(&u, &f, 4); return u; }
 static inline int lowest_bit(unsigned m) { return __builtin_ffs((int)m) - 1; }
 static inline int highest_bit(unsigned m) { return 31 - __builtin_clz(m); }
 static inline int popc_(unsigned m) { return __builtin_popcount(m); }
@@ -105,22 +107,32 @@ void emu_init_record(const plen_config *c, float *rec) { init_record(c, rec); }
 static void run_ticks(const DevConfig &dc, const float *tab, float *records, const float *tgt, int n, int n_ticks,
                       const DebugOut *dbg0, int lane) {
     static WarpScratch ws;
-    static std::vector<float> srec, Gs(PLEN_SOLVE_ROBOTS * PLEN_GS_WORDS);
-    if (lane == 0) srec.assign((size_t)n * SR_WORDS, 0.0f);
+    static std::vector<float> srec, srx, Gs(PLEN_SOLVE_ROBOTS * PLEN_GS_WORDS), Xs(PLEN_SOLVE_ROBOTS * PLEN_XS_WORDS);
+    static std::vector<uint8_t> keys;
+    if (lane == 0) { srec.assign((size_t)n * SR_WORDS, 0.0f); srx.assign((size_t)n * XR_WORDS, 0.0f); keys.assign(n, 0); }
     bar();
     for (int t = 0; t < n_ticks; t++) {
         for (int e = 0; e < n; e++) {
             LaneState L;
             load_record(records + 96 * e, ws, L, lane);
             if (lane >= 6 && lane < 24) L.tgt = tgt ? tgt[18 * e + lane - 6] : 0.0f;
-            tick_dynamics(dc, tab, ws, L, lane, srec.data() + (size_t)e * SR_WORDS, nullptr,
-                          (e == 0 && t == n_ticks - 1) ? dbg0 : nullptr);
+            tick_dynamics(dc, tab, ws, L, lane, srec.data() + (size_t)e * SR_WORDS, keys.data() + e,
+                          (e == 0 && t == n_ticks - 1) ? dbg0 : nullptr, srx.data() + (size_t)e * XR_WORDS);
         }
         for (int b = 0; b < n; b += PLEN_SOLVE_ROBOTS) {
             const int r = b + (lane >> 2);
             const bool valid = r < n;
             const int rr = valid ? r : 0;
-            solve_tick(dc, srec.data() + (size_t)rr * SR_WORDS, Gs.data() + (lane >> 2) * PLEN_GS_WORDS, records + 96 * rr, lane, valid);
+            // groups are run through the instance k_rank would route them to: EXT iff one of the eight robots has box contacts
+            bool anyx = false;
+            for (int k = b; k < b + PLEN_SOLVE_ROBOTS && k < n; k++) anyx = anyx || keys[k] == PLEN_KEY_EXT;
+            if (anyx) {
+                const int nx = (valid && keys[rr] == PLEN_KEY_EXT) ? (int)srx[(size_t)rr * XR_WORDS + XR_NX] : 0;
+                solve_tick<true>(dc, srec.data() + (size_t)rr * SR_WORDS, Gs.data() + (lane >> 2) * PLEN_GS_WORDS, records + 96 * rr, lane, valid,
+                                 srx.data() + (size_t)rr * XR_WORDS, Xs.data() + (lane >> 2) * PLEN_XS_WORDS, nx);
+            } else {
+                solve_tick<false>(dc, srec.data() + (size_t)rr * SR_WORDS, Gs.data() + (lane >> 2) * PLEN_GS_WORDS, records + 96 * rr, lane, valid);
+            }
             bar();
         }
     }

@@ -94,3 +94,98 @@ def test_f32_emulation_free_flight_one_step(oracle_lib):
     assert np.abs(got["qpos"][:, :7] - ref["qpos"][:, :7]).max() < 1e-4
     assert np.abs(obs[:, :24] - oo[:, :24]).max() < 1e-4
     assert (done == od).all()
+
+
+def _fallen_states(o, rng, depth=0.002):
+    """Random tilted poses lowered until the lowest collider point (box vertex or sole corner) is `depth` under the ground."""
+    n = o.n
+    st = o.get_state()
+    st["qpos"][:, 7:] = rng.uniform(-0.7, 0.7, (n, 18))
+    ang = rng.uniform(-0.3, 0.3, (n, 3))
+    ang[:, 2] = rng.uniform(-3, 3, n)
+    lying = rng.integers(0, 2, n)                      # lying on the front / back (pitch) or on a side (roll)
+    ang[np.arange(n), lying] = rng.choice([-1, 1], n) * rng.uniform(1.2, 1.9, n)
+    for e in range(n):
+        cr, sr, cp, sp, cy, sy = (f(a / 2) for a in ang[e] for f in (np.cos, np.sin))
+        st["qpos"][e, 3:7] = [sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy, cr * cp * cy + sr * sp * sy]
+    st["qpos"][:, 2] = 0.5
+    st["qvel"][:, :6] = rng.normal(size=(n, 6)) * 0.1
+    st["qvel"][:, 6:] = rng.normal(size=(n, 18)) * 0.5
+    st["lam_n"][:] = 0
+    st["in_manifold"][:] = 0
+    o.set_state(st)
+    for e in range(n):
+        pos, rot = o.fk(e)
+        low = np.inf
+        for b in o.tree["boxes"]:
+            R, p = rot[b["link"] + 1], pos[b["link"] + 1]
+            Rb, c, h = R @ np.array(b["rot"]), p + R @ np.array(b["center"]), np.array(b["half"])
+            low = min(low, c[2] - np.abs(Rb[2]) @ h)
+        lowf = min((pos[f["link"] + 1] + np.array(f["points"]) @ rot[f["link"] + 1].T)[:, 2].min() - 0.001 for f in o.tree["feet"])
+        st["qpos"][e, 2] -= max(low, lowf - 0.004) + depth      # a box on the ground, the soles at most ~6 mm under it
+    o.set_state(st)
+    return st
+
+
+def test_f64_emulation_box_contacts_match_oracle(oracle_lib):
+    """knees / hands / torso boxes against the ground.  The device source in float64 follows the oracle (same
+    4-deepest-points cap) through one tick from fallen poses; robots of the same solver warp without box contacts are
+    unaffected by sharing it."""
+    emu = Emu(double=True)
+    n = 11
+    o = oracle_lib.PlenOracle(n)
+    o.reset()
+    rng = np.random.default_rng(3)
+    st = _fallen_states(o, rng)
+    st["qpos"][n - 1, 2] += 0.3                       # one robot of the second warp stays airborne
+    st["qpos"][n - 2, 3:7] = [0, -np.sqrt(0.5), 0, np.sqrt(0.5)]      # and one lies flat on its back, joints at zero:
+    st["qpos"][n - 2, 7:] = 0                                          # many boxes touch, the 4-point cap binds
+    st["qpos"][n - 2, 2] = 0.0235
+    o.set_state(st)
+    worst_qd, worst_q, pts = [], [], []
+    for tick in range(3):
+        st = o.get_state()
+        rec = np.stack([record_from_oracle_state(st, e, dtype=emu.real) for e in range(n)])
+        tg = rng.uniform(-1, 1, (n, 18))
+        for e in range(n):
+            for k in range(18):
+                o.states[e].target[k] = tg[e, k]
+        emu.tick(rec, tg, 1)
+        for e in range(n):
+            o.tick(e)
+        got, ref = oracle_state_from_record(rec), o.get_state()
+        worst_qd.append(np.abs(got["qvel"] - ref["qvel"]).max(1))
+        worst_q.append(np.abs(got["qpos"] - ref["qpos"]).max(1))
+        pts.append([o.states[e].last_box_points for e in range(n)])
+    pts, worst_qd, worst_q = np.array(pts), np.array(worst_qd), np.array(worst_q)
+    assert (pts[0, :n - 1] > 0).mean() > 0.5 and pts[0, n - 1] == 0 and pts[0, n - 2] == 4     # box rows exercised, incl. the cap
+    assert np.median(worst_qd) < 2e-5 and np.quantile(worst_qd, 0.8) < 1e-3, (np.median(worst_qd), np.quantile(worst_qd, 0.8))
+    assert np.median(worst_q) < 1e-6
+
+
+def test_f32_emulation_box_contacts_keep_the_robot_above_the_floor(oracle_lib):
+    """float32 build: a robot dropped on its hands and knees is held by the box contacts (round 1 let it sink through
+    the floor until z < 0.08 tripped) and tracks the oracle's torso height."""
+    emu = Emu(double=False)
+    n = 8
+    o = oracle_lib.PlenOracle(n)
+    o.reset()
+    rng = np.random.default_rng(4)
+    st = _fallen_states(o, rng, depth=0.0005)
+    st["qvel"][:] = 0
+    o.set_state(st)
+    st = o.get_state()
+    rec = np.stack([record_from_oracle_state(st, e, dtype=np.float32) for e in range(n)])
+    tg = np.array(st["qpos"][:, 7:])
+    for e in range(n):
+        for k in range(18):
+            o.states[e].target[k] = tg[e, k]
+    z0 = st["qpos"][:, 2].copy()
+    for _ in range(24):
+        emu.tick(rec, tg, 1)
+        for e in range(n):
+            o.tick(e)
+    got, ref = oracle_state_from_record(rec), o.get_state()
+    # 0.1 s of free fall would be 49 mm; resting on its colliders a robot settles / tips by far less
+    assert (z0 - got["qpos"][:, 2]).max() < 0.03 and (z0 - ref["qpos"][:, 2]).max() < 0.03
+    assert np.median(np.abs(got["qpos"][:, 2] - ref["qpos"][:, 2])) < 2e-3

@@ -67,37 +67,154 @@ def test_free_flight_one_step(mods):
     assert np.abs(qvel - ref["qvel"]).max() < 5e-3                    # velocities up to ~70 rad/s
 
 
+def _quantiles(x):
+    return np.quantile(x, [0.5, 0.75, 0.9, 0.99])
+
+
 def test_teacher_forced_contact_steps(mods):
-    """Config 2 shape: random actions from the reset pose, oracle state forced into the GPU env before every step."""
+    """BASELINE config 2 as written: 64 envs x 200 steps of random actions from the reset pose, the oracle's state forced
+    into the GPU env before every step.  The bound has a TAIL: the solver both sides restate is chaotic at contact (a 1e-13
+    perturbation of the oracle's own input moves 14 % of the samples by > 1e-3 rad within one step), so the yardstick is
+    the oracle's own sensitivity to an fp32-sized perturbation -- a second oracle stepped from the SAME state rounded to
+    float32.  Quantile by quantile (p50 / p75 / p90 / p99) the GPU-vs-oracle error must not exceed 3x that control
+    (+ 1e-4, the free-flight tolerance)."""
     oracle, PlenVecEnv = mods
-    n, steps = 64, 40
+    n, steps = 64, 200
     rng = np.random.default_rng(2)
     o = oracle.PlenOracle(n, n_threads=8)
+    ctl = oracle.PlenOracle(n, n_threads=8)
     env = PlenVecEnv(n, auto_reset=False)
     o_obs = o.reset()
+    ctl.reset()
     g_obs = env.reset().cpu().numpy()
     assert np.abs(o_obs - g_obs).max() < 1e-5          # reset = start pose + 8 settle ticks (in contact)
-    q_err, b_err, flag_mis, done_mis, total = [], [], 0, 0, 0
+    q_err, b_err, q_ctl, b_ctl, flag_mis, flag_ctl, done_mis, total = [], [], [], [], 0, 0, 0, 0
     for t in range(steps):
-        env.set_state(*abi_from_oracle(o.get_state()))
+        st = o.get_state()
+        env.set_state(*abi_from_oracle(st))
+        rounded = {k: (v.astype(np.float32).astype(np.float64) if v.dtype == np.float64 else v.copy()) for k, v in st.items()}
+        ctl.set_state(rounded)
         act = rng.uniform(-1, 1, (n, 18)).astype(np.float32)
         oo, orw, od, _ = o.step(act.astype(np.float64))
+        co, _, _, _ = ctl.step(act.astype(np.float64))
         go, grw, gd, _ = env.step(torch.from_numpy(act).cuda())
         go, gd = go.cpu().numpy(), gd.cpu().numpy()
         q_err.append(np.abs(go[:, :18] - oo[:, :18]).max(1))
         b_err.append(np.abs(go[:, 18:24] - oo[:, 18:24]).max(1))
+        q_ctl.append(np.abs(co[:, :18] - oo[:, :18]).max(1))
+        b_ctl.append(np.abs(co[:, 18:24] - oo[:, 18:24]).max(1))
         flag_mis += int((go[:, 24:] != oo[:, 24:]).sum())
+        flag_ctl += int((co[:, 24:] != oo[:, 24:]).sum())
         done_mis += int((gd != od).sum())
         total += n
         for e in np.where(od)[0]:
             o.reset_one(int(e))
-    q_err, b_err = np.concatenate(q_err), np.concatenate(b_err)
-    print("joint err median %.2e p90 %.2e max %.2e | base err median %.2e p90 %.2e | flag mismatches %d / %d, done %d"
-          % (np.median(q_err), np.quantile(q_err, .9), q_err.max(), np.median(b_err), np.quantile(b_err, .9),
-             flag_mis, 2 * total, done_mis))
+    q_err, b_err, q_ctl, b_ctl = (np.concatenate(x) for x in (q_err, b_err, q_ctl, b_ctl))
+    print("joint err p50/p75/p90/p99 %s max %.2e | control (oracle vs fp32-rounded oracle) %s max %.2e | base %s vs %s | "
+          "flag mismatches %d (control %d) / %d, done %d" % (_quantiles(q_err), q_err.max(), _quantiles(q_ctl), q_ctl.max(),
+                                                             _quantiles(b_err), _quantiles(b_ctl), flag_mis, flag_ctl, 2 * total, done_mis))
     assert np.median(q_err) < 1e-4 and np.median(b_err) < 1e-4
-    assert np.mean(q_err < 1e-3) > 0.6                 # impacts (non-convergent PGS) are the documented exception
-    assert flag_mis <= 0.02 * 2 * total and done_mis <= 0.02 * total
+    assert (_quantiles(q_err) <= 3.0 * _quantiles(q_ctl) + 1e-4).all()
+    assert (_quantiles(b_err) <= 3.0 * _quantiles(b_ctl) + 1e-4).all()
+    assert q_err.max() <= 3.0 * q_ctl.max() + 0.05
+    assert flag_mis <= max(0.02 * 2 * total, 2 * flag_ctl) and done_mis <= 0.02 * total
+
+
+def test_free_running_distributions_random_actions(mods):
+    """No teacher forcing: 4,096 envs x 500 steps of random actions with auto-reset on both sides (different random streams
+    would do; the same one is used).  Trajectories decorrelate within a second, so the comparison is distributional:
+    episode-length histogram, mean reward per step, contact duty cycles, fall fraction."""
+    oracle, PlenVecEnv = mods
+    n, steps = 4096, 500
+    rng = np.random.default_rng(3)
+    o = oracle.PlenOracle(n, n_threads=16)
+    env = PlenVecEnv(n, auto_reset=True)
+    o.reset()
+    env.reset()
+    stats = {}
+    for name in ("gpu", "oracle"):
+        stats[name] = dict(len=[], rew=0.0, nrew=0, duty=np.zeros(2), cur=np.zeros(n, dtype=np.int64), dead=0, ndone=0)
+    for t in range(steps):
+        act = rng.uniform(-1, 1, (n, 18)).astype(np.float32)
+        oo, orw, od, otm = o.step(act.astype(np.float64), auto_reset=True)
+        go, grw, gd, info = env.step(torch.from_numpy(act).cuda())
+        gobs = torch.where(gd[:, None], info["terminal_obs"], go).cpu().numpy()
+        for name, obs, rew, done, tmo in (("gpu", gobs, grw.cpu().numpy(), gd.cpu().numpy(), info["timeout"].cpu().numpy()),
+                                          ("oracle", oo, orw, od, otm)):
+            s = stats[name]
+            s["cur"] += 1
+            s["len"] += list(s["cur"][done])
+            s["cur"][done] = 0
+            ok = np.isfinite(rew)
+            s["rew"] += float(rew[ok].sum()); s["nrew"] += int(ok.sum())
+            s["duty"] += obs[:, 24:26].sum(0)
+            s["dead"] += int((done & ~tmo).sum()); s["ndone"] += int(done.sum())
+    g, r = stats["gpu"], stats["oracle"]
+    lg, lr = np.sort(np.array(g["len"])), np.sort(np.array(r["len"]))
+    grid = np.arange(1, 501)
+    ks = np.abs(np.searchsorted(lg, grid, side="right") / len(lg) - np.searchsorted(lr, grid, side="right") / len(lr)).max()
+    print("episodes gpu %d oracle %d | mean length %.2f vs %.2f | KS %.4f | reward/step %.4f vs %.4f | duty R %.4f vs %.4f L %.4f vs %.4f | "
+          "fall fraction %.4f vs %.4f" % (len(lg), len(lr), lg.mean(), lr.mean(), ks, g["rew"] / g["nrew"], r["rew"] / r["nrew"],
+                                          g["duty"][0] / (n * steps), r["duty"][0] / (n * steps), g["duty"][1] / (n * steps),
+                                          r["duty"][1] / (n * steps), g["dead"] / max(1, g["ndone"]), r["dead"] / max(1, r["ndone"])))
+    assert abs(lg.mean() - lr.mean()) < 0.03 * lr.mean()
+    assert ks < 0.03
+    assert abs(g["rew"] / g["nrew"] - r["rew"] / r["nrew"]) < 0.03 * abs(r["rew"] / r["nrew"]) + 0.02
+    assert np.abs(g["duty"] - r["duty"]).max() / (n * steps) < 0.01
+    assert abs(g["dead"] / max(1, g["ndone"]) - r["dead"] / max(1, r["ndone"])) < 0.01
+
+
+def test_box_contacts_on_fallen_poses(mods):
+    """knee / hand / torso boxes against the ground.  Robots lying on the ground (one box vertex 2 mm under
+    it), one env step teacher-forced from the oracle's state: same distributional bound as through sole contact, and
+    the GPU robots are held up like the oracle's (round 1 let them sink until z < 0.08 tripped)."""
+    oracle, PlenVecEnv = mods
+    n = 64
+    rng = np.random.default_rng(5)
+    o = oracle.PlenOracle(n, n_threads=8)
+    ctl = oracle.PlenOracle(n, n_threads=8)
+    env = PlenVecEnv(n, auto_reset=False)
+    o.reset(); ctl.reset(); env.reset()
+    st = o.get_state()
+    st["qpos"][:, 7:] = rng.uniform(-0.7, 0.7, (n, 18))
+    ang = rng.uniform(-0.3, 0.3, (n, 3))
+    ang[:, 2] = rng.uniform(-3, 3, n)
+    ang[np.arange(n), rng.integers(0, 2, n)] = rng.choice([-1, 1], n) * rng.uniform(1.2, 1.9, n)
+    cr, sr, cp, sp, cy, sy = np.cos(ang[:, 0] / 2), np.sin(ang[:, 0] / 2), np.cos(ang[:, 1] / 2), np.sin(ang[:, 1] / 2), np.cos(ang[:, 2] / 2), np.sin(ang[:, 2] / 2)
+    st["qpos"][:, 3:7] = np.stack([sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy, cr * cp * cy + sr * sp * sy], 1)
+    st["qpos"][:, 2] = 0.5
+    st["qvel"][:] = 0
+    st["lam_n"][:] = 0; st["in_manifold"][:] = 0
+    o.set_state(st)
+    for e in range(n):
+        pos, rot = o.fk(e)
+        low = min((pos[b["link"] + 1] + rot[b["link"] + 1] @ np.array(b["center"]))[2] -
+                  np.abs((rot[b["link"] + 1] @ np.array(b["rot"]))[2]) @ np.array(b["half"]) for b in o.tree["boxes"])
+        lowf = min((pos[f["link"] + 1] + np.array(f["points"]) @ rot[f["link"] + 1].T)[:, 2].min() - 0.001 for f in o.tree["feet"])
+        st["qpos"][e, 2] -= max(low, lowf - 0.004) + 0.002
+    o.set_state(st)
+    z0 = st["qpos"][:, 2].copy()
+    q_err, q_ctl, pts = [], [], []
+    for t in range(12):
+        st = o.get_state()
+        env.set_state(*abi_from_oracle(st))
+        ctl.set_state({k: (v.astype(np.float32).astype(np.float64) if v.dtype == np.float64 else v.copy()) for k, v in st.items()})
+        act = rng.uniform(-0.5, 0.5, (n, 18)).astype(np.float32)
+        oo, _, _, _ = o.step(act.astype(np.float64))
+        co, _, _, _ = ctl.step(act.astype(np.float64))
+        go = env.step(torch.from_numpy(act).cuda())[0].cpu().numpy()
+        q_err.append(np.abs(go[:, :19] - oo[:, :19]).max(1))
+        q_ctl.append(np.abs(co[:, :19] - oo[:, :19]).max(1))
+        pts.append([o.states[e].last_box_points for e in range(n)])
+    q_err, q_ctl, pts = np.concatenate(q_err), np.concatenate(q_ctl), np.array(pts)
+    print("box points per robot-step: mean %.2f, share with any %.2f | err p50/p75/p90/p99 %s | control %s"
+          % (pts.mean(), (pts > 0).mean(), _quantiles(q_err), _quantiles(q_ctl)))
+    assert (pts > 0).mean() > 0.5                                   # the box rows were exercised
+    assert (_quantiles(q_err) <= 3.0 * _quantiles(q_ctl) + 1e-4).all()
+    # free running from the last forced state: nobody sinks through the floor (0.2 s of free fall would be 0.2 m)
+    for _ in range(12):
+        go = env.step(torch.zeros((n, 18), device="cuda"))[0]
+    assert float(go[:, 18].min()) > 0.015
 
 
 def test_reward_on_same_state(mods):

@@ -84,7 +84,9 @@ def test_free_flight_conserves_momentum(oracle_lib):
 
 
 def test_settle_height_and_standing(oracle_lib):
-    """reset + stand with zero joint targets: torso settles near init_height = 0.160178937611 (plen_env.py:70)."""
+    """reset + stand with zero joint targets in the joint_act variant (rolling friction 0.01, linear damping 0.1,
+    plen_env.py:439-481): the robot stands, ~4e-4 m below the RL-mode constant init_height = 0.160178937611 (plen_env.py:70).
+    The 1e-4 comparison with that constant belongs to the RL-mode env: tests/test_physics_pins.py."""
     o = oracle_lib.PlenOracle(1, joint_act=True)
     o.reset()
     z = []
