@@ -49,8 +49,8 @@ SOLVE_DRAM_BYTES_PER_ROBOT = (207.10e6 + 9.92e6) / 32768
 FLOP_DYN_PER_ROBOT_TICK, FLOP_SOLVE_PER_ROBOT_TICK = 44.8e3, 58.1e3
 FLOP_PER_ENV_STEP = 4 * (FLOP_DYN_PER_ROBOT_TICK + FLOP_SOLVE_PER_ROBOT_TICK)
 # the same workload through the REFERENCE ALGORITHM (33-link ABA + velocity-space PGS with 24-wide rows), counted by the
-# oracle's instrumented FLOP counter (plen_oracle_state.flops; scripts/oracle_flops.py): 1.34 Mflop per env-step
-REF_ALGO_FLOP_PER_ENV_STEP = 1.34e6
+# oracle's instrumented FLOP counter (plen_oracle_state.flops; scripts/oracle_flops.py): 1.32 Mflop per env-step
+REF_ALGO_FLOP_PER_ENV_STEP = 1.32e6
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 
 
@@ -342,7 +342,7 @@ def main():
                          "note": "flop = executed FADD + FMUL + 2 FFMA thread operations counted by ncu (frozen in BASELINE.md); "
                                  "the limiter is the dependency latency of the Gauss-Seidel row chain at 2 warps per scheduler, "
                                  "not the pipe; reference_algorithm = the same env-steps/s priced at the oracle's instrumented "
-                                 "flop count of Bullet's ABA + velocity-space PGS (this solver does 3.3x less arithmetic for "
+                                 "flop count of Bullet's ABA + velocity-space PGS (this solver does 3.2x less arithmetic for "
                                  "the same rows); traffic = ncu DRAM bytes per robot (32768-robot capture) x robots per launch"},
             "roofline_hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak,
                              "peak_source": peak_src, "kernel": "k_solve",

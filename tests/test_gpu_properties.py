@@ -199,10 +199,10 @@ def test_numeric_guard_retires_a_robot_with_a_non_finite_state():
     _rollout(a, 5, seed=41)
     qpos, qvel, aux = _snapshot(a)
     b.reset(); b.set_state(qpos, qvel, aux)
-    # (an infinite VELOCITY is not a fault: the +-100 coordinate-velocity clamp, Bullet's maxCoordinateVelocity, tames it)
-    bad_qvel = qvel.clone(); bad_qvel[9, 7] = float("nan")
-    bad_qpos = qpos.clone(); bad_qpos[40, 0] = float("inf")
-    a.set_state(bad_qpos, bad_qvel, aux)
+    # (a non-finite VELOCITY is not a fault by itself: the +-100 coordinate-velocity clamp -- Bullet's maxCoordinateVelocity,
+    # fminf / fmaxf drop a NaN operand -- turns it into a finite one; the guard watches the pose)
+    bad_qpos = qpos.clone(); bad_qpos[9, 7 + 1] = float("nan"); bad_qpos[40, 0] = float("inf")
+    a.set_state(bad_qpos, qvel, aux)
     reset_obs = _mk(1).reset().clone()                   # the post-reset observation (a constant)
     act = torch.zeros((n, 18), device="cuda")
     oa, ra, da, _ = a.step(act)
