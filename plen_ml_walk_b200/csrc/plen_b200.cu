@@ -22,19 +22,27 @@
 using namespace plen;
 
 // warps per CTA of the warp-per-robot kernels (k_dyn, k_post)
-#define DYN_WPC 4
+#ifndef DYN_WPC
+#define DYN_WPC 10
+#endif
+#ifndef DYN_CTAS
+#define DYN_CTAS 2     // resident k_dyn CTAs per SM the register cap is chosen for (2 x 10 warps; r2_ab4/5: 5 x 4 is 2.6 % slower with box contacts)
+#endif
 #ifndef PLEN_FAN_MAX_N
 #define PLEN_FAN_MAX_N (1 << 30)     // plen_step of at most this many (and at least two sort tiles of) robots runs as concurrent ranges (0: never)
 #endif
 #ifndef PLEN_FAN_RANGES
 #define PLEN_FAN_RANGES 2   // ... this many (<= PLEN_HOST_PIPE); measured: 2 beats 3 / 4 at every batch size (profiles/r1_v9_summary.md)
 #endif
+#ifndef PLEN_MERGE_MAX
+#define PLEN_MERGE_MAX 32768  // ranges of at most this many robots solve box-contact groups inside k_solve, larger ones in k_solve_x (env PLEN_MERGE_MAX overrides: a dev knob)
+#endif
 #ifndef PLEN_HOST_PIPE
 #define PLEN_HOST_PIPE 4      // ranges plen_step_host pipelines (copy of one range under the kernels of the others)
 #endif
 
 struct plen_ctx {
-    int n, device, sm_count;
+    int n, device, sm_count, merge_max;
     plen_config cfg;
     plen_model model;
     DevConfig dc;
@@ -96,7 +104,7 @@ __device__ __forceinline__ DynSmem &stage_table(const float *tab_g) {
 //   actions != NULL : agent-space actions of a new env step; the servo targets are derived (agent_to_env) and kept in tgt
 //   actions == NULL : tgt holds the targets already (NULL = zero targets, the reset pose)
 // 5 CTAs (20 warps) per SM: the register cap (<= 102) costs 16 B of spills outside the hot loops and measured +2.4 %
-__global__ void __launch_bounds__(DYN_WPC * 32, 5)
+__global__ void __launch_bounds__(DYN_WPC * 32, DYN_CTAS)
 k_dyn(const __grid_constant__ DevConfig dc, const __grid_constant__ EnvRanges er, const float *__restrict__ tab_g,
       const float *__restrict__ state, int n, const float *__restrict__ actions, float *__restrict__ tgt,
       float *__restrict__ srec, uint8_t *__restrict__ keys, float *dbg_minv, float *dbg_pos, float *dbg_rot,
@@ -143,45 +151,49 @@ k_dyn(const __grid_constant__ DevConfig dc, const __grid_constant__ EnvRanges er
 // have similar active-point counts (mean per-foot loop length 2.6 -> 1.9 slots on the bench workload) and the heavy
 // warps of every tile are dispatched first.  The sort is stable, so the grouping is reproducible.
 #define RANK_TILE 1024
+#define RANK_KEY_MAX (PLEN_KEY_EXT + PLEN_MAX_BOX_POINTS - 1)
+#define RANK_CLASSES 160      // RANK_KEY_MAX + 1 keys and one class for the slots beyond n, rounded up to a multiple of 32
+static_assert(RANK_KEY_MAX + 2 <= RANK_CLASSES && RANK_CLASSES % 32 == 0 && RANK_KEY_MAX <= 255, "k_rank class table");
 __global__ void __launch_bounds__(RANK_TILE)
 k_rank(const uint8_t *__restrict__ keys, int n, int *__restrict__ perm, int *__restrict__ xgroups) {
     // STABLE counting sort (robots of a class keep their index order), so the grouping of robots into solver warps -- and
     // with it every bit of the step -- is reproducible run to run: rank inside the warp from match_any, warps of a class
     // in warp order through a [warp][class] count table.
-    __shared__ unsigned short s_wcnt[RANK_TILE / 32][128];
-    __shared__ int s_base[128];
+    __shared__ unsigned short s_wcnt[RANK_TILE / 32][RANK_CLASSES];
+    __shared__ int s_base[RANK_CLASSES];
     const int t = threadIdx.x, r = blockIdx.x * RANK_TILE + t, w = t >> 5, lane = t & 31;
-    for (int i = t; i < (RANK_TILE / 32) * 128; i += RANK_TILE) (&s_wcnt[0][0])[i] = 0;
+    for (int i = t; i < (RANK_TILE / 32) * RANK_CLASSES; i += RANK_TILE) (&s_wcnt[0][0])[i] = 0;
     __syncthreads();
-    // class 0 = heaviest; robots beyond n sort last
-    const int cls = (r < n) ? 126 - min(gld_u8(keys + r), 126) : 127;
+    // class 0 = heaviest (key RANK_KEY_MAX: box contacts, most points); robots beyond n sort last
+    const int cls = (r < n) ? RANK_KEY_MAX - min(gld_u8(keys + r), RANK_KEY_MAX) : RANK_CLASSES - 1;
     const unsigned peers = __match_any_sync(0xffffffffu, cls);
     const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
     if (rank_in_warp == 0) s_wcnt[w][cls] = (unsigned short)__popc(peers);
     __syncthreads();
-    if (t < 128) {           // class totals, then (below) their exclusive scan
+    if (t < RANK_CLASSES) {  // class totals, then (below) their exclusive scan
         int tot = 0;
         for (int k = 0; k < RANK_TILE / 32; k++) tot += s_wcnt[k][t];
         s_base[t] = tot;
     }
     __syncthreads();
-    if (t < 32) {            // exclusive scan of the 128 class counts: 4 per lane
-        int c[4], sum = 0;
+    if (t < 32) {            // exclusive scan of the class counts: RANK_CLASSES / 32 per lane
+        constexpr int PER = RANK_CLASSES / 32;
+        int c[PER], sum = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) { c[k] = s_base[4 * t + k]; sum += c[k]; }
+        for (int k = 0; k < PER; k++) { c[k] = s_base[PER * t + k]; sum += c[k]; }
         int incl = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (t >= d) incl += o; }
         int run = incl - sum;
 #pragma unroll
-        for (int k = 0; k < 4; k++) { s_base[4 * t + k] = run; run += c[k]; }
+        for (int k = 0; k < PER; k++) { s_base[PER * t + k] = run; run += c[k]; }
     }
     __syncthreads();
     int pos = rank_in_warp;
     for (int k = 0; k < w; k++) pos += s_wcnt[k][cls];
     perm[blockIdx.x * RANK_TILE + s_base[cls] + pos] = r;
-    // class 0 = robots with box contacts (key PLEN_KEY_EXT): they lead the tile; so many solver groups hold one
-    if (t == 0 && xgroups) xgroups[blockIdx.x] = (s_base[1] + PLEN_SOLVE_ROBOTS - 1) / PLEN_SOLVE_ROBOTS;
+    // classes 0 .. PLEN_MAX_BOX_POINTS - 1 = robots with box contacts: they lead the tile; so many solver groups hold one
+    if (t == 0 && xgroups) xgroups[blockIdx.x] = (s_base[PLEN_MAX_BOX_POINTS] + PLEN_SOLVE_ROBOTS - 1) / PLEN_SOLVE_ROBOTS;
 }
 
 // Second half of a tick, 4 lanes per robot: PGS + delta-v + integration, state record updated in place.
@@ -190,24 +202,41 @@ k_rank(const uint8_t *__restrict__ keys, int n, int *__restrict__ perm, int *__r
 #ifndef PLEN_SOLVE_MAXREG
 #define PLEN_SOLVE_MAXREG 255
 #endif
+// MERGED = false: the plain instance only; groups that hold a box-contact robot return at once and k_solve_x takes them.
+// MERGED = true : those groups run the EXT instance inside this launch (same footprint: the EXT rows are read from global
+//                 memory).  Measured (r2_ab1): at 4,096 robots the merged launch saves the serial tail of a second, nearly
+//                 empty launch per tick (0.751 vs 1.062 ms per env step); at 131,072 robots the plain kernel compiled alone
+//                 is 1-2 % faster (251 registers, smaller code), so launch_ticks picks by range size (PLEN_MERGE_MAX).
+template <bool MERGED>
 __global__ void __maxnreg__(PLEN_SOLVE_MAXREG)
 k_solve(const __grid_constant__ DevConfig dc, const float *__restrict__ srec, const int *__restrict__ perm,
-        float *__restrict__ state, int n, int n_tiles, const int *__restrict__ xgroups) {
+        float *__restrict__ state, int n, int n_tiles, const int *__restrict__ xgroups, const float *__restrict__ srx,
+        const uint8_t *__restrict__ keys) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *Gs = reinterpret_cast<float *>(smem_raw);
     const int lane = threadIdx.x;
     const int tile = blockIdx.x % n_tiles, grp = blockIdx.x / n_tiles;
-    if (xgroups && grp < gld_i(xgroups + tile)) return;      // a group with a box-contact robot: k_solve_x takes it
+    // the first xgroups[tile] groups of a tile hold the robots whose link boxes touch the ground (k_rank sorts them to the front)
+    const bool xgrp = xgroups && grp < gld_i(xgroups + tile);
+    if (!MERGED && xgrp) return;
     const int robot = gld_i(perm + tile * RANK_TILE + grp * PLEN_SOLVE_ROBOTS + (lane >> 2));
     const bool valid = robot < n;
     const size_t r = valid ? (size_t)robot : 0;
-    solve_tick<false>(dc, srec + r * SR_WORDS, Gs + (size_t)(lane >> 2) * PLEN_GS_WORDS, state + r * PLEN_STATE_WORDS, lane, valid);
+    if (MERGED && xgrp) {
+        const bool isx = valid && gld_u8(keys + r) >= PLEN_KEY_EXT;
+        const int nx = isx ? (int)gld(srx + r * XR_WORDS + XR_NX) : 0;
+        solve_tick<1>(dc, srec + r * SR_WORDS, Gs + (size_t)(lane >> 2) * PLEN_GS_WORDS, state + r * PLEN_STATE_WORDS, lane, valid,
+                         srx + r * XR_WORDS, nx);
+    } else {
+        solve_tick<0>(dc, srec + r * SR_WORDS, Gs + (size_t)(lane >> 2) * PLEN_GS_WORDS, state + r * PLEN_STATE_WORDS, lane, valid);
+    }
 }
 
-// The same solve for the groups that hold a robot whose link boxes touch the ground (the first xgroups[tile] groups of a
-// tile): EXT instance, with the box-contact rows of the extension records staged behind G.  XS_SPLIT CTAs per tile walk the
-// tile's groups, so the grid does not grow with the (unknown to the host) number of such groups; most CTAs find none.
-#define XS_SPLIT 8
+// The EXT instance as its own launch (large ranges): XS_SPLIT CTAs per tile walk the tile's box-contact groups, so the grid
+// does not grow with the (unknown to the host) number of such groups; most CTAs find none.
+#ifndef XS_SPLIT
+#define XS_SPLIT 16
+#endif
 __global__ void __maxnreg__(255)
 k_solve_x(const __grid_constant__ DevConfig dc, const float *__restrict__ srec, const float *__restrict__ srx,
           const uint8_t *__restrict__ keys, const int *__restrict__ perm, float *__restrict__ state, int n, int n_tiles,
@@ -222,10 +251,10 @@ k_solve_x(const __grid_constant__ DevConfig dc, const float *__restrict__ srec, 
         const int robot = gld_i(perm + tile * RANK_TILE + grp * PLEN_SOLVE_ROBOTS + (lane >> 2));
         const bool valid = robot < n;
         const size_t r = valid ? (size_t)robot : 0;
-        const bool isx = valid && gld_u8(keys + r) == PLEN_KEY_EXT;
+        const bool isx = valid && gld_u8(keys + r) >= PLEN_KEY_EXT;
         const int nx = isx ? (int)gld(srx + r * XR_WORDS + XR_NX) : 0;
-        solve_tick<true>(dc, srec + r * SR_WORDS, Gs + (size_t)(lane >> 2) * PLEN_GS_WORDS, state + r * PLEN_STATE_WORDS, lane, valid,
-                         srx + r * XR_WORDS, Xs + (size_t)(lane >> 2) * PLEN_XS_WORDS, nx);
+        solve_tick<2>(dc, srec + r * SR_WORDS, Gs + (size_t)(lane >> 2) * PLEN_GS_WORDS, state + r * PLEN_STATE_WORDS, lane, valid,
+                         srx + r * XR_WORDS, nx, Xs + (size_t)(lane >> 2) * PLEN_XS_WORDS);
         __syncwarp();
     }
 }
@@ -504,12 +533,19 @@ static void launch_ticks(plen_ctx *ctx, float *state, int n, const float *action
         if (ev) cudaEventRecord(ev[2 * t + 1], st);
         const int nt = rank_tiles(n);
         k_rank<<<nt, RANK_TILE, 0, st>>>(key, n, perm, xg);
-        k_solve<<<nt * (RANK_TILE / PLEN_SOLVE_ROBOTS), 32, SOLVE_SMEM, st>>>(ctx->dc, srec, perm, state, n, nt, xg);
-        ctx->launches += 3;
-        if (boxes) {
+        const int ng = nt * (RANK_TILE / PLEN_SOLVE_ROBOTS);
+        if (!boxes) {
+            k_solve<false><<<ng, 32, SOLVE_SMEM, st>>>(ctx->dc, srec, perm, state, n, nt, nullptr, nullptr, key);
+        } else if (n > ctx->merge_max) {
+            // (k_solve_x on a side stream next to k_solve, fork / join per tick, was measured 1.4 % SLOWER at 131,072 robots
+            // than running it behind k_solve -- r2_ab2: its few long warps take SM slots from the main launch early)
+            k_solve<false><<<ng, 32, SOLVE_SMEM, st>>>(ctx->dc, srec, perm, state, n, nt, xg, srx, key);
             k_solve_x<<<nt * XS_SPLIT, 32, SOLVE_X_SMEM, st>>>(ctx->dc, srec, srx, key, perm, state, n, nt, xg);
             ctx->launches += 1;
+        } else {
+            k_solve<true><<<ng, 32, SOLVE_SMEM, st>>>(ctx->dc, srec, perm, state, n, nt, xg, srx, key);
         }
+        ctx->launches += 3;
     }
 }
 
@@ -571,15 +607,18 @@ void plen_destroy(plen_ctx *ctx) {
 
 static int create_impl(plen_ctx *ctx) {
     const int n = ctx->n;
+    ctx->merge_max = getenv("PLEN_MERGE_MAX") ? atoi(getenv("PLEN_MERGE_MAX")) : PLEN_MERGE_MAX;
     CK(ctx, cudaSetDevice(ctx->device));
     CK(ctx, cudaFuncSetAttribute(k_dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DYN_SMEM));
     CK(ctx, cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DYN_SMEM));
     CK(ctx, cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DYN_SMEM));
-    CK(ctx, cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
+    CK(ctx, cudaFuncSetAttribute(k_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
+    CK(ctx, cudaFuncSetAttribute(k_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
     CK(ctx, cudaFuncSetAttribute(k_solve_x, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_X_SMEM));
+    CK(ctx, cudaFuncSetAttribute(k_solve<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(ctx, cudaFuncSetAttribute(k_solve_x, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     // both hot kernels are occupancy-limited by shared memory: ask for the largest carve-out (7 k_solve CTAs per SM)
-    CK(ctx, cudaFuncSetAttribute(k_solve, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(ctx, cudaFuncSetAttribute(k_solve<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(ctx, cudaFuncSetAttribute(k_dyn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ctx->pipe[0] = ctx->stream;

@@ -131,7 +131,10 @@ enum {
     XR_J = 0, XR_B = 32, XR_BB = 64, XR_RHS = 70, XR_DINV = 71, XR_D = 72, XR_ROW_WORDS = 80,
     XR_WORDS = XR_ROWS + 3 * PLEN_MAX_BOX_POINTS * XR_ROW_WORDS
 };
-#define PLEN_KEY_EXT 126     // sort key of a robot with box contacts: its own (heaviest) class, first in every tile of k_rank
+// sort keys of a robot with nx = 1 .. PLEN_MAX_BOX_POINTS box contact points: PLEN_KEY_EXT + nx - 1, above every foot-only key
+// (<= 124), so these robots lead every tile of k_rank, those with the most points first (a solver warp loops to the largest
+// point count of its eight robots)
+#define PLEN_KEY_EXT 125
 
 // index (0..3) of the k-th set bit of a 4-bit mask, -1 if there are fewer
 PLEN_DEV int nth_bit4(unsigned m, int k) {
@@ -319,6 +322,9 @@ PLEN_DEV void row_entries(int type, const float *a, const float *m, const float 
 struct DebugOut { float *minv, *pos, *rot; };   // [24*24], [24*3], [24*9] of one env; all nullable
 
 PLEN_DEV_NOINLINE void box_rows(const DevConfig &cfg, const float *tab, WarpScratch &ws, int lane, float vstar, int nx, float *srx);
+PLEN_DEV_NOINLINE int box_points(const DevConfig &cfg, const float *tab, WarpScratch &ws, int lane, bool touch, float cz, float rz0,
+                                 float rz1, float rz2, int bl, float R0, float R1, float R2, float R3, float R4, float R5, float R6,
+                                 float R7, float R8, float p0, float p1, float p2);
 
 PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch &ws, LaneState &L, int lane,
                             float *srec, uint8_t *sort_key, const DebugOut *dbg = nullptr, float *srx = nullptr) {
@@ -735,80 +741,11 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
         const float cz = L.pos[2] + pz + r20 * tab[(T_BOX_C + 0) * 32 + lane] + r21 * tab[(T_BOX_C + 1) * 32 + lane] +
                          r22 * tab[(T_BOX_C + 2) * 32 + lane];
         const bool touch = lane < cfg.n_boxes && cz - (fabsf(az[0]) + fabsf(az[1]) + fabsf(az[2])) <= 0.0f;
-        if (ballot(touch)) {
-            // incident face: axis ks most aligned with the ground normal (first maximum), walked towards the ground;
-            // vertex v = (+-) along ki = ks + 1, (+-) along kj = ks + 2 (mod 3), bit 0 / bit 1 of v
-            const int ks = (fabsf(rz[1]) > fabsf(rz[0])) ? ((fabsf(rz[2]) > fabsf(rz[1])) ? 2 : 1) : ((fabsf(rz[2]) > fabsf(rz[0])) ? 2 : 0);
-            const float zs = (ks == 0) ? az[0] : ((ks == 1) ? az[1] : az[2]);
-            const float zi = (ks == 0) ? az[1] : ((ks == 1) ? az[2] : az[0]);
-            const float zj = (ks == 0) ? az[2] : ((ks == 1) ? az[0] : az[1]);
-            float depth[4];
-            unsigned cand = 0;
-#pragma unroll
-            for (int v = 0; v < 4; v++) {
-                const float vz = cz - fabsf(zs) + ((v & 1) ? zi : -zi) + ((v & 2) ? zj : -zj);
-                depth[v] = -vz;
-                if (touch && depth[v] >= 0.0f) cand |= 1u << v;
-            }
-            unsigned mine = 0;
-            for (int q = 0; q < PLEN_MAX_BOX_POINTS; q++) {
-                float bd = -1.0f;
-                int bv = 0;
-#pragma unroll
-                for (int v = 0; v < 4; v++)
-                    if (((cand & ~mine) >> v) & 1u) { if (depth[v] > bd) { bd = depth[v]; bv = v; } }
-                const unsigned key = (bd >= 0.0f) ? f_bits(bd) + 1u : 0u;     // depth >= 0: the bit pattern orders like the value
-                const unsigned best = redux_max(key);
-                if (best == 0u) break;
-                if (lane == lowest_bit(ballot(key == best))) mine |= 1u << bv;
-                nx++;
-            }
-            if (nx) {
-                // slots in (box, vertex) order; the owning lane publishes point, depth, body lane and restitution factor
-                int below = 0;
-#pragma unroll
-                for (int b = 0; b < 4; b++) below += popc_(ballot((mine >> b) & 1u) & ((1u << lane) - 1u));
-                float Rb[9], pb[3];
-#pragma unroll
-                for (int k = 0; k < 9; k++) Rb[k] = shfl(Rw[k], bl);
-#pragma unroll
-                for (int k = 0; k < 3; k++) pb[k] = shfl(pw[k], bl);
-                if (mine) {
-                    float ax[3][3], c[3];     // ax[k] = box axis k in world axes times its half extent; c = box centre rel. base origin
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        const float h = tab[(T_BOX_H + k) * 32 + lane];
-#pragma unroll
-                        for (int r = 0; r < 3; r++)
-                            ax[k][r] = (Rb[3 * r] * tab[(T_BOX_R + k) * 32 + lane] + Rb[3 * r + 1] * tab[(T_BOX_R + 3 + k) * 32 + lane] +
-                                        Rb[3 * r + 2] * tab[(T_BOX_R + 6 + k) * 32 + lane]) * h;
-                    }
-#pragma unroll
-                    for (int r = 0; r < 3; r++)
-                        c[r] = pb[r] + Rb[3 * r] * tab[(T_BOX_C + 0) * 32 + lane] + Rb[3 * r + 1] * tab[(T_BOX_C + 1) * 32 + lane] +
-                               Rb[3 * r + 2] * tab[(T_BOX_C + 2) * 32 + lane];
-                    const float sg = (zs > 0.0f) ? -1.0f : 1.0f;
-                    int slot = below;
-#pragma unroll
-                    for (int v = 0; v < 4; v++) {
-                        if (!((mine >> v) & 1u)) continue;
-                        const float si = (v & 1) ? 1.0f : -1.0f, sj = (v & 2) ? 1.0f : -1.0f;
-#pragma unroll
-                        for (int r = 0; r < 3; r++) {
-                            const float as_ = (ks == 0) ? ax[0][r] : ((ks == 1) ? ax[1][r] : ax[2][r]);
-                            const float ai_ = (ks == 0) ? ax[1][r] : ((ks == 1) ? ax[2][r] : ax[0][r]);
-                            const float aj_ = (ks == 0) ? ax[2][r] : ((ks == 1) ? ax[0][r] : ax[1][r]);
-                            ws.xp[slot][r] = c[r] + sg * as_ + si * ai_ + sj * aj_;
-                        }
-                        ws.xp[slot][3] = depth[v];
-                        ws.xp[slot][4] = (float)bl;
-                        ws.xp[slot][5] = tab[T_BOX_REST * 32 + lane];
-                        slot++;
-                    }
-                }
-                warp_sync();
-            }
-        }
+        // rare branch, kept out of line: k_dyn is an instruction-fetch-bound straight line (no_instruction stalls are 8-14 % of
+        // its warp latency, profiles/r2_summary.md) and must not carry this code in the middle of its hot path
+        if (ballot(touch))
+            nx = box_points(cfg, tab, ws, lane, touch, cz, rz[0], rz[1], rz[2], bl, Rw[0], Rw[1], Rw[2], Rw[3], Rw[4], Rw[5], Rw[6],
+                            Rw[7], Rw[8], pw[0], pw[1], pw[2]);
     }
     const bool ext = nx > 0;
 
@@ -1006,13 +943,101 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
         srec[SR_BASE + 15] = L.motor_s;           // ... and the servo impulse bound of this robot
         // k_solve groups robots of similar contact load into the same warp (tile-local sort by this key)
         const int n0 = popc_(man_new & 15u), n1 = popc_((man_new >> 4) & 15u);
-        if (sort_key) *sort_key = ext ? (uint8_t)PLEN_KEY_EXT : (uint8_t)((n0 > n1 ? n0 : n1) * 25 + n0 * 5 + n1);
+        if (sort_key) *sort_key = ext ? (uint8_t)(PLEN_KEY_EXT + nx - 1) : (uint8_t)((n0 > n1 ? n0 : n1) * 25 + n0 * 5 + n1);
     }
     warp_sync();
     if (ext) box_rows(cfg, tab, ws, lane, vstar, nx, srx);
 }
 
-// Rare path of tick_dynamics: the rows of the nx selected box contact points (ws.xp), as explicit operational-space vectors.
+// Rare path of tick_dynamics, part 1: some link box of this robot touches the ground.  Lane b holds box b (touch, centre height
+// cz, z components rz of its axes, owning body lane bl) and the world frame Rw / pw of its OWN body; selects the
+// PLEN_MAX_BOX_POINTS deepest penetrating vertices of the robot, publishes them in ws.xp in (box, vertex) order and returns
+// their number.  Not inlined (see the call site).
+PLEN_DEV_NOINLINE int box_points(const DevConfig &cfg, const float *tab, WarpScratch &ws, int lane, bool touch, float cz, float rz0,
+                                 float rz1, float rz2, int bl, float R0, float R1, float R2, float R3, float R4, float R5, float R6,
+                                 float R7, float R8, float p0, float p1, float p2) {
+    const float Rw[9] = {R0, R1, R2, R3, R4, R5, R6, R7, R8}, pw[3] = {p0, p1, p2};
+    const float rz[3] = {rz0, rz1, rz2};
+    float az[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) az[k] = rz[k] * tab[(T_BOX_H + k) * 32 + lane];
+    int nx = 0;
+    // incident face: axis ks most aligned with the ground normal (first maximum), walked towards the ground;
+    // vertex v = (+-) along ki = ks + 1, (+-) along kj = ks + 2 (mod 3), bit 0 / bit 1 of v
+    const int ks = (fabsf(rz[1]) > fabsf(rz[0])) ? ((fabsf(rz[2]) > fabsf(rz[1])) ? 2 : 1) : ((fabsf(rz[2]) > fabsf(rz[0])) ? 2 : 0);
+    const float zs = (ks == 0) ? az[0] : ((ks == 1) ? az[1] : az[2]);
+    const float zi = (ks == 0) ? az[1] : ((ks == 1) ? az[2] : az[0]);
+    const float zj = (ks == 0) ? az[2] : ((ks == 1) ? az[0] : az[1]);
+    float depth[4];
+    unsigned cand = 0;
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+        const float vz = cz - fabsf(zs) + ((v & 1) ? zi : -zi) + ((v & 2) ? zj : -zj);
+        depth[v] = -vz;
+        if (touch && depth[v] >= 0.0f) cand |= 1u << v;
+    }
+    unsigned mine = 0;
+    for (int q = 0; q < PLEN_MAX_BOX_POINTS; q++) {
+        float bd = -1.0f;
+        int bv = 0;
+#pragma unroll
+        for (int v = 0; v < 4; v++)
+            if (((cand & ~mine) >> v) & 1u) { if (depth[v] > bd) { bd = depth[v]; bv = v; } }
+        const unsigned key = (bd >= 0.0f) ? f_bits(bd) + 1u : 0u;     // depth >= 0: the bit pattern orders like the value
+        const unsigned best = redux_max(key);
+        if (best == 0u) break;
+        if (lane == lowest_bit(ballot(key == best))) mine |= 1u << bv;
+        nx++;
+    }
+    if (nx) {
+        // slots in (box, vertex) order; the owning lane publishes point, depth, body lane and restitution factor
+        int below = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) below += popc_(ballot((mine >> b) & 1u) & ((1u << lane) - 1u));
+        float Rb[9], pb[3];
+#pragma unroll
+        for (int k = 0; k < 9; k++) Rb[k] = shfl(Rw[k], bl);
+#pragma unroll
+        for (int k = 0; k < 3; k++) pb[k] = shfl(pw[k], bl);
+        if (mine) {
+            float ax[3][3], c[3];     // ax[k] = box axis k in world axes times its half extent; c = box centre rel. base origin
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float h = tab[(T_BOX_H + k) * 32 + lane];
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+                    ax[k][r] = (Rb[3 * r] * tab[(T_BOX_R + k) * 32 + lane] + Rb[3 * r + 1] * tab[(T_BOX_R + 3 + k) * 32 + lane] +
+                                Rb[3 * r + 2] * tab[(T_BOX_R + 6 + k) * 32 + lane]) * h;
+            }
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+                c[r] = pb[r] + Rb[3 * r] * tab[(T_BOX_C + 0) * 32 + lane] + Rb[3 * r + 1] * tab[(T_BOX_C + 1) * 32 + lane] +
+                       Rb[3 * r + 2] * tab[(T_BOX_C + 2) * 32 + lane];
+            const float sg = (zs > 0.0f) ? -1.0f : 1.0f;
+            int slot = below;
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                if (!((mine >> v) & 1u)) continue;
+                const float si = (v & 1) ? 1.0f : -1.0f, sj = (v & 2) ? 1.0f : -1.0f;
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    const float as_ = (ks == 0) ? ax[0][r] : ((ks == 1) ? ax[1][r] : ax[2][r]);
+                    const float ai_ = (ks == 0) ? ax[1][r] : ((ks == 1) ? ax[2][r] : ax[0][r]);
+                    const float aj_ = (ks == 0) ? ax[2][r] : ((ks == 1) ? ax[0][r] : ax[1][r]);
+                    ws.xp[slot][r] = c[r] + sg * as_ + si * ai_ + sj * aj_;
+                }
+                ws.xp[slot][3] = depth[v];
+                ws.xp[slot][4] = (float)bl;
+                ws.xp[slot][5] = tab[T_BOX_REST * 32 + lane];
+                slot++;
+            }
+        }
+        warp_sync();
+    }
+    return nx;
+}
+
+// Rare path of tick_dynamics, part 2: the rows of the nx selected box contact points (ws.xp), as explicit operational-space vectors.
 // For a unit impulse along direction d at point p of body b, with generalized Jacobian Jg (support: base lanes 0..5 and the
 // chain of b) and response Bg = M^-1 Jg^T:
 //   Jx: base twist = right-foot twist - sum_{j in right leg} s_j qd_j   =>   slots of the right-foot twist carry Jg_base,

@@ -54,7 +54,7 @@ namespace plen {
 #define PLEN_GS_COLS 24
 #define PLEN_GS_WORDS (PLEN_GS_COLS * 32 + 4)
 #define PLEN_SOLVE_ROBOTS 8      // robots per warp
-// EXT instance only: the Jx / Bx vectors of the 3 x PLEN_MAX_BOX_POINTS box-contact rows of a robot (plen_device.cuh, XR_*),
+// EXT == 2 only: the Jx / Bx vectors of the 3 x PLEN_MAX_BOX_POINTS box-contact rows of a robot (plen_device.cuh, XR_*),
 // [row][Jx 32 | Bx 32] plus the same one-float4 skew between robots
 #define PLEN_XS_WORDS (3 * PLEN_MAX_BOX_POINTS * 64 + 4)
 
@@ -166,6 +166,12 @@ PLEN_DEV void apply_vec6(float (&o)[8], const vec4 &a, const vec4 &b, float d) {
     fma2(o[6], o[7], b.z, b.w, d);
 }
 
+// vec4 number v4 of part (0: Jx, 1: Bx) of row `row` of an extension record; zeros for a robot without that row
+PLEN_DEV vec4 x_vec(const float *srx, int row, int part, int v4, bool on) {
+    const vec4 z4 = {0.0f, 0.0f, 0.0f, 0.0f};
+    return on ? gld4(srx + XR_ROWS + row * XR_ROW_WORDS + 32 * part + 4 * v4) : z4;
+}
+
 PLEN_DEV void load8(const float *p, float (&o)[8]) {
     const vec4 a = gld4(p), b = gld4(p + 4);      // solve-record / state words: L2 only
     o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
@@ -173,12 +179,12 @@ PLEN_DEV void load8(const float *p, float (&o)[8]) {
 
 // One robot = lanes (lane & 28) .. +3 of the warp.  srec: this robot's solve record (global); Gs: this robot's
 // PLEN_GS_WORDS shared staging area; state: this robot's 96-word state record (global), updated in place.
-// EXT: the instance that also iterates the box-contact rows of the extension record srx (nx points of this robot, 0 for a
-// robot without any; Xs = this robot's PLEN_XS_WORDS staging area).  Only warps that hold such a robot run it (k_rank puts
-// them first in every tile), so the plain instance keeps its registers and its shared-memory footprint.
-template <bool EXT>
+// EXT != 0: the instance that also iterates the box-contact rows of the extension record srx (nx points of this robot, 0 for a
+// robot without any).  Only warps that hold such a robot run it (k_rank puts them first in every tile), so the plain
+// instance keeps its instruction stream.
+template <int EXT>
 PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, float *Gs, float *__restrict__ state,
-                         int lane, bool valid, const float *__restrict__ srx = nullptr, float *Xs = nullptr, int nx = 0) {
+                         int lane, bool valid, const float *__restrict__ srx = nullptr, int nx = 0, float *Xs = nullptr) {
     const LoopConsts lc = pin_loop_consts(cfg, lane);
     const int g = lc.g;      // lane & 3, pinned in a register
 #define GSH(v, l) shfl4((v), (l))
@@ -298,23 +304,33 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
     float resX = 0.0f;
     if (EXT) {
         nxmax = (int)redux_max((unsigned)nx);
-        for (int q = 0; q < nxmax; q++) {
+        // the 64-word Jx | Bx vectors of every row are read from the extension record where they are used (ld.global.v4: a
+        // robot's 3 KB stay in L1 / L2 for the 50 iterations): no shared memory, so this instance runs in the same launch
+        // and with the same footprint as the plain one.  Robots without box contacts (nx = 0) get zero vectors.
+        if (valid && g < nx) {
 #pragma unroll
             for (int r = 0; r < 3; r++) {
-                const float *row = srx + XR_ROWS + (3 * q + r) * XR_ROW_WORDS;
-                vec4 *dst = reinterpret_cast<vec4 *>(Xs + (3 * q + r) * 64);
-                const vec4 z4 = {0.0f, 0.0f, 0.0f, 0.0f};
-                const bool on = valid && q < nx;
-                // this lane's slices: words 8 g .. 8 g + 7 of Jx and of Bx
-                dst[2 * g] = on ? gld4(row + XR_J + 8 * g) : z4;
-                dst[2 * g + 1] = on ? gld4(row + XR_J + 8 * g + 4) : z4;
-                dst[8 + 2 * g] = on ? gld4(row + XR_B + 8 * g) : z4;
-                dst[8 + 2 * g + 1] = on ? gld4(row + XR_B + 8 * g + 4) : z4;
-                if (on && g == q) { x_rhs[r] = gld(row + XR_RHS); x_dinv[r] = gld(row + XR_DINV); x_d[r] = gld(row + XR_D); }
+                const float *row = srx + XR_ROWS + (3 * g + r) * XR_ROW_WORDS;
+                x_rhs[r] = gld(row + XR_RHS); x_dinv[r] = gld(row + XR_DINV); x_d[r] = gld(row + XR_D);
             }
         }
+        // EXT == 2 (k_solve_x, a launch of its own with room for it): the vectors are staged in shared memory instead,
+        // [row][Jx 32 | Bx 32] per robot (PLEN_XS_WORDS); 1 % of the step at 131,072 robots against the global reads (r2_ab3)
+        if (EXT == 2) {
+            for (int row = 0; row < 3 * nxmax; row++) {
+                vec4 *dst = reinterpret_cast<vec4 *>(Xs + row * 64);
+#pragma unroll
+                for (int v4 = 0; v4 < 2; v4++) {
+                    dst[2 * g + v4] = x_vec(srx, row, 0, 2 * g + v4, valid && row < 3 * nx);
+                    dst[8 + 2 * g + v4] = x_vec(srx, row, 1, 2 * g + v4, valid && row < 3 * nx);
+                }
+            }
+            warp_sync();
+        }
     }
-#define X_VEC(row, part, half) (reinterpret_cast<const vec4 *>(Xs + (row) * 64 + 32 * (part))[2 * g + (half)])
+#define X_VEC(row, part, half)                                                                              \
+    ((EXT == 2) ? reinterpret_cast<const vec4 *>(Xs + (row) * 64 + 32 * (part))[2 * g + (half)]              \
+                : x_vec(srx, (row), (part), 2 * g + (half), valid && (row) < 3 * nx))
 #define X_DOT(row, out)                                                                                     \
     {                                                                                                       \
         const vec4 xja_ = X_VEC(row, 0, 0), xjb_ = X_VEC(row, 0, 1);                                          \

@@ -21,6 +21,8 @@ lib.plen_step.argtypes = [vp] * 8
 lib.plen_reset.argtypes = [vp] * 4
 cfg = _abi.PlenConfigC()
 lib.plen_default_config(C.byref(cfg), 0)
+if os.environ.get("PLEN_AB_NOLINKS"):
+    cfg.link_contacts = 0      # round-1 behaviour: only the soles touch the ground
 model = _abi.model_to_c(packaged_model())
 ctx = lib.plen_create(C.byref(cfg), C.byref(model), E, 0)
 assert ctx
@@ -35,7 +37,7 @@ lib.plen_reset(ctx, None, P(obs), st)
 def step(a):
     rc = lib.plen_step(ctx, P(a), P(obs), P(rew), P(done), P(tmo), None, st)
     assert rc == 0
-for w in range(5):
+for w in range(int(os.environ.get("PLEN_AB_WARM", "5"))):
     step(acts[w % 8])
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

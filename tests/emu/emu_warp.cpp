@@ -107,7 +107,7 @@ void emu_init_record(const plen_config *c, float *rec) { init_record(c, rec); }
 static void run_ticks(const DevConfig &dc, const float *tab, float *records, const float *tgt, int n, int n_ticks,
                       const DebugOut *dbg0, int lane) {
     static WarpScratch ws;
-    static std::vector<float> srec, srx, Gs(PLEN_SOLVE_ROBOTS * PLEN_GS_WORDS), Xs(PLEN_SOLVE_ROBOTS * PLEN_XS_WORDS);
+    static std::vector<float> srec, srx, Gs(PLEN_SOLVE_ROBOTS * PLEN_GS_WORDS);
     static std::vector<uint8_t> keys;
     if (lane == 0) { srec.assign((size_t)n * SR_WORDS, 0.0f); srx.assign((size_t)n * XR_WORDS, 0.0f); keys.assign(n, 0); }
     bar();
@@ -125,13 +125,13 @@ static void run_ticks(const DevConfig &dc, const float *tab, float *records, con
             const int rr = valid ? r : 0;
             // groups are run through the instance k_rank would route them to: EXT iff one of the eight robots has box contacts
             bool anyx = false;
-            for (int k = b; k < b + PLEN_SOLVE_ROBOTS && k < n; k++) anyx = anyx || keys[k] == PLEN_KEY_EXT;
+            for (int k = b; k < b + PLEN_SOLVE_ROBOTS && k < n; k++) anyx = anyx || keys[k] >= PLEN_KEY_EXT;
             if (anyx) {
-                const int nx = (valid && keys[rr] == PLEN_KEY_EXT) ? (int)srx[(size_t)rr * XR_WORDS + XR_NX] : 0;
-                solve_tick<true>(dc, srec.data() + (size_t)rr * SR_WORDS, Gs.data() + (lane >> 2) * PLEN_GS_WORDS, records + 96 * rr, lane, valid,
-                                 srx.data() + (size_t)rr * XR_WORDS, Xs.data() + (lane >> 2) * PLEN_XS_WORDS, nx);
+                const int nx = (valid && keys[rr] >= PLEN_KEY_EXT) ? (int)srx[(size_t)rr * XR_WORDS + XR_NX] : 0;
+                solve_tick<1>(dc, srec.data() + (size_t)rr * SR_WORDS, Gs.data() + (lane >> 2) * PLEN_GS_WORDS, records + 96 * rr, lane, valid,
+                                 srx.data() + (size_t)rr * XR_WORDS, nx);
             } else {
-                solve_tick<false>(dc, srec.data() + (size_t)rr * SR_WORDS, Gs.data() + (lane >> 2) * PLEN_GS_WORDS, records + 96 * rr, lane, valid);
+                solve_tick<0>(dc, srec.data() + (size_t)rr * SR_WORDS, Gs.data() + (lane >> 2) * PLEN_GS_WORDS, records + 96 * rr, lane, valid);
             }
             bar();
         }

@@ -97,6 +97,28 @@ def test_step_is_deterministic_run_to_run():
         assert _same(a, b)
 
 
+def test_box_contact_solver_instances_agree_bit_for_bit(monkeypatch):
+    """Robots whose link boxes touch the ground are solved by the EXT instance of the PGS: inside k_solve for small ranges
+    (rows read from global memory), in k_solve_x for large ones (rows staged in shared memory).  The choice (PLEN_MERGE_MAX,
+    read at plen_create) must not change one bit; the rollout is long enough for most robots to have fallen."""
+    n = 8192
+    g = torch.Generator(device="cuda"); g.manual_seed(23)
+    acts = [torch.empty((n, 18), device="cuda").uniform_(-1, 1, generator=g) for _ in range(70)]
+    res = []
+    for merge_max in ("0", "1000000000"):
+        monkeypatch.setenv("PLEN_MERGE_MAX", merge_max)
+        env = _mk(n, auto_reset=False)
+        env.reset()
+        ever_done = torch.zeros(n, dtype=torch.bool, device="cuda")
+        for a in acts:
+            _, _, d, _ = env.step(a)
+            ever_done |= d
+        res.append(_snapshot(env) + [env._obs.clone(), env._reward.clone()])
+        assert ever_done.float().mean().item() > 0.3          # plenty of robots went down (and kept lying there)
+    for a, b in zip(*res):
+        assert _same(a, b)
+
+
 def test_one_million_robots_config5_full_size():
     """1,048,576 robots on ONE GPU (6.7 GB of solve records): the first 4096 robots reproduce a 4096-robot context bit
     for bit over 6 steps with auto-reset, and robots with identical inputs stay identical across the whole batch."""
