@@ -266,6 +266,15 @@ int plen_td3_default_hyper(plen_td3_hyper *h);
 plen_td3 *plen_td3_create(int max_batch, int device);            /* workspace for minibatches of <= max_batch rows */
 void plen_td3_destroy(plen_td3 *t);
 long long plen_td3_launches(const plen_td3 *t);                  /* kernels launched so far (bench accounting) */
+/* Precision of the learner's matrix products (td3.py:259-356 runs them in fp32 torch): 0 = FP32 CUDA cores, within 1e-5 of
+ * torch (default, the parity path); 1 = for minibatches >= 512 every product that fills a 128-row tile (forward,
+ * backward-data and backward-weight of the 256-wide layers and of fc1) runs on the 5th-generation tensor cores --
+ * tcgen05.mma kind::tf32 with every operand split into two TF32 parts (3xTF32: A_lo B_hi + A_hi B_lo + A_hi B_hi, FP32
+ * accumulation in TMEM), which keeps fp32-level accuracy (one-pass TF32 flips ReLU masks and moves hidden-layer gradients by
+ * 2-5 %; measured).  Gradients within 1e-3 of autograd relative to the largest entry of each tensor (tested).  At the
+ * reference's batch of 100 the update is launch bound and stays on the FP32 path either way. */
+int plen_td3_set_precision(plen_td3 *t, int tf32);
+int plen_td3_tc_timed_out(void);     /* diagnostic: 1 if a tensor-core learner launch ever abandoned an mbarrier wait */
 /* minibatch: drawn from the replay ring (uniform with replacement, td3.py:175) or given explicitly */
 int plen_td3_sample(plen_td3 *t, plen_replay *rb, int batch, unsigned long long seed, void *stream);
 int plen_td3_set_batch(plen_td3 *t, const float *state_dev, const float *action_dev, const float *next_state_dev,

@@ -86,7 +86,7 @@ EXPORTS = (
     "plen_reset", "plen_step", "plen_step_host", "plen_fault_count", "plen_get_state", "plen_set_state", "plen_set_env_scales", "plen_tick",
     "plen_debug_dynamics", "plen_debug_records", "plen_gait_ik", "plen_profile_enable", "plen_profile_read", "plen_measure_fp32_peak",
     "plen_replay_create", "plen_replay_destroy", "plen_replay_size", "plen_replay_ptr", "plen_replay_storage",
-    "plen_replay_add", "plen_replay_sample", "plen_actor_forward", "plen_actor_forward_tc", "plen_actor_tc_timed_out", "plen_td3_last_error",
+    "plen_replay_add", "plen_replay_sample", "plen_actor_forward", "plen_actor_forward_tc", "plen_actor_tc_timed_out", "plen_td3_last_error", "plen_td3_set_precision", "plen_td3_tc_timed_out",
     "plen_td3_default_hyper", "plen_td3_create", "plen_td3_destroy", "plen_td3_launches", "plen_td3_sample",
     "plen_td3_set_batch", "plen_td3_critic_grads", "plen_td3_actor_grads", "plen_td3_adam", "plen_td3_soft_update",
     "plen_td3_train",
@@ -164,6 +164,7 @@ def load_library(path: str = LIB_PATH):
     L.plen_td3_create.restype = vp
     L.plen_td3_destroy.argtypes = [vp]
     L.plen_td3_destroy.restype = None
+    L.plen_td3_set_precision.argtypes = [vp, ip]
     L.plen_td3_launches.argtypes = [vp]
     L.plen_td3_launches.restype = ll
     L.plen_td3_sample.argtypes = [vp, vp, ip, ull, vp]

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRCS = [os.path.join(HERE, "csrc", "plen_b200.cu"), os.path.join(HERE, "csrc", "plen_td3.cu"),
         os.path.join(HERE, "csrc", "plen_td3_learn.cu"), os.path.join(HERE, "csrc", "plen_actor_tc.cu")]
-DEPS = SRCS + [os.path.join(HERE, "csrc", f) for f in ("plen_device.cuh", "plen_solve.cuh", "plen_env.cuh", "plen_host_tables.h")] + \
+DEPS = SRCS + [os.path.join(HERE, "csrc", f) for f in ("plen_device.cuh", "plen_solve.cuh", "plen_env.cuh", "plen_host_tables.h", "plen_tc_common.cuh", "plen_gemm_tc.cuh")] + \
        [os.path.join(ROOT, "include", "plen_b200.h")]
 OUT = os.path.join(HERE, "libplen_b200.so")
 

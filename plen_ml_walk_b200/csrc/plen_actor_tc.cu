@@ -21,10 +21,13 @@
 #include <stdint.h>
 
 #include "../../include/plen_b200.h"
+#include "plen_tc_common.cuh"
 
 extern "C" int plen_td3_set_error(int code, const char *msg, const char *detail);      // plen_td3.cu
 
 namespace {
+
+using namespace plen_tc;
 
 constexpr int TM = 128, HID = 256, K1 = 32, N3 = 32;
 constexpr uint32_t OFF_W2 = 0, OFF_W1 = OFF_W2 + HID * HID * 2, OFF_W3 = OFF_W1 + HID * K1 * 2, OFF_A = OFF_W3 + N3 * HID * 2,
@@ -38,56 +41,6 @@ static_assert(TC_SMEM <= 232448, "shared memory budget of one CTA");
 __device__ __forceinline__ uint32_t canon(int row, int k, int R) {
     return (uint32_t)((k >> 3) * (R * 16) + (row >> 3) * 128 + (row & 7) * 16 + (k & 7) * 2);
 }
-
-// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start >> 4 [0,14), LBO >> 4 [16,30), SBO >> 4 [32,46),
-// version 1 [46,48), layout type 0 = no swizzle [61,64)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
-}
-
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = F16 (format 0 at [7,10) and [10,13)), both
-// K-major, N >> 3 at [17,23), M >> 4 at [24,29)
-__device__ __forceinline__ uint32_t instr_desc(int M, int N) {
-    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-        :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
-}
-__device__ int g_tc_timeout = 0;     // set when an mbarrier wait gave up (never expected; keeps a protocol bug from hanging the GPU)
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    for (int tries = 0; tries < (1 << 22); tries++) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (ok) return;
-    }
-    g_tc_timeout = 1;
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // two fp32 -> packed FP16 (saturating: a hidden activation beyond +-65504 would otherwise become inf)
 __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
@@ -153,6 +106,7 @@ k_actor_forward_tc(const float *__restrict__ w1, const float *__restrict__ b1, c
     const uint32_t lane_base = tmem + ((uint32_t)(32 * warp) << 16);       // this warp's 32 TMEM lanes (rows 32 warp ..)
     const uint32_t idesc256 = instr_desc(TM, HID), idesc32 = instr_desc(TM, N3);
     uint32_t parity = 0;
+    bool poisoned = false;                                                  // an mbarrier wait was abandoned: write NaN actions
     const int row = tid;                                                    // row of the tile owned in every epilogue
 
     const int n_tiles = (n + TM - 1) / TM;
@@ -174,7 +128,7 @@ k_actor_forward_tc(const float *__restrict__ w1, const float *__restrict__ b1, c
                          smem_desc(sbase + OFF_W1 + ks * 2 * (HID * 16), HID * 16, 128), idesc256, ks > 0);
             mma_commit(bar);
         }
-        mbar_wait(bar, parity); parity ^= 1;
+        poisoned |= !mbar_wait(bar, parity); parity ^= 1;
         fence_after();
         // ---- epilogue 1: A <- fp16(relu(D1 + b1))
 #pragma unroll 1
@@ -202,7 +156,7 @@ k_actor_forward_tc(const float *__restrict__ w1, const float *__restrict__ b1, c
                          smem_desc(sbase + OFF_W2 + ks * 2 * (HID * 16), HID * 16, 128), idesc256, ks > 0);
             mma_commit(bar);
         }
-        mbar_wait(bar, parity); parity ^= 1;
+        poisoned |= !mbar_wait(bar, parity); parity ^= 1;
         fence_after();
 #pragma unroll 1
         for (int c = 0; c < HID / 32; c++) {
@@ -229,7 +183,7 @@ k_actor_forward_tc(const float *__restrict__ w1, const float *__restrict__ b1, c
                          smem_desc(sbase + OFF_W3 + ks * 2 * (N3 * 16), N3 * 16, 128), idesc32, ks > 0);
             mma_commit(bar);
         }
-        mbar_wait(bar, parity); parity ^= 1;
+        poisoned |= !mbar_wait(bar, parity); parity ^= 1;
         fence_after();
         {
             uint32_t r[32];
@@ -244,7 +198,7 @@ k_actor_forward_tc(const float *__restrict__ w1, const float *__restrict__ b1, c
                         v += noise_std * sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
                         v = fminf(fmaxf(v, -max_action), max_action);
                     }
-                    act[(size_t)grow * PLEN_NJ + j] = v;
+                    act[(size_t)grow * PLEN_NJ + j] = poisoned ? __int_as_float(0x7fc00000) : v;
                 }
             }
         }
@@ -286,6 +240,6 @@ extern "C" int plen_actor_forward_tc(int device, const float *w1, const float *b
 /* 1 if any tensor-core actor launch on the current device ever abandoned an mbarrier wait (diagnostic, synchronises) */
 extern "C" int plen_actor_tc_timed_out(void) {
     int v = 0;
-    if (cudaMemcpyFromSymbol(&v, g_tc_timeout, sizeof v) != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(&v, plen_tc::g_tc_timeout, sizeof v) != cudaSuccess) return -1;
     return v;
 }

@@ -182,6 +182,10 @@ __global__ void __launch_bounds__(GT) k_gemm(const Gemm g) {
         }
 }
 
+}  // namespace
+#include "plen_gemm_tc.cuh"      // k_gemm_tc: the same products on tcgen05 (TF32), see launch()
+namespace {
+
 // minibatch rows drawn uniformly with replacement (td3.py:175), written as the concatenated critic inputs:
 // sa = [s | a], s2a = [s' | .] (the action columns are filled by the target actor), spi = [s | .] (filled by the actor)
 __global__ void k_sample_sa(const float *__restrict__ store, long long size, int batch, uint64_t seed, float *__restrict__ sa,
@@ -277,12 +281,24 @@ __global__ void k_soft_update(float *__restrict__ tgt, const float *__restrict__
 // minibatch size from which the dW products are split along K (= the minibatch) and accumulated atomically
 constexpr int SPLIT_K_MIN_BATCH = 512;
 
+// precision of the products of the entry point being enqueued: 0 = FP32 CUDA cores (parity path, default), 1 = 3xTF32 on the
+// tensor cores for every product that fills a 128-row tile (plen_td3_set_precision, minibatches >= SPLIT_K_MIN_BATCH); set by
+// the entry points from their context
+thread_local int s_tc = 0;
+
 int launch(Gemm g, cudaStream_t st) {
     g.splits = 1; g.k_chunk = g.K;
     if (g.epi == EPI_NONE && g.rowsum != nullptr && g.K >= SPLIT_K_MIN_BATCH) {      // dW = dY^T X of a large minibatch
         g.splits = g.K / 256 < 16 ? g.K / 256 : 16;
         g.k_chunk = ((g.K + g.splits - 1) / g.splits + 31) / 32 * 32;
         g.splits = (g.K + g.k_chunk - 1) / g.k_chunk;
+    }
+    if (s_tc && g.M >= 128 && g.N >= 16 && g.K >= 16) {
+        // the three product kinds of the wide layers (the 18- and 1-column products stay on the FP32 path)
+        dim3 grid((g.N + tcg::BN - 1) / tcg::BN, (g.M + tcg::BM - 1) / tcg::BM, g.nz * g.splits);
+        if (g.ak == 1 && g.bk == 1 && g.epi == EPI_BIAS_RELU) { tcg::k_gemm_tc<true, true, EPI_BIAS_RELU><<<grid, tcg::NT, tcg::SMEM, st>>>(g); return 1; }
+        if (g.ak == 1 && g.bk != 1 && g.epi == EPI_RELUMASK) { tcg::k_gemm_tc<true, false, EPI_RELUMASK><<<grid, tcg::NT, tcg::SMEM, st>>>(g); return 1; }
+        if (g.ak != 1 && g.bk != 1 && g.epi == EPI_NONE && g.splits > 1) { tcg::k_gemm_tc<false, false, EPI_NONE><<<grid, tcg::NT, tcg::SMEM, st>>>(g); return 1; }
     }
     // wide tiles only when they still give every SM a CTA
     if ((long long)((g.N + 63) / 64) * ((g.M + 63) / 64) * g.nz * g.splits >= 148) {
@@ -335,6 +351,7 @@ Gemm bwd_weight(const float *dy, long long ldy, long long dyz, const float *x, l
 
 struct plen_td3 {
     int device, max_batch, batch;
+    int tc;                             // plen_td3_set_precision: 1 = TF32 tensor-core products
     float *ws;                          // one allocation, carved below
     float *sa, *s2a, *spi, *r, *nd;
     float *at_h1, *at_h2, *ct_h1, *ct_h2, *qt;
@@ -412,6 +429,28 @@ void plen_td3_destroy(plen_td3 *t) {
 
 long long plen_td3_launches(const plen_td3 *t) { return t ? t->launches : 0; }
 
+int plen_td3_set_precision(plen_td3 *t, int tf32) {
+    if (!t || (tf32 != 0 && tf32 != 1)) return plen_td3_set_error(PLEN_E_ARG, "plen_td3_set_precision: bad arguments", "");
+    if (tf32) {
+        LCK(cudaSetDevice(t->device));
+        LCK(cudaFuncSetAttribute(tcg::k_gemm_tc<true, true, EPI_BIAS_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcg::SMEM));
+        LCK(cudaFuncSetAttribute(tcg::k_gemm_tc<true, false, EPI_RELUMASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcg::SMEM));
+        LCK(cudaFuncSetAttribute(tcg::k_gemm_tc<false, false, EPI_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcg::SMEM));
+    }
+    if (t->tc != tf32) {      // the captured update graphs bake the kernels in
+        for (int k = 0; k < 2; k++)
+            if (t->exec[k]) { cudaGraphExecDestroy(t->exec[k]); t->exec[k] = nullptr; }
+    }
+    t->tc = tf32;
+    return PLEN_OK;
+}
+
+int plen_td3_tc_timed_out(void) {
+    int v = 0;
+    if (cudaMemcpyFromSymbol(&v, plen_tc::g_tc_timeout, sizeof v) != cudaSuccess) return -1;
+    return v;
+}
+
 int plen_td3_sample(plen_td3 *t, plen_replay *rb, int batch, unsigned long long seed, void *stream) {
     if (!t || !rb || batch <= 0 || batch > t->max_batch) return plen_td3_set_error(PLEN_E_ARG, "plen_td3_sample: bad arguments", "");
     const long long size = plen_replay_size(rb);
@@ -446,6 +485,7 @@ int plen_td3_critic_grads(plen_td3 *t, const plen_td3_params *P, const plen_td3_
     const int B = t->batch;
     const long long BH = (long long)B * H;
     int n = 0;
+    s_tc = (t->tc && B >= SPLIT_K_MIN_BATCH) ? 1 : 0;      // (below that the gradient buffers are not zeroed and the update is launch bound)
     // ---- target Q (no gradient), td3.py:303-313
     const float *at = P->actor_target;
     n += launch(fwd(t->s2a, SA, 0, at + AW1, S, 0, at + AB1, t->at_h1, H, 0, B, H, S, 1, EPI_BIAS_RELU), st);
@@ -487,6 +527,7 @@ int plen_td3_actor_grads(plen_td3 *t, const plen_td3_params *P, const plen_td3_h
     cudaStream_t st = (cudaStream_t)stream;
     const int B = t->batch;
     int n = 0;
+    s_tc = (t->tc && B >= SPLIT_K_MIN_BATCH) ? 1 : 0;      // (below that the gradient buffers are not zeroed and the update is launch bound)
     // ---- actor_loss = -critic.Q1(state, actor(state)).mean(), td3.py:342
     const float *ac = P->actor, *c = P->critic;
     n += launch(fwd(t->spi, SA, 0, ac + AW1, S, 0, ac + AB1, t->a_h1, H, 0, B, H, S, 1, EPI_BIAS_RELU), st);

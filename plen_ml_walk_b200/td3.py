@@ -65,6 +65,9 @@ class Critic(nn.Module):                                   # td3.py:60-117
         return self.fc3(F.relu(self.fc2(F.relu(self.fc1(sa)))))
 
 
+_tc_checked = False
+
+
 def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -95,6 +98,12 @@ def actor_forward(actor: Actor, obs: torch.Tensor, noise_std: float = 0.0, seed:
                                     C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
     if rc != 0:
         raise RuntimeError("plen_actor_forward: %s" % lib.plen_td3_last_error().decode())
+    global _tc_checked
+    if precision == "fp16" and not _tc_checked:
+        # once per process (it synchronises): a tensor-core launch that abandoned an mbarrier wait wrote NaN actions
+        _tc_checked = True
+        if lib.plen_actor_tc_timed_out() != 0:
+            raise RuntimeError("plen_actor_forward_tc abandoned an mbarrier wait (tcgen05 pipeline protocol error)")
     return out
 
 
@@ -201,7 +210,14 @@ class TD3Agent:                                            # td3.py:196-376
     same rule in plain PyTorch as the fp32 reference the tests compare against (and for CPU-only checkpoint tooling)."""
 
     def __init__(self, state_dim=STATE_DIM, action_dim=ACTION_DIM, max_action=1.0, discount=0.99, tau=0.005,
-                 policy_noise=0.2, noise_clip=0.5, policy_freq=2, device="cuda:0", lr=3e-4, max_batch=4096, seed=0):
+                 policy_noise=0.2, noise_clip=0.5, policy_freq=2, device="cuda:0", lr=3e-4, max_batch=4096, seed=0,
+                 precision="fp32"):
+        """precision: "fp32" = every product on the FP32 CUDA cores, within 1e-5 of torch (the parity path); "tf32" = the
+        products of minibatches >= 128 rows on the tcgen05 tensor cores (TF32 operands, FP32 accumulation; gradients within
+        1e-3 of the fp32 path) -- for minibatches >= 1024, where the update is FLOP bound."""
+        if precision not in ("fp32", "tf32"):
+            raise ValueError("precision must be 'fp32' or 'tf32'")
+        self.precision = precision
         self.device = torch.device(device)
         self.actor = Actor(state_dim, action_dim, max_action).to(self.device)
         self.actor_target = copy.deepcopy(self.actor)
@@ -244,6 +260,7 @@ class TD3Agent:                                            # td3.py:196-376
                 raise RuntimeError("plen_td3_create: %s" % lib.plen_td3_last_error().decode())
             self._hyper = _abi.PlenTd3HyperC()
             lib.plen_td3_default_hyper(C.byref(self._hyper))
+            self._check(lib, lib.plen_td3_set_precision(self._learner, 1 if self.precision == "tf32" else 0))
         h = self._hyper
         h.discount, h.tau, h.policy_noise, h.noise_clip = self.discount, self.tau, self.policy_noise, self.noise_clip
         h.max_action, h.lr, h.policy_freq = self.max_action, self.lr, self.policy_freq
@@ -381,7 +398,11 @@ class TD3Agent:                                            # td3.py:196-376
         torch.save(self.actor.state_dict(), filename + "_actor")
         torch.save(self.actor_optimizer.state_dict(), filename + "_actor_optimizer")
 
-    def load(self, filename, optimizers=True):
+    def load(self, filename, optimizers=True, sync_targets=False):
+        """TD3Agent.load (td3.py:366-376).  Like the reference, the TARGET networks are left untouched (there they keep
+        whatever they held before the call); sync_targets=True copies the loaded weights into them, which is what one wants
+        before continuing training from a checkpoint.  The reference's optimizer files are python-2 era pickles and need
+        weights_only=False -- only load optimizer files you trust, or pass optimizers=False (inference needs none)."""
         # load_state_dict copies in place, so the parameters stay views of the flat vectors
         self.critic.load_state_dict(torch.load(filename + "_critic", map_location=self.device))
         self.actor.load_state_dict(torch.load(filename + "_actor", map_location=self.device))
@@ -390,8 +411,9 @@ class TD3Agent:                                            # td3.py:196-376
             self.actor_optimizer.load_state_dict(torch.load(filename + "_actor_optimizer", map_location=self.device, weights_only=False))
             self.critic_steps = self._load_optimizer_state(self.critic_optimizer, self.critic, self._adam["critic_m"], self._adam["critic_v"])
             self.actor_steps = self._load_optimizer_state(self.actor_optimizer, self.actor, self._adam["actor_m"], self._adam["actor_v"])
-        self._flat["actor_target"].copy_(self._flat["actor"])          # td3.py:372, :376 (targets = deep copies)
-        self._flat["critic_target"].copy_(self._flat["critic"])
+        if sync_targets:
+            self._flat["actor_target"].copy_(self._flat["actor"])
+            self._flat["critic_target"].copy_(self._flat["critic"])
 
     def close(self):
         if getattr(self, "_learner", None):

@@ -95,6 +95,7 @@ class PlenVecEnv:
         self._reward = torch.empty(n, dtype=torch.float32, device=dev)
         self._done = torch.empty(n, dtype=torch.uint8, device=dev)
         self._timeout = torch.empty(n, dtype=torch.uint8, device=dev)
+        self._scales = {}                                                  # per-env scales set so far (set_env_scales)
 
     # ---- plumbing
     def _check(self, rc):
@@ -200,15 +201,22 @@ class PlenVecEnv:
 
     def set_env_scales(self, friction=None, motor_force=None, motor_gain=None):
         """Per-env domain randomisation: scale factors [N] of the foot friction coefficients, the servo force
-        limit and the servo position gain; None leaves a quantity unchanged, 1.0 is the reference's constant."""
+        limit and the servo position gain; None leaves a quantity unchanged, 1.0 is the reference's constant.
+
+        Approximation: a reset (explicit or in-kernel auto-reset) restores the ONE post-reset snapshot that was settled for 8
+        ticks under unit scales at creation, whatever the robot's own scales are; its first steps then run under its scales."""
         arr = [None if x is None else self._dev_f32(x, (self.num_envs,)) for x in (friction, motor_force, motor_gain)]
+        for k, x in zip(("friction", "motor_force", "motor_gain"), arr):
+            if x is not None:
+                self._scales[k] = x.clone()               # mirror kept for save_state (the library has no getter)
         with torch.cuda.device(self.device):
             self._check(self.lib.plen_set_env_scales(self._ctx, *[self._p(x) for x in arr], self._stream()))
 
     def save_state(self, path):
         """Snapshot of every env (pose, velocities, contact cache, env bookkeeping) to one .pt file."""
         qpos, qvel, aux = self.get_state()
-        torch.save({"num_envs": self.num_envs, "joint_act": self.joint_act, "qpos": qpos.cpu(), "qvel": qvel.cpu(), "aux": aux.cpu()}, path)
+        torch.save({"num_envs": self.num_envs, "joint_act": self.joint_act, "qpos": qpos.cpu(), "qvel": qvel.cpu(), "aux": aux.cpu(),
+                    "scales": {k: v.cpu() for k, v in self._scales.items()}}, path)
 
     def load_state(self, path):
         """Restore a save_state snapshot; stepping on from it reproduces the original run bit for bit."""
@@ -216,6 +224,10 @@ class PlenVecEnv:
         if int(d["num_envs"]) != self.num_envs or bool(d["joint_act"]) != self.joint_act:
             raise ValueError("snapshot is for %d envs (joint_act=%s)" % (d["num_envs"], d["joint_act"]))
         self.set_state(d["qpos"], d["qvel"], d["aux"])
+        sc = d.get("scales", {})
+        if sc or self._scales:      # per-env scales travel with the snapshot; a snapshot without any restores the unit scales
+            ones = torch.ones(self.num_envs)
+            self.set_env_scales(*[sc.get(k, ones) for k in ("friction", "motor_force", "motor_gain")])
 
     def tick(self, targets, n_ticks=1):
         """Raw physics: n_ticks of 1/240 s with joint targets in radians, no env logic (move_joints + stepSimulation)."""

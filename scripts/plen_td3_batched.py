@@ -34,6 +34,7 @@ def run(n_envs, total_env_steps, updates_per_step, start_timesteps=10000, expl_n
     gen.manual_seed(seed)
     state = env.reset().clone()
     ep_ret = torch.zeros(n_envs, device=dev)
+    ep_len = torch.zeros(n_envs, dtype=torch.int32, device=dev)
     done_count = torch.zeros((), device=dev)           # episode statistics stay on the device: no host sync in the loop
     ret_sum = torch.zeros((), device=dev)
     updates, t = 0, 0
@@ -46,7 +47,11 @@ def run(n_envs, total_env_steps, updates_per_step, start_timesteps=10000, expl_n
         else:
             action = agent.select_action(state, expl_noise=expl_noise, precision=actor_precision)  # plen_td3.py:101-104
         obs, reward, done, info = env.step(action)
-        done_bool = done & ~info["timeout"]                                                      # plen_td3.py:109-110
+        # plen_td3.py:109-110: done_bool = float(done) if episode_timesteps < env._max_episode_steps else 0 -- also 0 for a
+        # robot that falls exactly on the last step of the time limit (info["timeout"] alone is 0 there: TimeLimit semantics)
+        ep_len += 1
+        done_bool = done & (ep_len < env._max_episode_steps)
+        ep_len *= ~done
         next_state = torch.where(done[:, None], info["terminal_obs"], obs)
         rb.add(state, action, next_state, reward, done_bool)
         ep_ret += reward

@@ -18,8 +18,9 @@ rb = ReplayBuffer(max_size=200000, device=dev)
 s = torch.randn(200000, 26, device=dev); a = torch.rand(200000, 18, device=dev) * 2 - 1
 rb.add(s, a, s + 0.01, -(a ** 2).sum(1), torch.zeros(200000, dtype=torch.bool, device=dev))
 out = {}
-for B in (100, 256, 1024, 4096):
-    agent = TD3Agent(device=dev, max_batch=4096)
+BATCHES = (100, 256, 1024, 4096, 16384)
+for B in BATCHES:
+    agent = TD3Agent(device=dev, max_batch=max(BATCHES))
     for _ in range(20):
         agent.train(rb, B)
     torch.cuda.synchronize()
@@ -41,7 +42,19 @@ for B in (100, 256, 1024, 4096):
         ref.train_torch(rb.sample(B))
     torch.cuda.synchronize()
     wall_ref = time.perf_counter() - t1
-    out["batch_%d" % B] = {"cuda_updates_per_s": K / wall, "cuda_device_us_per_update": 1e3 * e0.elapsed_time(e1) / K,
+    # the same update with the products of >= 128-row tiles on the tcgen05 tensor cores (TF32 operands)
+    tc = TD3Agent(device=dev, max_batch=max(BATCHES), precision="tf32")
+    for _ in range(20):
+        tc.train(rb, B)
+    torch.cuda.synchronize()
+    t0, t1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(K):
+        tc.train(rb, B)
+    t1_.record(); torch.cuda.synchronize()
+    tc_us = 1e3 * t0.elapsed_time(t1_) / K
+    out["batch_%d" % B] = {"tf32_device_us_per_update": tc_us, "tf32_samples_per_s": B / tc_us * 1e6,
+                           "fp32_samples_per_s": B * K / (1e-3 * e0.elapsed_time(e1)), "cuda_updates_per_s": K / wall, "cuda_device_us_per_update": 1e3 * e0.elapsed_time(e1) / K,
                            "launches_per_update": (agent.kernel_launches() - l0) / K,
                            "torch_eager_updates_per_s": kr / wall_ref, "speedup": (K / wall) / (kr / wall_ref)}
 print(json.dumps(out))

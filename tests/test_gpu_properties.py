@@ -258,6 +258,10 @@ def test_snapshot_to_disk_and_back_continues_bit_exact(tmp_path):
     """save_state / load_state: a run restored from disk into a fresh context continues exactly."""
     n = 3000
     a = _mk(n)
+    # per-env domain-randomisation scales travel with the snapshot (they change the physics of every step after it)
+    gs = torch.Generator(device="cuda"); gs.manual_seed(30)
+    a.set_env_scales(friction=torch.empty(n, device="cuda").uniform_(0.6, 1.2, generator=gs),
+                     motor_gain=torch.empty(n, device="cuda").uniform_(0.8, 1.1, generator=gs))
     _rollout(a, 15, seed=31)
     path = str(tmp_path / "plen_state.pt")
     a.save_state(path)

@@ -87,11 +87,16 @@ def test_actor_forward_kernel_vs_reference_checkpoint_and_torch():
     assert not torch.equal(noisy, actor_forward(b, obs, noise_std=0.1, seed=8))
 
 
-def _twin_agents(dev, seed=0):
+def _abi_lib():
+    from plen_ml_walk_b200 import _abi
+    return _abi.load_library()
+
+
+def _twin_agents(dev, seed=0, precision="fp32", twin_precision="fp32"):
     """Two agents with identical parameters: one stepped by the CUDA learner, one by the PyTorch fp32 reference."""
     from plen_ml_walk_b200.td3 import TD3Agent
     torch.manual_seed(seed)
-    a, b = TD3Agent(device=dev), TD3Agent(device=dev)
+    a, b = TD3Agent(device=dev, precision=precision), TD3Agent(device=dev, precision=twin_precision)
     for k in ("actor", "actor_target", "critic", "critic_target"):
         b._flat[k].copy_(a._flat[k])
     return a, b
@@ -170,6 +175,80 @@ def test_td3_gradients_match_autograd():
     la = -b.critic.Q1(s, b.actor(s)).mean()
     ga = torch.cat([x.reshape(-1) for x in torch.autograd.grad(la, list(b.actor.parameters()))])
     assert float((seen[77330] - ga).abs().max()) < 1e-5 * max(1.0, float(ga.abs().max()))
+
+
+def _layer_slices(module):
+    out, off = [], 0
+    for name, p in module.named_parameters():
+        out.append((name, off, off + p.numel()))
+        off += p.numel()
+    return out
+
+
+@pytest.mark.parametrize("B", [1024, 4096, 1000])
+def test_td3_tensor_core_gradients_vs_autograd(B):
+    """precision="tf32": the learner's products on tcgen05 (kind::tf32).  Every gradient tensor (per layer, weight and bias)
+    stays within 1e-3 of fp32 autograd relative to the tensor's largest entry, the losses within 1e-3 relative; B = 1000 has
+    a ragged last 128-row tile.  The same call with precision="fp32" must hold 1e-5 (it does at B = 100 above)."""
+    import torch.nn.functional as F
+    dev = torch.device("cuda:0")
+    a, b = _twin_agents(dev, seed=11, precision="tf32")
+    g = torch.Generator(device=dev); g.manual_seed(17)
+    s = torch.randn(B, 26, device=dev, generator=g); ac = torch.rand(B, 18, device=dev, generator=g) * 2 - 1
+    s2 = torch.randn(B, 26, device=dev, generator=g); r = torch.randn(B, 1, device=dev, generator=g)
+    nd = (torch.rand(B, 1, device=dev, generator=g) > 0.1).float(); nz = torch.randn(B, 18, device=dev, generator=g)
+    seen = {}
+    a.total_it = 1                                                  # next call is a policy update
+    la_g, lc_g = a.train(None, batch=(s, ac, s2, r, nd), noise=nz, return_losses=True,
+                         grad_hook=lambda gflat: seen.setdefault(gflat.numel(), gflat.clone()))
+    with torch.no_grad():
+        n2 = (nz * b.policy_noise).clamp(-b.noise_clip, b.noise_clip)
+        a2 = (b.actor_target(s2) + n2).clamp(-1, 1)
+        q1t, q2t = b.critic_target(s2, a2)
+        y = r + nd * b.discount * torch.min(q1t, q2t)
+    q1, q2 = b.critic(s, ac)
+    loss = F.mse_loss(q1, y) + F.mse_loss(q2, y)
+    gc = torch.cat([x.reshape(-1) for x in torch.autograd.grad(loss, list(b.critic.parameters()), retain_graph=True)])
+    assert abs(float(lc_g) - float(loss)) < 1e-3 * max(1.0, abs(float(loss)))
+    worst = 0.0
+    for name, lo, hi in _layer_slices(b.critic):
+        err = float((seen[155138][lo:hi] - gc[lo:hi]).abs().max()) / max(float(gc[lo:hi].abs().max()), 1e-12)
+        worst = max(worst, err)
+        assert err < 1e-3, (name, err)
+    b.critic_optimizer.zero_grad(); loss.backward(); b.critic_optimizer.step()
+    la = -b.critic.Q1(s, b.actor(s)).mean()
+    ga = torch.cat([x.reshape(-1) for x in torch.autograd.grad(la, list(b.actor.parameters()))])
+    assert abs(float(la_g) - float(la)) < 1e-3 * max(1.0, abs(float(la)))
+    for name, lo, hi in _layer_slices(b.actor):
+        err = float((seen[77330][lo:hi] - ga[lo:hi]).abs().max()) / max(float(ga[lo:hi].abs().max()), 1e-12)
+        worst = max(worst, err)
+        assert err < 1e-3, (name, err)
+    assert _abi_lib().plen_td3_tc_timed_out() == 0
+    print("tf32 learner, B = %d: worst per-tensor gradient error %.2e" % (B, worst))
+
+
+def test_td3_tensor_core_update_trains_like_fp32():
+    """20 whole updates (graph path, minibatches drawn from the replay ring with the same seeds) in tf32 and fp32: the
+    parameters stay close (Adam normalises the step, so a 1e-3 gradient error moves a parameter by << lr per step)."""
+    dev = torch.device("cuda:0")
+    from plen_ml_walk_b200.td3 import ReplayBuffer
+    a, b = _twin_agents(dev, seed=21, precision="tf32", twin_precision="fp32")
+    g = torch.Generator(device=dev); g.manual_seed(23)
+    n = 20000
+    rbs = [ReplayBuffer(n, device=dev, seed=5) for _ in range(2)]
+    st = torch.randn(n, 26, device=dev, generator=g); ac = torch.rand(n, 18, device=dev, generator=g) * 2 - 1
+    s2 = torch.randn(n, 26, device=dev, generator=g); r = torch.randn(n, device=dev, generator=g)
+    dn = torch.rand(n, device=dev, generator=g) < 0.05
+    for rb in rbs:
+        rb.add(st, ac, s2, r, dn)
+    for _ in range(20):
+        a.train(rbs[0], 2048)
+        b.train(rbs[1], 2048)
+    for k in ("actor", "critic", "actor_target", "critic_target"):
+        d = float((a._flat[k] - b._flat[k]).abs().max())
+        assert d < 20 * 3e-4 * 0.5, (k, d)      # far below 20 full Adam steps of lr = 3e-4
+        assert torch.isfinite(a._flat[k]).all()
+    assert a.kernel_launches() > 0 and _abi_lib().plen_td3_tc_timed_out() == 0
 
 
 def test_td3_update_follows_reference_rule():
