@@ -198,6 +198,72 @@ def time_steps(env, acts, K, dev, flush=None):
     return tot / K
 
 
+def td3_leg(dev, dist, rank, world, vector_steps=24, envs=16384, batch=4096, updates_per_step=2):
+    """BASELINE configs 4 / 5, the learner side: 16,384 device-resident envs per GPU feeding a device replay ring, TD3
+    updates (plen_td3_*: tcgen05 3xTF32 products, minibatch 4096 per GPU) between env steps, and -- at N > 1 -- the ONE
+    collective of the path family: an NCCL all-reduce (mean) of the flat gradient vectors (155,138 critic + 77,330 actor
+    floats) between the gradient kernels and Adam.  Timed on the device (CUDA events), max over ranks."""
+    import torch
+    from plen_ml_walk_b200.sharding import env_seed, max_over_ranks
+    from plen_ml_walk_b200.td3 import ReplayBuffer, TD3Agent
+    from plen_ml_walk_b200.vec_env import PlenVecEnv
+    torch.manual_seed(0)                                   # identical initial networks on every rank
+    agent = TD3Agent(device=dev, seed=env_seed(0, rank), max_batch=batch, precision="tf32")
+    env = PlenVecEnv(envs, device=dev)
+    rb = ReplayBuffer(envs * (vector_steps + 8), device=dev, seed=env_seed(0, rank))
+    gen = torch.Generator(device=dev); gen.manual_seed(env_seed(1, rank))
+    ar_bytes = [0]
+
+    def allreduce_mean(flat_grad):
+        if dist:
+            dist.all_reduce(flat_grad)
+            flat_grad.mul_(1.0 / world)
+            ar_bytes[0] += flat_grad.numel() * 4
+
+    hook = allreduce_mean if dist else None                # N = 1: the whole update is one captured CUDA graph
+    state = env.reset().clone()
+
+    def one(train):
+        action = torch.empty((envs, 18), device=dev).uniform_(-1, 1, generator=gen)
+        obs, reward, done, info = env.step(action)
+        rb.add(state, action, torch.where(done[:, None], info["terminal_obs"], obs), reward, done & ~info["timeout"])
+        state.copy_(obs)
+        for _ in range(updates_per_step if train else 0):
+            agent.train(rb, batch, grad_hook=hook)
+
+    for w in range(4):
+        one(w >= 2)
+    torch.cuda.synchronize(dev)
+    if dist:
+        dist.barrier()
+    ar_bytes[0] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(vector_steps):
+        one(True)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = max_over_ranks(e0.elapsed_time(e1), dist, dev)
+    chk = torch.stack([agent._flat[k].double().sum() for k in ("actor", "critic", "actor_target", "critic_target")])
+    same = True
+    if dist:
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        same = all(bool(torch.equal(c, allc[0])) for c in allc)
+    n_up = vector_steps * updates_per_step
+    out = {"value": world * envs * vector_steps / (ms * 1e-3), "unit": UNIT, "envs_per_gpu": envs, "vector_steps": vector_steps,
+           "updates": n_up, "minibatch_per_gpu": batch, "updates_per_s": n_up / (ms * 1e-3),
+           "samples_per_s": world * batch * n_up / (ms * 1e-3), "samples_per_env_step": batch * updates_per_step / envs,
+           "learner_precision": "3xTF32 on tcgen05 (plen_td3_set_precision 1)",
+           "allreduce": ("NCCL all-reduce (mean) of the flat gradients, %.2f MB per update, parameters identical across ranks: %s"
+                         % (ar_bytes[0] / max(1, n_up) / 1e6, same)) if dist else "none (1 GPU)",
+           "td3_kernel_launches": agent.kernel_launches(),
+           "note": "env step + replay add + %d TD3 updates per vector step; the reference does 1 update of 100 samples per "
+                   "env step (plen_td3.py:122-129), i.e. 100 samples per env-step" % updates_per_step}
+    env.close(); agent.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -208,6 +274,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--no-td3-leg", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -357,7 +424,12 @@ def main():
     env.close()
     del env, acts, h_act, h_obs
     torch.cuda.empty_cache()
+    td3 = None
+    if not args.no_td3_leg:
+        td3 = td3_leg(dev, dist, rank, world)              # every rank takes part (all-reduce at N > 1)
     if rank == 0:
+        if td3 is not None:
+            line.setdefault("other_configs", {})["config4_td3_%s" % ("dp%d" % world if world > 1 else "1gpu")] = td3
         if world == 1 and not args.no_other_configs:
             # the other BASELINE configs that fit this run, device-resident, CUDA events, same seed discipline: round 1's
             # 131,072-env shard (weak-scaling unit; 256 MiB L2 flush between steps) and config 2 (4,096 envs, which under-fills
@@ -375,7 +447,7 @@ def main():
                 ms2 = time_steps(e2, a2, k2, dev, fl)
                 other[name] = {"value": n2 / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2, "steps": k2, "note": note}
                 e2.close()
-            line["other_configs"] = other
+            line.setdefault("other_configs", {}).update(other)
         if not args.no_cpu_baseline and world == 1:
             cores = len(os.sched_getaffinity(0))
             probe, _, _ = cpu_port_throughput(cores, 8, 4, seed=1)

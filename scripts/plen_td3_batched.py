@@ -24,11 +24,11 @@ from plen_ml_walk_b200.vec_env import PlenVecEnv
 
 
 def run(n_envs, total_env_steps, updates_per_step, start_timesteps=10000, expl_noise=0.1, batch_size=100, seed=0,
-        device="cuda:0", replay_size=1000000, learner=True, actor_precision="fp32"):
+        device="cuda:0", replay_size=1000000, learner=True, actor_precision="fp32", learner_precision="fp32"):
     dev = torch.device(device)
     torch.manual_seed(seed)
     env = PlenVecEnv(n_envs, device=dev, seed=seed)
-    agent = TD3Agent(26, 18, 1.0, device=dev)
+    agent = TD3Agent(26, 18, 1.0, device=dev, max_batch=max(4096, batch_size), precision=learner_precision)
     rb = ReplayBuffer(replay_size, device=dev, seed=seed)
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed)
@@ -69,7 +69,8 @@ def run(n_envs, total_env_steps, updates_per_step, start_timesteps=10000, expl_n
     return {"envs": n_envs, "env_steps": vec_steps * n_envs, "vector_steps": vec_steps, "updates": updates,
             "update_to_data": updates / max(1, vec_steps * n_envs), "seconds": dt, "env_steps_per_s": vec_steps * n_envs / dt,
             "episodes": int(done_count), "mean_episode_return": float(ret_sum) / max(1, int(done_count)), "replay_len": len(rb),
-            "learner": learner, "batch_size": batch_size, "actor_precision": actor_precision,
+            "learner": learner, "batch_size": batch_size, "actor_precision": actor_precision, "learner_precision": learner_precision,
+            "samples_per_env_step": updates * batch_size / max(1, vec_steps * n_envs),
             "td3_kernel_launches": agent.kernel_launches()}
 
 
@@ -82,6 +83,9 @@ if __name__ == "__main__":
     ap.add_argument("--batch-size", type=int, default=100)
     ap.add_argument("--start-timesteps", type=int, default=10000)
     ap.add_argument("--actor-precision", default="fp32", choices=["fp32", "fp16"])
+    ap.add_argument("--learner-precision", default="fp32", choices=["fp32", "tf32"],
+                    help="tf32: the learner's products on tcgen05 (3xTF32), for minibatches >= 512")
     a = ap.parse_args()
     print(json.dumps(run(a.envs, a.env_steps, a.updates_per_step, learner=not a.no_learner, batch_size=a.batch_size,
-                         start_timesteps=a.start_timesteps, actor_precision=a.actor_precision)))
+                         start_timesteps=a.start_timesteps, actor_precision=a.actor_precision,
+                         learner_precision=a.learner_precision)))
