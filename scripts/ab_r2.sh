@@ -1,8 +1,3 @@
-O=gpurun_out/${1:-r2_g1}; mkdir -p $O
-timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; tail -3 $O/pytest_gpu.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; tail -1 $O/smoke.log
-timeout 900 python bench.py > $O/bench.json 2> $O/bench.err; cat $O/bench.json; tail -3 $O/bench.err
-timeout 600 python scripts/plen_td3_batched.py --envs 16384 --env-steps 1048576 --updates-per-step 4 --batch-size 4096 --learner-precision tf32 --actor-precision fp16 > $O/config4_u4_b4096_tf32.json 2> $O/config4.err; cat $O/config4_u4_b4096_tf32.json
-timeout 600 python scripts/plen_td3_batched.py --envs 16384 --env-steps 1048576 --updates-per-step 4 --batch-size 4096 --actor-precision fp16 > $O/config4_u4_b4096_fp32.json 2>> $O/config4.err; cat $O/config4_u4_b4096_fp32.json
-timeout 600 python scripts/plen_td3_batched.py --envs 16384 --env-steps 524288 --updates-per-step 25 --batch-size 16384 --learner-precision tf32 --actor-precision fp16 > $O/config4_u25_b16384_tf32.json 2>> $O/config4.err; cat $O/config4_u25_b16384_tf32.json
-tail -3 $O/config4.err
+O=gpurun_out/${1:-r2_n2}; mkdir -p $O
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > $O/bench_n2.json 2> $O/bench_n2.err; cat $O/bench_n2.json; tail -5 $O/bench_n2.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 5 --warmup 1 > $O/bench_ref_n2.json 2> $O/bench_ref_n2.err; cat $O/bench_ref_n2.json
