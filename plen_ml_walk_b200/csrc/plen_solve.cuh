@@ -409,9 +409,14 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
         const float nl_ = alive ? clampf(ol_ + x_, 0.0f, up_) : ol_;                     \
         const float dl_ = (nl_ - ol_) * ldir_;                                           \
         const float db_ = GSH(dl_, b);                                                   \
+        warp_sync();      /* lanes without a joint at slot k read word 0 above: keep that read ahead of lane 0's write */ \
         if (g == (b)) L_LAM(8 * g + (k)) = nl_;                                          \
+        /* lane 3's slice of column j includes the L_LAM word (row 24, an unused slot of x): order its read after the  \
+           owner's write -- the value is never used, but the access pair is a hazard for racecheck (rare path: free) */ \
+        warp_sync();                                                                     \
         res = fmaxf(res, fabsf(db_));                                                    \
         apply_col(s, Gl, 8 * (b) + (k), db_);                                            \
+        warp_sync();                                                                     \
     }
 
     // spinning / rolling row of point k of foot f: own twist component c, friction coefficient mu
