@@ -42,12 +42,14 @@ TICKS_PER_STEP = 4
 # measured DRAM traffic of one k_solve launch per robot (ncu --set full, profiles/r1_v9_summary.md): it reads the
 # 6.4 KB solve record k_dyn wrote for the tick -- a deliberate trade of HBM bytes for issue slots
 SOLVE_DRAM_BYTES_PER_ROBOT = (207.10e6 + 9.92e6) / 32768
-# FROZEN in BASELINE.md ("Work per env-step"): executed FP32 work per robot-tick, counted by ncu (smsp__sass_thread_inst_executed_op_{fadd,fmul,ffma}_pred_on, FFMA = 2
-# flop; 32768-robot capture, profiles/r1_v9_summary.md): k_dyn 44.8 kflop + k_solve 58.1 kflop.  It replaces SURVEY 8d's
-# estimate (0.65-1.6 Mflop per env-step for Bullet's ABA + velocity-space PGS): this solver iterates in the 30-dim
-# operational space, so a row update is 30 FMAs instead of a Jacobian-wide one.
-FLOP_DYN_PER_ROBOT_TICK, FLOP_SOLVE_PER_ROBOT_TICK = 44.8e3, 58.1e3
-FLOP_PER_ENV_STEP = 4 * (FLOP_DYN_PER_ROBOT_TICK + FLOP_SOLVE_PER_ROBOT_TICK)
+# FROZEN in BASELINE.md ("Work per env-step", re-measured in round 2): executed FP32 work per robot-tick ON THIS WORKLOAD,
+# counted by ncu (smsp__sass_thread_inst_executed_op_{fadd,fmul,ffma}_pred_on, FFMA = 2 flop) over one whole env step of
+# 131,072 robots at step 30 after the reset, the middle of the timed region (profiles/r2_flops_step30_v12.csv; step 60 agrees
+# to 1.5 %): k_dyn 44.0 kflop, k_solve 25.9 kflop + k_solve_x 2.7 kflop (the bracket of "k_solve" covers both), k_post
+# 17.0 kflop per env step.  Round 1's 44.8 + 58.1 kflop were captured on the first steps after a reset, where every robot
+# stands on both feet with all eight sole points down -- the largest row set, twice the workload's mean.
+FLOP_DYN_PER_ROBOT_TICK, FLOP_SOLVE_PER_ROBOT_TICK, FLOP_POST_PER_ENV_STEP = 44.0e3, 28.6e3, 17.0e3
+FLOP_PER_ENV_STEP = 4 * (FLOP_DYN_PER_ROBOT_TICK + FLOP_SOLVE_PER_ROBOT_TICK) + FLOP_POST_PER_ENV_STEP
 # the same workload through the REFERENCE ALGORITHM (33-link ABA + velocity-space PGS with 24-wide rows), counted by the
 # oracle's instrumented FLOP counter (plen_oracle_state.flops; scripts/oracle_flops.py): 1.32 Mflop per env-step
 REF_ALGO_FLOP_PER_ENV_STEP = 1.32e6
@@ -423,10 +425,10 @@ def main():
                          "reference_algorithm": {"flop_per_env_step": REF_ALGO_FLOP_PER_ENV_STEP,
                                                  "equivalent_tflops": REF_ALGO_FLOP_PER_ENV_STEP * value / world / 1e12,
                                                  "equivalent_frac": REF_ALGO_FLOP_PER_ENV_STEP * value / world / 1e12 / fp32_peak},
-                         "note": "flop = executed FADD + FMUL + 2 FFMA thread operations counted by ncu (frozen in BASELINE.md); "
+                         "note": "flop = executed FADD + FMUL + 2 FFMA thread operations counted by ncu on this workload (frozen in BASELINE.md, re-measured in round 2: round 1's count was taken right after a reset and was twice the workload's mean); "
                                  "the limiter is the dependency latency of the Gauss-Seidel row chain at 2 warps per scheduler, "
                                  "not the pipe; reference_algorithm = the same env-steps/s priced at the oracle's instrumented "
-                                 "flop count of Bullet's ABA + velocity-space PGS (this solver does 3.2x less arithmetic for "
+                                 "flop count of Bullet's ABA + velocity-space PGS (this solver does 4.3x less arithmetic for "
                                  "the same rows); traffic = ncu DRAM bytes per robot (32768-robot capture) x robots per launch"},
             "roofline_hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak,
                              "peak_source": peak_src, "kernel": "k_solve",
