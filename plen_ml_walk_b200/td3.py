@@ -278,8 +278,11 @@ class TD3Agent:                                            # td3.py:196-376
     def select_action(self, state, expl_noise=0.0, precision="fp32"):
         """Batched: state [N,26] on the device -> action [N,18]; expl_noise = plen_td3.py:101-104 (std = max_action * expl_noise)."""
         self._draws += 1
+        # the noise stream is keyed by the agent's seed as well as the draw counter: data-parallel ranks (one agent per GPU,
+        # seeded per rank) must not explore with identical noise rows
         return actor_forward(self.actor, torch.as_tensor(state, device=self.device).reshape(-1, STATE_DIM),
-                             noise_std=self.max_action * expl_noise, seed=self._draws, precision=precision)
+                             noise_std=self.max_action * expl_noise, seed=(self._seed * 1000003 + self._draws) & (2 ** 64 - 1),
+                             precision=precision)
 
     def train(self, replay_buffer, batch_size=100, batch=None, noise=None, return_losses=False, grad_hook=None):
         """One TD3 update (td3.py:259-356) in the CUDA library.
