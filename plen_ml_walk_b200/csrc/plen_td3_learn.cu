@@ -17,6 +17,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -362,6 +363,11 @@ struct plen_td3 {
     CallParams *d_cp;
     bool use_cp;                        // the piecewise entry points read seed / ring size / Adam scalars from d_cp
     cudaStream_t cap;                   // capture stream
+    cudaStream_t side2;                 // third branch (plen_td3_train): the actor forward / the critic's target update next to the critic step
+    bool serial;                        // env PLEN_TD3_SERIAL (read at create): every branch on the caller's stream -- the order the branches are tested against
+    bool actor_fwd_done;                // the actor forward of this update was already enqueued (plen_td3_train)
+    cudaStream_t side;                  // second branch of an update: independent products run next to the main chain (fork / join with ev)
+    cudaEvent_t ev[8];
     cudaGraphExec_t exec[2];
     unsigned long long key[2];          // hash of everything a captured graph bakes in (pointers, batch, hyper-parameters)
     int nodes[2];
@@ -388,6 +394,7 @@ plen_td3 *plen_td3_create(int max_batch, int device) {
     if (!t) return nullptr;
     memset(t, 0, sizeof *t);
     t->device = device; t->max_batch = max_batch;
+    t->serial = getenv("PLEN_TD3_SERIAL") != nullptr && atoi(getenv("PLEN_TD3_SERIAL")) != 0;
     const size_t Bm = (size_t)max_batch;
     const size_t words = 3 * Bm * SA + 2 * Bm + 2 * Bm * H + 4 * Bm * H + 2 * Bm + 4 * Bm * H + 4 * Bm + 4 * Bm * H +
                          4 * Bm * H + 2 * Bm + 2 * Bm * H + Bm * A + 2 * Bm * H;
@@ -407,7 +414,10 @@ plen_td3 *plen_td3_create(int max_batch, int device) {
     t->a_h1 = take(Bm * H); t->a_h2 = take(Bm * H); t->p_h1 = take(Bm * H); t->p_h2 = take(Bm * H);
     t->qpi = take(Bm); t->dqpi = take(Bm); t->dp_h2 = take(Bm * H); t->dp_h1 = take(Bm * H); t->da3 = take(Bm * A);
     t->da_h2 = take(Bm * H); t->da_h1 = take(Bm * H);
-    if (cudaMalloc(&t->d_cp, sizeof(CallParams)) != cudaSuccess || cudaStreamCreateWithFlags(&t->cap, cudaStreamNonBlocking) != cudaSuccess) {
+    bool ok = cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&t->side2, cudaStreamNonBlocking) == cudaSuccess;
+    for (int k = 0; k < 8 && ok; k++) ok = cudaEventCreateWithFlags(&t->ev[k], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok || cudaMalloc(&t->d_cp, sizeof(CallParams)) != cudaSuccess || cudaStreamCreateWithFlags(&t->cap, cudaStreamNonBlocking) != cudaSuccess) {
         plen_td3_set_error(PLEN_E_CUDA, "plen_td3_create: call-parameter buffer / capture stream", "");
         cudaFree(t->ws); delete t;
         return nullptr;
@@ -422,6 +432,10 @@ void plen_td3_destroy(plen_td3 *t) {
     for (int k = 0; k < 2; k++)
         if (t->exec[k]) cudaGraphExecDestroy(t->exec[k]);
     if (t->cap) cudaStreamDestroy(t->cap);
+    if (t->side) cudaStreamDestroy(t->side);
+    if (t->side2) cudaStreamDestroy(t->side2);
+    for (int k = 0; k < 8; k++)
+        if (t->ev[k]) cudaEventDestroy(t->ev[k]);
     cudaFree(t->d_cp);
     cudaFree(t->ws);
     delete t;
@@ -486,7 +500,21 @@ int plen_td3_critic_grads(plen_td3 *t, const plen_td3_params *P, const plen_td3_
     const long long BH = (long long)B * H;
     int n = 0;
     s_tc = (t->tc && B >= SPLIT_K_MIN_BATCH) ? 1 : 0;      // (below that the gradient buffers are not zeroed and the update is launch bound)
-    // ---- target Q (no gradient), td3.py:303-313
+    // Two branches (fork / join with events; captured as parallel graph branches by plen_td3_train): the update is a chain of
+    // small launches whose fixed costs add up, so everything that does not depend on the chain runs next to it on t->side --
+    // the current-Q forward next to the target chain, every dW = dY^T X next to the dX = dY W that continues the chain.
+    cudaStream_t sd = t->serial ? st : t->side;
+    auto fork = [&](int i) { if (sd != st) { cudaEventRecord(t->ev[i], st); cudaStreamWaitEvent(sd, t->ev[i], 0); } };      // side continues after st's work so far
+    auto join = [&](int i) { if (sd != st) { cudaEventRecord(t->ev[i], sd); cudaStreamWaitEvent(st, t->ev[i], 0); } };      // st continues after side's work so far
+    fork(0);
+    // ---- side: current Q, td3.py:316 (and the zeroed gradient vector the split-K products accumulate into)
+    const float *c = P->critic;
+    float *gr = P->critic_grad;
+    n += launch(fwd(t->sa, SA, 0, c + CW1, SA, TOWER_N, c + CB1, t->c_h1, H, BH, B, H, SA, 2, EPI_BIAS_RELU), sd);
+    n += launch(fwd(t->c_h1, H, BH, c + CW2, H, TOWER_N, c + CB2, t->c_h2, H, BH, B, H, H, 2, EPI_BIAS_RELU), sd);
+    n += launch(fwd(t->c_h2, H, BH, c + CW3, H, TOWER_N, c + CB3, t->q, 1, B, B, 1, H, 2, EPI_BIAS), sd);
+    if (B >= SPLIT_K_MIN_BATCH) { LCK(cudaMemsetAsync(gr, 0, sizeof(float) * CRITIC_N, sd)); n += 1; }      // split-K accumulates
+    // ---- main: target Q (no gradient), td3.py:303-313
     const float *at = P->actor_target;
     n += launch(fwd(t->s2a, SA, 0, at + AW1, S, 0, at + AB1, t->at_h1, H, 0, B, H, S, 1, EPI_BIAS_RELU), st);
     n += launch(fwd(t->at_h1, H, 0, at + AW2, H, 0, at + AB2, t->at_h2, H, 0, B, H, H, 1, EPI_BIAS_RELU), st);
@@ -499,24 +527,37 @@ int plen_td3_critic_grads(plen_td3 *t, const plen_td3_params *P, const plen_td3_
     n += launch(fwd(t->s2a, SA, 0, ct + CW1, SA, TOWER_N, ct + CB1, t->ct_h1, H, BH, B, H, SA, 2, EPI_BIAS_RELU), st);
     n += launch(fwd(t->ct_h1, H, BH, ct + CW2, H, TOWER_N, ct + CB2, t->ct_h2, H, BH, B, H, H, 2, EPI_BIAS_RELU), st);
     n += launch(fwd(t->ct_h2, H, BH, ct + CW3, H, TOWER_N, ct + CB3, t->qt, 1, B, B, 1, H, 2, EPI_BIAS), st);
-    // ---- current Q, td3.py:316
-    const float *c = P->critic;
-    n += launch(fwd(t->sa, SA, 0, c + CW1, SA, TOWER_N, c + CB1, t->c_h1, H, BH, B, H, SA, 2, EPI_BIAS_RELU), st);
-    n += launch(fwd(t->c_h1, H, BH, c + CW2, H, TOWER_N, c + CB2, t->c_h2, H, BH, B, H, H, 2, EPI_BIAS_RELU), st);
-    n += launch(fwd(t->c_h2, H, BH, c + CW3, H, TOWER_N, c + CB3, t->q, 1, B, B, 1, H, 2, EPI_BIAS), st);
+    join(1);
     k_td_loss<<<1, 256, 0, st>>>(B, h->discount, t->qt, t->q, t->r, t->nd, t->dq, critic_loss_dev);
     n += 1;
-    // ---- backward through both towers, td3.py:333 (gradients land in P->critic_grad, flat layout of the critic)
-    float *gr = P->critic_grad;
-    if (B >= SPLIT_K_MIN_BATCH) { LCK(cudaMemsetAsync(gr, 0, sizeof(float) * CRITIC_N, st)); n += 1; }      // split-K accumulates
-    n += launch(bwd_weight(t->dq, 1, B, t->c_h2, H, BH, gr + CW3, H, gr + CB3, TOWER_N, B, 1, H, 2), st);
+    // ---- backward through both towers, td3.py:333 (gradients land in P->critic_grad, flat layout of the critic):
+    //      dX chain on the main branch, dW products on the side branch
+    fork(2);
+    n += launch(bwd_weight(t->dq, 1, B, t->c_h2, H, BH, gr + CW3, H, gr + CB3, TOWER_N, B, 1, H, 2), sd);
     n += launch(bwd_data(t->dq, 1, B, c + CW3, H, TOWER_N, t->dh2, H, BH, B, H, 1, 2, EPI_RELUMASK, t->c_h2, H, BH), st);
-    n += launch(bwd_weight(t->dh2, H, BH, t->c_h1, H, BH, gr + CW2, H, gr + CB2, TOWER_N, B, H, H, 2), st);
+    fork(3);
+    n += launch(bwd_weight(t->dh2, H, BH, t->c_h1, H, BH, gr + CW2, H, gr + CB2, TOWER_N, B, H, H, 2), sd);
     n += launch(bwd_data(t->dh2, H, BH, c + CW2, H, TOWER_N, t->dh1, H, BH, B, H, H, 2, EPI_RELUMASK, t->c_h1, H, BH), st);
-    n += launch(bwd_weight(t->dh1, H, BH, t->sa, SA, 0, gr + CW1, SA, gr + CB1, TOWER_N, B, H, SA, 2), st);
+    fork(4);
+    n += launch(bwd_weight(t->dh1, H, BH, t->sa, SA, 0, gr + CW1, SA, gr + CB1, TOWER_N, B, H, SA, 2), sd);
+    join(5);
     t->launches += n;
     LCK(cudaGetLastError());
     return PLEN_OK;
+}
+
+// actor(state) for the policy step: spi = [s | actor(s)] (3 launches).  Depends on the actor's parameters and the minibatch only.
+static int actor_forward_launches(plen_td3 *t, const plen_td3_params *P, const plen_td3_hyper *h, cudaStream_t st) {
+    const int B = t->batch;
+    const float *ac = P->actor;
+    int n = 0;
+    s_tc = (t->tc && B >= SPLIT_K_MIN_BATCH) ? 1 : 0;
+    n += launch(fwd(t->spi, SA, 0, ac + AW1, S, 0, ac + AB1, t->a_h1, H, 0, B, H, S, 1, EPI_BIAS_RELU), st);
+    n += launch(fwd(t->a_h1, H, 0, ac + AW2, H, 0, ac + AB2, t->a_h2, H, 0, B, H, H, 1, EPI_BIAS_RELU), st);
+    Gemm g = fwd(t->a_h2, H, 0, ac + AW3, H, 0, ac + AB3, t->spi + S, SA, 0, B, A, H, 1, EPI_BIAS_TANH);
+    g.p0 = h->max_action;
+    n += launch(g, st);
+    return n;
 }
 
 int plen_td3_actor_grads(plen_td3 *t, const plen_td3_params *P, const plen_td3_hyper *h, float *actor_loss_dev, void *stream) {
@@ -530,13 +571,8 @@ int plen_td3_actor_grads(plen_td3 *t, const plen_td3_params *P, const plen_td3_h
     s_tc = (t->tc && B >= SPLIT_K_MIN_BATCH) ? 1 : 0;      // (below that the gradient buffers are not zeroed and the update is launch bound)
     // ---- actor_loss = -critic.Q1(state, actor(state)).mean(), td3.py:342
     const float *ac = P->actor, *c = P->critic;
-    n += launch(fwd(t->spi, SA, 0, ac + AW1, S, 0, ac + AB1, t->a_h1, H, 0, B, H, S, 1, EPI_BIAS_RELU), st);
-    n += launch(fwd(t->a_h1, H, 0, ac + AW2, H, 0, ac + AB2, t->a_h2, H, 0, B, H, H, 1, EPI_BIAS_RELU), st);
-    {
-        Gemm g = fwd(t->a_h2, H, 0, ac + AW3, H, 0, ac + AB3, t->spi + S, SA, 0, B, A, H, 1, EPI_BIAS_TANH);
-        g.p0 = h->max_action;
-        n += launch(g, st);
-    }
+    if (!t->actor_fwd_done) n += actor_forward_launches(t, P, h, st);      // (plen_td3_train runs it next to the critic step)
+    t->actor_fwd_done = false;
     n += launch(fwd(t->spi, SA, 0, c + CW1, SA, 0, c + CB1, t->p_h1, H, 0, B, H, SA, 1, EPI_BIAS_RELU), st);
     n += launch(fwd(t->p_h1, H, 0, c + CW2, H, 0, c + CB2, t->p_h2, H, 0, B, H, H, 1, EPI_BIAS_RELU), st);
     n += launch(fwd(t->p_h2, H, 0, c + CW3, H, 0, c + CB3, t->qpi, 1, 0, B, 1, H, 1, EPI_BIAS), st);
@@ -551,13 +587,21 @@ int plen_td3_actor_grads(plen_td3 *t, const plen_td3_params *P, const plen_td3_h
         g.p0 = h->max_action;
         n += launch(g, st);
     }
+    // dX chain on the main branch, dW products on the side branch (see plen_td3_critic_grads)
+    cudaStream_t sd = t->serial ? st : t->side;
+    auto fork = [&](int i) { if (sd != st) { cudaEventRecord(t->ev[i], st); cudaStreamWaitEvent(sd, t->ev[i], 0); } };
+    auto join = [&](int i) { if (sd != st) { cudaEventRecord(t->ev[i], sd); cudaStreamWaitEvent(st, t->ev[i], 0); } };
     float *gr = P->actor_grad;
-    if (B >= SPLIT_K_MIN_BATCH) { LCK(cudaMemsetAsync(gr, 0, sizeof(float) * ACTOR_N, st)); n += 1; }
-    n += launch(bwd_weight(t->da3, A, 0, t->a_h2, H, 0, gr + AW3, H, gr + AB3, 0, B, A, H, 1), st);
+    fork(0);
+    if (B >= SPLIT_K_MIN_BATCH) { LCK(cudaMemsetAsync(gr, 0, sizeof(float) * ACTOR_N, sd)); n += 1; }
+    n += launch(bwd_weight(t->da3, A, 0, t->a_h2, H, 0, gr + AW3, H, gr + AB3, 0, B, A, H, 1), sd);
     n += launch(bwd_data(t->da3, A, 0, ac + AW3, H, 0, t->da_h2, H, 0, B, H, A, 1, EPI_RELUMASK, t->a_h2, H, 0), st);
-    n += launch(bwd_weight(t->da_h2, H, 0, t->a_h1, H, 0, gr + AW2, H, gr + AB2, 0, B, H, H, 1), st);
+    fork(1);
+    n += launch(bwd_weight(t->da_h2, H, 0, t->a_h1, H, 0, gr + AW2, H, gr + AB2, 0, B, H, H, 1), sd);
     n += launch(bwd_data(t->da_h2, H, 0, ac + AW2, H, 0, t->da_h1, H, 0, B, H, H, 1, EPI_RELUMASK, t->a_h1, H, 0), st);
-    n += launch(bwd_weight(t->da_h1, H, 0, t->spi, SA, 0, gr + AW1, S, gr + AB1, 0, B, H, S, 1), st);
+    fork(2);
+    n += launch(bwd_weight(t->da_h1, H, 0, t->spi, SA, 0, gr + AW1, S, gr + AB1, 0, B, H, S, 1), sd);
+    join(3);
     t->launches += n;
     LCK(cudaGetLastError());
     return PLEN_OK;
@@ -604,23 +648,36 @@ static int enqueue_train(plen_td3 *t, const plen_td3_params *P, const plen_td3_h
     t->use_cp = true;
     do {
         if (rb) { rc = plen_td3_sample(t, rb, batch, 0, st); if (rc) break; }
+        cudaStream_t s2 = t->serial ? st : t->side2;
+        if (policy) {       // third branch: the actor forward needs the minibatch and the actor only -- it runs next to the critic step
+            if (s2 != st) { cudaEventRecord(t->ev[6], st); cudaStreamWaitEvent(s2, t->ev[6], 0); }
+            t->launches += actor_forward_launches(t, P, h, s2);
+            t->actor_fwd_done = true;
+        }
         rc = plen_td3_critic_grads(t, P, h, nullptr, 0, losses_dev ? losses_dev + 1 : nullptr, st);
         if (rc) break;
         rc = adam_launch(P->critic, P->critic_grad, P->critic_m, P->critic_v, CRITIC_N, 1, h, t->device, st, t->d_cp->adam_c);
         if (rc) break;
         t->launches += 1;
         if (policy) {       // delayed policy update, td3.py:339-360
+            // ... and so does the critic's Polyak update once its Adam step is in (the policy step reads the critic, not its target)
+            if (s2 != st) {
+                cudaEventRecord(t->ev[7], s2); cudaStreamWaitEvent(st, t->ev[7], 0);          // join: spi is complete
+                cudaEventRecord(t->ev[6], st); cudaStreamWaitEvent(s2, t->ev[6], 0);          // fork after the critic's Adam step
+            }
+            rc = plen_td3_soft_update(P->critic_target, P->critic, CRITIC_N, h->tau, t->device, s2);
+            if (rc) break;
             rc = plen_td3_actor_grads(t, P, h, losses_dev, st);
             if (rc) break;
             rc = adam_launch(P->actor, P->actor_grad, P->actor_m, P->actor_v, ACTOR_N, 1, h, t->device, st, t->d_cp->adam_a);
             if (rc) break;
-            rc = plen_td3_soft_update(P->critic_target, P->critic, CRITIC_N, h->tau, t->device, st);
-            if (rc) break;
             rc = plen_td3_soft_update(P->actor_target, P->actor, ACTOR_N, h->tau, t->device, st);
             if (rc) break;
+            if (s2 != st) { cudaEventRecord(t->ev[7], s2); cudaStreamWaitEvent(st, t->ev[7], 0); }      // join the target update
             t->launches += 3;
         }
     } while (0);
+    t->actor_fwd_done = false;
     t->use_cp = false;
     return rc;
 }

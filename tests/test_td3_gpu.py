@@ -251,6 +251,36 @@ def test_td3_tensor_core_update_trains_like_fp32():
     assert a.kernel_launches() > 0 and _abi_lib().plen_td3_tc_timed_out() == 0
 
 
+def test_td3_update_branches_equal_the_serial_order(monkeypatch):
+    """plen_td3_train enqueues an update as three branches (current-Q forward and every dW next to the target / dX chain, the
+    actor forward and the critic's Polyak update next to the critic step; captured as parallel graph branches).  With
+    PLEN_TD3_SERIAL=1 the same launches go down ONE stream: below 512 rows (no split-K atomics) 40 updates must agree bit for
+    bit, i.e. no branch runs ahead of a producer it depends on."""
+    from plen_ml_walk_b200.td3 import ReplayBuffer, TD3Agent
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev); g.manual_seed(41)
+    n = 20000
+    st = torch.randn(n, 26, device=dev, generator=g); ac = torch.rand(n, 18, device=dev, generator=g) * 2 - 1
+    s2 = torch.randn(n, 26, device=dev, generator=g); r = torch.randn(n, device=dev, generator=g)
+    dn = torch.rand(n, device=dev, generator=g) < 0.05
+    for B in (100, 384):
+        res = []
+        for serial in ("1", "0"):
+            monkeypatch.setenv("PLEN_TD3_SERIAL", serial)
+            torch.manual_seed(43)
+            agent = TD3Agent(device=dev, seed=7)
+            rb = ReplayBuffer(n, device=dev, seed=5)
+            rb.add(st, ac, s2, r, dn)
+            losses = [agent.train(rb, B, return_losses=True) for _ in range(40)]
+            res.append((agent, [x[1] for x in losses]))
+        (a, la), (b, lb) = res
+        for k in ("actor", "critic", "actor_target", "critic_target"):
+            assert torch.equal(a._flat[k], b._flat[k]), (B, k)
+        assert all(torch.equal(x, y) for x, y in zip(la, lb))
+        for k in ("actor_m", "actor_v", "critic_m", "critic_v"):
+            assert torch.equal(a._adam[k], b._adam[k]), (B, k)
+
+
 def test_td3_update_follows_reference_rule():
     """TD3Agent.train (td3.py:259-356) sampling from the device replay ring inside the library: critic step every call,
     actor + Polyak every policy_freq calls; the critic loss on a fixed synthetic buffer goes down; checkpoints round-trip
