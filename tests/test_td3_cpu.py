@@ -42,3 +42,25 @@ def test_state_dict_keys_match_reference_checkpoints():
     assert list(Actor().state_dict().keys()) == ["fc%d.%s" % (i, p) for i in (1, 2, 3) for p in ("weight", "bias")]
     assert list(Critic().state_dict().keys()) == ["fc%d.%s" % (i, p) for i in range(1, 7) for p in ("weight", "bias")]
     assert sum(p.numel() for p in Critic().parameters()) == 155138
+
+
+def test_agent_host_logic_without_a_gpu(tmp_path):
+    """Host side of TD3Agent that needs no device: argument checking, the reference's four-file checkpoint round trip and its
+    load() semantics (td3.py:366-376 leaves the TARGET networks untouched), and the loud failure of train() off the GPU."""
+    import pytest
+    from plen_ml_walk_b200.td3 import TD3Agent
+    with pytest.raises(ValueError):
+        TD3Agent(device="cpu", precision="bf16")
+    torch.manual_seed(1)
+    a = TD3Agent(device="cpu")
+    a.save(str(tmp_path / "ck"))
+    torch.manual_seed(2)
+    b = TD3Agent(device="cpu")
+    tgt0 = b._flat["actor_target"].clone()
+    b.load(str(tmp_path / "ck"))
+    assert torch.equal(b._flat["actor"], a._flat["actor"]) and torch.equal(b._flat["critic"], a._flat["critic"])
+    assert torch.equal(b._flat["actor_target"], tgt0)                       # as the reference: targets keep their old values
+    b.load(str(tmp_path / "ck"), sync_targets=True)
+    assert torch.equal(b._flat["actor_target"], a._flat["actor"]) and torch.equal(b._flat["critic_target"], a._flat["critic"])
+    with pytest.raises(RuntimeError):
+        a.train(None, batch=(torch.zeros(4, 26), torch.zeros(4, 18), torch.zeros(4, 26), torch.zeros(4, 1), torch.ones(4, 1)))
