@@ -1,5 +1,9 @@
-O=gpurun_out/${1:-r2_tc9}; mkdir -p $O
-timeout 600 python -m pytest tests/test_td3_gpu.py -m gpu -x -q > $O/pytest_td3.log 2>&1; tail -3 $O/pytest_td3.log
-timeout 600 python scripts/td3_bench.py 300 > $O/td3_bench.json 2> $O/td3_bench.err; python -c "
-import json; d=json.load(open('$O/td3_bench.json'))
-for k,v in d.items(): print(k, 'fp32 %.1f us  tf32 %.1f us  launches %.1f' % (v['cuda_device_us_per_update'], v['tf32_device_us_per_update'], v['launches_per_update']))"; tail -3 $O/td3_bench.err
+O=gpurun_out/${1:-r2_c4}; mkdir -p $O
+R="python scripts/plen_td3_batched.py --envs 16384 --actor-precision fp16"
+timeout 600 $R --env-steps 4194304 --no-learner > $O/config4_nolearner.json 2> $O/err.txt; cat $O/config4_nolearner.json
+timeout 600 $R --env-steps 4194304 --updates-per-step 8 --batch-size 100 > $O/config4_u8_b100_fp32.json 2>> $O/err.txt; cat $O/config4_u8_b100_fp32.json
+timeout 600 $R --env-steps 4194304 --updates-per-step 4 --batch-size 4096 --learner-precision tf32 > $O/config4_u4_b4096_tf32.json 2>> $O/err.txt; cat $O/config4_u4_b4096_tf32.json
+timeout 600 $R --env-steps 4194304 --updates-per-step 4 --batch-size 4096 > $O/config4_u4_b4096_fp32.json 2>> $O/err.txt; cat $O/config4_u4_b4096_fp32.json
+timeout 600 $R --env-steps 2097152 --updates-per-step 8 --batch-size 16384 --learner-precision tf32 > $O/config4_u8_b16384_tf32.json 2>> $O/err.txt; cat $O/config4_u8_b16384_tf32.json
+timeout 600 $R --env-steps 524288 --updates-per-step 100 --batch-size 16384 --learner-precision tf32 > $O/config4_u100_b16384_tf32.json 2>> $O/err.txt; cat $O/config4_u100_b16384_tf32.json
+tail -3 $O/err.txt
