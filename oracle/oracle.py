@@ -22,7 +22,7 @@ from . import urdf_tree
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_build", "libplen_oracle.so")
 
-MAXL, NDOF, NJ, NFEET, NPTS, MAXBOX = 32, 24, 18, 2, 4, 32
+MAXL, NDOF, NJ, NFEET, NPTS, MAXBOX, MAXHULL = 32, 24, 18, 2, 4, 32, 256
 
 
 class Model(C.Structure):
@@ -36,6 +36,7 @@ class Model(C.Structure):
         ("foot_break", C.c_double * NFEET),
         ("n_boxes", C.c_int), ("box_link", C.c_int * MAXBOX), ("box_center", (C.c_double * 3) * MAXBOX),
         ("box_rot", (C.c_double * 9) * MAXBOX), ("box_half", (C.c_double * 3) * MAXBOX),
+        ("n_hull", C.c_int * NFEET), ("foot_hull", ((C.c_double * 3) * MAXHULL) * NFEET),
     ]
 
 
@@ -51,6 +52,7 @@ class Config(C.Structure):
         ("linear_slop", C.c_double), ("warmstart_factor", C.c_double), ("restitution_vel_threshold", C.c_double),
         ("hull_margin", C.c_double), ("max_coord_velocity", C.c_double), ("implicit_cone", C.c_int),
         ("link_contacts", C.c_int), ("mu_link", C.c_double), ("restitution_base", C.c_double), ("max_contact_points", C.c_int),
+        ("manifold_mode", C.c_int),
     ]
 
 
@@ -63,6 +65,7 @@ class State(C.Structure):
         ("last", C.c_double * 6), ("sums", C.c_double * 9), ("ep_ret", C.c_double),
         ("last_iterations", C.c_int), ("last_rows", C.c_int), ("last_box_points", C.c_int),
         ("last_boxes_touching", C.c_int), ("flops", C.c_longlong),
+        ("man_n", C.c_int * NFEET), ("man_local", ((C.c_double * 3) * NPTS) * NFEET), ("man_world", ((C.c_double * 3) * NPTS) * NFEET),
     ]
 
 
@@ -135,6 +138,11 @@ def model_from_tree(tree) -> Model:
         for p in range(NPTS):
             for k in range(3):
                 m.foot_pts[f][p][k] = foot["points"][p][k]
+        hull = foot.get("hull", [])                      # manifold_mode 1 only
+        m.n_hull[f] = min(len(hull), MAXHULL)
+        for i in range(m.n_hull[f]):
+            for k in range(3):
+                m.foot_hull[f][i][k] = hull[i][k]
     boxes = tree.get("boxes", [])
     m.n_boxes = len(boxes)
     for b, bx in enumerate(boxes):

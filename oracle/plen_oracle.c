@@ -463,6 +463,105 @@ static void plane_space(const double *n, double *p, double *q) {
 static double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
 /* ------------------------------------------------------------------ 4. tick */
+/* EXPERIMENT (plen_oracle_config.manifold_mode == 1): the sole contact of a foot as btConvexPlaneCollisionAlgorithm +
+ * btPersistentManifold produce it, restated from the published sources as recalled ([RECALL], like the rest of the physics):
+ *   collideSingleContact : support vertex of the hull towards the ground (first maximum over the point list), moved out by the
+ *                          collision margin; a contact if its distance is below the breaking threshold
+ *   addContactPoint      : getCacheEntry (nearest cached point, in the foot's frame, within the threshold) -> replace it and keep
+ *                          its impulse; else add; a full cache goes through sortCachedPoints (keep the deepest, drop the point
+ *                          whose removal leaves the largest quadrilateral)
+ *   refreshContactPoints : world positions and distance of every cached point from its two local copies; points that separated
+ *                          by more than the threshold or drifted sideways by more than it are removed (last index swapped in)
+ * Fills cp_pos / cp_dist of the cached points (slot k = cache index k) and s->in_manifold / s->lam_n accordingly. */
+static void manifold_update(const plen_oracle_model *m, const plen_oracle_config *cfg, plen_oracle_state *s, const work_t *w,
+                            double cp_pos[ORC_NFEET][ORC_NPTS][3], double cp_dist[ORC_NFEET][ORC_NPTS]) {
+    for (int f = 0; f < ORC_NFEET; f++) {
+        const int L = m->foot_link[f];
+        const double *R = w->Rw[L + 1], *p = w->pw[L + 1];
+        const double thr = m->foot_break[f];
+        /* support vertex: lowest world z; ties -> first in the list */
+        int best = -1;
+        double zbest = 1e300;
+        for (int i = 0; i < m->n_hull[f]; i++) {
+            const double *v = m->foot_hull[f][i];
+            const double z = p[2] + R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+            if (z < zbest) { zbest = z; best = i; }
+        }
+        if (best >= 0 && zbest - cfg->hull_margin < thr) {
+            /* point on the inflated hull (world), its copy in the foot frame, and its projection on the plane */
+            double t[3], pa[3], la[3], pb[3];
+            mat3_vec(R, m->foot_hull[f][best], t);
+            pa[0] = p[0] + t[0]; pa[1] = p[1] + t[1]; pa[2] = p[2] + t[2] - cfg->hull_margin;
+            const double d[3] = {pa[0] - p[0], pa[1] - p[1], pa[2] - p[2]};
+            for (int c = 0; c < 3; c++) la[c] = R[c] * d[0] + R[3 + c] * d[1] + R[6 + c] * d[2];      /* R^T d */
+            pb[0] = pa[0]; pb[1] = pa[1]; pb[2] = 0.0;
+            const double dist = pa[2];
+            int n = s->man_n[f], slot = -1;
+            double nearest = thr * thr;
+            for (int k = 0; k < n; k++) {           /* getCacheEntry */
+                double dd = 0;
+                for (int c = 0; c < 3; c++) { const double e = s->man_local[f][k][c] - la[c]; dd += e * e; }
+                if (dd < nearest) { nearest = dd; slot = k; }
+            }
+            if (slot < 0) {
+                if (n < ORC_NPTS) { slot = n; s->man_n[f] = n + 1; s->lam_n[f][slot] = 0.0; }
+                else {                                   /* sortCachedPoints */
+                    int deepest = -1;
+                    double maxpen = dist;
+                    for (int k = 0; k < ORC_NPTS; k++) {
+                        const double zk = p[2] + R[6] * s->man_local[f][k][0] + R[7] * s->man_local[f][k][1] + R[8] * s->man_local[f][k][2];
+                        if (zk < maxpen) { deepest = k; maxpen = zk; }
+                    }
+                    static const int other[4][3] = {{1, 2, 3}, {0, 2, 3}, {0, 1, 3}, {0, 1, 2}};
+                    double res[4] = {0, 0, 0, 0};
+                    for (int k = 0; k < 4; k++) {
+                        if (k == deepest) continue;
+                        const double *q0 = s->man_local[f][other[k][0]], *q1 = s->man_local[f][other[k][1]], *q2 = s->man_local[f][other[k][2]];
+                        /* as Bullet pairs them: a = new - first remaining, b = third remaining - second remaining */
+                        const double a[3] = {la[0] - q0[0], la[1] - q0[1], la[2] - q0[2]};
+                        const double b[3] = {q2[0] - q1[0], q2[1] - q1[1], q2[2] - q1[2]};
+                        double cr[3];
+                        cross3(a, b, cr);
+                        res[k] = cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2];
+                    }
+                    slot = 0;
+                    for (int k = 1; k < 4; k++) if (res[k] > res[slot]) slot = k;
+                    s->lam_n[f][slot] = 0.0;
+                }
+            }
+            for (int c = 0; c < 3; c++) { s->man_local[f][slot][c] = la[c]; s->man_world[f][slot][c] = pb[c]; }
+        }
+        /* refreshContactPoints, last to first */
+        for (int k = s->man_n[f] - 1; k >= 0; k--) {
+            double t[3], pa[3];
+            mat3_vec(R, s->man_local[f][k], t);
+            for (int c = 0; c < 3; c++) pa[c] = p[c] + t[c];
+            const double dist = pa[2] - s->man_world[f][k][2];
+            const double dx = s->man_world[f][k][0] - pa[0], dy = s->man_world[f][k][1] - pa[1];
+            if (dist > thr || dx * dx + dy * dy > thr * thr) {
+                const int last = s->man_n[f] - 1;
+                if (k != last) {
+                    memcpy(s->man_local[f][k], s->man_local[f][last], sizeof s->man_local[f][k]);
+                    memcpy(s->man_world[f][k], s->man_world[f][last], sizeof s->man_world[f][k]);
+                    s->lam_n[f][k] = s->lam_n[f][last];
+                }
+                s->lam_n[f][last] = 0.0;
+                s->man_n[f] = last;
+            }
+        }
+        for (int k = 0; k < ORC_NPTS; k++) {
+            s->in_manifold[f][k] = k < s->man_n[f];
+            cp_dist[f][k] = 0.0;
+            for (int c = 0; c < 3; c++) cp_pos[f][k][c] = 0.0;
+            if (k >= s->man_n[f]) { s->lam_n[f][k] = 0.0; continue; }
+            double t[3];
+            mat3_vec(R, s->man_local[f][k], t);
+            for (int c = 0; c < 3; c++) cp_pos[f][k][c] = p[c] + t[c];
+            cp_dist[f][k] = cp_pos[f][k][2] - s->man_world[f][k][2];
+        }
+    }
+}
+
 void plen_oracle_tick(const plen_oracle_model *m, const plen_oracle_config *cfg, plen_oracle_state *s) {
     work_t w;
     double acc[ORC_NDOF], vstar[ORC_NDOF], dv[ORC_NDOF];
@@ -484,6 +583,8 @@ void plen_oracle_tick(const plen_oracle_model *m, const plen_oracle_config *cfg,
 
     /* (b) collision detection at the start-of-tick poses: sole vertices vs the plane z = 0 */
     double cp_pos[ORC_NFEET][ORC_NPTS][3], cp_dist[ORC_NFEET][ORC_NPTS];
+    if (cfg->manifold_mode == 1) manifold_update(m, cfg, s, &w, cp_pos, cp_dist);
+    else
     for (int f = 0; f < ORC_NFEET; f++) {
         int L = m->foot_link[f];
         for (int k = 0; k < ORC_NPTS; k++) {
@@ -806,6 +907,7 @@ void plen_oracle_reset(const plen_oracle_model *m, const plen_oracle_config *cfg
     memset(s->q, 0, sizeof s->q); memset(s->qd, 0, sizeof s->qd);
     /* the teleport invalidates every cached manifold point (positions are stored per body) */
     memset(s->lam_n, 0, sizeof s->lam_n); memset(s->in_manifold, 0, sizeof s->in_manifold);
+    memset(s->man_n, 0, sizeof s->man_n);
     memset(s->target, 0, sizeof s->target);                    /* move_joints(zeros), raw radians, :568 */
     for (int i = 0; i < cfg->reset_ticks; i++) plen_oracle_tick(m, cfg, s);   /* :569-570 */
     if (obs) plen_oracle_observe(m, cfg, s, obs, 0);           /* :574 (history side effects cleared below) */

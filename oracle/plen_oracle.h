@@ -31,6 +31,7 @@ extern "C" {
 #define ORC_NPTS 4       /* contact points per foot (persistent-manifold capacity) */
 #define ORC_MAXBOX 32    /* box colliders besides the two foot hulls (plen.urdf: torso + 30 links) */
 #define ORC_MAXXP (ORC_MAXBOX * 4)   /* contact points they can produce: <= 4 per box (btBoxBoxDetector's manifold) */
+#define ORC_MAXHULL 256  /* convex-hull vertices of a foot mesh (plen.urdf feet: 209 each) */
 #define ORC_MAXROWS (2 * ORC_NJ + ORC_NJ + ORC_NFEET * ORC_NPTS * 6 + 3 * ORC_MAXXP)
 
 typedef struct {
@@ -55,6 +56,9 @@ typedef struct {
     double box_center[ORC_MAXBOX][3];           /* collision origin in the link frame */
     double box_rot[ORC_MAXBOX][9];              /* collision rpy as a rotation, link frame (row major) */
     double box_half[ORC_MAXBOX][3];             /* half extents */
+    /* convex-hull vertices of the two foot meshes, link frame (manifold_mode 1 only) */
+    int n_hull[ORC_NFEET];
+    double foot_hull[ORC_NFEET][ORC_MAXHULL][3];
 } plen_oracle_model;
 
 typedef struct {
@@ -92,6 +96,15 @@ typedef struct {
     double restitution_base;   /* torso 0 (not in the changeDynamics loop, plen_env.py:476-481) * plane 0.5 */
     int max_contact_points;    /* at most this many box contact points per tick, deepest first (-1: no cap = Bullet; the CUDA
                                   path keeps 4 and the parity tests give the oracle the same cap) */
+    /* --- EXPERIMENT (profiles/r2_physics_pin.md section 5): how the sole contact points are generated ---
+     * 0 (default, what the CUDA path does): the four extreme sole corners, each in the manifold while within the breaking
+     *   threshold of the ground -- the limiting 4-point set of Bullet's manifold reduction, present from the first tick.
+     * 1: btConvexPlaneCollisionAlgorithm + btPersistentManifold as recalled: ONE new point per tick (the hull's support
+     *   vertex towards the ground, if within the breaking threshold), merged into a cache of <= 4 points per foot (replace the
+     *   nearest cached point within the threshold, else add, else sortCachedPoints: keep the deepest, maximise the area), then
+     *   refreshContactPoints (drop points that separated or drifted by more than the threshold); impulses travel with the
+     *   cached points. */
+    int manifold_mode;
 } plen_oracle_config;
 
 typedef struct {
@@ -106,6 +119,10 @@ typedef struct {
     /* diagnostics of the last tick */
     int last_iterations, last_rows, last_box_points, last_boxes_touching;
     long long flops;                     /* instrumented FLOP counter (adds+muls), whole life */
+    /* manifold_mode 1: the persistent manifold of either foot (lam_n / in_manifold above are its impulses / occupancy) */
+    int man_n[ORC_NFEET];
+    double man_local[ORC_NFEET][ORC_NPTS][3];    /* point on the (inflated) hull, foot link frame */
+    double man_world[ORC_NFEET][ORC_NPTS][3];    /* point on the plane, world frame */
 } plen_oracle_state;
 
 void plen_oracle_default_config(plen_oracle_config *cfg, int joint_act);

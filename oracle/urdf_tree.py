@@ -101,6 +101,15 @@ def sole_corner_points(verts_link):
     return pts, sole
 
 
+def hull_vertices(verts_link):
+    """Vertices of the convex hull of a foot mesh (link frame), in the order of the STL's unique-vertex list: the support-vertex
+    search of the persistent-manifold experiment (plen_oracle_config.manifold_mode) walks them as btConvexHullShape would walk
+    its point list after optimizeConvexHull ([RECALL]; only the first-maximum tie break depends on the order)."""
+    from scipy.spatial import ConvexHull
+    idx = np.sort(ConvexHull(verts_link).vertices)
+    return verts_link[idx]
+
+
 def build_tree(urdf_path, mesh_dir, inertia_from_urdf=False):
     root = ET.parse(urdf_path).getroot()
     links = {l.get("name"): l for l in root.findall("link")}
@@ -203,7 +212,8 @@ def build_tree(urdf_path, mesh_dir, inertia_from_urdf=False):
         assert pr["hull"] is not None, pr["name"]
         pts, sole = sole_corner_points(pr["hull"])
         feet.append(dict(link=link, name=pr["name"], points=pts.tolist(), n_sole_vertices=int(len(sole)),
-                         breaking_threshold=CONTACT_BREAKING_FACTOR * pr["angular_motion_disc"]))
+                         breaking_threshold=CONTACT_BREAKING_FACTOR * pr["angular_motion_disc"],
+                         hull=hull_vertices(pr["hull"]).tolist()))
     tree["feet"] = feet
     # box colliders of every link but the feet, Bullet link index (-1 = base), for the link-vs-ground contacts
     boxes = [dict(link=-1, name=base_name, **base["box"])]

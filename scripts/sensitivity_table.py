@@ -131,6 +131,10 @@ VARIANTS = [
     ("mu_lateral 0.64 -> 0.4 (plane 0.5)", {"mu_lateral": 0.4}),
     ("mu_link 0.4 -> 0.8", {"mu_link": 0.8}),
     ("inertia from the URDF tensors instead of the collision AABB", {"__tree__": "urdf_inertia"}),
+    # the structural experiment: Bullet's one-point-per-tick persistent manifold instead of the four fixed sole corners
+    ("sole contact as btPersistentManifold (manifold_mode 1)", {"manifold_mode": 1}),
+    ("manifold_mode 1, warmstart 0.1 -> 0.85", {"manifold_mode": 1, "warmstart_factor": 0.85}),
+    ("manifold_mode 1, foot breaking threshold x4", {"manifold_mode": 1, "foot_break_scale": 4.0}),
 ]
 
 
