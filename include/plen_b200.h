@@ -39,6 +39,9 @@ extern "C" {
 #define PLEN_STATE_WORDS 96    /* per-env state record in HBM: 3 x 128 B lines, one word per lane per line */
 #define PLEN_MAX_BOXES 32      /* box colliders besides the two feet (plen.urdf: torso + 30 links): one per lane of a warp */
 #define PLEN_MAX_BOX_POINTS 4  /* box-vs-ground contact points kept per robot and tick (the deepest ones) */
+#define PLEN_MAX_HULL 256      /* convex-hull vertices of a foot collider (plen.urdf feet: 209 each) */
+#define PLEN_MAN_WORDS 52      /* per-robot persistent sole manifold (sole_manifold = 1): [foot][point][local xyz | plane xyz] = 48
+                                  floats, the two point counts, 2 spare */
 
 #define PLEN_OK 0
 #define PLEN_E_ARG (-1)
@@ -69,6 +72,10 @@ typedef struct {
     float box_half[PLEN_MAX_BOXES][3];     /* half extents */
     float box_rest[PLEN_MAX_BOXES];        /* factor on config.restitution: 0 for the base link (its restitution stays 0:
                                               it is not in the changeDynamics loop, plen_env.py:476-481), 1 otherwise */
+    /* Convex-hull vertices of the two foot colliders in the foot body frame (plen.urdf:1097, :1263 -> the STL meshes):
+     * the support-vertex search of the persistent sole manifold (config.sole_manifold = 1) walks them. */
+    int32_t n_hull[2];
+    float foot_hull[2][PLEN_MAX_HULL][3];
 } plen_model;
 
 /* Every constant of the path; defaults = the reference literals (cited) or the PyBullet defaults they rely on. */
@@ -102,6 +109,15 @@ typedef struct {
                                   the caller, plen_td3.py:122-129) */
     int32_t link_contacts;     /* 1: the box colliders of the non-foot links collide with the ground (default); 0: soles only */
     float mu_link;             /* 0.5*0.8: URDF default lateral friction of a link x the plane's, plen_env.py:309 */
+    int32_t sole_manifold;     /* how the sole contact points of a foot come into being.  0 (default): the four extreme sole
+                                  corners, each in contact while within the breaking threshold of the ground -- the limiting set
+                                  of Bullet's manifold reduction, present from the first tick.  1: as Bullet's
+                                  btConvexPlaneCollisionAlgorithm + btPersistentManifold do it ([RECALL]): ONE new point per tick
+                                  (the hull's support vertex towards the ground) merged into a cache of <= 4 points per foot
+                                  (replace the nearest within the threshold / add / keep the deepest and the largest area), points
+                                  that separated or drifted by more than the threshold dropped; impulses travel with the points.
+                                  profiles/r2_physics_pin.md section 5: the shipped policy's mean return moves from -5 to +56
+                                  against +68 in Bullet. */
 } plen_config;
 
 typedef struct plen_ctx plen_ctx;
@@ -160,6 +176,13 @@ int plen_fault_count(plen_ctx *ctx, unsigned long long *count_host);
  * resetBasePositionAndOrientation / resetJointState (plen_env.py:561-565) for all envs; any pointer may be NULL. */
 int plen_get_state(plen_ctx *ctx, float *qpos_dev, float *qvel_dev, float *aux_dev, void *stream);
 int plen_set_state(plen_ctx *ctx, const float *qpos_dev, const float *qvel_dev, const float *aux_dev, void *stream);
+
+/* The persistent sole manifolds (config.sole_manifold = 1; PLEN_E_STATE otherwise): [N,PLEN_MAN_WORDS] device floats, per robot
+ * [foot 0|1][point 0..3][x y z of the point on the inflated hull in the foot frame | x y z of its partner on the plane, world]
+ * followed by the two point counts (as floats).  The cached normal impulses of the points are words of the state record
+ * (plen_get_state's aux).  Used by the teacher-forced parity tests and by snapshots. */
+int plen_get_manifold(plen_ctx *ctx, float *man_dev, void *stream);
+int plen_set_manifold(plen_ctx *ctx, const float *man_dev, void *stream);
 
 /* Per-env domain randomisation (the reference lists it as future work, README.md:75-76): scale factors of
  * the three foot friction coefficients (plen_env.py:309, 439-452), of the servo force limit (setJointMotorControlArray

@@ -269,6 +269,28 @@ class PlenOracle:
             book_f[e, 15] = s.ep_ret
         return dict(qpos=qpos, qvel=qvel, lam_n=lam, in_manifold=man, target=target, book_i=book_i, book_f=book_f)
 
+    def get_manifold(self):
+        """Persistent sole manifolds (manifold_mode 1) in the C ABI's layout (PLEN_MAN_WORDS = 52 per robot): per foot the local
+        xyz of 4 points, then the plane xyz of 4 points; then the two point counts."""
+        out = np.zeros((self.n, 52))
+        for e in range(self.n):
+            s = self.states[e]
+            for f in range(NFEET):
+                out[e, 24 * f:24 * f + 12] = np.array([list(r) for r in s.man_local[f]]).ravel()
+                out[e, 24 * f + 12:24 * f + 24] = np.array([list(r) for r in s.man_world[f]]).ravel()
+                out[e, 48 + f] = s.man_n[f]
+        return out
+
+    def set_manifold(self, man):
+        for e in range(self.n):
+            s = self.states[e]
+            for f in range(NFEET):
+                s.man_n[f] = int(round(float(man[e, 48 + f])))
+                for k in range(NPTS):
+                    for c in range(3):
+                        s.man_local[f][k][c] = float(man[e, 24 * f + 3 * k + c])
+                        s.man_world[f][k][c] = float(man[e, 24 * f + 12 + 3 * k + c])
+
     def set_state(self, st):
         for e in range(self.n):
             s = self.states[e]

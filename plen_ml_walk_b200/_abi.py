@@ -18,6 +18,8 @@ LIB_PATH = os.path.join(HERE, "libplen_b200.so")
 
 STATE_WORDS = 96
 AUX_WORDS = 29
+MAX_HULL = 256
+MAN_WORDS = 52          # PLEN_MAN_WORDS
 OBS_DIM = 26
 ACT_DIM = 18
 
@@ -30,6 +32,7 @@ class PlenModelC(C.Structure):
         ("foot_lane", C.c_int32 * 2), ("foot_pts", ((C.c_float * 3) * 4) * 2), ("foot_break", C.c_float * 2),
         ("n_boxes", C.c_int32), ("box_lane", C.c_int32 * MAX_BOXES), ("box_center", (C.c_float * 3) * MAX_BOXES),
         ("box_rot", (C.c_float * 9) * MAX_BOXES), ("box_half", (C.c_float * 3) * MAX_BOXES), ("box_rest", C.c_float * MAX_BOXES),
+        ("n_hull", C.c_int32 * 2), ("foot_hull", ((C.c_float * 3) * MAX_HULL) * 2),
     ]
 
 
@@ -44,7 +47,7 @@ class PlenConfigC(C.Structure):
         ("residual_threshold", C.c_float), ("erp_contact", C.c_float), ("erp_joint", C.c_float),
         ("linear_slop", C.c_float), ("warmstart_factor", C.c_float), ("restitution_vel_threshold", C.c_float),
         ("hull_margin", C.c_float), ("max_coord_velocity", C.c_float), ("auto_reset", C.c_int32),
-        ("link_contacts", C.c_int32), ("mu_link", C.c_float),
+        ("link_contacts", C.c_int32), ("mu_link", C.c_float), ("sole_manifold", C.c_int32),
     ]
 
 
@@ -69,6 +72,12 @@ def model_to_c(model: PlenModel) -> PlenModelC:
         for p in range(4):
             for k in range(3):
                 m.foot_pts[f][p][k] = float(model.foot_pts[f][p][k])
+    for f in range(2):
+        hull = model.foot_hull[f]
+        m.n_hull[f] = min(len(hull), MAX_HULL)
+        for i in range(m.n_hull[f]):
+            for k in range(3):
+                m.foot_hull[f][i][k] = float(hull[i][k])
     m.n_boxes = int(model.n_boxes)
     for b in range(int(model.n_boxes)):
         m.box_lane[b] = int(model.box_lane[b])
@@ -83,7 +92,7 @@ def model_to_c(model: PlenModel) -> PlenModelC:
 
 EXPORTS = (
     "plen_version", "plen_default_config", "plen_create", "plen_destroy", "plen_last_error", "plen_num_envs", "plen_kernel_launches",
-    "plen_reset", "plen_step", "plen_step_host", "plen_fault_count", "plen_get_state", "plen_set_state", "plen_set_env_scales", "plen_tick",
+    "plen_reset", "plen_step", "plen_step_host", "plen_fault_count", "plen_get_state", "plen_set_state", "plen_set_env_scales", "plen_get_manifold", "plen_set_manifold", "plen_tick",
     "plen_debug_dynamics", "plen_debug_records", "plen_gait_ik", "plen_profile_enable", "plen_profile_read", "plen_measure_fp32_peak",
     "plen_replay_create", "plen_replay_destroy", "plen_replay_size", "plen_replay_ptr", "plen_replay_storage",
     "plen_replay_add", "plen_replay_sample", "plen_actor_forward", "plen_actor_forward_tc", "plen_actor_tc_timed_out", "plen_td3_last_error", "plen_td3_set_precision", "plen_td3_tc_timed_out",
@@ -138,6 +147,8 @@ def load_library(path: str = LIB_PATH):
     L.plen_set_state.argtypes = [vp] * 5
     L.plen_set_env_scales.argtypes = [vp] * 5
     L.plen_tick.argtypes = [vp, vp, ip, vp]
+    L.plen_get_manifold.argtypes = [vp, vp, vp]
+    L.plen_set_manifold.argtypes = [vp, vp, vp]
     L.plen_debug_dynamics.argtypes = [vp] * 5
     L.plen_debug_records.argtypes = [vp] * 3
     L.plen_profile_enable.argtypes = [vp, ip]

@@ -52,6 +52,8 @@ struct plen_ctx {
     float *d_srx;    // [n][XR_WORDS] extension records: box-contact rows of the robots whose link boxes touch the ground (rare)
     int *d_xgroups;  // [n_tiles] leading solver groups of every tile that hold such a robot (k_rank -> k_solve / k_solve_x)
     float *d_tgt;    // [n][18] servo targets of the current env step
+    float *d_man;    // [n][PLEN_MAN_WORDS] persistent sole manifolds (cfg.sole_manifold = 1; NULL otherwise)
+    float *d_hull;   // [2][PLEN_MAX_HULL][3] hull vertices of the feet (ditto)
     float *d_scale;  // [n][4] per-robot scales: friction, servo force limit, servo gain, reserved (plen_set_env_scales; all 1)
     uint8_t *d_key;  // [n] contact-load sort key of the current tick (k_dyn -> k_rank)
     int *d_perm;     // [n_tiles * RANK_TILE] robots ordered by contact load inside each tile (k_rank -> k_solve)
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(DYN_WPC * 32, DYN_CTAS)
 k_dyn(const __grid_constant__ DevConfig dc, const __grid_constant__ EnvRanges er, const float *__restrict__ tab_g,
       const float *__restrict__ state, int n, const float *__restrict__ actions, float *__restrict__ tgt,
       float *__restrict__ srec, uint8_t *__restrict__ keys, float *dbg_minv, float *dbg_pos, float *dbg_rot,
-      const float *__restrict__ scale, float *__restrict__ srx) {
+      const float *__restrict__ scale, float *__restrict__ srx, float *__restrict__ man) {
     // The 4 KB model table is staged with cp.async while every warp already fetches its robot's state record and targets:
     // the two latencies overlap instead of adding up (the table wait used to sit in front of everything).
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -143,7 +145,7 @@ k_dyn(const __grid_constant__ DevConfig dc, const __grid_constant__ EnvRanges er
     DebugOut dbg{dbg_minv ? dbg_minv + (size_t)env * 576 : nullptr, dbg_pos ? dbg_pos + (size_t)env * 72 : nullptr,
                  dbg_rot ? dbg_rot + (size_t)env * 216 : nullptr};
     tick_dynamics(dc, sm.tab, ws, L, lane, srec + (size_t)env * SR_WORDS, keys + env, (dbg_minv || dbg_pos || dbg_rot) ? &dbg : nullptr,
-                  srx ? srx + (size_t)env * XR_WORDS : nullptr);
+                  srx ? srx + (size_t)env * XR_WORDS : nullptr, man ? man + (size_t)env * PLEN_MAN_WORDS : nullptr);
 }
 
 // Robots are grouped by contact load before the solve: k_rank counting-sorts the keys k_dyn wrote inside tiles of
@@ -274,7 +276,8 @@ __global__ void k_set_scales(float *__restrict__ scale, int n, const float *fric
 __global__ void __launch_bounds__(DYN_WPC * 32)
 k_post(const __grid_constant__ DevConfig dc, const float *__restrict__ tab_g, float *__restrict__ state, int n,
        float *__restrict__ obs, float *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ timeout,
-       float *__restrict__ terminal_obs, const float *__restrict__ snapshot, unsigned long long *__restrict__ faults) {
+       float *__restrict__ terminal_obs, const float *__restrict__ snapshot, unsigned long long *__restrict__ faults,
+       float *__restrict__ man) {
     DynSmem &sm = stage_table(tab_g);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * DYN_WPC + warp;
@@ -283,7 +286,8 @@ k_post(const __grid_constant__ DevConfig dc, const float *__restrict__ tab_g, fl
     LaneState L;
     load_record(state + (size_t)env * PLEN_STATE_WORDS, ws, L, lane);
     StepIO io{nullptr, obs + (size_t)env * PLEN_OBS, reward + env, done + env, timeout ? timeout + env : nullptr,
-              terminal_obs ? terminal_obs + (size_t)env * PLEN_OBS : nullptr, snapshot, faults};
+              terminal_obs ? terminal_obs + (size_t)env * PLEN_OBS : nullptr, snapshot, faults,
+              man ? man + (size_t)env * PLEN_MAN_WORDS : nullptr};
     env_post(dc, sm.tab, ws, L, lane, io);
     store_record(state + (size_t)env * PLEN_STATE_WORDS, ws, L, lane);
 }
@@ -304,7 +308,7 @@ k_observe(const float *__restrict__ state, int n, float *__restrict__ obs) {
 
 // PlenWalkEnv.reset (plen_env.py:558-614): copy the post-reset snapshot into the selected envs
 __global__ void k_reset(float *__restrict__ state, int n, const uint8_t *__restrict__ mask,
-                        const float *__restrict__ snapshot, float *__restrict__ obs) {
+                        const float *__restrict__ snapshot, float *__restrict__ obs, float *__restrict__ man) {
     const int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (env >= n) return;
     if (mask && !mask[env]) return;
@@ -313,6 +317,9 @@ __global__ void k_reset(float *__restrict__ state, int n, const uint8_t *__restr
     rec[32 + lane] = snapshot[32 + lane];
     rec[64 + lane] = snapshot[64 + lane];
     if (obs && lane < PLEN_OBS) obs[(size_t)env * PLEN_OBS + lane] = snapshot[PLEN_STATE_WORDS + lane];
+    if (man) {
+        for (int w = lane; w < PLEN_MAN_WORDS; w += 32) man[(size_t)env * PLEN_MAN_WORDS + w] = snapshot[PLEN_SNAP_MAN + w];
+    }
 }
 
 __global__ void k_fill(float *__restrict__ state, int n, const float *__restrict__ rec96) {
@@ -525,11 +532,13 @@ static void launch_ticks(plen_ctx *ctx, float *state, int n, const float *action
     const bool boxes = ctx->dc.link_contacts != 0;
     float *srx = boxes ? ctx->d_srx + off * XR_WORDS : nullptr;
     int *xg = boxes ? ctx->d_xgroups + off / RANK_TILE : nullptr;
+    // persistent sole manifolds: the snapshot robot keeps its own behind its record
+    float *man = !ctx->d_man ? nullptr : (state == ctx->d_snapshot ? ctx->d_snapshot + PLEN_SNAP_MAN : ctx->d_man + off * PLEN_MAN_WORDS);
     for (int t = 0; t < n_ticks; t++) {
         if (ev) cudaEventRecord(ev[2 * t], st);
         k_dyn<<<dyn_grid(n), DYN_WPC * 32, DYN_SMEM, st>>>(ctx->dc, ctx->er, ctx->d_tab, state, n, t == 0 ? actions : nullptr,
                                                           tgt, srec, key, nullptr, nullptr, nullptr,
-                                                          (state == ctx->d_snapshot || !ctx->d_scale) ? nullptr : ctx->d_scale + 4 * off, srx);
+                                                          (state == ctx->d_snapshot || !ctx->d_scale) ? nullptr : ctx->d_scale + 4 * off, srx, man);
         if (ev) cudaEventRecord(ev[2 * t + 1], st);
         const int nt = rank_tiles(n);
         k_rank<<<nt, RANK_TILE, 0, st>>>(key, n, perm, xg);
@@ -558,7 +567,7 @@ static void launch_step_range(plen_ctx *ctx, size_t off, int cnt, const float *a
     k_post<<<dyn_grid(cnt), DYN_WPC * 32, DYN_SMEM, st>>>(ctx->dc, ctx->d_tab, state, cnt, obs_dev + off * PLEN_OBS, reward_dev + off,
                                                          done_dev + off, timeout_dev ? timeout_dev + off : nullptr,
                                                          terminal_obs_dev ? terminal_obs_dev + off * PLEN_OBS : nullptr, ctx->d_snapshot,
-                                                         ctx->d_faults);
+                                                         ctx->d_faults, ctx->d_man ? ctx->d_man + off * PLEN_MAN_WORDS : nullptr);
     ctx->launches += 1;
     if (ev) cudaEventRecord(ev[nev - 1], st);
 }
@@ -589,7 +598,7 @@ unsigned long long plen_kernel_launches(const plen_ctx *ctx) { return ctx ? ctx-
 void plen_destroy(plen_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->d_tab); cudaFree(ctx->d_state); cudaFree(ctx->d_snapshot); cudaFree(ctx->d_srec); cudaFree(ctx->d_srx); cudaFree(ctx->d_xgroups); cudaFree(ctx->d_tgt); cudaFree(ctx->d_key); cudaFree(ctx->d_perm); cudaFree(ctx->d_scale);
+    cudaFree(ctx->d_tab); cudaFree(ctx->d_state); cudaFree(ctx->d_snapshot); cudaFree(ctx->d_srec); cudaFree(ctx->d_srx); cudaFree(ctx->d_xgroups); cudaFree(ctx->d_tgt); cudaFree(ctx->d_key); cudaFree(ctx->d_perm); cudaFree(ctx->d_scale); cudaFree(ctx->d_man); cudaFree(ctx->d_hull);
     cudaFree(ctx->d_act); cudaFree(ctx->d_obs); cudaFree(ctx->d_rew); cudaFree(ctx->d_done); cudaFree(ctx->d_tmo); cudaFree(ctx->d_faults);
     for (int k = 1; k < PLEN_HOST_PIPE; k++)
         if (ctx->pipe[k]) cudaStreamDestroy(ctx->pipe[k]);
@@ -631,7 +640,14 @@ static int create_impl(plen_ctx *ctx) {
     build_devconfig(&ctx->model, &ctx->cfg, &ctx->dc, &ctx->er);
     CK(ctx, cudaMalloc(&ctx->d_tab, sizeof tab));
     CK(ctx, cudaMalloc(&ctx->d_state, sizeof(float) * PLEN_STATE_WORDS * (size_t)n));
-    CK(ctx, cudaMalloc(&ctx->d_snapshot, sizeof(float) * (PLEN_STATE_WORDS + 32)));
+    CK(ctx, cudaMalloc(&ctx->d_snapshot, sizeof(float) * PLEN_SNAP_WORDS));
+    CK(ctx, cudaMemset(ctx->d_snapshot, 0, sizeof(float) * PLEN_SNAP_WORDS));
+    if (ctx->dc.sole_manifold) {
+        CK(ctx, cudaMalloc(&ctx->d_man, sizeof(float) * PLEN_MAN_WORDS * (size_t)n));
+        CK(ctx, cudaMalloc(&ctx->d_hull, sizeof(float) * 2 * PLEN_MAX_HULL * 3));
+        CK(ctx, cudaMemcpy(ctx->d_hull, ctx->model.foot_hull, sizeof(float) * 2 * PLEN_MAX_HULL * 3, cudaMemcpyHostToDevice));
+        ctx->dc.hull = ctx->d_hull;
+    }
     CK(ctx, cudaMalloc(&ctx->d_srec, sizeof(float) * SR_WORDS * (size_t)n));
     if (ctx->dc.link_contacts) {
         CK(ctx, cudaMalloc(&ctx->d_srx, sizeof(float) * XR_WORDS * ((size_t)n + 1)));      // + 1: the snapshot robot's record
@@ -655,7 +671,7 @@ static int create_impl(plen_ctx *ctx) {
     CK(ctx, cudaMemcpy(ctx->d_snapshot, rec, sizeof rec, cudaMemcpyHostToDevice));
     launch_ticks(ctx, ctx->d_snapshot, 1, nullptr, nullptr, ctx->cfg.reset_ticks, ctx->stream);
     k_observe<<<1, 32, DYN_SMEM, ctx->stream>>>(ctx->d_snapshot, 1, ctx->d_snapshot + PLEN_STATE_WORDS);
-    k_reset<<<(n * 32 + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_state, n, nullptr, ctx->d_snapshot, nullptr);
+    k_reset<<<(n * 32 + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_state, n, nullptr, ctx->d_snapshot, nullptr, ctx->d_man);
     CK(ctx, cudaGetLastError());
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     return PLEN_OK;
@@ -688,7 +704,7 @@ plen_ctx *plen_create(const plen_config *cfg, const plen_model *model, int n_env
 int plen_reset(plen_ctx *ctx, const uint8_t *mask_dev, float *obs_dev, void *stream) {
     if (!ctx) return fail(nullptr, PLEN_E_ARG, "ctx is NULL");
     CK(ctx, cudaSetDevice(ctx->device));
-    k_reset<<<(ctx->n * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->d_state, ctx->n, mask_dev, ctx->d_snapshot, obs_dev);
+    k_reset<<<(ctx->n * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->d_state, ctx->n, mask_dev, ctx->d_snapshot, obs_dev, ctx->d_man);
     ctx->launches += 1;
     CK(ctx, cudaGetLastError());
     CK(ctx, mark_work(ctx, (cudaStream_t)stream));
@@ -772,6 +788,23 @@ int plen_set_env_scales(plen_ctx *ctx, const float *friction_scale_dev, const fl
     return PLEN_OK;
 }
 
+int plen_get_manifold(plen_ctx *ctx, float *man_dev, void *stream) {
+    if (!ctx || !man_dev) return fail(ctx, PLEN_E_ARG, "plen_get_manifold: bad arguments");
+    if (!ctx->d_man) return fail(ctx, PLEN_E_STATE, "plen_get_manifold: the context was created with sole_manifold = 0");
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemcpyAsync(man_dev, ctx->d_man, sizeof(float) * PLEN_MAN_WORDS * (size_t)ctx->n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return PLEN_OK;
+}
+
+int plen_set_manifold(plen_ctx *ctx, const float *man_dev, void *stream) {
+    if (!ctx || !man_dev) return fail(ctx, PLEN_E_ARG, "plen_set_manifold: bad arguments");
+    if (!ctx->d_man) return fail(ctx, PLEN_E_STATE, "plen_set_manifold: the context was created with sole_manifold = 0");
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemcpyAsync(ctx->d_man, man_dev, sizeof(float) * PLEN_MAN_WORDS * (size_t)ctx->n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    CK(ctx, mark_work(ctx, (cudaStream_t)stream));
+    return PLEN_OK;
+}
+
 int plen_fault_count(plen_ctx *ctx, unsigned long long *count_host) {
     if (!ctx || !count_host) return fail(ctx, PLEN_E_ARG, "plen_fault_count: bad arguments");
     CK(ctx, cudaSetDevice(ctx->device));
@@ -814,7 +847,8 @@ int plen_debug_dynamics(plen_ctx *ctx, float *minv_dev, float *pos_dev, float *r
     if (!ctx) return fail(nullptr, PLEN_E_ARG, "ctx is NULL");
     CK(ctx, cudaSetDevice(ctx->device));
     k_dyn<<<dyn_grid(ctx->n), DYN_WPC * 32, DYN_SMEM, (cudaStream_t)stream>>>(ctx->dc, ctx->er, ctx->d_tab, ctx->d_state, ctx->n,
-                                                                            nullptr, nullptr, ctx->d_srec, ctx->d_key, minv_dev, pos_dev, rot_dev, ctx->d_scale, ctx->d_srx);
+                                                                            nullptr, nullptr, ctx->d_srec, ctx->d_key, minv_dev, pos_dev, rot_dev, ctx->d_scale, ctx->d_srx,
+                                                                            nullptr /* diagnostics must not advance the manifolds */);
     CK(ctx, cudaGetLastError());
     return PLEN_OK;
 }

@@ -100,6 +100,10 @@ struct DevConfig {
     float start_pos[3];
     int foot_lane[2];
     int substeps, reset_ticks, iterations, joint_act, max_episode_steps, auto_reset, link_contacts, n_boxes;
+    // persistent sole manifold (plen_config.sole_manifold): hull vertices [2][PLEN_MAX_HULL][3] of the feet (device memory; the
+    // warp-emulation harness points it at host memory), their counts
+    int sole_manifold, n_hull[2];
+    const float *hull;
 };
 
 // ---- solve record: per robot, per tick, written by k_dyn and consumed by k_solve (global memory, words)
@@ -212,6 +216,8 @@ struct PLEN_ALIGN16 WarpScratch {
     };
     float obs[32];
     float xp[PLEN_MAX_BOX_POINTS][8];   // selected box contact points: x y z (rel. base origin), depth, body lane, restitution factor
+    float mn[2][28];      // sole_manifold: per foot local xyz of 4 points | plane xyz of 4 points | count | 3 spare
+    float mlam[8];        // ... and the cached normal impulses of the 2 x 4 slots while the manifolds are updated
 };
 
 struct LaneState {
@@ -326,8 +332,16 @@ PLEN_DEV_NOINLINE int box_points(const DevConfig &cfg, const float *tab, WarpScr
                                  float rz1, float rz2, int bl, float R0, float R1, float R2, float R3, float R4, float R5, float R6,
                                  float R7, float R8, float p0, float p1, float p2);
 
+PLEN_DEV_NOINLINE void manifold_merge(const DevConfig &cfg, float *mn, float *lam, const float *Rf, const float *pf, const float *pos,
+                                      int f, int idx);
+
+PLEN_DEV_NOINLINE unsigned sole_manifold_contacts(const DevConfig &cfg, WarpScratch &ws, int lane, float *man, float pos0, float pos1,
+                                                  float pos2, float lam_in, float R0, float R1, float R2, float R3, float R4, float R5,
+                                                  float R6, float R7, float R8, float p0, float p1, float p2);
+
 PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch &ws, LaneState &L, int lane,
-                            float *srec, uint8_t *sort_key, const DebugOut *dbg = nullptr, float *srx = nullptr) {
+                            float *srec, uint8_t *sort_key, const DebugOut *dbg = nullptr, float *srx = nullptr,
+                            float *man = nullptr) {
     const bool is_joint = lane >= 6 && lane < 24;
     const int cs = (int)tab[T_CS * 32 + lane], ce = (int)tab[T_CE * 32 + lane];
     float Rw[9], pw[3];
@@ -697,7 +711,13 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
 
     // ---- contacts: sole vertices vs z = 0 at the start-of-tick pose; lanes 24..31 own one candidate point each
     unsigned man_new;
-    {
+    if (cfg.sole_manifold && man != nullptr) {
+        // persistent manifold per foot, out of line (an option: it must not cost the default path registers or fetches)
+        man_new = sole_manifold_contacts(cfg, ws, lane, man, L.pos[0], L.pos[1], L.pos[2], L.lam, Rw[0], Rw[1], Rw[2], Rw[3], Rw[4],
+                                         Rw[5], Rw[6], Rw[7], Rw[8], pw[0], pw[1], pw[2]);
+        L.man = man_new;
+        L.lam = (lane >= 24) ? ws.mlam[lane - 24] : L.lam;
+    } else {
         const int i = lane - 24, f = (lane >= 28) ? 1 : 0;
         const int src = cfg.foot_lane[f];
         float Rf[9], pf[3];
@@ -947,6 +967,150 @@ PLEN_DEV void tick_dynamics(const DevConfig &cfg, const float *tab, WarpScratch 
     }
     warp_sync();
     if (ext) box_rows(cfg, tab, ws, lane, vstar, nx, srx);
+}
+
+// Persistent sole manifolds (plen_config.sole_manifold = 1; restates btConvexPlaneCollisionAlgorithm + btPersistentManifold as
+// the oracle's manifold_mode 1 does): one new point per tick and foot = the hull's support vertex towards the ground, merged
+// into a cache of <= 4 points; slot k of foot f is contact slot 4 f + k and its impulse travels with it.  The vertex search runs
+// across the warp, the (scalar, short) cache update on lane 0.  Fills ws.cp, leaves the slots' cached impulses in ws.mlam,
+// returns the manifold bits.  Not inlined: an option must not cost the default path registers or instruction fetches.
+PLEN_DEV_NOINLINE unsigned sole_manifold_contacts(const DevConfig &cfg, WarpScratch &ws, int lane, float *man, float pos0, float pos1,
+                                                  float pos2, float lam_in, float R0, float R1, float R2, float R3, float R4, float R5,
+                                                  float R6, float R7, float R8, float p0, float p1, float p2) {
+    const float Rw[9] = {R0, R1, R2, R3, R4, R5, R6, R7, R8}, pw[3] = {p0, p1, p2}, pos[3] = {pos0, pos1, pos2};
+    unsigned man_new = 0;
+    float lam_out = 0.0f;
+    // Persistent manifold per foot (plen_config.sole_manifold = 1; restates btConvexPlaneCollisionAlgorithm +
+    // btPersistentManifold as the oracle's manifold_mode 1 does): one new point per tick = the hull's support vertex
+    // towards the ground, merged into a cache of <= 4 points; slot k of foot f is contact slot 4 f + k, its impulse travels
+    // with it.  The search runs across the warp, the (scalar, short) cache update on lane 0 out of line.
+    if (lane < 24) { ws.mn[0][lane] = man[lane]; ws.mn[1][lane] = man[24 + lane]; }
+    if (lane < 2) ws.mn[lane][24] = man[48 + lane];
+    if (lane >= 24) ws.mlam[lane - 24] = lam_in;
+    warp_sync();
+#pragma unroll 1
+    for (int f = 0; f < 2; f++) {
+        const int src = cfg.foot_lane[f];
+        float Rf[9], pf[3];
+#pragma unroll
+        for (int k = 0; k < 9; k++) Rf[k] = shfl(Rw[k], src);
+#pragma unroll
+        for (int k = 0; k < 3; k++) pf[k] = shfl(pw[k], src);
+        float zb = 3.0e38f;
+        int ib = 0x7fffffff;
+        const float *hv = cfg.hull + (size_t)f * PLEN_MAX_HULL * 3;
+        for (int i = lane; i < cfg.n_hull[f]; i += 32) {
+            const float z = Rf[6] * hv[3 * i] + Rf[7] * hv[3 * i + 1] + Rf[8] * hv[3 * i + 2];
+            if (z < zb) { zb = z; ib = i; }
+        }
+        float zmin = zb;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) zmin = fminf(zmin, shfl_xor(zmin, d));
+        int idx = (zb == zmin) ? ib : 0x7fffffff;      // ties: the first vertex of the list, as a serial search finds it
+        idx = 0x7fffffff - (int)redux_max((unsigned)(0x7fffffff - idx));       // the smallest index
+        if (lane == 0) manifold_merge(cfg, ws.mn[f], ws.mlam + 4 * f, Rf, pf, pos, f, idx);
+        warp_sync();
+    }
+    {
+        const int i = lane - 24, f = (lane >= 28) ? 1 : 0, k = i & 3;
+        const int src = cfg.foot_lane[f];
+        float Rf[9], pf[3];
+#pragma unroll
+        for (int q = 0; q < 9; q++) Rf[q] = shfl(Rw[q], src);
+#pragma unroll
+        for (int q = 0; q < 3; q++) pf[q] = shfl(pw[q], src);
+        bool in = false;
+        if (lane >= 24) {
+            in = k < (int)ws.mn[f][24];
+            float w[3] = {0.0f, 0.0f, 0.0f};
+            if (in) { mat3_vec(Rf, &ws.mn[f][3 * k], w); w[0] += pf[0]; w[1] += pf[1]; w[2] += pf[2]; }
+            ws.cp[i][0] = w[0]; ws.cp[i][1] = w[1]; ws.cp[i][2] = w[2];
+            ws.cp[i][3] = in ? (pos[2] + w[2]) - ws.mn[f][12 + 3 * k + 2] : 0.0f;
+            lam_out = in ? ws.mlam[i] : 0.0f;
+        }
+        man_new = ballot(in) >> 24;
+    }
+    warp_sync();
+    if (lane < 24) { man[lane] = ws.mn[0][lane]; man[24 + lane] = ws.mn[1][lane]; }
+    if (lane < 2) man[48 + lane] = ws.mn[lane][24];
+    warp_sync();
+    if (lane >= 24) ws.mlam[lane - 24] = lam_out;
+    warp_sync();
+    return man_new;
+}
+
+// Cache update of one foot's persistent manifold (lane 0 only; see sole_manifold_contacts).  mn: local xyz of 4 points | plane xyz of 4
+// points | count; lam: the four cached impulses; Rf / pf: world rotation and origin (relative to the base origin) of the foot
+// frame; pos: base position; idx: the hull's support vertex towards the ground.  Restates oracle/plen_oracle.c:manifold_update.
+PLEN_DEV_NOINLINE void manifold_merge(const DevConfig &cfg, float *mn, float *lam, const float *Rf, const float *pf, const float *pos,
+                                      int f, int idx) {
+    float *loc = mn, *pln = mn + 12;
+    int n = (int)mn[24];
+    const float thr = cfg.foot_break[f];
+    const float fx = pos[0] + pf[0], fy = pos[1] + pf[1], fz = pos[2] + pf[2];      // foot frame origin, world
+    if (idx >= 0 && idx < cfg.n_hull[f]) {
+        const float *v = cfg.hull + ((size_t)f * PLEN_MAX_HULL + idx) * 3;
+        // point on the inflated hull: the vertex moved by the margin towards the ground (world -z = -(third row of Rf) locally)
+        const float la[3] = {v[0] - cfg.hull_margin * Rf[6], v[1] - cfg.hull_margin * Rf[7], v[2] - cfg.hull_margin * Rf[8]};
+        float t[3];
+        mat3_vec(Rf, la, t);
+        const float pa[3] = {fx + t[0], fy + t[1], fz + t[2]};
+        const float dist = pa[2];
+        if (dist < thr) {
+            int slot = -1;
+            float nearest = thr * thr;
+            for (int k = 0; k < n; k++) {           // getCacheEntry
+                const float e0 = loc[3 * k] - la[0], e1 = loc[3 * k + 1] - la[1], e2 = loc[3 * k + 2] - la[2];
+                const float dd = e0 * e0 + e1 * e1 + e2 * e2;
+                if (dd < nearest) { nearest = dd; slot = k; }
+            }
+            if (slot < 0) {
+                if (n < 4) { slot = n; n = n + 1; lam[slot] = 0.0f; }
+                else {                               // sortCachedPoints: keep the deepest, drop the one that leaves the largest area
+                    int deepest = -1;
+                    float maxpen = dist;
+                    for (int k = 0; k < 4; k++) {
+                        const float zk = fz + Rf[6] * loc[3 * k] + Rf[7] * loc[3 * k + 1] + Rf[8] * loc[3 * k + 2];
+                        if (zk < maxpen) { deepest = k; maxpen = zk; }
+                    }
+                    float best = -1.0f;
+                    slot = 0;
+                    for (int k = 0; k < 4; k++) {
+                        float res = 0.0f;
+                        if (k != deepest) {
+                            const int o0 = (k == 0) ? 1 : 0, o1 = (k <= 1) ? 2 : 1, o2 = (k <= 2) ? 3 : 2;
+                            const float a[3] = {la[0] - loc[3 * o0], la[1] - loc[3 * o0 + 1], la[2] - loc[3 * o0 + 2]};
+                            const float b[3] = {loc[3 * o2] - loc[3 * o1], loc[3 * o2 + 1] - loc[3 * o1 + 1], loc[3 * o2 + 2] - loc[3 * o1 + 2]};
+                            float c[3];
+                            cross(a, b, c);
+                            res = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+                        }
+                        if (res > best) { best = res; slot = k; }
+                    }
+                    lam[slot] = 0.0f;
+                }
+            }
+            loc[3 * slot] = la[0]; loc[3 * slot + 1] = la[1]; loc[3 * slot + 2] = la[2];
+            pln[3 * slot] = pa[0]; pln[3 * slot + 1] = pa[1]; pln[3 * slot + 2] = 0.0f;
+        }
+    }
+    // refreshContactPoints, last to first
+    for (int k = n - 1; k >= 0; k--) {
+        float t[3];
+        mat3_vec(Rf, loc + 3 * k, t);
+        const float dist = (fz + t[2]) - pln[3 * k + 2];
+        const float dx = pln[3 * k] - (fx + t[0]), dy = pln[3 * k + 1] - (fy + t[1]);
+        if (dist > thr || dx * dx + dy * dy > thr * thr) {
+            const int last = n - 1;
+            if (k != last) {
+                for (int c = 0; c < 3; c++) { loc[3 * k + c] = loc[3 * last + c]; pln[3 * k + c] = pln[3 * last + c]; }
+                lam[k] = lam[last];
+            }
+            lam[last] = 0.0f;
+            n = last;
+        }
+    }
+    mn[24] = (float)n;
 }
 
 // Rare path of tick_dynamics, part 1: some link box of this robot touches the ground.  Lane b holds box b (touch, centre height

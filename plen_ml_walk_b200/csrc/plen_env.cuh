@@ -77,6 +77,10 @@ PLEN_DEV void observe(WarpScratch &ws, const LaneState &L, int lane) {
     warp_sync();
 }
 
+// post-reset snapshot: record (96) | observation (26, padded to 32) | sole manifolds (PLEN_MAN_WORDS)
+#define PLEN_SNAP_MAN (PLEN_STATE_WORDS + 32)
+#define PLEN_SNAP_WORDS (PLEN_SNAP_MAN + PLEN_MAN_WORDS)
+
 struct StepIO {
     const float *action;      // [18] this env
     float *obs;               // [26]
@@ -85,6 +89,7 @@ struct StepIO {
     float *terminal_obs;      // [26] nullable
     const float *snapshot;    // [96 + 26] post-reset record and its observation
     unsigned long long *faults;   // device counter of numeric faults (nullable)
+    float *man;               // this robot's persistent sole manifold (sole_manifold = 1), nullable: reset with the record
 };
 
 // env_ranges of plen_env.py:148-167 are kept in double so that the a = +-1 inset branch (plen_env.py:707-711) takes
@@ -213,6 +218,9 @@ PLEN_DEV void env_post(const DevConfig &cfg, const float *tab, WarpScratch &ws, 
         if (io.terminal_obs && lane < 26) io.terminal_obs[lane] = fault ? io.snapshot[96 + lane] : ws.obs[lane];
         load_record(io.snapshot, ws, L, lane);
         if (lane < 26) io.obs[lane] = io.snapshot[96 + lane];
+        if (io.man) {       // the manifolds of the post-reset snapshot sit behind its record and observation
+            for (int w = lane; w < PLEN_MAN_WORDS; w += 32) io.man[w] = io.snapshot[PLEN_SNAP_MAN + w];
+        }
     } else {
         if (lane < 26) io.obs[lane] = ws.obs[lane];
         if (done && io.terminal_obs && lane < 26) io.terminal_obs[lane] = ws.obs[lane];

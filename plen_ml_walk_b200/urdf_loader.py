@@ -84,6 +84,13 @@ def _stl_points(path):
     return np.unique(pts, axis=0)
 
 
+def _hull_vertices(pts):
+    """The points of a collider's vertex cloud that are vertices of its convex hull, in the order of the (sorted) cloud --
+    what the support-vertex search of the persistent sole manifold walks (plen_config.sole_manifold)."""
+    from scipy.spatial import ConvexHull
+    return pts[np.sort(ConvexHull(pts).vertices)]
+
+
 def _largest_quad(poly):
     """Indices of the 4 polygon vertices (ccw order) enclosing the largest area -- O(n^4) is fine for n = 32."""
     n = len(poly)
@@ -131,6 +138,7 @@ class PlenModel:
     foot_pts: np.ndarray = field(default_factory=lambda: np.zeros((2, 4, 3)))
     foot_break: np.ndarray = field(default_factory=lambda: np.zeros(2))
     foot_margin: float = 0.001     # collision margin of the foot shape (convex hull: 1 mm, box: 0) -> plen_config.hull_margin
+    foot_hull: list = field(default_factory=lambda: [[], []])   # convex-hull vertices of either foot collider, foot body frame
     # box colliders of every link except the feet (ground contact of knees / hands / torso ...), in Bullet's
     # link order (base first, then DFS pre-order over the joints in file order); pose in the frame of the BODY (lane) the
     # link is folded into
@@ -310,6 +318,7 @@ def load_plen_model(urdf_path, mesh_dir) -> PlenModel:
         model.foot_pts[f] = quad
         model.foot_break[f] = BREAKING_FACTOR * link.aabb_disc
         model.foot_margin = float(link.hull_margin)     # -> plen_config.hull_margin (PlenVecEnv applies it)
+        model.foot_hull[f] = _hull_vertices(hull).tolist()
     return model
 
 

@@ -199,6 +199,18 @@ class PlenVecEnv:
         with torch.cuda.device(self.device):
             self._check(self.lib.plen_set_state(self._ctx, self._p(qpos), self._p(qvel), self._p(aux), self._stream()))
 
+    def get_manifold(self):
+        """Persistent sole manifolds [N, 52] (config_overrides={"sole_manifold": 1} only; layout: include/plen_b200.h)."""
+        man = torch.empty((self.num_envs, _abi.MAN_WORDS), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.plen_get_manifold(self._ctx, self._p(man), self._stream()))
+        return man
+
+    def set_manifold(self, man):
+        man = self._dev_f32(man, (self.num_envs, _abi.MAN_WORDS))
+        with torch.cuda.device(self.device):
+            self._check(self.lib.plen_set_manifold(self._ctx, self._p(man), self._stream()))
+
     def set_env_scales(self, friction=None, motor_force=None, motor_gain=None):
         """Per-env domain randomisation: scale factors [N] of the foot friction coefficients, the servo force
         limit and the servo position gain; None leaves a quantity unchanged, 1.0 is the reference's constant.
@@ -216,7 +228,8 @@ class PlenVecEnv:
         """Snapshot of every env (pose, velocities, contact cache, env bookkeeping) to one .pt file."""
         qpos, qvel, aux = self.get_state()
         torch.save({"num_envs": self.num_envs, "joint_act": self.joint_act, "qpos": qpos.cpu(), "qvel": qvel.cpu(), "aux": aux.cpu(),
-                    "scales": {k: v.cpu() for k, v in self._scales.items()}}, path)
+                    "scales": {k: v.cpu() for k, v in self._scales.items()},
+                    "manifold": self.get_manifold().cpu() if int(self.cfg.sole_manifold) else None}, path)
 
     def load_state(self, path):
         """Restore a save_state snapshot; stepping on from it reproduces the original run bit for bit."""
@@ -224,6 +237,8 @@ class PlenVecEnv:
         if int(d["num_envs"]) != self.num_envs or bool(d["joint_act"]) != self.joint_act:
             raise ValueError("snapshot is for %d envs (joint_act=%s)" % (d["num_envs"], d["joint_act"]))
         self.set_state(d["qpos"], d["qvel"], d["aux"])
+        if d.get("manifold") is not None:
+            self.set_manifold(d["manifold"])
         sc = d.get("scales", {})
         if sc or self._scales:      # per-env scales travel with the snapshot; a snapshot without any restores the unit scales
             ones = torch.ones(self.num_envs)

@@ -1,9 +1,10 @@
-O=gpurun_out/${1:-r2_c4}; mkdir -p $O
-R="python scripts/plen_td3_batched.py --envs 16384 --actor-precision fp16"
-timeout 600 $R --env-steps 4194304 --no-learner > $O/config4_nolearner.json 2> $O/err.txt; cat $O/config4_nolearner.json
-timeout 600 $R --env-steps 4194304 --updates-per-step 8 --batch-size 100 > $O/config4_u8_b100_fp32.json 2>> $O/err.txt; cat $O/config4_u8_b100_fp32.json
-timeout 600 $R --env-steps 4194304 --updates-per-step 4 --batch-size 4096 --learner-precision tf32 > $O/config4_u4_b4096_tf32.json 2>> $O/err.txt; cat $O/config4_u4_b4096_tf32.json
-timeout 600 $R --env-steps 4194304 --updates-per-step 4 --batch-size 4096 > $O/config4_u4_b4096_fp32.json 2>> $O/err.txt; cat $O/config4_u4_b4096_fp32.json
-timeout 600 $R --env-steps 2097152 --updates-per-step 8 --batch-size 16384 --learner-precision tf32 > $O/config4_u8_b16384_tf32.json 2>> $O/err.txt; cat $O/config4_u8_b16384_tf32.json
-timeout 600 $R --env-steps 524288 --updates-per-step 100 --batch-size 16384 --learner-precision tf32 > $O/config4_u100_b16384_tf32.json 2>> $O/err.txt; cat $O/config4_u100_b16384_tf32.json
+O=gpurun_out/${1:-r2_man2}; mkdir -p $O
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_properties.py -m gpu -x -q -s -k "manifold" > $O/pytest_man.log 2>&1; grep "manifold mode\|passed\|failed\|Error\|assert" $O/pytest_man.log | tail -12
+for m in 0 1; do
+  timeout 600 python scripts/walk_eval_batched.py --envs 4096 --sigma 0.1 --sole-manifold $m > $O/walk_eval_sigma0.1_man$m.json 2>> $O/err.txt; cat $O/walk_eval_sigma0.1_man$m.json
+done
+for L in scripts/ab/libplen_cur.so plen_ml_walk_b200/libplen_b200.so; do
+  python scripts/ab_time.py $L 131072 50 2>&1 | tail -1 | tee -a $O/ab.txt
+  python scripts/ab_time.py $L 4096 200 2>&1 | tail -1 | tee -a $O/ab.txt
+done
 tail -3 $O/err.txt

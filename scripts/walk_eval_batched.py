@@ -31,13 +31,15 @@ def main():
     ap.add_argument("--sigma", type=float, default=0.05)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp16"])
     ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--sole-manifold", type=int, default=0, choices=[0, 1],
+                    help="plen_config.sole_manifold: 1 = Bullet's one-point-per-tick persistent manifold (profiles/r2_physics_pin.md 5)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     g = np.load(GOLD)
     actor = Actor().to(dev)
     actor.load_state_dict({k: torch.from_numpy(g["actor_" + k.replace(".", "_")]).to(dev) for k in actor.state_dict().keys()})
     n = a.envs
-    env = PlenVecEnv(n, device=dev, auto_reset=False)
+    env = PlenVecEnv(n, device=dev, auto_reset=False, config_overrides={"sole_manifold": a.sole_manifold})
     state = env.reset().clone()
     alive = torch.ones(n, dtype=torch.bool, device=dev)
     ep_len = torch.zeros(n, device=dev); ep_ret = torch.zeros(n, device=dev)
@@ -56,10 +58,11 @@ def main():
     L, R, X = ep_len.cpu().numpy(), ep_ret.cpu().numpy(), x_end.cpu().numpy()
     print(json.dumps({
         "policy": "plen_walk_gazebo_3229999 (reference checkpoint)", "envs": n, "steps": a.steps, "sigma": a.sigma,
-        "precision": a.precision,
+        "precision": a.precision, "sole_manifold": a.sole_manifold,
         "deterministic": {"episode_length": float(L[0]), "return": float(R[0]), "x_final_m": float(X[0])},
         "noisy": {"episode_length_mean": float(L[1:].mean()), "episode_length_median": float(np.median(L[1:])),
                   "survived_all_steps_frac": float((L[1:] >= a.steps).mean()), "return_mean": float(R[1:].mean()),
+                  "return_quantiles_5_25_50_75_95": [float(q) for q in np.quantile(R[1:], [0.05, 0.25, 0.5, 0.75, 0.95])],
                   "x_final_mean_m": float(X[1:].mean()), "x_final_std_m": float(X[1:].std())}}))
 
 

@@ -94,6 +94,9 @@ template <class F> void run_warp(F body) {
 }
 }  // namespace
 
+// persistent sole manifolds of the robots being ticked ([n][PLEN_MAN_WORDS], set by emu_set_manifold; nullptr = option off)
+static float *g_man = nullptr;
+
 extern "C" {
 
 int emu_default_config(plen_config *c, int joint_act) { return default_config(c, joint_act); }
@@ -101,6 +104,7 @@ int emu_real_bytes() { return (int)sizeof(float); }
 int emu_sizeof_config() { return (int)sizeof(plen_config); }
 int emu_sizeof_model() { return (int)sizeof(plen_model); }
 void emu_init_record(const plen_config *c, float *rec) { init_record(c, rec); }
+void emu_set_manifold(float *man) { g_man = man; }
 
 // (k_dyn, k_solve) x n_ticks over n robots, exactly as plen_b200.cu launches them: one emulated warp per robot for the
 // dynamics, then one emulated warp per 8 robots for the solver (identity permutation: grouping never changes a result).  tgt [n][18] nullable (zero targets).
@@ -117,7 +121,8 @@ static void run_ticks(const DevConfig &dc, const float *tab, float *records, con
             load_record(records + 96 * e, ws, L, lane);
             if (lane >= 6 && lane < 24) L.tgt = tgt ? tgt[18 * e + lane - 6] : 0.0f;
             tick_dynamics(dc, tab, ws, L, lane, srec.data() + (size_t)e * SR_WORDS, keys.data() + e,
-                          (e == 0 && t == n_ticks - 1) ? dbg0 : nullptr, srx.data() + (size_t)e * XR_WORDS);
+                          (e == 0 && t == n_ticks - 1) ? dbg0 : nullptr, srx.data() + (size_t)e * XR_WORDS,
+                          g_man ? g_man + (size_t)e * PLEN_MAN_WORDS : nullptr);
         }
         for (int b = 0; b < n; b += PLEN_SOLVE_ROBOTS) {
             const int r = b + (lane >> 2);
@@ -145,6 +150,9 @@ void emu_tick(const plen_model *m, const plen_config *c, float *records, const f
     DevConfig dc; EnvRanges er;
     build_table(m, c, tab.data());
     build_devconfig(m, c, &dc, &er);
+    std::vector<float> hull(2 * PLEN_MAX_HULL * 3);      // (the model struct holds real floats even in the float64 build)
+    for (size_t i = 0; i < hull.size(); i++) hull[i] = (&m->foot_hull[0][0][0])[i];
+    dc.hull = hull.data();
     DebugOut dbg{dbg_minv, dbg_pos, dbg_rot};
     run_warp([&](int lane) { run_ticks(dc, tab.data(), records, targets, n, n_ticks, dbg_minv ? &dbg : nullptr, lane); });
     if (iters_out) for (int e = 0; e < n; e++) iters_out[e] = (int)records[96 * e + W_ITERS];
@@ -156,6 +164,9 @@ void emu_step(const plen_model *m, const plen_config *c, float *records, const f
     DevConfig dc; EnvRanges er;
     build_table(m, c, tab.data());
     build_devconfig(m, c, &dc, &er);
+    std::vector<float> hull(2 * PLEN_MAX_HULL * 3);      // (the model struct holds real floats even in the float64 build)
+    for (size_t i = 0; i < hull.size(); i++) hull[i] = (&m->foot_hull[0][0][0])[i];
+    dc.hull = hull.data();
     for (int e = 0; e < n; e++)
         for (int j = 0; j < 18; j++) tgt[18 * e + j] = agent_target(dc, er, j, actions[18 * e + j]);
     static WarpScratch ws;

@@ -37,6 +37,12 @@ class Emu:
         assert self.L.emu_sizeof_config() == C.sizeof(PlenConfigC)
         assert self.L.emu_sizeof_model() == C.sizeof(PlenModelC)
 
+    def set_manifold(self, man):
+        """man: [n,52] array of self.real kept alive by the caller (the harness updates it in place); None switches the option's
+        storage off."""
+        self._man = man
+        self.L.emu_set_manifold(man.ctypes.data_as(C.c_void_p) if man is not None else None)
+
     def init_record(self, n=1):
         rec = np.zeros((n, 96), dtype=self.real)
         for e in range(n):

@@ -189,3 +189,78 @@ def test_f32_emulation_box_contacts_keep_the_robot_above_the_floor(oracle_lib):
     # 0.1 s of free fall would be 49 mm; resting on its colliders a robot settles / tips by far less
     assert (z0 - got["qpos"][:, 2]).max() < 0.03 and (z0 - ref["qpos"][:, 2]).max() < 0.03
     assert np.median(np.abs(got["qpos"][:, 2] - ref["qpos"][:, 2])) < 2e-3
+
+
+def test_f64_emulation_persistent_sole_manifold_matches_oracle(oracle_lib):
+    """plen_config.sole_manifold = 1 against the oracle's manifold_mode = 1 (profiles/r2_physics_pin.md section 5): from the
+    reset pose, random actions, state AND manifolds teacher-forced from the oracle before every tick.  The float64 build of the
+    device source must build the same manifolds (same support vertex, same merge / reduction / refresh decisions: point counts
+    equal, cached points within 2e-8 m) and follow the oracle's velocities like the four-corner path does."""
+    emu = Emu(double=True)
+    emu.cfg.sole_manifold = 1
+    n = 6
+    o = oracle_lib.PlenOracle(n)
+    o.cfg.manifold_mode = 1
+    o.reset()
+    rng = np.random.default_rng(9)
+    worst_qd, counts, man_err, n_ticks, max_count = [], [], [], 160, 0
+    amp = np.where(np.arange(n) % 2 == 0, 0.04, 0.3)[:, None]      # half of the robots only sway (their manifolds fill up and are
+    tg = rng.uniform(-1, 1, (n, 18)) * amp                           # reduced), the others fall over
+    for tick in range(n_ticks):
+        if tick % 4 == 0:
+            tg = np.clip(tg + rng.normal(0, 1.0, (n, 18)) * amp, -1.2, 1.2)
+        st = o.get_state()
+        rec = np.stack([record_from_oracle_state(st, e, dtype=emu.real) for e in range(n)])
+        man = o.get_manifold().astype(emu.real)
+        emu.set_manifold(man)
+        for e in range(n):
+            for k in range(18):
+                o.states[e].target[k] = tg[e, k]
+        emu.tick(rec, tg, 1)
+        for e in range(n):
+            o.tick(e)
+        got, ref = oracle_state_from_record(rec), o.get_state()
+        mref = o.get_manifold()
+        max_count = max(max_count, int(mref[:, 48:50].max()))
+        worst_qd.append(np.abs(got["qvel"] - ref["qvel"]).max(1))
+        counts.append((man[:, 48:50] == mref[:, 48:50]).all(1))
+        same = (man[:, 48:50] == mref[:, 48:50]).all(1)
+        for e in np.where(same)[0]:
+            for f in range(2):
+                k = int(mref[e, 48 + f])
+                man_err.append(np.abs(man[e, 24 * f:24 * f + 3 * k] - mref[e, 24 * f:24 * f + 3 * k]).max() if k else 0.0)
+        assert (got["in_manifold"][same] == ref["in_manifold"][same]).all()
+    emu.set_manifold(None)
+    worst_qd, counts = np.array(worst_qd), np.array(counts)
+    seen = np.array([o.states[e].man_n[f] for e in range(n) for f in range(2)])
+    print("manifold: counts equal on %.3f of the robot-ticks, cached points max err %.2e, qd err median %.2e p90 %.2e, final counts %s, max %d"
+          % (counts.mean(), max(man_err), np.median(worst_qd), np.quantile(worst_qd, 0.9), seen, max_count))
+    assert max_count == 4                            # the cache filled up: merge, reduction and refresh all ran
+    assert counts.mean() > 0.97                      # a support vertex chosen among near-ties may differ at the 1e-16 level
+    assert max(man_err) < 2e-8                       # the hull vertices reach the device code as float32 (C ABI struct)
+    assert np.median(worst_qd) < 2e-5 and np.quantile(worst_qd, 0.8) < 1e-3
+
+
+def test_persistent_sole_manifold_reset_f64_exact_f32_bounded(oracle_lib):
+    """The reset of sole_manifold = 1 (8 free-running settle ticks from the start pose, manifolds empty): the float64 build of the
+    device source reproduces the oracle's manifold_mode = 1 reset (observation within 1e-7, same point counts); the float32
+    build picks other support vertices among the nearly coplanar sole vertices from the first tick on and lands within 1e-2 --
+    the bound tests/test_gpu_parity.py::test_persistent_sole_manifold_vs_oracle puts on the GPU's reset."""
+    o = oracle_lib.PlenOracle(1)
+    o.cfg.manifold_mode = 1
+    ref = o.reset()
+    err = {}
+    for dbl in (True, False):
+        emu = Emu(double=dbl)
+        emu.cfg.sole_manifold = 1
+        rec = emu.init_record(1)
+        man = np.zeros((1, 52), dtype=emu.real)
+        emu.set_manifold(man)
+        emu.tick(rec, np.zeros((1, 18)), int(emu.cfg.reset_ticks))
+        emu.set_manifold(None)
+        err[dbl] = np.abs(emu.observe(rec) - ref).max()
+        if dbl:
+            assert (man[0, 48:50] == o.get_manifold()[0, 48:50]).all()
+        assert 0 < man[0, 48:50].sum() <= 8
+    print("manifold reset: obs err f64 %.2e, f32 %.2e" % (err[True], err[False]))
+    assert err[True] < 1e-7 and err[False] < 1e-2

@@ -324,3 +324,43 @@ def test_step_captured_in_a_cuda_graph_replays_bit_exact(n):
         term = torch.where(done[:, None], info["terminal_obs"], torch.zeros_like(obs))
         for u, v in zip(direct[k], (obs, rew, done, b._timeout.bool(), term)):
             assert _same(u, v), "graph replay %d differs from the direct call" % k
+
+
+def test_persistent_sole_manifold_properties(tmp_path):
+    """sole_manifold = 1: the manifolds are per-robot state like everything else -- a permutation of the batch permutes the
+    results bit for bit (auto-reset restores the snapshot's manifolds), a snapshot to disk and back continues exactly, and
+    the option changes the physics (the default context differs after a few steps)."""
+    n = 3000
+    kw = dict(config_overrides={"sole_manifold": 1})
+    a = _mk(n, **kw)
+    _rollout(a, 40, seed=51)
+    st, man = _snapshot(a), a.get_manifold().clone()
+    assert 0 < float(man[:, 48:50].mean()) < 4 and int(man[:, 48:50].max()) == 4
+    path = str(tmp_path / "plen_state_manifold.pt")
+    a.save_state(path)
+    g = torch.Generator(device="cuda"); g.manual_seed(53)
+    acts = [torch.empty((n, 18), device="cuda").uniform_(-1, 1, generator=g) for _ in range(6)]
+    ref = [_step_out(a, x) for x in acts]
+    ref_man = a.get_manifold().clone()
+    perm = torch.randperm(n, device="cuda", generator=g)
+    b = _mk(n, **kw)
+    b.reset()
+    b.set_state(*[t[perm] for t in st]); b.set_manifold(man[perm])
+    for x, r in zip(acts, ref):
+        got = _step_out(b, x[perm])
+        for p, q in zip(r, got):
+            assert _same(p[perm], q)
+    assert _same(ref_man[perm], b.get_manifold())
+    assert any(bool(r[2].any()) for r in ref)                       # some episodes ended: the auto-reset path ran
+    c = _mk(n, **kw)
+    c.reset()
+    c.load_state(path)
+    for x, r in zip(acts, ref):
+        got = _step_out(c, x)
+        for p, q in zip(r, got):
+            assert _same(p, q)
+    d = _mk(n)
+    _rollout(d, 40, seed=51)
+    assert not _same(_snapshot(d)[0], st[0])
+    with pytest.raises(RuntimeError):
+        d.get_manifold()
