@@ -42,13 +42,17 @@ TICKS_PER_STEP = 4
 # measured DRAM traffic of one k_solve launch per robot (ncu --set full, profiles/r1_v9_summary.md): it reads the
 # 6.4 KB solve record k_dyn wrote for the tick -- a deliberate trade of HBM bytes for issue slots
 SOLVE_DRAM_BYTES_PER_ROBOT = (207.10e6 + 9.92e6) / 32768
-# FROZEN in BASELINE.md ("Work per env-step", re-measured in round 2): executed FP32 work per robot-tick ON THIS WORKLOAD,
-# counted by ncu (smsp__sass_thread_inst_executed_op_{fadd,fmul,ffma}_pred_on, FFMA = 2 flop) over one whole env step of
-# 131,072 robots at step 30 after the reset, the middle of the timed region (profiles/r2_flops_step30_v12.csv; step 60 agrees
-# to 1.5 %): k_dyn 44.0 kflop, k_solve 25.9 kflop + k_solve_x 2.7 kflop (the bracket of "k_solve" covers both), k_post
-# 17.0 kflop per env step.  Round 1's 44.8 + 58.1 kflop were captured on the first steps after a reset, where every robot
-# stands on both feet with all eight sole points down -- the largest row set, twice the workload's mean.
-FLOP_DYN_PER_ROBOT_TICK, FLOP_SOLVE_PER_ROBOT_TICK, FLOP_POST_PER_ENV_STEP = 44.0e3, 28.6e3, 17.0e3
+# FROZEN in BASELINE.md ("Work per env-step"): executed FP32 work per robot-tick ON THIS WORKLOAD, counted from the SASS-level
+# execution counts of ncu's source page (scripts/flops_sass.py: FFMA2 = 4 flop, FFMA = 2, FADD / FMUL = 1 per predicated-on
+# thread instruction) over every launch of ONE env step of 131,072 robots at step 30 after the reset, the middle of the
+# timed region (profiles/r2_flops_sass.md): k_dyn 44.0 kflop, k_solve 166.3 kflop + k_solve_x 12.2 kflop (the bracket of
+# "k_solve" covers both), k_post 17.0 kflop per env step.  The earlier figure (25.9 + 2.7 kflop for the solve) came from
+# smsp__sass_thread_inst_executed_op_{fadd,fmul,ffma}_pred_on, which do NOT count the packed FFMA2 (fma.rn.f32x2) that
+# carries every row update of k_solve: 30.6 % of its issued instructions, 84 % of its flops (cross-checked against
+# sm__pipe_fma_cycles_active of the same launches to 1.6 %).
+FLOP_DYN_PER_ROBOT_TICK, FLOP_SOLVE_PER_ROBOT_TICK, FLOP_POST_PER_ENV_STEP = 44.0e3, 178.5e3, 17.0e3
+# what ncu's three op metrics see of the same step (scalar FADD + FMUL + 2 FFMA only): kept for comparison with round 1 / 2 lines
+FLOP_PER_ENV_STEP_NCU_OP_METRICS = 0.306e6
 FLOP_PER_ENV_STEP = 4 * (FLOP_DYN_PER_ROBOT_TICK + FLOP_SOLVE_PER_ROBOT_TICK) + FLOP_POST_PER_ENV_STEP
 # the same workload through the REFERENCE ALGORITHM (33-link ABA + velocity-space PGS with 24-wide rows), counted by the
 # oracle's instrumented FLOP counter (plen_oracle_state.flops; scripts/oracle_flops.py): 1.32 Mflop per env-step
@@ -421,15 +425,17 @@ def main():
                          "kernel_ms_per_launch": solve_ms, "launches_per_step": TICKS_PER_STEP,
                          "measured_over": "%d bracketed steps behind the timed region (single-stream order, kernel alone on the GPU)" % Kb,
                          "flop_per_launch": E * FLOP_SOLVE_PER_ROBOT_TICK, "flop_per_robot_tick": FLOP_SOLVE_PER_ROBOT_TICK,
-                         "whole_step": {"achieved": step_tf, "frac": step_tf / fp32_peak, "flop_per_env_step": FLOP_PER_ENV_STEP},
+                         "whole_step": {"achieved": step_tf, "frac": step_tf / fp32_peak, "flop_per_env_step": FLOP_PER_ENV_STEP,
+                                        "frac_by_ncu_op_metrics_without_ffma2": FLOP_PER_ENV_STEP_NCU_OP_METRICS * value / world / 1e12 / fp32_peak},
                          "reference_algorithm": {"flop_per_env_step": REF_ALGO_FLOP_PER_ENV_STEP,
                                                  "equivalent_tflops": REF_ALGO_FLOP_PER_ENV_STEP * value / world / 1e12,
                                                  "equivalent_frac": REF_ALGO_FLOP_PER_ENV_STEP * value / world / 1e12 / fp32_peak},
-                         "note": "flop = executed FADD + FMUL + 2 FFMA thread operations counted by ncu on this workload (frozen in BASELINE.md, re-measured in round 2: round 1's count was taken right after a reset and was twice the workload's mean); "
-                                 "the limiter is the dependency latency of the Gauss-Seidel row chain at 2 warps per scheduler, "
-                                 "not the pipe; reference_algorithm = the same env-steps/s priced at the oracle's instrumented "
-                                 "flop count of Bullet's ABA + velocity-space PGS (this solver does 4.3x less arithmetic for "
-                                 "the same rows); traffic = ncu DRAM bytes per robot (32768-robot capture) x robots per launch"},
+                         "note": "flop = executed FADD + FMUL + 2 FFMA + 4 FFMA2 thread operations counted from the SASS execution counts of "
+                                 "ncu's source page on this workload (frozen in BASELINE.md; ncu's op_ffma metric does not count the packed "
+                                 "FFMA2 that is 84 % of k_solve's flops, so lines before this build quoted a 6.3x smaller solve count); "
+                                 "k_solve keeps the FMA pipe 34 % busy at 2 warps per scheduler: what is left is the dependency latency of "
+                                 "the Gauss-Seidel row chain; reference_algorithm = the same env-steps/s priced at the oracle's instrumented "
+                                 "flop count of Bullet's ABA + velocity-space PGS; traffic = ncu DRAM bytes per robot (32768-robot capture) x robots per launch"},
             "roofline_hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak,
                              "peak_source": peak_src, "kernel": "k_solve",
                              "algorithmic_bytes_per_launch": E * BYTES_PER_ENV_STEP / TICKS_PER_STEP,

@@ -118,6 +118,10 @@ typedef struct {
                                   that separated or drifted by more than the threshold dropped; impulses travel with the points.
                                   profiles/r2_physics_pin.md section 5: the shipped policy's mean return moves from -5 to +56
                                   against +68 in Bullet. */
+    float support_tie;         /* sole_manifold = 1: hull vertices within this distance (m) of the lowest one count as equally
+                                  low, and the first of them in the vertex list is the support vertex.  1e-7 (default): a foot flat
+                                  on the ground -- the reset pose -- is an exact tie that rounding would decide, differently in
+                                  float32 and in the float64 oracle; 0: plain first-minimum search */
 } plen_config;
 
 typedef struct plen_ctx plen_ctx;

@@ -52,7 +52,7 @@ class Config(C.Structure):
         ("linear_slop", C.c_double), ("warmstart_factor", C.c_double), ("restitution_vel_threshold", C.c_double),
         ("hull_margin", C.c_double), ("max_coord_velocity", C.c_double), ("implicit_cone", C.c_int),
         ("link_contacts", C.c_int), ("mu_link", C.c_double), ("restitution_base", C.c_double), ("max_contact_points", C.c_int),
-        ("manifold_mode", C.c_int),
+        ("manifold_mode", C.c_int), ("support_tie", C.c_double),
     ]
 
 

@@ -479,13 +479,19 @@ static void manifold_update(const plen_oracle_model *m, const plen_oracle_config
         const int L = m->foot_link[f];
         const double *R = w->Rw[L + 1], *p = w->pw[L + 1];
         const double thr = m->foot_break[f];
-        /* support vertex: lowest world z; ties -> first in the list */
+        /* support vertex: lowest world z; vertices within support_tie of the lowest are ties -> first in the list.  (The height
+         * is compared relative to the foot origin, as the device code does.) */
         int best = -1;
-        double zbest = 1e300;
+        double zmin = 1e300, zbest = 1e300;
         for (int i = 0; i < m->n_hull[f]; i++) {
             const double *v = m->foot_hull[f][i];
-            const double z = p[2] + R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
-            if (z < zbest) { zbest = z; best = i; }
+            const double z = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+            if (z < zmin) zmin = z;
+        }
+        for (int i = 0; i < m->n_hull[f]; i++) {
+            const double *v = m->foot_hull[f][i];
+            const double z = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+            if (z <= zmin + cfg->support_tie) { zbest = p[2] + z; best = i; break; }
         }
         if (best >= 0 && zbest - cfg->hull_margin < thr) {
             /* point on the inflated hull (world), its copy in the foot frame, and its projection on the plane */
@@ -840,6 +846,7 @@ void plen_oracle_default_config(plen_oracle_config *c, int joint_act) {
     c->erp_contact = 0.08; c->erp_joint = 0.2; c->linear_slop = 1e-5; c->warmstart_factor = 0.1;
     c->restitution_vel_threshold = 0.2; c->hull_margin = 0.001; c->max_coord_velocity = 100.0; c->implicit_cone = 1;
     c->link_contacts = 1; c->mu_link = 0.5 * 0.8; c->restitution_base = 0.0 * 0.5; c->max_contact_points = -1;
+    c->manifold_mode = 0; c->support_tie = 1e-7;
 }
 
 void plen_oracle_init_state(const plen_oracle_config *cfg, plen_oracle_state *s) {

@@ -105,6 +105,12 @@ typedef struct {
      *   refreshContactPoints (drop points that separated or drifted by more than the threshold); impulses travel with the
      *   cached points. */
     int manifold_mode;
+    /* manifold_mode 1: hull vertices within this distance (m) of the lowest one count as equally low and the FIRST of them in
+     * the vertex list is the support vertex.  A foot that is flat on the ground (the reset pose: every sole vertex at the same
+     * height) makes the search an exact tie that rounding decides -- differently in float64 and float32, and the episode that
+     * follows is sensitive to it (profiles/r2_physics_pin.md section 6).  1e-7 m: far above float32 rounding of a vertex height
+     * (4e-9 m), resolved by a tilt of 2e-6 rad across a sole.  0 restores the plain first-minimum search. */
+    double support_tie;
 } plen_oracle_config;
 
 typedef struct {

@@ -47,7 +47,7 @@ class PlenConfigC(C.Structure):
         ("residual_threshold", C.c_float), ("erp_contact", C.c_float), ("erp_joint", C.c_float),
         ("linear_slop", C.c_float), ("warmstart_factor", C.c_float), ("restitution_vel_threshold", C.c_float),
         ("hull_margin", C.c_float), ("max_coord_velocity", C.c_float), ("auto_reset", C.c_int32),
-        ("link_contacts", C.c_int32), ("mu_link", C.c_float), ("sole_manifold", C.c_int32),
+        ("link_contacts", C.c_int32), ("mu_link", C.c_float), ("sole_manifold", C.c_int32), ("support_tie", C.c_float),
     ]
 
 

@@ -104,6 +104,7 @@ struct DevConfig {
     // warp-emulation harness points it at host memory), their counts
     int sole_manifold, n_hull[2];
     const float *hull;
+    float support_tie;
 };
 
 // ---- solve record: per robot, per tick, written by k_dyn and consumed by k_solve (global memory, words)
@@ -996,17 +997,19 @@ PLEN_DEV_NOINLINE unsigned sole_manifold_contacts(const DevConfig &cfg, WarpScra
         for (int k = 0; k < 9; k++) Rf[k] = shfl(Rw[k], src);
 #pragma unroll
         for (int k = 0; k < 3; k++) pf[k] = shfl(pw[k], src);
-        float zb = 3.0e38f;
-        int ib = 0x7fffffff;
         const float *hv = cfg.hull + (size_t)f * PLEN_MAX_HULL * 3;
-        for (int i = lane; i < cfg.n_hull[f]; i += 32) {
-            const float z = Rf[6] * hv[3 * i] + Rf[7] * hv[3 * i + 1] + Rf[8] * hv[3 * i + 2];
-            if (z < zb) { zb = z; ib = i; }
-        }
-        float zmin = zb;
+        float zmin = 3.0e38f;
+        for (int i = lane; i < cfg.n_hull[f]; i += 32)
+            zmin = fminf(zmin, Rf[6] * hv[3 * i] + Rf[7] * hv[3 * i + 1] + Rf[8] * hv[3 * i + 2]);
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) zmin = fminf(zmin, shfl_xor(zmin, d));
-        int idx = (zb == zmin) ? ib : 0x7fffffff;      // ties: the first vertex of the list, as a serial search finds it
+        // vertices within support_tie of the lowest are ties (a foot flat on the ground): the first of them in the list
+        const float zlim = zmin + cfg.support_tie;
+        int idx = 0x7fffffff;
+        for (int i = lane; i < cfg.n_hull[f]; i += 32) {
+            const float z = Rf[6] * hv[3 * i] + Rf[7] * hv[3 * i + 1] + Rf[8] * hv[3 * i + 2];
+            if (z <= zlim && i < idx) idx = i;
+        }
         idx = 0x7fffffff - (int)redux_max((unsigned)(0x7fffffff - idx));       // the smallest index
         if (lane == 0) manifold_merge(cfg, ws.mn[f], ws.mlam + 4 * f, Rf, pf, pos, f, idx);
         warp_sync();

@@ -60,7 +60,7 @@ inline void build_devconfig(const plen_model *m, const plen_config *c, DevConfig
     // persistent sole manifold: needs the hull vertex lists; d->hull is set by the owner of the table memory
     d->sole_manifold = (c->sole_manifold && m->n_hull[0] > 0 && m->n_hull[1] > 0) ? 1 : 0;
     for (int f = 0; f < 2; f++) d->n_hull[f] = m->n_hull[f] < PLEN_MAX_HULL ? m->n_hull[f] : PLEN_MAX_HULL;
-    d->hull = nullptr;
+    d->hull = nullptr; d->support_tie = c->support_tie;
     for (int f = 0; f < 2; f++) {
         d->foot_break[f] = m->foot_break[f];
         d->foot_lane[f] = m->foot_lane[f];
@@ -99,7 +99,7 @@ inline int default_config(plen_config *c, int joint_act) {
     c->restitution_vel_threshold = 0.2f; c->hull_margin = 0.001f; c->max_coord_velocity = 100.0f;
     c->auto_reset = 1;
     c->link_contacts = 1; c->mu_link = 0.5f * 0.8f;
-    c->sole_manifold = 0;
+    c->sole_manifold = 0; c->support_tie = 1.0e-7f;
     return 0;
 }
 

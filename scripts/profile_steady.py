@@ -1,5 +1,6 @@
 """Dev tool for ncu: E robots, W warm-up env steps with random actions (robots fall, lie, reset: the steady state of the bench
-workload), then S more.  PLEN_AB_NOLINKS=1 switches the link-box contacts off.   python scripts/profile_steady.py E W S"""
+workload), then S more.  PLEN_AB_NOLINKS=1 switches the link-box contacts off.   python scripts/profile_steady.py E W S
+The last S steps sit between cudaProfilerStart / cudaProfilerStop (ncu --profile-from-start off captures exactly them)."""
 import ctypes as C
 import os
 import sys
@@ -28,6 +29,10 @@ st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 P = lambda t: C.c_void_p(t.data_ptr())
 lib.plen_reset(ctx, None, P(obs), st)
 for k in range(W + S):
+    if k == W:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     assert lib.plen_step(ctx, P(acts[k % 8]), P(obs), P(rew), P(done), P(tmo), None, st) == 0
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("ok", float(done.float().mean()))
