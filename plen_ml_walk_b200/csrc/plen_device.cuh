@@ -984,34 +984,47 @@ PLEN_DEV_NOINLINE unsigned sole_manifold_contacts(const DevConfig &cfg, WarpScra
     // Persistent manifold per foot (plen_config.sole_manifold = 1; restates btConvexPlaneCollisionAlgorithm +
     // btPersistentManifold as the oracle's manifold_mode 1 does): one new point per tick = the hull's support vertex
     // towards the ground, merged into a cache of <= 4 points; slot k of foot f is contact slot 4 f + k, its impulse travels
-    // with it.  The search runs across the warp, the (scalar, short) cache update on lane 0 out of line.
+    // with it.  The search runs across the warp, the (scalar, short) cache updates on lanes 0 / 1 out of line.
     if (lane < 24) { ws.mn[0][lane] = man[lane]; ws.mn[1][lane] = man[24 + lane]; }
     if (lane < 2) ws.mn[lane][24] = man[48 + lane];
     if (lane >= 24) ws.mlam[lane - 24] = lam_in;
     warp_sync();
-#pragma unroll 1
+    // support vertices of both feet: every lane keeps the heights of its <= 8 vertices in registers (one pass over the list)
+    int idx2[2];
+#pragma unroll
     for (int f = 0; f < 2; f++) {
         const int src = cfg.foot_lane[f];
-        float Rf[9], pf[3];
-#pragma unroll
-        for (int k = 0; k < 9; k++) Rf[k] = shfl(Rw[k], src);
-#pragma unroll
-        for (int k = 0; k < 3; k++) pf[k] = shfl(pw[k], src);
+        const float r6 = shfl(Rw[6], src), r7 = shfl(Rw[7], src), r8 = shfl(Rw[8], src);
         const float *hv = cfg.hull + (size_t)f * PLEN_MAX_HULL * 3;
+        const int nh = cfg.n_hull[f];
+        float z[PLEN_MAX_HULL / 32];
         float zmin = 3.0e38f;
-        for (int i = lane; i < cfg.n_hull[f]; i += 32)
-            zmin = fminf(zmin, Rf[6] * hv[3 * i] + Rf[7] * hv[3 * i + 1] + Rf[8] * hv[3 * i + 2]);
+#pragma unroll
+        for (int j = 0; j < PLEN_MAX_HULL / 32; j++) {
+            const int i = lane + 32 * j;
+            z[j] = 3.0e38f;
+            if (i < nh) z[j] = r6 * hv[3 * i] + r7 * hv[3 * i + 1] + r8 * hv[3 * i + 2];
+            zmin = fminf(zmin, z[j]);
+        }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) zmin = fminf(zmin, shfl_xor(zmin, d));
         // vertices within support_tie of the lowest are ties (a foot flat on the ground): the first of them in the list
         const float zlim = zmin + cfg.support_tie;
         int idx = 0x7fffffff;
-        for (int i = lane; i < cfg.n_hull[f]; i += 32) {
-            const float z = Rf[6] * hv[3 * i] + Rf[7] * hv[3 * i + 1] + Rf[8] * hv[3 * i + 2];
-            if (z <= zlim && i < idx) idx = i;
-        }
-        idx = 0x7fffffff - (int)redux_max((unsigned)(0x7fffffff - idx));       // the smallest index
-        if (lane == 0) manifold_merge(cfg, ws.mn[f], ws.mlam + 4 * f, Rf, pf, pos, f, idx);
+#pragma unroll
+        for (int j = PLEN_MAX_HULL / 32 - 1; j >= 0; j--)
+            if (z[j] <= zlim && lane + 32 * j < nh) idx = lane + 32 * j;
+        idx2[f] = 0x7fffffff - (int)redux_max((unsigned)(0x7fffffff - idx));       // the smallest index
+    }
+    {
+        // the (scalar, short) cache updates of the two feet run side by side on lanes 0 and 1
+        const int f = lane & 1, src = cfg.foot_lane[f];
+        float Rf[9], pf[3];
+#pragma unroll
+        for (int k = 0; k < 9; k++) Rf[k] = shfl(Rw[k], src);
+#pragma unroll
+        for (int k = 0; k < 3; k++) pf[k] = shfl(pw[k], src);
+        if (lane < 2) manifold_merge(cfg, ws.mn[f], ws.mlam + 4 * f, Rf, pf, pos, f, f ? idx2[1] : idx2[0]);
         warp_sync();
     }
     {
@@ -1042,7 +1055,7 @@ PLEN_DEV_NOINLINE unsigned sole_manifold_contacts(const DevConfig &cfg, WarpScra
     return man_new;
 }
 
-// Cache update of one foot's persistent manifold (lane 0 only; see sole_manifold_contacts).  mn: local xyz of 4 points | plane xyz of 4
+// Cache update of one foot's persistent manifold (lane f for foot f; see sole_manifold_contacts).  mn: local xyz of 4 points | plane xyz of 4
 // points | count; lam: the four cached impulses; Rf / pf: world rotation and origin (relative to the base origin) of the foot
 // frame; pos: base position; idx: the hull's support vertex towards the ground.  Restates oracle/plen_oracle.c:manifold_update.
 PLEN_DEV_NOINLINE void manifold_merge(const DevConfig &cfg, float *mn, float *lam, const float *Rf, const float *pf, const float *pos,
