@@ -43,6 +43,9 @@ namespace plen {
 #ifndef PLEN_LA_LATERAL
 #define PLEN_LA_LATERAL 0
 #endif
+#ifndef PLEN_TORSION_BLOCK
+#define PLEN_TORSION_BLOCK 1   // spinning / rolling rows of a foot as one private chain of the owner lane + one column update per functional
+#endif
 
 // Shared memory holds 24 of the 30 columns of G per robot: the 18 joint columns and the linear (vx vy vz) columns of
 // either foot.  The six ANGULAR foot columns -- the ones the contact rows use most (normal 2 of 3, spinning, rolling,
@@ -435,6 +438,18 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
         apply_reg(s, A[f][c], db_);                                                                       \
     }
 
+    // one spinning / rolling row inside the owner's private chain (PLEN_TORSION_BLOCK): u = the owner's current value of the
+    // row's twist component, sum += the impulse change; leaves the change in dl_own_ for the caller's updates of u
+#define TORSION_OWN(k, f, c, mu, u, sum)                                                                  \
+        const float x_##c##k = fmaf(-(u), t_dinv[c], t_rhs[c]);                                           \
+        const float lim_##c##k = (mu) * c_lam[k][5];                                                      \
+        const bool on_##c##k = c_lam[k][5] > 0.0f;                                                        \
+        const float lo_##c##k = on_##c##k ? -lim_##c##k - c_lam[k][c] : 0.0f;                             \
+        const float hi_##c##k = on_##c##k ? lim_##c##k - c_lam[k][c] : 0.0f;                              \
+        dl_own_ = fminf(fmaxf(x_##c##k, lo_##c##k), hi_##c##k);                                           \
+        (sum) += dl_own_;                                                                                 \
+        if (g == 2 + (f)) { c_lam[k][c] += dl_own_; resT[c] = fmaxf(resT[c], fabsf(dl_own_)); }
+
     float mu_spin = lc.mu_spin * fric_s, mu_roll = lc.mu_roll * fric_s, mu_lat = lc.mu_lat * fric_s;      // opened at the freeze
     float mu_link = EXT ? cfg.mu_link * fric_s : 0.0f;
     const float res_thr = lc.res_thr;
@@ -522,6 +537,48 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
         }
         if (man_any) {
             // ---- all spinning rows, then the rolling rows point by point (t1, t2)
+#if PLEN_TORSION_BLOCK
+            // The spinning rows of a foot's points are consecutive in the row list and are the SAME functional (the foot's wz);
+            // the rolling rows (t1, t2 point by point) are two functionals (wy, wx).  A block of them therefore interacts only
+            // through one (two) entries of x and the 1 x 1 (2 x 2) diagonal block of G, both of which the owner lane holds: it
+            // runs the block's Gauss-Seidel chain privately (TORSION_OWN: FFMA -> FMNMX -> FMNMX -> FFMA per row, no SHFL) and
+            // broadcasts the SUM of the impulse changes per functional -- x += G[:,c] (sum of deltas) is the same update by
+            // linearity (re-associated: equal to the row-by-row form up to rounding).  n rows cost one column application
+            // instead of n, and the SHFL round trip leaves the chain except once per block.
+#pragma unroll
+            for (int f = 0; f < 2; f++) {
+                if ((f ? nmax1 : nmax0) == 0) continue;
+                float u2_ = s[4], sum2_ = 0.0f;
+                const float a22_ = A[f][2][4];
+                float dl_own_;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (k >= (f ? nmax1 : nmax0)) break;
+                    TORSION_OWN(k, f, 2, mu_spin, u2_, sum2_);
+                    u2_ = fmaf(a22_, dl_own_, u2_);
+                }
+                apply_reg(s, A[f][2], GSH(sum2_, 2 + f));
+            }
+#pragma unroll
+            for (int f = 0; f < 2; f++) {
+                if ((f ? nmax1 : nmax0) == 0) continue;
+                float u1_ = s[3], u0_ = s[2], sum1_ = 0.0f, sum0_ = 0.0f;
+                // response of (wx, wy) of this foot to unit impulses on wy (column 1) and wx (column 0)
+                const float a11_ = A[f][1][3], a01_ = A[f][1][2], a10_ = A[f][0][3], a00_ = A[f][0][2];
+                float dl_own_;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (k >= (f ? nmax1 : nmax0)) break;
+                    TORSION_OWN(k, f, 1, mu_roll, u1_, sum1_);
+                    u1_ = fmaf(a11_, dl_own_, u1_); u0_ = fmaf(a01_, dl_own_, u0_);
+                    TORSION_OWN(k, f, 0, mu_roll, u0_, sum0_);
+                    u0_ = fmaf(a00_, dl_own_, u0_); u1_ = fmaf(a10_, dl_own_, u1_);
+                }
+                const float d1_ = GSH(sum1_, 2 + f), d0_ = GSH(sum0_, 2 + f);
+                apply_reg(s, A[f][1], d1_);
+                apply_reg(s, A[f][0], d0_);
+            }
+#else
             FOR_ACTIVE_POINTS {
                 if (PLEN_LA_TORSION && k == 0) OWN_SYNC6();
                 TORSION_ROW(k, f, 2, mu_spin);
@@ -531,6 +588,7 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
                 TORSION_ROW(k, f, 1, mu_roll);
                 TORSION_ROW(k, f, 0, mu_roll);
             }
+#endif
             // ---- lateral pairs with the implicit friction cone (resolveConeFrictionConstraintRows)
             FOR_ACTIVE_POINTS {
                 if (PLEN_LA_LATERAL && k == 0) OWN_SYNC6();
@@ -757,6 +815,7 @@ PLEN_DEV void solve_tick(const DevConfig &cfg, const float *__restrict__ srec, f
 #undef LIMIT_ROW
 #undef L_LAM
 #undef TORSION_ROW
+#undef TORSION_OWN
 #undef NORMAL_COLUMN
 }
 

@@ -32,7 +32,8 @@ dev = torch.device("cuda:0")
 obs = torch.empty((E, 26), device=dev); rew = torch.empty(E, device=dev)
 done = torch.empty(E, dtype=torch.uint8, device=dev); tmo = torch.empty(E, dtype=torch.uint8, device=dev)
 g = torch.Generator(device=dev); g.manual_seed(0)
-acts = [torch.empty((E, 18), device=dev).uniform_(-1, 1, generator=g) for _ in range(8)]
+amp = float(os.environ.get("PLEN_AB_AMP", "1"))      # < 1: small random actions, the robots stay on their feet (8 sole points)
+acts = [torch.empty((E, 18), device=dev).uniform_(-amp, amp, generator=g) for _ in range(8)]
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 P = lambda t: C.c_void_p(t.data_ptr())
 lib.plen_reset(ctx, None, P(obs), st)

@@ -126,15 +126,18 @@ def test_teacher_forced_contact_steps(mods):
     assert flag_mis <= max(0.02 * 2 * total, 2 * flag_ctl) and done_mis <= 0.02 * total
 
 
-def test_free_running_distributions_random_actions(mods):
+@pytest.mark.parametrize("manifold", [0, 1])
+def test_free_running_distributions_random_actions(mods, manifold):
     """No teacher forcing: 4,096 envs x 500 steps of random actions with auto-reset on both sides (different random streams
     would do; the same one is used).  Trajectories decorrelate within a second, so the comparison is distributional:
-    episode-length histogram, mean reward per step, contact duty cycles, fall fraction."""
+    episode-length histogram, mean reward per step, contact duty cycles, fall fraction.  manifold = 1: the persistent sole
+    manifold option (plen_config.sole_manifold) against the oracle's manifold_mode 1, auto-reset restoring the manifolds."""
     oracle, PlenVecEnv = mods
     n, steps = 4096, 500
     rng = np.random.default_rng(3)
     o = oracle.PlenOracle(n, n_threads=16)
-    env = PlenVecEnv(n, auto_reset=True)
+    o.cfg.manifold_mode = manifold
+    env = PlenVecEnv(n, auto_reset=True, config_overrides={"sole_manifold": manifold})
     o.reset()
     env.reset()
     stats = {}
@@ -159,6 +162,7 @@ def test_free_running_distributions_random_actions(mods):
     lg, lr = np.sort(np.array(g["len"])), np.sort(np.array(r["len"]))
     grid = np.arange(1, 501)
     ks = np.abs(np.searchsorted(lg, grid, side="right") / len(lg) - np.searchsorted(lr, grid, side="right") / len(lr)).max()
+    print("sole_manifold %d:" % manifold, end=" ")
     print("episodes gpu %d oracle %d | mean length %.2f vs %.2f | KS %.4f | reward/step %.4f vs %.4f | duty R %.4f vs %.4f L %.4f vs %.4f | "
           "fall fraction %.4f vs %.4f" % (len(lg), len(lr), lg.mean(), lr.mean(), ks, g["rew"] / g["nrew"], r["rew"] / r["nrew"],
                                           g["duty"][0] / (n * steps), r["duty"][0] / (n * steps), g["duty"][1] / (n * steps),
