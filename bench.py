@@ -45,14 +45,14 @@ SOLVE_DRAM_BYTES_PER_ROBOT = (207.10e6 + 9.92e6) / 32768
 # FROZEN in BASELINE.md ("Work per env-step"): executed FP32 work per robot-tick ON THIS WORKLOAD, counted from the SASS-level
 # execution counts of ncu's source page (scripts/flops_sass.py: FFMA2 = 4 flop, FFMA = 2, FADD / FMUL = 1 per predicated-on
 # thread instruction) over every launch of ONE env step of 131,072 robots at step 30 after the reset, the middle of the
-# timed region (profiles/r2_flops_sass.md): k_dyn 44.0 kflop, k_solve 166.3 kflop + k_solve_x 12.2 kflop (the bracket of
-# "k_solve" covers both), k_post 17.0 kflop per env step.  The earlier figure (25.9 + 2.7 kflop for the solve) came from
+# timed region (profiles/r2_flops_sass.md, final build): k_dyn 44.0 kflop, k_solve 163.9 kflop + k_solve_x 12.0 kflop (the
+# bracket of "k_solve" covers both), k_post 17.0 kflop per env step.  The earlier figure (25.9 + 2.7 kflop for the solve) came from
 # smsp__sass_thread_inst_executed_op_{fadd,fmul,ffma}_pred_on, which do NOT count the packed FFMA2 (fma.rn.f32x2) that
-# carries every row update of k_solve: 30.6 % of its issued instructions, 84 % of its flops (cross-checked against
-# sm__pipe_fma_cycles_active of the same launches to 1.6 %).
-FLOP_DYN_PER_ROBOT_TICK, FLOP_SOLVE_PER_ROBOT_TICK, FLOP_POST_PER_ENV_STEP = 44.0e3, 178.5e3, 17.0e3
+# carries every row update of k_solve: 28.9 % of its issued instructions, 82 % of its flops (cross-checked against
+# sm__pipe_fma_cycles_active of the same launches to 1.9 %).
+FLOP_DYN_PER_ROBOT_TICK, FLOP_SOLVE_PER_ROBOT_TICK, FLOP_POST_PER_ENV_STEP = 44.0e3, 175.9e3, 17.0e3
 # what ncu's three op metrics see of the same step (scalar FADD + FMUL + 2 FFMA only): kept for comparison with round 1 / 2 lines
-FLOP_PER_ENV_STEP_NCU_OP_METRICS = 0.306e6
+FLOP_PER_ENV_STEP_NCU_OP_METRICS = 0.323e6
 FLOP_PER_ENV_STEP = 4 * (FLOP_DYN_PER_ROBOT_TICK + FLOP_SOLVE_PER_ROBOT_TICK) + FLOP_POST_PER_ENV_STEP
 # the same workload through the REFERENCE ALGORITHM (33-link ABA + velocity-space PGS with 24-wide rows), counted by the
 # oracle's instrumented FLOP counter (plen_oracle_state.flops; scripts/oracle_flops.py): 1.32 Mflop per env-step
@@ -432,7 +432,7 @@ def main():
                                                  "equivalent_frac": REF_ALGO_FLOP_PER_ENV_STEP * value / world / 1e12 / fp32_peak},
                          "note": "flop = executed FADD + FMUL + 2 FFMA + 4 FFMA2 thread operations counted from the SASS execution counts of "
                                  "ncu's source page on this workload (frozen in BASELINE.md; ncu's op_ffma metric does not count the packed "
-                                 "FFMA2 that is 84 % of k_solve's flops, so lines before this build quoted a 6.3x smaller solve count); "
+                                 "FFMA2 that is 82 % of k_solve's flops, so lines before this build quoted a 6.2x smaller solve count); "
                                  "k_solve keeps the FMA pipe 34 % busy at 2 warps per scheduler: what is left is the dependency latency of "
                                  "the Gauss-Seidel row chain; reference_algorithm = the same env-steps/s priced at the oracle's instrumented "
                                  "flop count of Bullet's ABA + velocity-space PGS; traffic = ncu DRAM bytes per robot (32768-robot capture) x robots per launch"},
