@@ -17,6 +17,8 @@ cfg = _abi.PlenConfigC()
 lib.plen_default_config(C.byref(cfg), 0)
 if os.environ.get("PLEN_AB_NOLINKS"):
     cfg.link_contacts = 0
+if os.environ.get("PLEN_AB_MANIFOLD"):
+    cfg.sole_manifold = 1      # persistent sole manifolds (plen_config.sole_manifold)
 model = _abi.model_to_c(packaged_model())
 ctx = lib.plen_create(C.byref(cfg), C.byref(model), E, 0)
 assert ctx

@@ -11,7 +11,8 @@ from plen_ml_walk_b200.vec_env import PlenVecEnv
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 131072
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 300
-a, b = PlenVecEnv(N), PlenVecEnv(N)
+OVR = {"sole_manifold": 1} if os.environ.get("PLEN_AB_MANIFOLD") else None      # the persistent sole manifold option
+a, b = PlenVecEnv(N, config_overrides=OVR), PlenVecEnv(N, config_overrides=OVR)
 g = torch.Generator(device="cuda"); g.manual_seed(0)
 a.reset(); b.reset()
 bad_steps = 0
