@@ -292,11 +292,13 @@ def main():
 
     import torch
     from plen_ml_walk_b200 import _abi
-    from plen_ml_walk_b200.sharding import env_seed, max_over_ranks
+    from plen_ml_walk_b200.sharding import bind_host_to_gpu, env_seed, max_over_ranks
     from plen_ml_walk_b200.vec_env import PlenVecEnv
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    # N > 1: every rank runs on (and pins its host buffers next to) the CPU cores local to its GPU
+    host_affinity = bind_host_to_gpu(local_rank) if world > 1 and not os.environ.get("PLEN_NO_BIND") else "unchanged"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
@@ -413,7 +415,8 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": ("config5: %d envs in total over %d GPU(s) = %d envs/GPU, random actions U(-1,1)^18, "
                                     "auto-reset, 4 ticks/step" % (E * world, world, E)),
-                       "total_envs": E * world, "envs_per_gpu": E, "l2": "256 MiB flush between timed steps"},
+                       "total_envs": E * world, "envs_per_gpu": E, "l2": "256 MiB flush between timed steps",
+                       "host_affinity": host_affinity},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": E * 18 * 4,
                     "d2h_bytes_per_step": E * (26 * 4 + 4 + 1), "steps": Ke},
             "gpu_launches": gpu_launches,

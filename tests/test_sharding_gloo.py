@@ -46,3 +46,18 @@ def test_two_ranks_over_gloo(tmp_path):
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     r = torch.load(out)
     assert r["owned_ok"] and r["t_max"] == 11.0 and r["total"] == 4097.0
+
+
+def test_bind_host_to_gpu_never_raises_and_reports():
+    """One process per GPU binds itself to the CPUs local to its GPU (NVML); without NVML / a GPU the call must leave the
+    affinity alone and say so."""
+    import os
+    from plen_ml_walk_b200.sharding import bind_host_to_gpu
+    before = os.sched_getaffinity(0)
+    msg = bind_host_to_gpu(0)
+    assert isinstance(msg, str) and (msg.startswith("unchanged") or msg.startswith("bound to"))
+    if msg.startswith("unchanged"):
+        assert os.sched_getaffinity(0) == before
+    else:
+        assert os.sched_getaffinity(0) <= before
+        os.sched_setaffinity(0, before)
