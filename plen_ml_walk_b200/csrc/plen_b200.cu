@@ -679,6 +679,12 @@ static int create_impl(plen_ctx *ctx) {
 
 plen_ctx *plen_create(const plen_config *cfg, const plen_model *model, int n_envs, int device) {
     if (!cfg || !model || n_envs <= 0) { fail(nullptr, PLEN_E_ARG, "plen_create: bad arguments"); return nullptr; }
+    if (cfg->sole_manifold && (model->n_hull[0] <= 0 || model->n_hull[1] <= 0 || model->n_hull[0] > PLEN_MAX_HULL ||
+                               model->n_hull[1] > PLEN_MAX_HULL || !(cfg->support_tie >= 0.0f))) {
+        fail(nullptr, PLEN_E_ARG, "plen_create: sole_manifold = 1 needs 1..%d hull vertices per foot in the model (got %d, %d) and "
+                                  "support_tie >= 0", PLEN_MAX_HULL, model->n_hull[0], model->n_hull[1]);
+        return nullptr;
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {

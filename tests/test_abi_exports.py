@@ -45,6 +45,26 @@ def test_struct_mirrors_and_defaults(lib):
     assert e.L.emu_sizeof_config() == C.sizeof(_abi.PlenConfigC) and e.L.emu_sizeof_model() == C.sizeof(_abi.PlenModelC)
 
 
+def test_sole_manifold_needs_hull_vertices(lib):
+    """plen_create checks its arguments before it looks for a device: sole_manifold = 1 on a model without hull vertices (or
+    with a negative tie tolerance) is refused with a message, not silently run as the four-corner path."""
+    from plen_ml_walk_b200 import _abi
+    from plen_ml_walk_b200.urdf_loader import packaged_model
+    cfg = _abi.PlenConfigC()
+    lib.plen_default_config(C.byref(cfg), 0)
+    assert cfg.sole_manifold == 0 and abs(cfg.support_tie - 1e-7) < 1e-12
+    model = _abi.model_to_c(packaged_model())
+    assert model.n_hull[0] == 209 and model.n_hull[1] == 209          # plen.urdf feet: the STL hulls
+    cfg.sole_manifold = 1
+    model.n_hull[1] = 0
+    assert not lib.plen_create(C.byref(cfg), C.byref(model), 4, 0)
+    assert b"hull vertices" in lib.plen_last_error(None)
+    model.n_hull[1] = 209
+    cfg.support_tie = -1.0
+    assert not lib.plen_create(C.byref(cfg), C.byref(model), 4, 0)
+    assert b"support_tie" in lib.plen_last_error(None)
+
+
 def test_no_cpu_fallback(lib):
     import torch
     if torch.cuda.is_available():
