@@ -133,6 +133,7 @@ VARIANTS = [
     ("inertia from the URDF tensors instead of the collision AABB", {"__tree__": "urdf_inertia"}),
     # the structural experiment: Bullet's one-point-per-tick persistent manifold instead of the four fixed sole corners
     ("sole contact as btPersistentManifold (manifold_mode 1)", {"manifold_mode": 1}),
+    ("manifold_mode 1, support_tie 1e-7 -> 0 (the reset's tie decided by rounding)", {"manifold_mode": 1, "support_tie": 0.0}),
     ("manifold_mode 1, warmstart 0.1 -> 0.85", {"manifold_mode": 1, "warmstart_factor": 0.85}),
     ("manifold_mode 1, foot breaking threshold x4", {"manifold_mode": 1, "foot_break_scale": 4.0}),
 ]

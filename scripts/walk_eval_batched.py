@@ -33,13 +33,19 @@ def main():
     ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--sole-manifold", type=int, default=0, choices=[0, 1],
                     help="plen_config.sole_manifold: 1 = Bullet's one-point-per-tick persistent manifold (profiles/r2_physics_pin.md 5)")
+    ap.add_argument("--config", action="append", default=[], metavar="KEY=VALUE",
+                    help="plen_config override (repeatable), e.g. --config warmstart_factor=0.85 --config support_tie=0")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     g = np.load(GOLD)
     actor = Actor().to(dev)
     actor.load_state_dict({k: torch.from_numpy(g["actor_" + k.replace(".", "_")]).to(dev) for k in actor.state_dict().keys()})
     n = a.envs
-    env = PlenVecEnv(n, device=dev, auto_reset=False, config_overrides={"sole_manifold": a.sole_manifold})
+    ovr = {"sole_manifold": a.sole_manifold}
+    for kv in a.config:
+        k, v = kv.split("=", 1)
+        ovr[k] = float(v) if ("." in v or "e" in v.lower()) else int(v)
+    env = PlenVecEnv(n, device=dev, auto_reset=False, config_overrides=ovr)
     state = env.reset().clone()
     alive = torch.ones(n, dtype=torch.bool, device=dev)
     ep_len = torch.zeros(n, device=dev); ep_ret = torch.zeros(n, device=dev)
@@ -58,7 +64,7 @@ def main():
     L, R, X = ep_len.cpu().numpy(), ep_ret.cpu().numpy(), x_end.cpu().numpy()
     print(json.dumps({
         "policy": "plen_walk_gazebo_3229999 (reference checkpoint)", "envs": n, "steps": a.steps, "sigma": a.sigma,
-        "precision": a.precision, "sole_manifold": a.sole_manifold,
+        "precision": a.precision, "sole_manifold": a.sole_manifold, "config_overrides": ovr,
         "deterministic": {"episode_length": float(L[0]), "return": float(R[0]), "x_final_m": float(X[0])},
         "noisy": {"episode_length_mean": float(L[1:].mean()), "episode_length_median": float(np.median(L[1:])),
                   "survived_all_steps_frac": float((L[1:] >= a.steps).mean()), "return_mean": float(R[1:].mean()),
