@@ -274,10 +274,11 @@ class PlenWalkEnv:
     TimeLimit(500) wrapper; like the reference it does NOT auto-reset (the caller does, plen_td3.py:122-129).
     """
 
-    def __init__(self, render=False, realtime=False, joint_act=False, device="cuda:0"):
+    def __init__(self, render=False, realtime=False, joint_act=False, device="cuda:0", config_overrides=None):
         if render or realtime:
             raise NotImplementedError("the B200 env is headless (PyBullet GUI / realtime modes are out of scope)")
-        self.vec = PlenVecEnv(1, device=device, joint_act=joint_act, auto_reset=False)
+        # config_overrides: plen_config fields, e.g. {"sole_manifold": 1} (gym.make passes keyword arguments through)
+        self.vec = PlenVecEnv(1, device=device, joint_act=joint_act, auto_reset=False, config_overrides=config_overrides)
         self.action_space, self.observation_space = self.vec.action_space, self.vec.observation_space
         self.env_ranges, self.real_ranges = ENV_RANGES, REAL_RANGES
         self._max_episode_steps = self.vec._max_episode_steps
