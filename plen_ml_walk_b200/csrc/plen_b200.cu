@@ -42,7 +42,7 @@ using namespace plen;
 #endif
 
 struct plen_ctx {
-    int n, device, sm_count, merge_max;
+    int n, device, sm_count, merge_max, host_ranges;
     plen_config cfg;
     plen_model model;
     DevConfig dc;
@@ -617,6 +617,7 @@ void plen_destroy(plen_ctx *ctx) {
 static int create_impl(plen_ctx *ctx) {
     const int n = ctx->n;
     ctx->merge_max = getenv("PLEN_MERGE_MAX") ? atoi(getenv("PLEN_MERGE_MAX")) : PLEN_MERGE_MAX;
+    ctx->host_ranges = getenv("PLEN_HOST_RANGES") ? atoi(getenv("PLEN_HOST_RANGES")) : 0;      // dev knob: ranges of plen_step_host (0 = by size)
     CK(ctx, cudaSetDevice(ctx->device));
     CK(ctx, cudaFuncSetAttribute(k_dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DYN_SMEM));
     CK(ctx, cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DYN_SMEM));
@@ -757,15 +758,22 @@ int plen_step_host(plen_ctx *ctx, const float *actions_host, float *obs_host, fl
     if (!actions_host || !obs_host || !reward_host || !done_host) return fail(ctx, PLEN_E_ARG, "plen_step_host: NULL buffer");
     const size_t n = ctx->n;
     CK(ctx, cudaSetDevice(ctx->device));
-    // The batch is cut into PLEN_HOST_PIPE ranges (multiples of the 1024-robot sort tile), each on its own stream:
+    // The batch is cut into up to PLEN_HOST_PIPE ranges (multiples of the 1024-robot sort tile), each on its own stream:
     // H2D of the range's actions -> its 13 kernels -> D2H of its obs / reward / done.  Robots are independent, so the
     // copies of one range overlap the kernels of the others and only the first H2D and the last D2H stay exposed.
-    size_t chunk = (n + PLEN_HOST_PIPE - 1) / PLEN_HOST_PIPE;
+    // How many ranges: measured per batch size (profiles/r2_ab_runs.txt, r2_host2: 1 / 2 / 3 / 4 ranges at 4,096 ... 1,048,576
+    // robots).  Small batches lose more to short grids than they gain from overlapped copies (4,096: one range +6 % over four,
+    // 16,384: two +8 %); from 65,536 robots on four ranges win (+1 %) -- except where a quarter of the batch falls just under
+    // PLEN_MERGE_MAX and would run the merged solver on a full GPU (131,072 robots: two ranges of 65,536 +3.6 % over four of
+    // 32,768).  More than PLEN_HOST_PIPE ranges (8, 16 at 1,048,576 robots) were measured and are never better.
+    int n_ranges = ctx->host_ranges;                   // dev knob PLEN_HOST_RANGES; 0 = by size
+    if (n_ranges <= 0) n_ranges = n <= 8192 ? 1 : n <= 32768 ? 2 : n <= 98304 ? 4 : n <= 196608 ? 2 : PLEN_HOST_PIPE;
+    size_t chunk = (n + n_ranges - 1) / n_ranges;
     chunk = (chunk + RANK_TILE - 1) / RANK_TILE * RANK_TILE;
     int used = 0;
     for (size_t off = 0; off < n; off += chunk, used++) {
         const size_t cnt = (n - off < chunk) ? n - off : chunk;
-        cudaStream_t st = ctx->pipe[used];
+        cudaStream_t st = ctx->pipe[used % PLEN_HOST_PIPE];
         // ordering contract (plen_b200.h): this call runs on the context's private streams, so it first waits for whatever
         // the last stream-taking entry point (reset / step / set_state / set_env_scales / tick) queued on the caller's stream
         CK(ctx, cudaStreamWaitEvent(st, ctx->last_work, 0));
@@ -779,7 +787,7 @@ int plen_step_host(plen_ctx *ctx, const float *actions_host, float *obs_host, fl
         if (timeout_host) CK(ctx, cudaMemcpyAsync(timeout_host + off, ctx->d_tmo + off, cnt, cudaMemcpyDeviceToHost, st));
     }
     CK(ctx, cudaGetLastError());
-    for (int k = 0; k < used; k++) CK(ctx, cudaStreamSynchronize(ctx->pipe[k]));
+    for (int k = 0; k < used && k < PLEN_HOST_PIPE; k++) CK(ctx, cudaStreamSynchronize(ctx->pipe[k]));
     return PLEN_OK;
 }
 
