@@ -763,9 +763,9 @@ int plen_step_host(plen_ctx *ctx, const float *actions_host, float *obs_host, fl
     // copies of one range overlap the kernels of the others and only the first H2D and the last D2H stay exposed.
     // How many ranges: measured per batch size (profiles/r2_ab_runs.txt, r2_host2: 1 / 2 / 3 / 4 ranges at 4,096 ... 1,048,576
     // robots).  Small batches lose more to short grids than they gain from overlapped copies (4,096: one range +6 % over four,
-    // 16,384: two +8 %); from 65,536 robots on four ranges win (+1 %) -- except where a quarter of the batch falls just under
-    // PLEN_MERGE_MAX and would run the merged solver on a full GPU (131,072 robots: two ranges of 65,536 +3.6 % over four of
-    // 32,768).  More than PLEN_HOST_PIPE ranges (8, 16 at 1,048,576 robots) were measured and are never better.
+    // 16,384: two +8 %); at 65,536 robots and from 262,144 on four ranges win by ~1 %, around 131,072 two ranges of 65,536 are
+    // 3.6 % faster than four of 32,768 (0.9 % of it is the merged solver that ranges <= PLEN_MERGE_MAX run, the rest the
+    // finer split itself: r2_merge).  More than PLEN_HOST_PIPE ranges (8, 16 at 1,048,576 robots) are never better.
     int n_ranges = ctx->host_ranges;                   // dev knob PLEN_HOST_RANGES; 0 = by size
     if (n_ranges <= 0) n_ranges = n <= 8192 ? 1 : n <= 32768 ? 2 : n <= 98304 ? 4 : n <= 196608 ? 2 : PLEN_HOST_PIPE;
     size_t chunk = (n + n_ranges - 1) / n_ranges;
