@@ -114,3 +114,31 @@ def test_loader_handles_the_box_foot_variant():
     if os.path.exists(os.path.join(ref, "plen_bullet/src/plen_new.urdf")):
         m = load_plen_model(os.path.join(ref, "plen_bullet/src/plen_new.urdf"), os.path.join(ref, "plen_ros/meshes_bin"))
         assert np.allclose(m.foot_pts, new.foot_pts) and np.allclose(m.inertia, new.inertia)
+
+
+def test_persistent_manifold_regression_fixture():
+    """tests/golden/manifold_golden.npz (scripts/make_manifold_golden.py): the oracle's manifold_mode = 1 with support_tie = 1e-7
+    replays its own committed trajectory -- observations, rewards, done flags AND the manifolds (cached points, point counts) after
+    every one of 80 steps of a swaying and a falling robot, resets included.  A regression pin of the restated procedure (it was
+    produced by this oracle, not by PyBullet): the kernels' sole_manifold option is judged against this oracle."""
+    import os
+    from oracle.oracle import PlenOracle
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "manifold_golden.npz"))
+    n = g["obs0"].shape[0]
+    o = PlenOracle(n)
+    o.cfg.manifold_mode = 1
+    o.cfg.support_tie = 1e-7
+    assert np.abs(o.reset() - g["obs0"]).max() < 1e-12
+    assert np.abs(o.get_manifold() - g["man0"]).max() < 1e-12
+    counts = set()
+    for t in range(g["actions"].shape[0]):
+        ob, r, d, _ = o.step(g["actions"][t])
+        assert (d == g["done"][t]).all(), "done flags differ at step %d" % t
+        assert np.abs(ob - g["obs"][t]).max() < 1e-9, "observation differs at step %d" % t
+        assert np.abs(np.nan_to_num(r, nan=-1e9) - g["reward"][t]).max() < 1e-8
+        m = o.get_manifold()
+        assert (m[:, 48:50] == g["manifold"][t][:, 48:50]).all() and np.abs(m - g["manifold"][t]).max() < 1e-9
+        counts |= set(m[:, 48:50].ravel().astype(int))
+        for e in np.where(d)[0]:
+            o.reset_one(int(e))
+    assert counts == {0, 1, 2, 3, 4} and g["done"].sum() >= 3      # every cache size and a few resets occur in the fixture
