@@ -162,8 +162,8 @@ int plen_step(plen_ctx *ctx, const float *actions_dev, float *obs_dev, float *re
 /* Same call with HOST buffers (pinned memory recommended): H2D of the actions, the step, D2H of obs / reward / done,
  * and a stream synchronise.  This is the end-to-end path a PyBullet user would see.
  * Ordering contract: the call runs on the context's PRIVATE streams (the batch is pipelined in ranges).  It first waits
- * (cudaStreamWaitEvent) for the work the last plen_reset / plen_step / plen_set_state / plen_set_env_scales / plen_tick
- * call queued on its caller stream, so `plen_reset(...); plen_step_host(...)` needs no synchronisation in between; it
+ * (cudaStreamWaitEvent) for the work the last plen_reset / plen_step / plen_set_state / plen_set_manifold / plen_set_env_scales /
+ * plen_tick call queued on its caller stream, so `plen_reset(...); plen_step_host(...)` needs no synchronisation in between; it
  * returns after its own streams have drained, so whatever the caller queues next is ordered after it.  (Work the caller
  * queued on a stream WITHOUT going through this library -- e.g. a torch kernel still writing the state through
  * plen_set_state's source buffer -- is the caller's to order.) */
